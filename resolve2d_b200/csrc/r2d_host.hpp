@@ -1,0 +1,328 @@
+// r2d_host.hpp — host-side runtime shared by the CUDA backend (r2d_runtime.cu): the per-world registry that mirrors
+// the reference's `Solver` containers (stable id -> dense slot, insertion order, swapRemove), scene construction
+// arithmetic (EntityFactory), joint colouring, and flattening of all worlds of a batch into one structure-of-arrays
+// image for upload.  Pure C++17 (no CUDA calls), so tests/emu/ can drive the same code on a CPU.
+//
+// Follows src/core/lib.zig:13-187,301-315 (EntityFactory, Solver.init/deinit/clear/removeRigidBody),
+// Bodies/Disc.zig:29-56, Bodies/Rectangle.zig:33-64.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "../../include/r2d_abi.h"
+#include "r2d_pipeline.cuh"
+
+namespace r2d {
+namespace host {
+
+struct Body {
+    uint32_t id = 0;
+    int32_t shape = 0;
+    bool is_static = false;
+    float pos_x = 0, pos_y = 0, angle = 0;
+    float mom_x = 0, mom_y = 0, ang_mom = 0;
+    float force_x = 0, force_y = 0, torque = 0;
+    float mass = 0, inertia = 0, mu = 0;
+    float aabb_x = 0, aabb_y = 0, aabb_hw = 0, aabb_hh = 0;
+    float a = 0, b = 0;  // disc: radius; rect: width, height
+};
+
+struct Joint {
+    int32_t type = 0;
+    uint32_t id1 = 0, id2 = 0;
+    float power_max = 0, power_min = 0, beta = 0;
+    float r1x = 0, r1y = 0, r2x = 0, r2y = 0;  // offset joint anchors | fixed joint target in (r1x, r1y)
+    float target = 0;                          // distance | omega
+};
+
+inline bool joint_has_two_bodies(const Joint& j) {
+    return j.type == R2D_JOINT_DISTANCE || j.type == R2D_JOINT_OFFSET_DISTANCE;
+}
+
+struct BatchBase;
+
+// One world = the containers of the reference's Solver (lib.zig:132-142).
+struct World {
+    BatchBase* batch = nullptr;
+    uint32_t index = 0;
+    bool owns_batch = false;
+    uint32_t current_body_id = 0;                       // lib.zig:134; survives clear() (Q16)
+    std::vector<Body> bodies;                           // AutoArrayHashMap: insertion order, swapRemove
+    std::unordered_map<uint32_t, uint32_t> slot_of;     // id -> slot
+    std::vector<float> gravities;                       // force_generators (only DownwardsGravity exists)
+    std::vector<Joint> joints;                          // constraints, list order = solve order in the reference
+    std::set<std::pair<uint32_t, uint32_t>> excluded;   // exclude_collision_pairs, both orders (Q22)
+
+    int find(uint32_t id) const {
+        auto it = slot_of.find(id);
+        return it == slot_of.end() ? -1 : (int)it->second;
+    }
+
+    // makeDiscBody / makeRectangleBody (lib.zig:73-93) + Disc.init / Rectangle.init + appendBody (lib.zig:66-71)
+    uint32_t make_body(const r2d_body_opts& o, int shape, float a, float b, bool is_static) {
+        Body bd;
+        bd.shape = shape;
+        bd.a = a;
+        bd.b = (shape == R2D_SHAPE_RECT) ? b : 0.0f;
+        float mass;
+        if (shape == R2D_SHAPE_DISC) {
+            const float pi = 3.14159265358979323846f;  // @as(f32, std.math.pi)
+            mass = o.mass_is_density ? fmul(fmul(fmul(pi, a), a), o.mass_value) : o.mass_value;
+            bd.inertia = fmul(fmul(fmul(0.5f, mass), a), a);                        // Disc.zig:42
+        } else {
+            mass = o.mass_is_density ? fmul(fmul(a, b), o.mass_value) : o.mass_value;
+            bd.inertia = fdiv(fmul(mass, fadd(fmul(a, a), fmul(b, b))), 12.0f);     // Rectangle.zig:51
+        }
+        bd.mass = mass;
+        bd.mu = o.mu;
+        bd.pos_x = o.pos_x;
+        bd.pos_y = o.pos_y;
+        bd.angle = o.angle;
+        bd.mom_x = fmul(o.vel_x, mass);       // lib.zig:79 / :90
+        bd.mom_y = fmul(o.vel_y, mass);
+        bd.ang_mom = fmul(o.omega, bd.inertia);
+        bd.is_static = is_static;
+        // updateAABB at init (Disc.zig:53, Rectangle.zig:62)
+        const uint32_t flags = (shape == R2D_SHAPE_RECT) ? FLAG_RECT : 0u;
+        aabb_half_extents(flags, bd.a, bd.b, cos_ref(bd.angle), sin_ref(bd.angle), bd.aabb_hw, bd.aabb_hh);
+        bd.aabb_x = bd.pos_x;
+        bd.aabb_y = bd.pos_y;
+        bd.id = current_body_id;
+        slot_of[bd.id] = (uint32_t)bodies.size();
+        bodies.push_back(bd);
+        current_body_id += 1;
+        return bd.id;
+    }
+    bool remove_body(uint32_t id) {  // lib.zig:308-310: swapRemove — the last body moves into the hole (Q17)
+        const int s = find(id);
+        if (s < 0) return false;
+        slot_of.erase(id);
+        if ((size_t)s != bodies.size() - 1) {
+            bodies[s] = bodies.back();
+            slot_of[bodies[s].id] = (uint32_t)s;
+        }
+        bodies.pop_back();
+        return true;
+    }
+    void clear() {  // lib.zig:181-187
+        bodies.clear();
+        slot_of.clear();
+        gravities.clear();
+        joints.clear();
+    }
+};
+
+// All worlds of a batch flattened for the device (layout: r2d_pipeline.cuh `Dev`).
+struct Image {
+    std::vector<float4> pos, mom, frc, prop, shape, aabb;
+    std::vector<uint32_t> world_base, grav_off;
+    std::vector<float> grav;
+    std::vector<uint64_t> excl;
+    // joints sorted by (colour, global list index)
+    std::vector<uint4> j_hdr;
+    std::vector<float4> j_par, j_vec;
+    std::vector<uint32_t> joint_color_start;   // n_joint_colors + 1
+    std::vector<uint32_t> joint_world, joint_local_index, joint_color;  // per sorted joint
+    uint32_t n_bodies = 0;
+};
+
+inline float4 mkf4(float x, float y, float z, float w) { return make_float4(x, y, z, w); }
+
+inline void body_to_image(const Body& b, uint32_t world, Image& im, size_t at) {
+    const uint32_t flags = (b.is_static ? FLAG_STATIC : 0u) | (b.shape == R2D_SHAPE_RECT ? FLAG_RECT : 0u) |
+                           (world << FLAG_WORLD_SHIFT);
+    im.pos[at] = mkf4(b.pos_x, b.pos_y, b.angle, 0.0f);
+    im.mom[at] = mkf4(b.mom_x, b.mom_y, b.ang_mom, 0.0f);
+    im.frc[at] = mkf4(b.force_x, b.force_y, b.torque, 0.0f);
+    im.prop[at] = mkf4(b.mass, b.inertia, b.mu, 0.0f);
+    im.shape[at] = mkf4(b.a, b.b, u2f(flags), u2f(b.id));
+    im.aabb[at] = mkf4(b.aabb_x, b.aabb_y, b.aabb_hw, b.aabb_hh);
+}
+
+// Returns R2D_OK or R2D_ERR_INVALID_BODY_ID (a joint names a body that no longer exists — the reference fails inside
+// process() with error.InvalidRigidBodyId, DistanceJoint.zig:44-46; here before any state is touched).
+inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image& im) {
+    const size_t nw = worlds.size();
+    im.world_base.assign(nw + 1, 0);
+    im.grav_off.assign(nw + 1, 0);
+    im.grav.clear();
+    for (size_t w = 0; w < nw; ++w) {
+        im.world_base[w + 1] = im.world_base[w] + (uint32_t)worlds[w]->bodies.size();
+        for (float g : worlds[w]->gravities) im.grav.push_back(g);
+        im.grav_off[w + 1] = (uint32_t)im.grav.size();
+    }
+    const size_t nb = im.world_base[nw];
+    im.n_bodies = (uint32_t)nb;
+    im.pos.resize(nb);
+    im.mom.resize(nb);
+    im.frc.resize(nb);
+    im.prop.resize(nb);
+    im.shape.resize(nb);
+    im.aabb.resize(nb);
+    im.excl.clear();
+    struct GJ {
+        Joint j;
+        uint32_t world, local, s1, s2, color;
+    };
+    std::vector<GJ> gj;
+    for (size_t w = 0; w < nw; ++w) {
+        const World& W = *worlds[w];
+        const uint32_t base = im.world_base[w];
+        for (size_t s = 0; s < W.bodies.size(); ++s) body_to_image(W.bodies[s], (uint32_t)w, im, base + s);
+        for (const auto& pr : W.excluded) {
+            const int s1 = W.find(pr.first), s2 = W.find(pr.second);
+            if (s1 < 0 || s2 < 0 || s1 == s2) continue;
+            const uint64_t lo = base + (uint32_t)std::min(s1, s2), hi = base + (uint32_t)std::max(s1, s2);
+            im.excl.push_back((lo << 32) | hi);
+        }
+        for (size_t k = 0; k < W.joints.size(); ++k) {
+            const Joint& j = W.joints[k];
+            const int s1 = W.find(j.id1);
+            const int s2 = joint_has_two_bodies(j) ? W.find(j.id2) : s1;
+            if (s1 < 0 || s2 < 0) return R2D_ERR_INVALID_BODY_ID;
+            gj.push_back({j, (uint32_t)w, (uint32_t)k, base + (uint32_t)s1, base + (uint32_t)s2, 0u});
+        }
+    }
+    std::sort(im.excl.begin(), im.excl.end());
+    im.excl.erase(std::unique(im.excl.begin(), im.excl.end()), im.excl.end());
+    // Joint colouring: greedy in list order; two joints conflict when they name a common body (static or not — the
+    // distance joints write momentum into static bodies too, Q10).  Sweep order = (colour, list index).
+    {
+        std::unordered_map<uint32_t, std::vector<uint32_t>> used;
+        uint32_t n_colors = 0;
+        for (GJ& g : gj) {
+            uint32_t c = 0;
+            for (;; ++c) {
+                bool taken = false;
+                for (uint32_t s : {g.s1, g.s2}) {
+                    auto& u = used[s];
+                    if (std::find(u.begin(), u.end(), c) != u.end()) taken = true;
+                }
+                if (!taken) break;
+            }
+            g.color = c;
+            used[g.s1].push_back(c);
+            if (g.s2 != g.s1) used[g.s2].push_back(c);
+            n_colors = std::max(n_colors, c + 1);
+        }
+        std::stable_sort(gj.begin(), gj.end(), [](const GJ& a, const GJ& b) { return a.color < b.color; });
+        const size_t nj = gj.size();
+        im.j_hdr.resize(nj);
+        im.j_par.resize(nj);
+        im.j_vec.resize(nj);
+        im.joint_world.resize(nj);
+        im.joint_local_index.resize(nj);
+        im.joint_color.resize(nj);
+        im.joint_color_start.assign(n_colors + 1, 0);
+        for (size_t k = 0; k < nj; ++k) {
+            const GJ& g = gj[k];
+            im.j_hdr[k] = make_uint4((uint32_t)g.j.type, g.s1, g.s2, 0u);
+            im.j_par[k] = mkf4(g.j.power_max, g.j.power_min, g.j.beta, g.j.target);
+            im.j_vec[k] = mkf4(g.j.r1x, g.j.r1y, g.j.r2x, g.j.r2y);
+            im.joint_world[k] = g.world;
+            im.joint_local_index[k] = g.local;
+            im.joint_color[k] = g.color;
+            im.joint_color_start[g.color + 1] += 1;
+        }
+        for (size_t c = 0; c < n_colors; ++c) im.joint_color_start[c + 1] += im.joint_color_start[c];
+    }
+    return R2D_OK;
+}
+
+struct RawManifold {   // one occupied pair slot of the last process(), slots are global
+    uint32_t ref, inc, normal_id, n_points, color;
+    float normal_x, normal_y;
+    float pos_x[2], pos_y[2], depth[2], ref_rx[2], ref_ry[2], inc_rx[2], inc_ry[2];
+};
+
+enum BodyField { FIELD_POS = 0, FIELD_MOM = 1, FIELD_FRC = 2 };  // float4 arrays a setter may touch
+
+// Backend-independent part of a batch: worlds + coherence protocol between the host mirror and the device arrays.
+struct BatchBase {
+    std::vector<std::unique_ptr<World>> worlds;
+    float cell_width = 2.0f;
+    uint32_t table_mult = 4;
+    int mode = R2D_MODE_PARITY;
+    bool host_fresh = true;   // host mirror holds the truth
+    bool dev_fresh = false;   // device arrays hold the truth (and the image layout is current)
+    Image image;              // layout of the last upload (world_base etc.)
+    r2d_step_stats stats{};
+
+    virtual ~BatchBase() {}
+    virtual int backend_upload() = 0;                                      // image -> device
+    virtual int backend_download() = 0;                                    // device -> worlds[*].bodies
+    virtual int backend_write(uint32_t gslot, BodyField f, int comp, int n, const float* v) = 0;
+    virtual int backend_process(float dt, uint32_t sub_steps, uint32_t iters) = 0;
+    // bulk access to device-resident state (valid while dev_fresh); [first, first + n) are global slots
+    virtual int backend_read_bodies(uint32_t first, uint32_t n, uint32_t* ids, float* pos_xy, float* angle,
+                                    float* momentum_xy, float* ang_momentum, float* aabb_xywh) = 0;
+    virtual int backend_write_forces(uint32_t first, uint32_t n, const float* force_xy_torque) = 0;
+    virtual int backend_read_pairs(std::vector<uint2>& slots) = 0;        // (owner, other) global slots, last process()
+    virtual int backend_read_manifolds(std::vector<RawManifold>& out) = 0; // pair-slot order, last process()
+    virtual int backend_sync() = 0;
+    virtual int backend_set_stream(void* stream) = 0;
+    virtual int backend_profile_enable(int on) = 0;
+    virtual int backend_profile_read(double* ms, uint64_t* launches, int reset) = 0;
+
+    float grid_cell() const { return mode == R2D_MODE_PARITY ? 4.0f : cell_width; }      // lib.zig:254-255 (Q2)
+    uint32_t grid_mult() const { return mode == R2D_MODE_PARITY ? 2u : (table_mult ? table_mult : 1u); }
+
+    int ensure_host() {
+        if (!host_fresh) {
+            const int st = backend_download();
+            if (st != R2D_OK) return st;
+            host_fresh = true;
+        }
+        return R2D_OK;
+    }
+    int touch_structure() {  // before any edit the device image cannot absorb in place
+        const int st = ensure_host();
+        if (st != R2D_OK) return st;
+        dev_fresh = false;
+        return R2D_OK;
+    }
+    int ensure_device() {
+        if (!dev_fresh) {
+            const int st = build_image(worlds, image);
+            if (st != R2D_OK) return st;
+            const int st2 = backend_upload();
+            if (st2 != R2D_OK) return st2;
+            dev_fresh = true;
+        }
+        return R2D_OK;
+    }
+    size_t total_bodies() const {
+        size_t n = 0;
+        for (auto& w : worlds) n += w->bodies.size();
+        return n;
+    }
+    // scalar setter: edits whichever copies are fresh
+    int set_field(World* w, uint32_t id, BodyField f, int comp, int n, const float* v) {
+        const int s = w->find(id);
+        if (s < 0) return R2D_ERR_NO_SUCH_ID;
+        if (host_fresh) {
+            Body& b = w->bodies[s];
+            float* dst[3][3] = {{&b.pos_x, &b.pos_y, &b.angle}, {&b.mom_x, &b.mom_y, &b.ang_mom}, {&b.force_x, &b.force_y, &b.torque}};
+            for (int k = 0; k < n; ++k) *dst[f][comp + k] = v[k];
+        }
+        if (dev_fresh) return backend_write(image.world_base[w->index] + (uint32_t)s, f, comp, n, v);
+        return R2D_OK;
+    }
+    int process(float dt, uint32_t sub_steps, uint32_t iters) {
+        const int st = ensure_device();
+        if (st != R2D_OK) return st;
+        const int st2 = backend_process(dt, sub_steps, iters);
+        if (st2 == R2D_OK || st2 == R2D_ERR_COLOR_OVERFLOW) host_fresh = false;
+        return st2;
+    }
+};
+
+}  // namespace host
+}  // namespace r2d

@@ -1,0 +1,564 @@
+// r2d_pipeline.cuh — device-state layout (structure-of-arrays in HBM) and the per-thread body of every kernel of
+// the step pipeline.  Each `*_thread` function is what ONE CUDA thread does for ONE element; r2d_kernels.cu wraps
+// them in grid-stride __global__ kernels.  They are host/device so that tests/emu/ can run the identical index and
+// filter logic serially on a CPU against the oracle (test tooling only — the product has no CPU path).
+//
+// Reference mapping (src/core): broadphase = SpatialHash.zig:19-137 + the filters of lib.zig:273-282; narrowphase =
+// collision.zig:221-363 (r2d_narrow.cuh); colouring is new (replaces the insertion-order sweep of lib.zig:226-236);
+// solve/integrate = lib.zig:199-250, collision.zig:102-218, Constraints/*.zig (r2d_solve.cuh).
+#pragma once
+#include "r2d_math.cuh"
+#include "r2d_narrow.cuh"
+#include "r2d_solve.cuh"
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#else
+// minimal vector types for the host-only test emulator
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+struct alignas(16) uint4 { uint32_t x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r; r.x = x; r.y = y; return r; }
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+#endif
+
+namespace r2d {
+
+constexpr uint32_t COLOR_NONE = 0xFFFFFFFFu;       // pair slot holds no manifold
+constexpr uint32_t COLOR_PENDING = 0xFFFFFFFEu;    // manifold not coloured yet
+constexpr uint32_t MAX_COLORS = 256;
+constexpr uint32_t COLOR_WORDS = MAX_COLORS / 64;
+constexpr uint32_t MAX_COLOR_ROUNDS = 4000;        // < 2^12 (round tag field of the priority word)
+constexpr uint32_t BIG_BODY_CELLS = 64;            // bodies covering more cells are walked by a whole CTA
+constexpr int64_t MAX_BODY_CELLS = 1 << 22;        // beyond this the pose is garbage (NaN/inf): R2D_ERR_GRID_RANGE
+
+constexpr uint32_t ERR_COLOR_OVERFLOW = 1u;
+constexpr uint32_t ERR_GRID_RANGE = 2u;
+constexpr uint32_t ERR_ROUNDS = 4u;
+
+// Device-side counters of one process() call (one 128-byte block, copied to pinned host memory once per step).
+struct Counters {
+    uint32_t n_entries;      // E
+    uint32_t n_pairs;        // P
+    uint32_t n_manifolds;    // M
+    uint32_t n_points;       // K
+    uint32_t n_colors;
+    uint32_t n_rounds;
+    uint32_t err;
+    uint32_t pad[25];
+};
+
+// Everything the kernels need, passed by value.
+struct Dev {
+    // ---- bodies (NB slots; world-major, slot = insertion index inside its world) ------------------------------
+    uint32_t n_bodies;
+    float4* pos;      // x, y, angle, -
+    float4* mom;      // momentum.x, momentum.y, ang_momentum, -
+    float4* frc;      // force.x, force.y, torque, -
+    float4* prop;     // mass, inertia, mu, -
+    float4* shape;    // a, b, bits(flags), bits(id)   flags: bit0 static, bit1 rect, bits 8.. world
+    float4* aabb;     // centre.x, centre.y, half_w, half_h   (as of the last refresh — stale on purpose, Q3)
+    float4* pose;     // x, y, cos(angle), sin(angle)  (scratch of one process())
+    uint32_t* ncells; // grid cells covered by the body's AABB
+    // ---- worlds ----------------------------------------------------------------------------------------------------
+    uint32_t n_worlds;
+    const uint32_t* world_base;   // n_worlds + 1
+    const uint32_t* grav_off;     // n_worlds + 1
+    const float* grav;            // g values, world-major
+    float cell;                   // grid cell size
+    uint32_t table_mult;          // buckets per body
+    // ---- hashed grid -----------------------------------------------------------------------------------------------
+    uint32_t n_buckets;           // T = table_mult * NB (world w owns [mult*base_w, mult*base_{w+1}))
+    uint32_t* bucket_cnt;         // T + 1, all zero between kernels pairs count/fill
+    uint32_t* bucket_start;       // T + 1 (exclusive scan of counts; [T] = E)
+    uint32_t cap_entries;
+    uint32_t* ent_body;           // E
+    uint32_t* ent_key;            // E
+    uint32_t* ent_off;            // E + 1: pairs emitted per entry, then its exclusive scan ([E] = P)
+    const uint64_t* excl;         // sorted (lo_slot << 32 | hi_slot)
+    uint32_t n_excl;
+    // ---- candidate pairs / raw manifolds (P slots) ------------------------------------------------------------------
+    uint32_t cap_pairs;
+    uint2* pairs;                 // (owner slot, other slot)
+    uint4* m_hdr;                 // ref slot, inc slot, n_points | normal_id << 8, -
+    float4* m_g0;                 // normal.x, normal.y, p0.pos.x, p0.pos.y
+    float4* m_g1;                 // p0.depth, p1.depth, p1.pos.x, p1.pos.y
+    float4* m_r0;                 // p0: ref_r.x, ref_r.y, inc_r.x, inc_r.y
+    float4* m_r1;                 // p1
+    uint32_t* m_color;            // COLOR_NONE / COLOR_PENDING / colour
+    // ---- colouring ---------------------------------------------------------------------------------------------------
+    unsigned long long* maxprio0; // NB: highest pending priority seen on the body, even rounds
+    unsigned long long* maxprio1; // NB: odd rounds
+    unsigned long long* used;     // NB * COLOR_WORDS: colours taken on the body
+    uint32_t* color_count;        // MAX_COLORS
+    uint32_t* color_start;        // MAX_COLORS + 1
+    uint32_t* color_cursor;       // MAX_COLORS
+    uint32_t* round_left;         // MAX_COLOR_ROUNDS
+    Counters* counters;
+    // ---- solver records, grouped by colour (M slots) -----------------------------------------------------------------
+    uint4* s_hdr;                 // ref slot, inc slot, n_points | static1 << 8 | static2 << 9, pair slot
+    float4* s_nf;                 // normal.x, normal.y, friction, -
+    float4* s_inv;                // inv_m1, inv_m2, inv_i1, inv_i2
+    float4* s_r0;                 // point 0: r1.x, r1.y, r2.x, r2.y
+    float4* s_r1;
+    float4* s_pm0;                // point 0: mass_n, mass_t, depth, -
+    float4* s_pm1;
+    float2* s_acc0;               // point 0: accumulated_pn, accumulated_pt
+    float2* s_acc1;
+    // ---- joints, grouped by colour -----------------------------------------------------------------------------------
+    uint32_t n_joints;
+    const uint4* j_hdr;           // type, slot1, slot2, -
+    const float4* j_par;          // power_max, power_min, beta, target (distance | omega)
+    const float4* j_vec;          // r1.x, r1.y, r2.x, r2.y  |  target.x, target.y, -, -
+};
+
+R2D_HD uint32_t body_flags(const Dev& d, uint32_t i) { return f2u(d.shape[i].z); }
+R2D_HD uint32_t body_id(const Dev& d, uint32_t i) { return f2u(d.shape[i].w); }
+
+// ---- atomics: real ones on the device, plain read-modify-write in the serial host emulator ---------------------------
+R2D_HD uint32_t atomic_add_u32(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    const uint32_t o = *p;
+    *p = o + v;
+    return o;
+#endif
+}
+R2D_HD uint32_t atomic_sub_u32(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return atomicSub(p, v);
+#else
+    const uint32_t o = *p;
+    *p = o - v;
+    return o;
+#endif
+}
+R2D_HD void atomic_max_u32(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    atomicMax(p, v);
+#else
+    if (*p < v) *p = v;
+#endif
+}
+R2D_HD void atomic_or_u32(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+R2D_HD void atomic_max_u64(unsigned long long* p, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    atomicMax(p, v);
+#else
+    if (*p < v) *p = v;
+#endif
+}
+
+// ---- broadphase ----------------------------------------------------------------------------------------------------
+struct CellRange {
+    int64_t min_xi, min_yi, max_xi, max_yi;
+    uint32_t bucket_base;   // first bucket of the body's world
+    uint32_t table_size;    // buckets of the body's world (T_w = table_mult * N_w)
+    uint32_t nx;            // cells per row
+    uint32_t count;         // total cells (0 if out of range)
+};
+
+// iterateAABBHashes (SpatialHash.zig:83-106): cell range of the STORED aabb
+R2D_HD CellRange cell_range(const Dev& d, uint32_t i) {
+    const float4 a = d.aabb[i];
+    CellRange r;
+    // getVertices (aabb.zig:25-32): min = pos - half, max = pos + half
+    r.min_xi = cell_coord(fsub(a.x, a.z), d.cell);
+    r.min_yi = cell_coord(fsub(a.y, a.w), d.cell);
+    r.max_xi = cell_coord(fadd(a.x, a.z), d.cell);
+    r.max_yi = cell_coord(fadd(a.y, a.w), d.cell);
+    const uint32_t w = body_flags(d, i) >> FLAG_WORLD_SHIFT;
+    const uint32_t b0 = d.world_base[w], b1 = d.world_base[w + 1];
+    r.bucket_base = d.table_mult * b0;
+    r.table_size = d.table_mult * (b1 - b0);
+    const int64_t nx = r.max_xi - r.min_xi + 1, ny = r.max_yi - r.min_yi + 1;
+    if (nx <= 0 || ny <= 0 || nx > MAX_BODY_CELLS || ny > MAX_BODY_CELLS || nx * ny > MAX_BODY_CELLS) {
+        r.nx = 0;
+        r.count = 0;
+        // an empty range is legal only for NaN poses; flag everything else that is not a sane box
+        if (!(nx <= 0 || ny <= 0) || a.x != a.x || a.y != a.y) atomic_or_u32(&d.counters->err, ERR_GRID_RANGE);
+    } else {
+        r.nx = (uint32_t)nx;
+        r.count = (uint32_t)(nx * ny);
+    }
+    return r;
+}
+// k-th cell of the range in the reference's visiting order (yi outer ascending, xi inner ascending) -> global bucket
+R2D_HD uint32_t cell_bucket(const CellRange& r, uint32_t k) {
+    const int64_t yi = r.min_yi + (int64_t)(k / r.nx);
+    const int64_t xi = r.min_xi + (int64_t)(k % r.nx);
+    return r.bucket_base + (uint32_t)cell_hash(xi, yi, (uint64_t)r.table_size);
+}
+
+// K2: pose cache + cell count (SpatialHash.zig:46-49).  Returns the cell range so the caller can walk big bodies
+// cooperatively; small bodies are counted here.
+R2D_HD CellRange count_body_thread(const Dev& d, uint32_t i, bool count_inline) {
+    const float4 p = d.pos[i];
+    d.pose[i] = make_float4(p.x, p.y, cos_ref(p.z), sin_ref(p.z));
+    const CellRange r = cell_range(d, i);
+    d.ncells[i] = r.count;
+    if (count_inline)
+        for (uint32_t k = 0; k < r.count; ++k) atomic_add_u32(&d.bucket_cnt[cell_bucket(r, k)], 1u);
+    return r;
+}
+// K4: fill (SpatialHash.zig:62-68): decrement-then-store; leaves bucket_cnt all zero again.
+R2D_HD void fill_cell(const Dev& d, uint32_t i, uint32_t bucket) {
+    const uint32_t left = atomic_sub_u32(&d.bucket_cnt[bucket], 1u) - 1u;
+    const uint32_t at = d.bucket_start[bucket] + left;
+    if (at < d.cap_entries) {
+        d.ent_body[at] = i;
+        d.ent_key[at] = bucket;
+    }
+}
+R2D_HD uint32_t bucket_end(const struct Dev& d, uint32_t bucket);
+// K4b: make the bucket order deterministic (ascending slot, duplicates adjacent)
+R2D_HD void sort_bucket_thread(const Dev& d, uint32_t bucket) {
+    const uint32_t s = d.bucket_start[bucket];
+    const uint32_t e = bucket_end(d, bucket);
+    for (uint32_t a = s + 1; a < e; ++a) {
+        const uint32_t v = d.ent_body[a];
+        uint32_t b = a;
+        while (b > s && d.ent_body[b - 1] > v) {
+            d.ent_body[b] = d.ent_body[b - 1];
+            --b;
+        }
+        d.ent_body[b] = v;
+    }
+}
+
+R2D_HD bool pair_excluded(const Dev& d, uint32_t i, uint32_t j) {  // lib.zig:275-276 (both orders stored, Q22)
+    if (d.n_excl == 0) return false;
+    const uint64_t key = ((uint64_t)(i < j ? i : j) << 32) | (uint64_t)(i < j ? j : i);
+    uint32_t lo = 0, hi = d.n_excl;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const uint64_t v = d.excl[mid];
+        if (v == key) return true;
+        if (v < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return false;
+}
+// end of a bucket, clamped so that an over-capacity step (detected and redone by the host) never reads out of bounds
+R2D_HD uint32_t bucket_end(const Dev& d, uint32_t bucket) {
+    const uint32_t e = d.bucket_start[bucket + 1];
+    return e < d.cap_entries ? e : d.cap_entries;
+}
+R2D_HD bool bucket_contains(const Dev& d, uint32_t bucket, uint32_t j) {
+    uint32_t lo = d.bucket_start[bucket], hi = bucket_end(d, bucket);
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const uint32_t v = d.ent_body[mid];
+        if (v == j) return true;
+        if (v < j)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return false;
+}
+
+// K5: candidate pairs owned by grid entry e = (bucket h, body i).  A pair {i, j} sharing several buckets is emitted
+// exactly once: by the body with fewer cells (ties: lower slot), in the lowest-numbered bucket they share.  Filters
+// are the reference's (lib.zig:273-282): both static, self, excluded, AABB — duplicates removed by construction instead
+// of by manifold-map probes.  `out` == nullptr counts only.
+R2D_HD uint32_t entry_pairs_thread(const Dev& d, uint32_t e, uint2* out) {
+    const uint32_t h = d.ent_key[e], i = d.ent_body[e];
+    const uint32_t bs = d.bucket_start[h], be = bucket_end(d, h);
+    if (e > bs && d.ent_body[e - 1] == i) return 0;  // i lists this bucket more than once: first occurrence only
+    const float4 ai = d.aabb[i];
+    const uint32_t fi = body_flags(d, i);
+    const uint32_t nci = d.ncells[i];
+    uint32_t n = 0, prev = 0xFFFFFFFFu;
+    for (uint32_t f = bs; f < be; ++f) {
+        const uint32_t j = d.ent_body[f];
+        if (j == prev) continue;
+        prev = j;
+        if (j == i) continue;                                        // :274
+        const uint32_t ncj = d.ncells[j];
+        if (!(nci < ncj || (nci == ncj && i < j))) continue;         // j owns this pair
+        if (fi & body_flags(d, j) & FLAG_STATIC) continue;          // :273
+        const float4 aj = d.aabb[j];
+        if (!aabb_intersects(ai.x, ai.y, ai.z, ai.w, aj.x, aj.y, aj.z, aj.w)) continue;  // :282
+        if (pair_excluded(d, i, j)) continue;                        // :275-276
+        if (nci > 1) {  // is h the lowest bucket shared with j?
+            const CellRange r = cell_range(d, i);
+            bool lower = false;
+            for (uint32_t k = 0; k < r.count && !lower; ++k) {
+                const uint32_t h2 = cell_bucket(r, k);
+                if (h2 < h && bucket_contains(d, h2, j)) lower = true;
+            }
+            if (lower) continue;
+        }
+        if (out) out[n] = make_uint2(i, j);
+        ++n;
+    }
+    return n;
+}
+
+// ---- narrowphase ---------------------------------------------------------------------------------------------------
+R2D_HD BodyView load_view(const Dev& d, uint32_t i) {
+    const float4 p = d.pose[i];
+    const float4 s = d.shape[i];
+    return make_view(p.x, p.y, p.z, p.w, s.x, s.y, f2u(s.z), f2u(s.w));
+}
+// K6: one candidate pair -> raw manifold slot.  Returns the number of contact points, or -1 if SAT finds a gap.
+R2D_HD int narrow_pair_thread(const Dev& d, uint32_t p) {
+    const uint2 pr = d.pairs[p];
+    const BodyView va = load_view(d, pr.x), vb = load_view(d, pr.y);
+    const bool a_lo = va.id < vb.id;  // performNarrowSAT orders the two passes by id (collision.zig:304-307)
+    const Manifold m = a_lo ? narrowphase(va, vb) : narrowphase(vb, va);
+    if (!m.collides) {
+        d.m_color[p] = COLOR_NONE;
+        return -1;
+    }
+    const uint32_t lo_slot = a_lo ? pr.x : pr.y, hi_slot = a_lo ? pr.y : pr.x;
+    const uint32_t ref = m.ref_is_lo ? lo_slot : hi_slot, inc = m.ref_is_lo ? hi_slot : lo_slot;
+    d.m_hdr[p] = make_uint4(ref, inc, (uint32_t)m.n_points | ((uint32_t)m.normal_id << 8), 0u);
+    const ContactPoint z = {mk2(0, 0), 0.0f, mk2(0, 0), mk2(0, 0)};
+    const ContactPoint p0 = m.n_points > 0 ? m.pt[0] : z, p1 = m.n_points > 1 ? m.pt[1] : z;
+    d.m_g0[p] = make_float4(m.normal.x, m.normal.y, p0.pos.x, p0.pos.y);
+    d.m_g1[p] = make_float4(p0.depth, p1.depth, p1.pos.x, p1.pos.y);
+    d.m_r0[p] = make_float4(p0.ref_r.x, p0.ref_r.y, p0.inc_r.x, p0.inc_r.y);
+    d.m_r1[p] = make_float4(p1.ref_r.x, p1.ref_r.y, p1.inc_r.x, p1.inc_r.y);
+    d.m_color[p] = COLOR_PENDING;
+    return m.n_points;
+}
+
+// ---- graph colouring (Jones-Plassmann with id-derived priorities; see contact_priority in r2d_solve.cuh) -----------------
+R2D_HD uint64_t manifold_priority(const Dev& d, uint32_t ref, uint32_t inc) {
+    const uint32_t ia = body_id(d, ref), ib = body_id(d, inc);
+    return contact_priority(ia < ib ? ia : ib, ia < ib ? ib : ia);
+}
+R2D_HD void color_post(const Dev& d, uint32_t ref, uint32_t inc, bool dyn1, bool dyn2, uint64_t prio, uint32_t round) {
+    unsigned long long* mp = (round & 1u) ? d.maxprio1 : d.maxprio0;
+    const unsigned long long v = ((unsigned long long)round << PRIO_ROUND_SHIFT) | prio;
+    if (dyn1) atomic_max_u64(&mp[ref], v);
+    if (dyn2) atomic_max_u64(&mp[inc], v);
+}
+// One colouring round for pair slot p.  Returns: 0 nothing pending, 1 coloured now, 2 still pending (re-posted).
+R2D_HD int color_round_thread(const Dev& d, uint32_t p, uint32_t round) {
+    if (d.m_color[p] != COLOR_PENDING) return 0;
+    const uint4 h = d.m_hdr[p];
+    const bool dyn1 = !(body_flags(d, h.x) & FLAG_STATIC), dyn2 = !(body_flags(d, h.y) & FLAG_STATIC);
+    const uint64_t prio = manifold_priority(d, h.x, h.y);
+    const unsigned long long mine = ((unsigned long long)round << PRIO_ROUND_SHIFT) | prio;
+    const unsigned long long* mp = (round & 1u) ? d.maxprio1 : d.maxprio0;
+    const bool win = (!dyn1 || mp[h.x] == mine) && (!dyn2 || mp[h.y] == mine);
+    if (!win) {
+        color_post(d, h.x, h.y, dyn1, dyn2, prio, round + 1);
+        return 2;
+    }
+    uint32_t color = MAX_COLORS;
+    for (uint32_t w = 0; w < COLOR_WORDS; ++w) {
+        unsigned long long u = 0;
+        if (dyn1) u |= d.used[(size_t)h.x * COLOR_WORDS + w];
+        if (dyn2) u |= d.used[(size_t)h.y * COLOR_WORDS + w];
+        if (~u) {
+            uint32_t b = 0;
+            while ((u >> b) & 1ull) ++b;
+            color = w * 64 + b;
+            break;
+        }
+    }
+    if (color >= MAX_COLORS) {
+        atomic_or_u32(&d.counters->err, ERR_COLOR_OVERFLOW);
+        color = MAX_COLORS - 1;
+    }
+    const unsigned long long bit = 1ull << (color & 63u);
+    if (dyn1) d.used[(size_t)h.x * COLOR_WORDS + (color >> 6)] |= bit;   // unique winner per body and round: no race
+    if (dyn2) d.used[(size_t)h.y * COLOR_WORDS + (color >> 6)] |= bit;
+    d.m_color[p] = color;
+    return 1;
+}
+
+// ---- colour partition + pre-step (collision.zig:102-133, evaluated once per process(): inputs are constant, Q5) -----------
+R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
+    const uint4 h = d.m_hdr[p];
+    const uint32_t np = h.z & 0xFFu;
+    const uint32_t f1 = body_flags(d, h.x), f2 = body_flags(d, h.y);
+    const bool st1 = (f1 & FLAG_STATIC) != 0, st2 = (f2 & FLAG_STATIC) != 0;
+    const float4 pr1 = d.prop[h.x], pr2 = d.prop[h.y];
+    const float4 g0 = d.m_g0[p], g1 = d.m_g1[p];
+    const ContactConst c = prestep_manifold(mk2(g0.x, g0.y), st1, st2, pr1.x, pr2.x, pr1.y, pr2.y, pr1.z, pr2.z);
+    d.s_hdr[at] = make_uint4(h.x, h.y, np | (st1 ? 0x100u : 0u) | (st2 ? 0x200u : 0u), p);
+    d.s_nf[at] = make_float4(c.normal.x, c.normal.y, c.friction, 0.0f);
+    d.s_inv[at] = make_float4(c.inv_m1, c.inv_m2, c.inv_i1, c.inv_i2);
+    if (np > 0) {
+        const float4 r = d.m_r0[p];
+        ContactPointConst pc;
+        pc.r1 = mk2(r.x, r.y);
+        pc.r2 = mk2(r.z, r.w);
+        pc.depth = g1.x;
+        prestep_point(c, pc);
+        d.s_r0[at] = r;
+        d.s_pm0[at] = make_float4(pc.mass_n, pc.mass_t, pc.depth, 0.0f);
+        d.s_acc0[at] = make_float2(0.0f, 0.0f);
+    }
+    if (np > 1) {
+        const float4 r = d.m_r1[p];
+        ContactPointConst pc;
+        pc.r1 = mk2(r.x, r.y);
+        pc.r2 = mk2(r.z, r.w);
+        pc.depth = g1.y;
+        prestep_point(c, pc);
+        d.s_r1[at] = r;
+        d.s_pm1[at] = make_float4(pc.mass_n, pc.mass_t, pc.depth, 0.0f);
+        d.s_acc1[at] = make_float2(0.0f, 0.0f);
+    }
+}
+
+// ---- solver sweeps --------------------------------------------------------------------------------------------------
+// K11: one manifold of the current colour (collision.zig:135-218).  Manifolds of one colour share no non-static body.
+R2D_HD void solve_contact_thread(const Dev& d, uint32_t m, float sub_dt) {
+    const uint4 h = d.s_hdr[m];
+    const int np = (int)(h.z & 0xFFu);
+    const bool st1 = (h.z & 0x100u) != 0, st2 = (h.z & 0x200u) != 0;
+    const float4 nf = d.s_nf[m], inv = d.s_inv[m];
+    ContactConst c;
+    c.normal = mk2(nf.x, nf.y);
+    c.tangent = rot90cw(c.normal);
+    c.friction = nf.z;
+    c.inv_m1 = inv.x;
+    c.inv_m2 = inv.y;
+    c.inv_i1 = inv.z;
+    c.inv_i2 = inv.w;
+    const float4 m1 = d.mom[h.x], m2 = d.mom[h.y];
+    BodyVel b1 = {mk2(m1.x, m1.y), m1.z}, b2 = {mk2(m2.x, m2.y), m2.z};
+    ContactPointConst pts[2];
+    v2 acc[2];
+    if (np > 0) {
+        const float4 r = d.s_r0[m], pm = d.s_pm0[m];
+        const float2 a = d.s_acc0[m];
+        pts[0].r1 = mk2(r.x, r.y);
+        pts[0].r2 = mk2(r.z, r.w);
+        pts[0].mass_n = pm.x;
+        pts[0].mass_t = pm.y;
+        pts[0].depth = pm.z;
+        acc[0] = mk2(a.x, a.y);
+    }
+    if (np > 1) {
+        const float4 r = d.s_r1[m], pm = d.s_pm1[m];
+        const float2 a = d.s_acc1[m];
+        pts[1].r1 = mk2(r.x, r.y);
+        pts[1].r2 = mk2(r.z, r.w);
+        pts[1].mass_n = pm.x;
+        pts[1].mass_t = pm.y;
+        pts[1].depth = pm.z;
+        acc[1] = mk2(a.x, a.y);
+    }
+    solve_contact(c, np, pts, acc, st1, st2, b1, b2, sub_dt);
+    if (np > 0) d.s_acc0[m] = make_float2(acc[0].x, acc[0].y);
+    if (np > 1) d.s_acc1[m] = make_float2(acc[1].x, acc[1].y);
+    // static bodies receive a zero impulse in the reference (`momentum += 0`); not writing them is the same value
+    if (!st1) d.mom[h.x] = make_float4(b1.mom.x, b1.mom.y, b1.ang, m1.w);
+    if (!st2) d.mom[h.y] = make_float4(b2.mom.x, b2.mom.y, b2.ang, m2.w);
+}
+
+R2D_HD JointBody load_joint_body(const Dev& d, uint32_t s) {
+    const float4 p = d.pos[s], m = d.mom[s], pr = d.prop[s], f = d.frc[s];
+    JointBody b;
+    b.pos = mk2(p.x, p.y);
+    b.angle = p.z;
+    b.mom = mk2(m.x, m.y);
+    b.ang = m.z;
+    b.mass = pr.x;
+    b.inertia = pr.y;
+    b.torque = f.z;
+    b.is_static = (body_flags(d, s) & FLAG_STATIC) != 0;
+    return b;
+}
+R2D_HD void store_joint_body(const Dev& d, uint32_t s, const JointBody& b) {
+    d.mom[s] = make_float4(b.mom.x, b.mom.y, b.ang, d.mom[s].w);
+}
+// K10: one joint of the current joint colour (Constraints/*.zig).  Joints of one colour name disjoint bodies.
+R2D_HD void solve_joint_thread(const Dev& d, uint32_t j, float sub_dt) {
+    const uint4 h = d.j_hdr[j];
+    const float4 par = d.j_par[j], vec = d.j_vec[j];
+    const float power_max = par.x, power_min = par.y, beta = par.z, target = par.w;
+    switch (h.x) {
+        case 0: {  // distance
+            JointBody b1 = load_joint_body(d, h.y), b2 = load_joint_body(d, h.z);
+            solve_distance(b1, b2, target, beta, power_min, power_max);
+            store_joint_body(d, h.y, b1);
+            store_joint_body(d, h.z, b2);
+        } break;
+        case 1: {  // offset distance
+            JointBody b1 = load_joint_body(d, h.y), b2 = load_joint_body(d, h.z);
+            solve_offset_distance(b1, b2, mk2(vec.x, vec.y), mk2(vec.z, vec.w), target, beta, power_min, power_max);
+            store_joint_body(d, h.y, b1);
+            store_joint_body(d, h.z, b2);
+        } break;
+        case 2: {  // fixed position
+            JointBody b = load_joint_body(d, h.y);
+            solve_fixed_position(b, mk2(vec.x, vec.y), beta, power_min, power_max);
+            store_joint_body(d, h.y, b);
+        } break;
+        default: {  // motor
+            JointBody b = load_joint_body(d, h.y);
+            solve_motor(b, target, beta, power_min, power_max, sub_dt);
+            store_joint_body(d, h.y, b);
+        } break;
+    }
+}
+
+// ---- integrators ------------------------------------------------------------------------------------------------------
+// K1: gravity (DownwardsGravity.zig:35-39) + AABB refresh (lib.zig:210) + momentum integration (lib.zig:211-215).
+// The reference refreshes the AABB in every substep; only the last refresh is observable (the next process() and the
+// accessors read it), so it is evaluated when `refresh_aabb` is set.
+R2D_HD void integrate_forces_thread(const Dev& d, uint32_t i, float sub_dt, bool refresh_aabb) {
+    const float4 s = d.shape[i];
+    const uint32_t flags = f2u(s.z);
+    if (refresh_aabb) {
+        const float4 p = d.pos[i];
+        float hw, hh;
+        if (flags & FLAG_RECT) {
+            aabb_half_extents(flags, s.x, s.y, cos_ref(p.z), sin_ref(p.z), hw, hh);
+        } else {
+            hw = s.x;
+            hh = s.x;
+        }
+        d.aabb[i] = make_float4(p.x, p.y, hw, hh);
+    }
+    if (flags & FLAG_STATIC) return;
+    float4 f = d.frc[i];
+    const float mass = d.prop[i].x;
+    const uint32_t w = flags >> FLAG_WORLD_SHIFT;
+    for (uint32_t g = d.grav_off[w]; g < d.grav_off[w + 1]; ++g) {  // force.addmult(g_vec = (0, -g), mass)
+        f.x = fadd(f.x, fmul(0.0f, mass));
+        f.y = fadd(f.y, fmul(-d.grav[g], mass));
+    }
+    float4 m = d.mom[i];
+    m.x = fadd(m.x, fmul(f.x, sub_dt));
+    m.y = fadd(m.y, fmul(f.y, sub_dt));
+    m.z = fadd(m.z, fmul(f.z, sub_dt));
+    d.mom[i] = m;
+    // force.xy is next read after the end-of-substep reset (positions kernel), so the gravity sum need not be stored
+}
+// K12: position integration and force reset (lib.zig:238-249)
+R2D_HD void integrate_positions_thread(const Dev& d, uint32_t i, float sub_dt) {
+    const uint32_t flags = body_flags(d, i);
+    if (flags & FLAG_STATIC) return;
+    const float4 m = d.mom[i], pr = d.prop[i];
+    float4 p = d.pos[i];
+    const float k = fdiv(sub_dt, pr.x);
+    p.x = fadd(p.x, fmul(m.x, k));
+    p.y = fadd(p.y, fmul(m.y, k));
+    p.z = fadd(p.z, fdiv(fmul(m.z, sub_dt), pr.y));
+    d.pos[i] = p;
+    d.frc[i] = make_float4(0.0f, 0.0f, 0.0f, d.frc[i].w);
+}
+
+}  // namespace r2d

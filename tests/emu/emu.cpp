@@ -1,0 +1,252 @@
+// emu.cpp — TEST TOOLING, NOT PRODUCT CODE.
+//
+// Serial CPU driver for the per-thread kernel bodies of resolve2d_b200/csrc/r2d_pipeline.cuh: every `*_thread`
+// function the CUDA kernels execute is run here in a plain loop, in the same pipeline order as r2d_runtime.cu, behind
+// the same C API (prefix emu_).  Its only purpose is to let the CPU-only test tier (-m "not gpu") check the kernels'
+// index / filter / colouring logic and the host registry against the oracle without a GPU.  Nothing under
+// resolve2d_b200/ links or loads it; the product path has no CPU fallback.
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "../../resolve2d_b200/csrc/r2d_host.hpp"
+
+namespace {
+
+using namespace r2d;
+using host::BatchBase;
+using host::BodyField;
+using host::RawManifold;
+
+struct EmuBatch : BatchBase {
+    Dev d{};
+    std::vector<float4> pos, mom, frc, prop, shape, aabb, pose;
+    std::vector<uint32_t> ncells, bucket_cnt, bucket_start, ent_body, ent_key, ent_off, m_color;
+    std::vector<uint2> pairs;
+    std::vector<uint4> m_hdr, s_hdr;
+    std::vector<float4> m_g0, m_g1, m_r0, m_r1, s_nf, s_inv, s_r0, s_r1, s_pm0, s_pm1;
+    std::vector<float2> s_acc0, s_acc1;
+    std::vector<unsigned long long> maxprio0, maxprio1, used;
+    std::vector<uint32_t> color_count, color_start, color_cursor, round_left;
+    Counters counters{};
+    uint32_t n_pairs_last = 0;
+
+    int backend_upload() override {
+        pos = image.pos;
+        mom = image.mom;
+        frc = image.frc;
+        prop = image.prop;
+        shape = image.shape;
+        aabb = image.aabb;
+        n_pairs_last = 0;
+        return R2D_OK;
+    }
+    int backend_download() override {
+        for (auto& w : worlds) {
+            const uint32_t base = image.world_base[w->index];
+            for (size_t s = 0; s < w->bodies.size(); ++s) {
+                host::Body& b = w->bodies[s];
+                const float4 p = pos[base + s], m = mom[base + s], f = frc[base + s], a = aabb[base + s];
+                b.pos_x = p.x; b.pos_y = p.y; b.angle = p.z;
+                b.mom_x = m.x; b.mom_y = m.y; b.ang_mom = m.z;
+                b.force_x = f.x; b.force_y = f.y; b.torque = f.z;
+                b.aabb_x = a.x; b.aabb_y = a.y; b.aabb_hw = a.z; b.aabb_hh = a.w;
+            }
+        }
+        return R2D_OK;
+    }
+    int backend_write(uint32_t gslot, BodyField f, int comp, int n, const float* v) override {
+        float4* arr = f == host::FIELD_POS ? pos.data() : (f == host::FIELD_MOM ? mom.data() : frc.data());
+        float* p = &arr[gslot].x;
+        for (int k = 0; k < n; ++k) p[comp + k] = v[k];
+        return R2D_OK;
+    }
+    int backend_read_bodies(uint32_t first, uint32_t n, uint32_t* ids, float* pos_xy, float* angle, float* momentum_xy,
+                            float* ang_momentum, float* aabb_xywh) override {
+        for (uint32_t k = 0; k < n; ++k) {
+            const uint32_t s = first + k;
+            if (ids) ids[k] = f2u(shape[s].w);
+            if (pos_xy) { pos_xy[2 * k] = pos[s].x; pos_xy[2 * k + 1] = pos[s].y; }
+            if (angle) angle[k] = pos[s].z;
+            if (momentum_xy) { momentum_xy[2 * k] = mom[s].x; momentum_xy[2 * k + 1] = mom[s].y; }
+            if (ang_momentum) ang_momentum[k] = mom[s].z;
+            if (aabb_xywh) memcpy(aabb_xywh + 4 * k, &aabb[s], 16);
+        }
+        return R2D_OK;
+    }
+    int backend_write_forces(uint32_t first, uint32_t n, const float* f) override {
+        for (uint32_t k = 0; k < n; ++k) {
+            frc[first + k].x = f[3 * k];
+            frc[first + k].y = f[3 * k + 1];
+            frc[first + k].z = f[3 * k + 2];
+        }
+        return R2D_OK;
+    }
+    int backend_read_pairs(std::vector<uint2>& out) override {
+        out.assign(pairs.begin(), pairs.begin() + n_pairs_last);
+        return R2D_OK;
+    }
+    int backend_read_manifolds(std::vector<RawManifold>& out) override {
+        out.clear();
+        for (uint32_t p = 0; p < n_pairs_last; ++p) {
+            if (m_color[p] == COLOR_NONE) continue;
+            RawManifold m{};
+            m.ref = m_hdr[p].x;
+            m.inc = m_hdr[p].y;
+            m.n_points = m_hdr[p].z & 0xFF;
+            m.normal_id = m_hdr[p].z >> 8;
+            m.color = m_color[p];
+            m.normal_x = m_g0[p].x;
+            m.normal_y = m_g0[p].y;
+            m.pos_x[0] = m_g0[p].z; m.pos_y[0] = m_g0[p].w;
+            m.depth[0] = m_g1[p].x; m.depth[1] = m_g1[p].y;
+            m.pos_x[1] = m_g1[p].z; m.pos_y[1] = m_g1[p].w;
+            m.ref_rx[0] = m_r0[p].x; m.ref_ry[0] = m_r0[p].y; m.inc_rx[0] = m_r0[p].z; m.inc_ry[0] = m_r0[p].w;
+            m.ref_rx[1] = m_r1[p].x; m.ref_ry[1] = m_r1[p].y; m.inc_rx[1] = m_r1[p].z; m.inc_ry[1] = m_r1[p].w;
+            out.push_back(m);
+        }
+        return R2D_OK;
+    }
+    int backend_sync() override { return R2D_OK; }
+    int backend_set_stream(void*) override { return R2D_OK; }
+    int backend_profile_enable(int) override { return R2D_OK; }
+    int backend_profile_read(double* ms, uint64_t* n, int) override {
+        for (int k = 0; k < R2D_KCLASS_COUNT; ++k) { ms[k] = 0; n[k] = 0; }
+        return R2D_OK;
+    }
+
+    static void exclusive_scan(uint32_t* a, uint32_t n) {  // a[0..n) -> exclusive prefix, a[n] = total
+        uint32_t run = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t v = a[i];
+            a[i] = run;
+            run += v;
+        }
+        a[n] = run;
+    }
+
+    int backend_process(float dt, uint32_t S, uint32_t I) override {
+        const uint32_t nb = image.n_bodies;
+        stats = r2d_step_stats{};
+        stats.n_bodies = nb;
+        stats.n_joints = (uint32_t)image.j_hdr.size();
+        stats.n_joint_colors = (uint32_t)image.joint_color_start.size() - 1;
+        if (nb == 0) return R2D_OK;
+        const float sub_dt = fdiv(dt, (float)S);   // lib.zig:190-191
+        d.n_bodies = nb;
+        d.pos = pos.data(); d.mom = mom.data(); d.frc = frc.data(); d.prop = prop.data(); d.shape = shape.data();
+        d.aabb = aabb.data();
+        pose.resize(nb); ncells.resize(nb);
+        d.pose = pose.data(); d.ncells = ncells.data();
+        d.n_worlds = (uint32_t)worlds.size();
+        d.world_base = image.world_base.data(); d.grav_off = image.grav_off.data(); d.grav = image.grav.data();
+        d.cell = grid_cell(); d.table_mult = grid_mult();
+        d.n_buckets = d.table_mult * nb;
+        bucket_cnt.assign(d.n_buckets + 1, 0); bucket_start.assign(d.n_buckets + 1, 0);
+        d.bucket_cnt = bucket_cnt.data(); d.bucket_start = bucket_start.data();
+        d.excl = image.excl.data(); d.n_excl = (uint32_t)image.excl.size();
+        counters = Counters{};
+        d.counters = &counters;
+        d.n_joints = (uint32_t)image.j_hdr.size();
+        d.j_hdr = image.j_hdr.data(); d.j_par = image.j_par.data(); d.j_vec = image.j_vec.data();
+
+        // ---- broadphase (K2..K5) ----
+        for (uint32_t i = 0; i < nb; ++i) count_body_thread(d, i, true);
+        memcpy(bucket_start.data(), bucket_cnt.data(), (d.n_buckets + 1) * 4);
+        exclusive_scan(bucket_start.data(), d.n_buckets);
+        const uint32_t E = bucket_start[d.n_buckets];
+        ent_body.assign(E + 1, 0); ent_key.assign(E + 1, 0); ent_off.assign(E + 2, 0);
+        d.cap_entries = E; d.ent_body = ent_body.data(); d.ent_key = ent_key.data(); d.ent_off = ent_off.data();
+        for (uint32_t i = 0; i < nb; ++i) {
+            const CellRange r = cell_range(d, i);
+            for (uint32_t k = 0; k < r.count; ++k) fill_cell(d, i, cell_bucket(r, k));
+        }
+        for (uint32_t b = 0; b < d.n_buckets; ++b) sort_bucket_thread(d, b);
+        for (uint32_t e = 0; e < E; ++e) ent_off[e] = entry_pairs_thread(d, e, nullptr);
+        exclusive_scan(ent_off.data(), E);
+        const uint32_t P = ent_off[E];
+        pairs.assign(P + 1, make_uint2(0, 0));
+        d.cap_pairs = P; d.pairs = pairs.data();
+        for (uint32_t e = 0; e < E; ++e) entry_pairs_thread(d, e, pairs.data() + ent_off[e]);
+        n_pairs_last = P;
+
+        // ---- narrowphase (K6) ----
+        m_hdr.assign(P + 1, make_uint4(0, 0, 0, 0)); m_color.assign(P + 1, COLOR_NONE);
+        m_g0.resize(P + 1); m_g1.resize(P + 1); m_r0.resize(P + 1); m_r1.resize(P + 1);
+        d.m_hdr = m_hdr.data(); d.m_g0 = m_g0.data(); d.m_g1 = m_g1.data(); d.m_r0 = m_r0.data(); d.m_r1 = m_r1.data();
+        d.m_color = m_color.data();
+        uint32_t M = 0, K = 0;
+        for (uint32_t p = 0; p < P; ++p) {
+            const int np = narrow_pair_thread(d, p);
+            if (np >= 0) { M += 1; K += (uint32_t)np; }
+        }
+
+        // ---- colouring (K8) ----
+        maxprio0.assign(nb, 0); maxprio1.assign(nb, 0); used.assign((size_t)nb * COLOR_WORDS, 0);
+        color_count.assign(MAX_COLORS, 0); color_start.assign(MAX_COLORS + 1, 0); color_cursor.assign(MAX_COLORS, 0);
+        d.maxprio0 = maxprio0.data(); d.maxprio1 = maxprio1.data(); d.used = used.data();
+        d.color_count = color_count.data(); d.color_start = color_start.data(); d.color_cursor = color_cursor.data();
+        for (uint32_t p = 0; p < P; ++p) {
+            if (m_color[p] != COLOR_PENDING) continue;
+            const uint4 h = m_hdr[p];
+            color_post(d, h.x, h.y, !(body_flags(d, h.x) & FLAG_STATIC), !(body_flags(d, h.y) & FLAG_STATIC),
+                       manifold_priority(d, h.x, h.y), 1);
+        }
+        uint32_t rounds = 0, n_colors = 0;
+        for (uint32_t round = 1; round < MAX_COLOR_ROUNDS; ++round) {
+            // Serial emulation caveat: a thread of round r must not see round-r writes of `used` by another winner on a
+            // shared body — there is none (unique winner per body and round) — nor round r+1 posts, which go to the
+            // other maxprio array.  So a plain loop is equivalent to the parallel round.
+            uint32_t left = 0;
+            for (uint32_t p = 0; p < P; ++p) {
+                const int r = color_round_thread(d, p, round);
+                if (r == 2) ++left;
+                if (r == 1) { color_count[m_color[p]] += 1; n_colors = std::max(n_colors, m_color[p] + 1); }
+            }
+            rounds = round;
+            if (left == 0) break;
+        }
+        if (counters.err & ERR_COLOR_OVERFLOW) return R2D_ERR_COLOR_OVERFLOW;
+        if (counters.err & ERR_GRID_RANGE) return R2D_ERR_GRID_RANGE;
+        for (uint32_t c = 0; c < n_colors; ++c) color_start[c + 1] = color_start[c] + color_count[c];
+
+        // ---- colour partition + pre-step ----
+        s_hdr.resize(M + 1); s_nf.resize(M + 1); s_inv.resize(M + 1); s_r0.resize(M + 1); s_r1.resize(M + 1);
+        s_pm0.resize(M + 1); s_pm1.resize(M + 1); s_acc0.resize(M + 1); s_acc1.resize(M + 1);
+        d.s_hdr = s_hdr.data(); d.s_nf = s_nf.data(); d.s_inv = s_inv.data(); d.s_r0 = s_r0.data(); d.s_r1 = s_r1.data();
+        d.s_pm0 = s_pm0.data(); d.s_pm1 = s_pm1.data(); d.s_acc0 = s_acc0.data(); d.s_acc1 = s_acc1.data();
+        for (uint32_t p = 0; p < P; ++p) {
+            if (m_color[p] >= MAX_COLORS) continue;
+            const uint32_t at = color_start[m_color[p]] + color_cursor[m_color[p]]++;
+            gather_prestep_thread(d, p, at);
+        }
+
+        // ---- substeps (lib.zig:199-250) ----
+        const auto& jcs = image.joint_color_start;
+        for (uint32_t s = 0; s < S; ++s) {
+            for (uint32_t i = 0; i < nb; ++i) integrate_forces_thread(d, i, sub_dt, s + 1 == S);
+            for (uint32_t it = 0; it < I; ++it) {
+                for (size_t c = 0; c + 1 < jcs.size(); ++c)
+                    for (uint32_t j = jcs[c]; j < jcs[c + 1]; ++j) solve_joint_thread(d, j, sub_dt);
+                for (uint32_t c = 0; c < n_colors; ++c)
+                    for (uint32_t m = color_start[c]; m < color_start[c + 1]; ++m) solve_contact_thread(d, m, sub_dt);
+            }
+            for (uint32_t i = 0; i < nb; ++i) integrate_positions_thread(d, i, sub_dt);
+        }
+        stats.n_buckets = d.n_buckets;
+        stats.n_entries = E;
+        stats.n_pairs = P;
+        stats.n_manifolds = M;
+        stats.n_points = K;
+        stats.n_colors = n_colors;
+        stats.n_color_rounds = rounds;
+        return R2D_OK;
+    }
+};
+
+}  // namespace
+
+static r2d::host::BatchBase* r2d_new_backend(int, std::string&) { return new EmuBatch(); }
+static int r2d_backend_device_count() { return 0; }
+#define R2D_API(name) emu_##name
+#include "../../resolve2d_b200/csrc/r2d_capi.inc"
