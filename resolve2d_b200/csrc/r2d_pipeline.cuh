@@ -159,6 +159,15 @@ R2D_HD void atomic_max_u64(unsigned long long* p, unsigned long long v) {
 #endif
 }
 
+// Loads of words that OTHER CTAs update inside the same cooperative kernel (between grid barriers): served from L2.
+R2D_HD unsigned long long ld_shared_u64(const unsigned long long* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+
 // ---- broadphase ----------------------------------------------------------------------------------------------------
 struct CellRange {
     int64_t min_xi, min_yi, max_xi, max_yi;
@@ -356,7 +365,7 @@ R2D_HD int color_round_thread(const Dev& d, uint32_t p, uint32_t round) {
     const uint64_t prio = manifold_priority(d, h.x, h.y);
     const unsigned long long mine = ((unsigned long long)round << PRIO_ROUND_SHIFT) | prio;
     const unsigned long long* mp = (round & 1u) ? d.maxprio1 : d.maxprio0;
-    const bool win = (!dyn1 || mp[h.x] == mine) && (!dyn2 || mp[h.y] == mine);
+    const bool win = (!dyn1 || ld_shared_u64(&mp[h.x]) == mine) && (!dyn2 || ld_shared_u64(&mp[h.y]) == mine);
     if (!win) {
         color_post(d, h.x, h.y, dyn1, dyn2, prio, round + 1);
         return 2;
@@ -364,8 +373,8 @@ R2D_HD int color_round_thread(const Dev& d, uint32_t p, uint32_t round) {
     uint32_t color = MAX_COLORS;
     for (uint32_t w = 0; w < COLOR_WORDS; ++w) {
         unsigned long long u = 0;
-        if (dyn1) u |= d.used[(size_t)h.x * COLOR_WORDS + w];
-        if (dyn2) u |= d.used[(size_t)h.y * COLOR_WORDS + w];
+        if (dyn1) u |= ld_shared_u64(&d.used[(size_t)h.x * COLOR_WORDS + w]);
+        if (dyn2) u |= ld_shared_u64(&d.used[(size_t)h.y * COLOR_WORDS + w]);
         if (~u) {
             uint32_t b = 0;
             while ((u >> b) & 1ull) ++b;
@@ -378,8 +387,15 @@ R2D_HD int color_round_thread(const Dev& d, uint32_t p, uint32_t round) {
         color = MAX_COLORS - 1;
     }
     const unsigned long long bit = 1ull << (color & 63u);
-    if (dyn1) d.used[(size_t)h.x * COLOR_WORDS + (color >> 6)] |= bit;   // unique winner per body and round: no race
-    if (dyn2) d.used[(size_t)h.y * COLOR_WORDS + (color >> 6)] |= bit;
+    // unique winner per body and round: a plain read-modify-write cannot race
+    if (dyn1) {
+        unsigned long long* u = &d.used[(size_t)h.x * COLOR_WORDS + (color >> 6)];
+        *u = ld_shared_u64(u) | bit;
+    }
+    if (dyn2) {
+        unsigned long long* u = &d.used[(size_t)h.y * COLOR_WORDS + (color >> 6)];
+        *u = ld_shared_u64(u) | bit;
+    }
     d.m_color[p] = color;
     return 1;
 }

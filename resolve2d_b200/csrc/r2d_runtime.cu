@@ -1,0 +1,543 @@
+// r2d_runtime.cu — the CUDA backend of libr2d_b200.so: device memory, stream, the launch sequence of one
+// `Solver.process` call (src/core/lib.zig:189-251) and the extern "C" ABI of include/r2d_abi.h (via r2d_capi.inc).
+//
+// One process() =
+//   updateManifolds (lib.zig:253-299):  k_grid_cells<count> -> scan -> k_grid_cells<fill> -> k_sort_buckets ->
+//        k_pairs<count> -> scan -> k_pairs<write> -> k_narrow -> k_color (cooperative) -> k_partition_prestep
+//   one small device->host copy (counters + colour offsets), the only synchronisation point of the call
+//   S x { k_integrate_forces ; I x { joint colours ; contact colours } ; k_integrate_positions }   (lib.zig:199-250)
+// There is no CPU fallback anywhere: a missing device is an error.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "r2d_host.hpp"
+#include "r2d_kernels.cuh"
+
+namespace {
+
+using namespace r2d;
+using host::BatchBase;
+using host::BodyField;
+using host::RawManifold;
+
+thread_local std::string g_cuda_error;
+
+#define R2D_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            char _buf[512];                                                                              \
+            snprintf(_buf, sizeof(_buf), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            g_cuda_error = _buf;                                                                         \
+            return _e == cudaErrorMemoryAllocation ? R2D_ERR_OUT_OF_MEMORY : R2D_ERR_CUDA;               \
+        }                                                                                                \
+    } while (0)
+
+#define R2D_TRY(expr)                 \
+    do {                              \
+        const int _st = (expr);       \
+        if (_st != R2D_OK) return _st; \
+    } while (0)
+
+// growable device array
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~DBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    // contents are NOT preserved on growth
+    int reserve(size_t n, bool zero = false, cudaStream_t st = 0) {
+        if (n <= cap) return R2D_OK;
+        release();
+        const size_t want = n + n / 4 + 64;
+        R2D_CUDA(cudaMalloc((void**)&p, want * sizeof(T)));
+        cap = want;
+        if (zero) R2D_CUDA(cudaMemsetAsync(p, 0, want * sizeof(T), st));
+        return R2D_OK;
+    }
+};
+
+struct PinnedStep {            // what the host learns about a step, one D2H copy
+    Counters counters;
+    uint32_t color_start[MAX_COLORS + 1];
+};
+
+struct CudaBatch : BatchBase {
+    int device = 0;
+    int n_sms = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int color_blocks = 0;
+    // bodies
+    DBuf<float4> pos, mom, frc, prop, shape, aabb, pose;
+    DBuf<uint32_t> ncells, world_base, grav_off;
+    DBuf<float> grav;
+    DBuf<uint64_t> excl;
+    DBuf<uint4> j_hdr;
+    DBuf<float4> j_par, j_vec;
+    // grid
+    DBuf<uint32_t> bucket_cnt, bucket_start, ent_body, ent_key, ent_off, tile_sums;
+    // pairs / manifolds
+    DBuf<uint2> pairs;
+    DBuf<uint4> m_hdr, s_hdr;
+    DBuf<float4> m_g0, m_g1, m_r0, m_r1, s_nf, s_inv, s_r0, s_r1, s_pm0, s_pm1;
+    DBuf<float2> s_acc0, s_acc1;
+    DBuf<uint32_t> m_color;
+    // colouring
+    DBuf<unsigned long long> maxprio0, maxprio1, used;
+    DBuf<uint32_t> color_misc;   // color_count[256] | color_start[257] | color_cursor[256] | round_left[MAX_COLOR_ROUNDS]
+    DBuf<Counters> counters;
+    // staging for the boundary copies
+    DBuf<unsigned char> staging;
+    PinnedStep* pinned = nullptr;
+    size_t cap_entries = 0, cap_pairs = 0;
+    uint32_t last_pairs = 0;
+    Dev d{};
+    // profiling
+    bool profiling = false;
+    struct Ev {
+        cudaEvent_t a, b;
+        int kclass;
+    };
+    std::vector<Ev> events;
+    std::vector<cudaEvent_t> event_pool;
+    double prof_ms[R2D_KCLASS_COUNT] = {0};
+    uint64_t prof_n[R2D_KCLASS_COUNT] = {0};
+    uint32_t launches = 0;
+
+    ~CudaBatch() override {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        for (auto& e : events) {
+            cudaEventDestroy(e.a);
+            cudaEventDestroy(e.b);
+        }
+        for (auto& e : event_pool) cudaEventDestroy(e);
+        if (pinned) cudaFreeHost(pinned);
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+
+    int init(int dev) {
+        device = dev;
+        R2D_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop_{};
+        R2D_CUDA(cudaGetDeviceProperties(&prop_, device));
+        if (prop_.major < 10) {
+            g_cuda_error = "libr2d_b200 is built for sm_100a (B200) only; found compute capability " +
+                           std::to_string(prop_.major) + "." + std::to_string(prop_.minor);
+            return R2D_ERR_NO_DEVICE;
+        }
+        n_sms = prop_.multiProcessorCount;
+        R2D_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+        stream = own_stream;
+        R2D_CUDA(cudaHostAlloc((void**)&pinned, sizeof(PinnedStep), cudaHostAllocDefault));
+        int per_sm = 0;
+        R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_color, TPB, 0));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;
+        color_blocks = per_sm * n_sms;
+        R2D_TRY(counters.reserve(1));
+        R2D_TRY(color_misc.reserve(MAX_COLORS * 3 + 1 + MAX_COLOR_ROUNDS));
+        return R2D_OK;
+    }
+
+    // ---- launch helpers -------------------------------------------------------------------------------------------
+    cudaEvent_t get_event() {
+        if (!event_pool.empty()) {
+            cudaEvent_t e = event_pool.back();
+            event_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void prof_begin(int kclass) {
+        if (!profiling) return;
+        Ev ev{get_event(), get_event(), kclass};
+        cudaEventRecord(ev.a, stream);
+        events.push_back(ev);
+    }
+    void prof_end() {
+        if (!profiling) return;
+        cudaEventRecord(events.back().b, stream);
+    }
+    int grid_for(size_t n, int tpb = TPB) const {  // fixed-shape grids: a multiple of the SM count, grid-stride inside
+        size_t blocks = (n + tpb - 1) / tpb;
+        const size_t cap = (size_t)n_sms * 8;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        return (int)blocks;
+    }
+#define R2D_LAUNCH(kclass, kernel, grid, block, ...)            \
+    do {                                                        \
+        prof_begin(kclass);                                     \
+        kernel<<<(grid), (block), 0, stream>>>(__VA_ARGS__);    \
+        prof_end();                                             \
+        launches += 1;                                          \
+    } while (0)
+
+    // exclusive scan of in[0..n) into out[0..n), out[n] = total (also *total_out); n = min(*n_ptr, n_max) if n_ptr
+    int scan(const uint32_t* in, uint32_t* out, const uint32_t* n_ptr, uint32_t n_max, uint32_t* total_out) {
+        const uint32_t tiles = (n_max + SCAN_TILE - 1) / SCAN_TILE;
+        R2D_TRY(tile_sums.reserve(tiles + 1));
+        R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_scan_reduce, tiles ? tiles : 1, SCAN_TPB, in, tile_sums.p, n_ptr, n_max);
+        R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_scan_spine, 1, SCAN_TPB, tile_sums.p, n_ptr, n_max, out, total_out);
+        R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_scan_down, tiles ? tiles : 1, SCAN_TPB, in, out, tile_sums.p, n_ptr, n_max);
+        return R2D_OK;
+    }
+
+    // ---- BatchBase backend ----------------------------------------------------------------------------------------
+    template <class T>
+    int up(DBuf<T>& dst, const std::vector<T>& src, size_t min_elems = 1) {
+        R2D_TRY(dst.reserve(std::max(src.size(), min_elems)));
+        if (!src.empty()) R2D_CUDA(cudaMemcpyAsync(dst.p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        return R2D_OK;
+    }
+    int backend_upload() override {
+        R2D_CUDA(cudaSetDevice(device));
+        int st;
+        if ((st = up(pos, image.pos)) || (st = up(mom, image.mom)) || (st = up(frc, image.frc)) || (st = up(prop, image.prop)) ||
+            (st = up(shape, image.shape)) || (st = up(aabb, image.aabb)) || (st = up(world_base, image.world_base)) ||
+            (st = up(grav_off, image.grav_off)) || (st = up(grav, image.grav)) || (st = up(excl, image.excl)) ||
+            (st = up(j_hdr, image.j_hdr)) || (st = up(j_par, image.j_par)) || (st = up(j_vec, image.j_vec)))
+            return st;
+        R2D_CUDA(cudaStreamSynchronize(stream));  // the image vectors are pageable and may change after we return
+        last_pairs = 0;
+        return R2D_OK;
+    }
+    int backend_download() override {
+        R2D_CUDA(cudaSetDevice(device));
+        const size_t nb = image.n_bodies;
+        if (nb == 0) return R2D_OK;
+        std::vector<float4> hp(nb), hm(nb), hf(nb), ha(nb);
+        R2D_CUDA(cudaMemcpyAsync(hp.data(), pos.p, nb * 16, cudaMemcpyDeviceToHost, stream));
+        R2D_CUDA(cudaMemcpyAsync(hm.data(), mom.p, nb * 16, cudaMemcpyDeviceToHost, stream));
+        R2D_CUDA(cudaMemcpyAsync(hf.data(), frc.p, nb * 16, cudaMemcpyDeviceToHost, stream));
+        R2D_CUDA(cudaMemcpyAsync(ha.data(), aabb.p, nb * 16, cudaMemcpyDeviceToHost, stream));
+        R2D_CUDA(cudaStreamSynchronize(stream));
+        for (auto& w : worlds) {
+            const uint32_t base = image.world_base[w->index];
+            for (size_t s = 0; s < w->bodies.size(); ++s) {
+                host::Body& b = w->bodies[s];
+                const float4 p = hp[base + s], m = hm[base + s], f = hf[base + s], a = ha[base + s];
+                b.pos_x = p.x; b.pos_y = p.y; b.angle = p.z;
+                b.mom_x = m.x; b.mom_y = m.y; b.ang_mom = m.z;
+                b.force_x = f.x; b.force_y = f.y; b.torque = f.z;
+                b.aabb_x = a.x; b.aabb_y = a.y; b.aabb_hw = a.z; b.aabb_hh = a.w;
+            }
+        }
+        return R2D_OK;
+    }
+    int backend_write(uint32_t gslot, BodyField f, int comp, int n, const float* v) override {
+        R2D_CUDA(cudaSetDevice(device));
+        float4* arr = f == host::FIELD_POS ? pos.p : (f == host::FIELD_MOM ? mom.p : frc.p);
+        float* dst = reinterpret_cast<float*>(arr + gslot) + comp;
+        R2D_CUDA(cudaMemcpyAsync(dst, v, (size_t)n * 4, cudaMemcpyHostToDevice, stream));
+        R2D_CUDA(cudaStreamSynchronize(stream));  // `v` lives on the caller's stack
+        return R2D_OK;
+    }
+    int backend_read_bodies(uint32_t first, uint32_t n, uint32_t* ids, float* pos_xy, float* angle, float* momentum_xy,
+                            float* ang_momentum, float* aabb_xywh) override {
+        R2D_CUDA(cudaSetDevice(device));
+        // repack the float4 SoA into the caller's layout on the device, then one copy per requested array
+        R2D_TRY(staging.reserve((size_t)n * 44 + 256));
+        unsigned char* s = staging.p;
+        uint32_t* d_ids = (uint32_t*)s;
+        float2* d_pos = (float2*)(s + (size_t)n * 4);
+        float* d_ang = (float*)(s + (size_t)n * 12);
+        float2* d_mom = (float2*)(s + (size_t)n * 16);
+        float* d_l = (float*)(s + (size_t)n * 24);
+        float4* d_aabb = (float4*)(s + (((size_t)n * 28 + 15) & ~(size_t)15));
+        fill_dev();
+        R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_export_bodies, grid_for(n), TPB, d, first, n, ids ? d_ids : nullptr,
+                   pos_xy ? d_pos : nullptr, angle ? d_ang : nullptr, momentum_xy ? d_mom : nullptr,
+                   ang_momentum ? d_l : nullptr, aabb_xywh ? d_aabb : nullptr);
+        if (ids) R2D_CUDA(cudaMemcpyAsync(ids, d_ids, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
+        if (pos_xy) R2D_CUDA(cudaMemcpyAsync(pos_xy, d_pos, (size_t)n * 8, cudaMemcpyDeviceToHost, stream));
+        if (angle) R2D_CUDA(cudaMemcpyAsync(angle, d_ang, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
+        if (momentum_xy) R2D_CUDA(cudaMemcpyAsync(momentum_xy, d_mom, (size_t)n * 8, cudaMemcpyDeviceToHost, stream));
+        if (ang_momentum) R2D_CUDA(cudaMemcpyAsync(ang_momentum, d_l, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
+        if (aabb_xywh) R2D_CUDA(cudaMemcpyAsync(aabb_xywh, d_aabb, (size_t)n * 16, cudaMemcpyDeviceToHost, stream));
+        R2D_CUDA(cudaStreamSynchronize(stream));
+        return R2D_OK;
+    }
+    int backend_write_forces(uint32_t first, uint32_t n, const float* f) override {
+        R2D_CUDA(cudaSetDevice(device));
+        R2D_TRY(staging.reserve((size_t)n * 44 + 256));
+        R2D_CUDA(cudaMemcpyAsync(staging.p, f, (size_t)n * 12, cudaMemcpyHostToDevice, stream));
+        fill_dev();
+        R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_import_forces, grid_for(n), TPB, d, first, n, (const float*)staging.p);
+        // pageable source buffers are consumed before cudaMemcpyAsync returns; pinned ones must stay valid until the
+        // next synchronising call (r2d_process synchronises once per step)
+        return R2D_OK;
+    }
+    int backend_read_pairs(std::vector<uint2>& out) override {
+        R2D_CUDA(cudaSetDevice(device));
+        out.resize(last_pairs);
+        if (last_pairs) {
+            R2D_CUDA(cudaMemcpyAsync(out.data(), pairs.p, (size_t)last_pairs * 8, cudaMemcpyDeviceToHost, stream));
+            R2D_CUDA(cudaStreamSynchronize(stream));
+        }
+        return R2D_OK;
+    }
+    int backend_read_manifolds(std::vector<RawManifold>& out) override {
+        R2D_CUDA(cudaSetDevice(device));
+        out.clear();
+        const size_t n = last_pairs;
+        if (!n) return R2D_OK;
+        std::vector<uint4> h(n);
+        std::vector<float4> g0(n), g1(n), r0(n), r1(n);
+        std::vector<uint32_t> col(n);
+        R2D_CUDA(cudaMemcpyAsync(h.data(), m_hdr.p, n * 16, cudaMemcpyDeviceToHost, stream));
+        R2D_CUDA(cudaMemcpyAsync(g0.data(), m_g0.p, n * 16, cudaMemcpyDeviceToHost, stream));
+        R2D_CUDA(cudaMemcpyAsync(g1.data(), m_g1.p, n * 16, cudaMemcpyDeviceToHost, stream));
+        R2D_CUDA(cudaMemcpyAsync(r0.data(), m_r0.p, n * 16, cudaMemcpyDeviceToHost, stream));
+        R2D_CUDA(cudaMemcpyAsync(r1.data(), m_r1.p, n * 16, cudaMemcpyDeviceToHost, stream));
+        R2D_CUDA(cudaMemcpyAsync(col.data(), m_color.p, n * 4, cudaMemcpyDeviceToHost, stream));
+        R2D_CUDA(cudaStreamSynchronize(stream));
+        for (size_t p = 0; p < n; ++p) {
+            if (col[p] == COLOR_NONE) continue;
+            RawManifold m{};
+            m.ref = h[p].x;
+            m.inc = h[p].y;
+            m.n_points = h[p].z & 0xFF;
+            m.normal_id = h[p].z >> 8;
+            m.color = col[p];
+            m.normal_x = g0[p].x; m.normal_y = g0[p].y;
+            m.pos_x[0] = g0[p].z; m.pos_y[0] = g0[p].w;
+            m.depth[0] = g1[p].x; m.depth[1] = g1[p].y;
+            m.pos_x[1] = g1[p].z; m.pos_y[1] = g1[p].w;
+            m.ref_rx[0] = r0[p].x; m.ref_ry[0] = r0[p].y; m.inc_rx[0] = r0[p].z; m.inc_ry[0] = r0[p].w;
+            m.ref_rx[1] = r1[p].x; m.ref_ry[1] = r1[p].y; m.inc_rx[1] = r1[p].z; m.inc_ry[1] = r1[p].w;
+            out.push_back(m);
+        }
+        return R2D_OK;
+    }
+    int backend_sync() override {
+        R2D_CUDA(cudaSetDevice(device));
+        R2D_CUDA(cudaStreamSynchronize(stream));
+        return R2D_OK;
+    }
+    int backend_set_stream(void* s) override {
+        R2D_CUDA(cudaSetDevice(device));
+        R2D_CUDA(cudaStreamSynchronize(stream));
+        stream = s ? (cudaStream_t)s : own_stream;
+        return R2D_OK;
+    }
+    int backend_profile_enable(int on) override {
+        profiling = on != 0;
+        return R2D_OK;
+    }
+    int backend_profile_read(double* ms, uint64_t* n, int reset) override {
+        R2D_CUDA(cudaSetDevice(device));
+        R2D_CUDA(cudaStreamSynchronize(stream));
+        for (auto& e : events) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess) {
+                prof_ms[e.kclass] += t;
+                prof_n[e.kclass] += 1;
+            }
+            event_pool.push_back(e.a);
+            event_pool.push_back(e.b);
+        }
+        events.clear();
+        for (int k = 0; k < R2D_KCLASS_COUNT; ++k) {
+            if (ms) ms[k] = prof_ms[k];
+            if (n) n[k] = prof_n[k];
+            if (reset) {
+                prof_ms[k] = 0;
+                prof_n[k] = 0;
+            }
+        }
+        return R2D_OK;
+    }
+
+    void fill_dev() {
+        d.n_bodies = image.n_bodies;
+        d.pos = pos.p; d.mom = mom.p; d.frc = frc.p; d.prop = prop.p; d.shape = shape.p; d.aabb = aabb.p;
+        d.pose = pose.p; d.ncells = ncells.p;
+        d.n_worlds = (uint32_t)worlds.size();
+        d.world_base = world_base.p; d.grav_off = grav_off.p; d.grav = grav.p;
+        d.cell = grid_cell(); d.table_mult = grid_mult();
+        d.n_buckets = d.table_mult * d.n_bodies;
+        d.bucket_cnt = bucket_cnt.p; d.bucket_start = bucket_start.p;
+        d.cap_entries = (uint32_t)cap_entries;
+        d.ent_body = ent_body.p; d.ent_key = ent_key.p; d.ent_off = ent_off.p;
+        d.excl = (const uint64_t*)excl.p; d.n_excl = (uint32_t)image.excl.size();
+        d.cap_pairs = (uint32_t)cap_pairs;
+        d.pairs = pairs.p; d.m_hdr = m_hdr.p; d.m_g0 = m_g0.p; d.m_g1 = m_g1.p; d.m_r0 = m_r0.p; d.m_r1 = m_r1.p;
+        d.m_color = m_color.p;
+        d.maxprio0 = maxprio0.p; d.maxprio1 = maxprio1.p; d.used = used.p;
+        d.color_count = color_misc.p;
+        d.color_start = color_misc.p + MAX_COLORS;
+        d.color_cursor = color_misc.p + 2 * MAX_COLORS + 1;
+        d.round_left = color_misc.p + 3 * MAX_COLORS + 1;
+        d.counters = counters.p;
+        d.s_hdr = s_hdr.p; d.s_nf = s_nf.p; d.s_inv = s_inv.p; d.s_r0 = s_r0.p; d.s_r1 = s_r1.p;
+        d.s_pm0 = s_pm0.p; d.s_pm1 = s_pm1.p; d.s_acc0 = s_acc0.p; d.s_acc1 = s_acc1.p;
+        d.n_joints = (uint32_t)image.j_hdr.size();
+        d.j_hdr = j_hdr.p; d.j_par = j_par.p; d.j_vec = j_vec.p;
+    }
+
+    int reserve_entries(size_t n) {
+        int st;
+        if ((st = ent_body.reserve(n)) || (st = ent_key.reserve(n)) || (st = ent_off.reserve(n + 2))) return st;
+        cap_entries = std::min(std::min(ent_body.cap, ent_key.cap), ent_off.cap - 2);
+        return R2D_OK;
+    }
+    int reserve_pairs(size_t n) {
+        int st;
+        if ((st = pairs.reserve(n)) || (st = m_hdr.reserve(n)) || (st = m_g0.reserve(n)) || (st = m_g1.reserve(n)) ||
+            (st = m_r0.reserve(n)) || (st = m_r1.reserve(n)) || (st = m_color.reserve(n)) || (st = s_hdr.reserve(n)) ||
+            (st = s_nf.reserve(n)) || (st = s_inv.reserve(n)) || (st = s_r0.reserve(n)) || (st = s_r1.reserve(n)) ||
+            (st = s_pm0.reserve(n)) || (st = s_pm1.reserve(n)) || (st = s_acc0.reserve(n)) || (st = s_acc1.reserve(n)))
+            return st;
+        cap_pairs = pairs.cap;
+        for (size_t c : {m_hdr.cap, m_g0.cap, m_g1.cap, m_r0.cap, m_r1.cap, m_color.cap, s_hdr.cap, s_nf.cap, s_inv.cap,
+                         s_r0.cap, s_r1.cap, s_pm0.cap, s_pm1.cap, s_acc0.cap, s_acc1.cap})
+            cap_pairs = std::min(cap_pairs, c);
+        return R2D_OK;
+    }
+
+    int backend_process(float dt, uint32_t S, uint32_t I) override {
+        R2D_CUDA(cudaSetDevice(device));
+        const uint32_t nb = image.n_bodies;
+        launches = 0;
+        stats = r2d_step_stats{};
+        stats.n_bodies = nb;
+        stats.n_joints = (uint32_t)image.j_hdr.size();
+        stats.n_joint_colors = (uint32_t)image.joint_color_start.size() - 1;
+        if (nb == 0) return R2D_OK;
+        const float sub_dt = dt / (float)S;  // lib.zig:190-191 (host f32 division, IEEE)
+        const uint32_t T = grid_mult() * nb;
+        int st;
+        if ((st = pose.reserve(nb)) || (st = ncells.reserve(nb)) || (st = maxprio0.reserve(nb)) || (st = maxprio1.reserve(nb)) ||
+            (st = used.reserve((size_t)nb * COLOR_WORDS)) || (st = bucket_cnt.reserve((size_t)T + 1, true, stream)) ||
+            (st = bucket_start.reserve((size_t)T + 1)))
+            return st;
+        if (cap_entries == 0 && (st = reserve_entries((size_t)nb * 3 + 4096))) return st;
+        if (cap_pairs == 0 && (st = reserve_pairs((size_t)nb * 6 + 4096))) return st;
+
+        for (int attempt = 0;; ++attempt) {
+            fill_dev();
+            R2D_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(Counters), stream));
+            R2D_CUDA(cudaMemsetAsync(color_misc.p, 0, (MAX_COLORS * 3 + 1 + MAX_COLOR_ROUNDS) * 4, stream));
+            R2D_CUDA(cudaMemsetAsync(maxprio0.p, 0, (size_t)nb * 8, stream));
+            R2D_CUDA(cudaMemsetAsync(maxprio1.p, 0, (size_t)nb * 8, stream));
+            R2D_CUDA(cudaMemsetAsync(used.p, 0, (size_t)nb * COLOR_WORDS * 8, stream));
+            // ---- broadphase ----
+            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_grid_cells<false>, grid_for(nb), TPB, d);
+            if ((st = scan(d.bucket_cnt, d.bucket_start, nullptr, T, &d.counters->n_entries))) return st;
+            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_grid_cells<true>, grid_for(nb), TPB, d);
+            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_sort_buckets, grid_for(T), TPB, d);
+            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_pairs<false>, grid_for(cap_entries), TPB, d);
+            if ((st = scan(d.ent_off, d.ent_off, &d.counters->n_entries, (uint32_t)cap_entries, &d.counters->n_pairs))) return st;
+            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_pairs<true>, grid_for(cap_entries), TPB, d);
+            // ---- narrowphase ----
+            R2D_LAUNCH(R2D_KCLASS_NARROWPHASE, k_narrow, grid_for(cap_pairs), TPB, d);
+            // ---- colouring + partition + pre-step ----
+            {
+                prof_begin(R2D_KCLASS_COLORING);
+                void* args[] = {(void*)&d};
+                R2D_CUDA(cudaLaunchCooperativeKernel((void*)k_color, dim3(color_blocks), dim3(TPB), args, 0, stream));
+                prof_end();
+                launches += 1;
+            }
+            R2D_LAUNCH(R2D_KCLASS_COLORING, k_partition_prestep, grid_for(cap_pairs), TPB, d);
+            // ---- the one synchronisation point of the step ----
+            R2D_CUDA(cudaMemcpyAsync(&pinned->counters, counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+            R2D_CUDA(cudaMemcpyAsync(pinned->color_start, d.color_start, (MAX_COLORS + 1) * 4, cudaMemcpyDeviceToHost, stream));
+            R2D_CUDA(cudaStreamSynchronize(stream));
+            R2D_CUDA(cudaGetLastError());
+            const Counters& c = pinned->counters;
+            if (c.n_entries > cap_entries || c.n_pairs > cap_pairs) {
+                if (attempt >= 4) {
+                    g_cuda_error = "broadphase buffers failed to converge";
+                    return R2D_ERR_OUT_OF_MEMORY;
+                }
+                if (c.n_entries > cap_entries && (st = reserve_entries((size_t)c.n_entries + c.n_entries / 4))) return st;
+                // P is only meaningful once all entries fit; grow generously when it is known to be too small
+                if (c.n_pairs > cap_pairs && (st = reserve_pairs((size_t)c.n_pairs + c.n_pairs / 4))) return st;
+                continue;
+            }
+            break;
+        }
+        const Counters c = pinned->counters;
+        last_pairs = c.n_pairs;
+        stats.n_buckets = T;
+        stats.n_entries = c.n_entries;
+        stats.n_pairs = c.n_pairs;
+        stats.n_manifolds = c.n_manifolds;
+        stats.n_points = c.n_points;
+        stats.n_colors = c.n_colors;
+        stats.n_color_rounds = c.n_rounds;
+        if (c.err & ERR_GRID_RANGE) {
+            g_cuda_error = "a body AABB covers an unreasonable number of grid cells (NaN/inf pose?)";
+            return R2D_ERR_GRID_RANGE;
+        }
+        if (c.err & (ERR_COLOR_OVERFLOW | ERR_ROUNDS)) {
+            g_cuda_error = "contact graph needs more than R2D_MAX_COLORS colours";
+            return R2D_ERR_COLOR_OVERFLOW;
+        }
+        // ---- substeps ----
+        const uint32_t* cs = pinned->color_start;
+        const auto& jcs = image.joint_color_start;
+        for (uint32_t s = 0; s < S; ++s) {
+            R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_integrate_forces, grid_for(nb), TPB, d, sub_dt, (int)(s + 1 == S));
+            for (uint32_t it = 0; it < I; ++it) {
+                for (size_t jc = 0; jc + 1 < jcs.size(); ++jc) {
+                    const uint32_t n = jcs[jc + 1] - jcs[jc];
+                    if (n) R2D_LAUNCH(R2D_KCLASS_SOLVE_JOINTS, k_solve_joints, (n + SOLVE_TPB - 1) / SOLVE_TPB, SOLVE_TPB, d, jcs[jc], jcs[jc + 1], sub_dt);
+                }
+                for (uint32_t col = 0; col < c.n_colors; ++col) {
+                    const uint32_t n = cs[col + 1] - cs[col];
+                    if (n) R2D_LAUNCH(R2D_KCLASS_SOLVE_CONTACTS, k_solve_contacts, (n + SOLVE_TPB - 1) / SOLVE_TPB, SOLVE_TPB, d, cs[col], cs[col + 1], sub_dt);
+                }
+            }
+            R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_integrate_positions, grid_for(nb), TPB, d, sub_dt);
+        }
+        R2D_CUDA(cudaGetLastError());
+        stats.n_launches = launches;
+        return R2D_OK;
+    }
+};
+
+}  // namespace
+
+static r2d::host::BatchBase* r2d_new_backend(int device, std::string& err) {
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        err = std::string("no CUDA device available (") + cudaGetErrorString(e) + "): libr2d_b200 has no CPU fallback";
+        return nullptr;
+    }
+    if (device < 0 || device >= n) {
+        err = "device index out of range";
+        return nullptr;
+    }
+    CudaBatch* b = new CudaBatch();
+    if (b->init(device) != R2D_OK) {
+        err = g_cuda_error;
+        delete b;
+        return nullptr;
+    }
+    return b;
+}
+static int r2d_backend_device_count() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+#define R2D_API(name) r2d_##name
+#define R2D_BACKEND_ERROR g_cuda_error
+#include "r2d_capi.inc"
