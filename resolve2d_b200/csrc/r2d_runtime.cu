@@ -251,12 +251,18 @@ struct CudaBatch : BatchBase {
         // repack the float4 SoA into the caller's layout on the device, then one copy per requested array
         R2D_TRY(staging.reserve((size_t)n * 44 + 256));
         unsigned char* s = staging.p;
-        uint32_t* d_ids = (uint32_t*)s;
-        float2* d_pos = (float2*)(s + (size_t)n * 4);
-        float* d_ang = (float*)(s + (size_t)n * 12);
-        float2* d_mom = (float2*)(s + (size_t)n * 16);
-        float* d_l = (float*)(s + (size_t)n * 24);
-        float4* d_aabb = (float4*)(s + (((size_t)n * 28 + 15) & ~(size_t)15));
+        size_t off = 0;
+        auto carve = [&](size_t bytes) {  // 16-byte aligned sub-buffers
+            unsigned char* q = s + off;
+            off += (bytes + 15) & ~(size_t)15;
+            return q;
+        };
+        uint32_t* d_ids = (uint32_t*)carve((size_t)n * 4);
+        float2* d_pos = (float2*)carve((size_t)n * 8);
+        float* d_ang = (float*)carve((size_t)n * 4);
+        float2* d_mom = (float2*)carve((size_t)n * 8);
+        float* d_l = (float*)carve((size_t)n * 4);
+        float4* d_aabb = (float4*)carve((size_t)n * 16);
         fill_dev();
         R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_export_bodies, grid_for(n), TPB, d, first, n, ids ? d_ids : nullptr,
                    pos_xy ? d_pos : nullptr, angle ? d_ang : nullptr, momentum_xy ? d_mom : nullptr,
