@@ -41,7 +41,7 @@ def workload_table():
     from resolve2d_b200 import scenes
     return {
         "box1k": (scenes.build_box1k, 60),
-        "pile100k": (scenes.build_pile100k, 100),
+        "pile100k": (scenes.build_pile100k, 200),
         "mixed1M": (scenes.build_mixed1M, 20),
         "pyramid20k": (scenes.build_pyramid20k, 30),
         "pile10k": (lambda s: scenes.build_pile(s, 200, 50), 60),
@@ -223,7 +223,11 @@ def run_ours(args, rank, world, local_rank):
         launches[0] += solver.stats().n_launches
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    if args.profile_range:
+        torch.cuda.cudart().cudaProfilerStart()
     sec = max_over_ranks(timed_steps(step, args.steps))
+    if args.profile_range:
+        torch.cuda.cudart().cudaProfilerStop()
     clocks = sampler.stop() if sampler else None
     value = world * n_bodies * args.steps / sec
     st = solver.stats()
@@ -350,7 +354,9 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=60)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--batch-worlds", type=int, default=4096, help="worlds per GPU of the `batched` leg (0 = skip)")
-    ap.add_argument("--batch-preroll", type=int, default=60)
+    ap.add_argument("--batch-preroll", type=int, default=100)
+    ap.add_argument("--profile-range", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

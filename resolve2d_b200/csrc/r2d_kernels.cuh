@@ -261,9 +261,9 @@ __global__ void __launch_bounds__(TPB) k_color(Dev d) {
         if (round >= MAX_COLOR_ROUNDS) atomicOr(&d.counters->err, ERR_ROUNDS);
         const uint32_t nc = __ldcg(&d.counters->n_colors);
         uint32_t run = 0;
-        for (uint32_t c = 0; c < nc; ++c) {
+        for (uint32_t c = 0; c < nc; ++c) {  // colour segments start on warp boundaries (dataflow sweep)
             d.color_start[c] = run;
-            run += __ldcg(&d.color_count[c]);
+            run = (run + __ldcg(&d.color_count[c]) + COLOR_ALIGN - 1u) & ~(COLOR_ALIGN - 1u);
         }
         d.color_start[nc] = run;
     }
@@ -273,6 +273,14 @@ __global__ void __launch_bounds__(TPB) k_color(Dev d) {
 __global__ void __launch_bounds__(TPB) k_partition_prestep(Dev d) {
     if (overflowed(d)) return;
     const uint32_t n = live_pairs(d);
+    if (blockIdx.x == 0) {  // mark the padding slots at the end of every colour segment
+        const uint32_t nc = d.counters->n_colors;
+        for (uint32_t k = threadIdx.x; k < nc * COLOR_ALIGN; k += blockDim.x) {
+            const uint32_t c = k / COLOR_ALIGN;
+            const uint32_t at = d.color_start[c] + d.color_count[c] + (k % COLOR_ALIGN);
+            if (at < d.color_start[c + 1]) d.s_hdr[at] = make_uint4(0u, 0u, S_EMPTY, 0u);
+        }
+    }
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         const uint32_t c = d.m_color[p];
         if (c >= MAX_COLORS) continue;
@@ -298,11 +306,62 @@ __global__ void __launch_bounds__(TPB) k_integrate_positions(Dev d, float sub_dt
 }
 __global__ void __launch_bounds__(SOLVE_TPB) k_solve_contacts(Dev d, uint32_t begin, uint32_t end, float sub_dt) {
     const uint32_t m = begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (m < end) solve_contact_thread(d, m, sub_dt);
+    if (m < end) solve_contact_thread<false>(d, m, sub_dt);
 }
 __global__ void __launch_bounds__(SOLVE_TPB) k_solve_joints(Dev d, uint32_t begin, uint32_t end, float sub_dt) {
     const uint32_t j = begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (j < end) solve_joint_thread(d, j, sub_dt);
+}
+
+// ---- the whole substep loop of lib.zig:199-250 as ONE persistent cooperative kernel ---------------------------------------------
+// Per substep:  [positions of the previous substep + forces, per body]  | grid barrier |
+//               I x { joint colours (a barrier each) ; ONE dataflow sweep over all contact colours }  | grid barrier |
+// Inside a sweep there is no barrier between colours, nor between iterations when the world has no joints: manifolds
+// synchronise through the per-body version words (solve_contact_thread<true>).  Thread t owns manifolds t, t + nth, ...
+// of the colour-sorted array, i.e. it walks its manifolds in ascending colour, which the dataflow order requires.
+// Colour ranges and counts are read from device memory, so the host never has to learn them before launching.
+// An abandoned attempt (buffer overflow, colouring error) leaves the body state untouched.
+__device__ __forceinline__ void stamp(const Dev& d, uint32_t slot) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && slot < 12) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        d.counters->stamp[slot] = t;
+        d.counters->n_stamps = slot + 1;
+    }
+}
+__global__ void __launch_bounds__(TPB) k_solve_persistent(Dev d, float sub_dt, uint32_t S, uint32_t I,
+                                                          const uint32_t* __restrict__ joint_color_start, uint32_t n_joint_colors) {
+    cg::grid_group grid = cg::this_grid();
+    if (overflowed(d) || d.counters->err != 0u) return;  // uniform across the grid
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const uint32_t n_manifolds = d.color_start[d.counters->n_colors];
+    stamp(d, 0);
+    for (uint32_t s = 0; s < S; ++s) {
+        if (s == 0)
+            for (uint32_t i = tid; i < d.n_bodies; i += nth) integrate_forces_thread(d, i, sub_dt, S == 1);
+        if (s == 0) stamp(d, 1);
+        grid.sync();
+        if (s == 0) stamp(d, 2);
+        for (uint32_t it = 0; it < I; ++it) {
+            for (uint32_t jc = 0; jc < n_joint_colors; ++jc) {
+                const uint32_t b = joint_color_start[jc], e = joint_color_start[jc + 1];
+                for (uint32_t j = b + tid; j < e; j += nth) solve_joint_thread(d, j, sub_dt);
+                grid.sync();
+            }
+            for (uint32_t m = tid; m < n_manifolds; m += nth) solve_contact_thread<true>(d, m, sub_dt, it);
+            if (s == 0) stamp(d, 3 + it);     // block 0 finished its part of sweep `it`
+            if (n_joint_colors) grid.sync();  // joints of the next iteration read what the contacts wrote
+        }
+        if (!n_joint_colors) grid.sync();
+        if (s == 0) stamp(d, 8);
+        // end of substep s fused with the start of substep s + 1: both are per-body, same thread, no barrier needed
+        for (uint32_t i = tid; i < d.n_bodies; i += nth) {
+            integrate_positions_thread(d, i, sub_dt);
+            if (s + 1 < S) integrate_forces_thread(d, i, sub_dt, s + 2 == S);
+        }
+        if (s == 0) stamp(d, 9);
+    }
+    stamp(d, 10);
 }
 
 // ---- boundary kernels: SoA export for bulk readback, force import ---------------------------------------------------------------

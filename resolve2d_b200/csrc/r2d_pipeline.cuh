@@ -30,6 +30,8 @@ namespace r2d {
 constexpr uint32_t COLOR_NONE = 0xFFFFFFFFu;       // pair slot holds no manifold
 constexpr uint32_t COLOR_PENDING = 0xFFFFFFFEu;    // manifold not coloured yet
 constexpr uint32_t MAX_COLORS = 256;
+constexpr uint32_t S_EMPTY = 0x400u;              // s_hdr.z: padding slot (colour segments are padded to whole warps)
+constexpr uint32_t COLOR_ALIGN = 32;
 constexpr uint32_t COLOR_WORDS = MAX_COLORS / 64;
 constexpr uint32_t MAX_COLOR_ROUNDS = 4000;        // < 2^12 (round tag field of the priority word)
 constexpr uint32_t BIG_BODY_CELLS = 64;            // bodies covering more cells are walked by a whole CTA
@@ -38,6 +40,7 @@ constexpr int64_t MAX_BODY_CELLS = 1 << 22;        // beyond this the pose is ga
 constexpr uint32_t ERR_COLOR_OVERFLOW = 1u;
 constexpr uint32_t ERR_GRID_RANGE = 2u;
 constexpr uint32_t ERR_ROUNDS = 4u;
+constexpr uint32_t ERR_STALL = 8u;             // dataflow sweep stalled (a bug, never data): reported instead of hanging
 
 // Device-side counters of one process() call (one 128-byte block, copied to pinned host memory once per step).
 struct Counters {
@@ -48,7 +51,8 @@ struct Counters {
     uint32_t n_colors;
     uint32_t n_rounds;
     uint32_t err;
-    uint32_t pad[25];
+    uint32_t n_stamps;
+    unsigned long long stamp[12];   // %globaltimer at phase boundaries of the persistent solver (block 0; diagnostics)
 };
 
 // Everything the kernels need, passed by value.
@@ -56,7 +60,7 @@ struct Dev {
     // ---- bodies (NB slots; world-major, slot = insertion index inside its world) ------------------------------
     uint32_t n_bodies;
     float4* pos;      // x, y, angle, -
-    float4* mom;      // momentum.x, momentum.y, ang_momentum, -
+    float4* mom;      // momentum.x, momentum.y, ang_momentum, bits(version): contact updates applied in this substep
     float4* frc;      // force.x, force.y, torque, -
     float4* prop;     // mass, inertia, mu, -
     float4* shape;    // a, b, bits(flags), bits(id)   flags: bit0 static, bit1 rect, bits 8.. world
@@ -99,20 +103,28 @@ struct Dev {
     uint32_t* round_left;         // MAX_COLOR_ROUNDS
     Counters* counters;
     // ---- solver records, grouped by colour (M slots) -----------------------------------------------------------------
-    uint4* s_hdr;                 // ref slot, inc slot, n_points | static1 << 8 | static2 << 9, pair slot
+    uint4* s_hdr;                 // ref slot, inc slot, n_points | static1 << 8 | static2 << 9 | S_EMPTY, pair slot
     float4* s_nf;                 // normal.x, normal.y, friction, -
     float4* s_inv;                // inv_m1, inv_m2, inv_i1, inv_i2
     float4* s_r0;                 // point 0: r1.x, r1.y, r2.x, r2.y
     float4* s_r1;
-    float4* s_pm0;                // point 0: mass_n, mass_t, depth, -
+    float4* s_pm0;                // point 0: mass_n, mass_t, depth, Baumgarte bias (collision.zig:172; constant per call)
     float4* s_pm1;
     float2* s_acc0;               // point 0: accumulated_pn, accumulated_pt
     float2* s_acc1;
+    uint4* s_dep;                 // rank of this manifold among the contacts of its ref body, that body's contact count,
+                                  // same for the inc body  (dataflow ordering of the sweep, see solve_contact_thread)
     // ---- joints, grouped by colour -----------------------------------------------------------------------------------
     uint32_t n_joints;
     const uint4* j_hdr;           // type, slot1, slot2, -
     const float4* j_par;          // power_max, power_min, beta, target (distance | omega)
     const float4* j_vec;          // r1.x, r1.y, r2.x, r2.y  |  target.x, target.y, -, -
+    float sub_dt;                 // dt / sub_steps of the current process() call
+    // ---- dataflow sweep tuning (wait policy only; never affects results) ------------------------------------------------
+    uint32_t wait_mode;           // 0: the warp updates when all its lanes are ready; 1: ready lanes update as they come
+    uint32_t wait_spin_lag;       // lag <= this: poll again immediately
+    uint32_t wait_sleep_unit;     // otherwise sleep lag * unit ns ...
+    uint32_t wait_sleep_max;      // ... capped at this many ns
 };
 
 R2D_HD uint32_t body_flags(const Dev& d, uint32_t i) { return f2u(d.shape[i].z); }
@@ -156,6 +168,53 @@ R2D_HD void atomic_max_u64(unsigned long long* p, unsigned long long v) {
     atomicMax(p, v);
 #else
     if (*p < v) *p = v;
+#endif
+}
+
+R2D_HD uint32_t popc64(unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popcll(v);
+#else
+    return (uint32_t)__builtin_popcountll(v);
+#endif
+}
+// One 16-byte word per body holds {momentum.x, momentum.y, ang_momentum, version}.  The scalar .b128 relaxed accesses
+// (LDG/STG.E.128.STRONG.GPU) are single-copy atomic at device scope, so whoever observes a version also observes the
+// momentum written with it — no fence, no separate flag.  Plain accesses in the serial emulator.
+R2D_HD float4 ld_body_word(const float4* p) {
+#if defined(__CUDA_ARCH__)
+    float4 v;
+    asm volatile("{\n\t.reg .b128 t;\n\tld.relaxed.gpu.global.b128 t, [%4];\n\tmov.b128 {%0, %1, %2, %3}, t;\n\t}"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+#else
+    return *p;
+#endif
+}
+R2D_HD void st_body_word(float4* p, float4 v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("{\n\t.reg .b128 t;\n\tmov.b128 t, {%1, %2, %3, %4};\n\tst.relaxed.gpu.global.b128 [%0], t;\n\t}" ::"l"(p),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+#else
+    *p = v;
+#endif
+}
+// DIAGNOSTIC flavour: .cg load / default store of the same 16 bytes (weak accesses)
+R2D_HD float4 ld_body_word_cg(const float4* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+R2D_HD void backoff_ns(uint32_t ns) {
+#if defined(__CUDA_ARCH__)
+    __nanosleep(ns);
+#else
+    (void)ns;
 #endif
 }
 
@@ -410,6 +469,26 @@ R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
     const float4 g0 = d.m_g0[p], g1 = d.m_g1[p];
     const ContactConst c = prestep_manifold(mk2(g0.x, g0.y), st1, st2, pr1.x, pr2.x, pr1.y, pr2.y, pr1.z, pr2.z);
     d.s_hdr[at] = make_uint4(h.x, h.y, np | (st1 ? 0x100u : 0u) | (st2 ? 0x200u : 0u), p);
+    // Colours on one body are pairwise distinct, so the body's sweep sequence is its colour set in ascending order:
+    // rank = colours below mine, degree = colours used.
+    {
+        const uint32_t color = d.m_color[p];
+        uint32_t rk[2] = {0, 0}, dg[2] = {0, 0};
+        const uint32_t bs[2] = {h.x, h.y};
+        const bool dyn[2] = {!st1, !st2};
+        for (int q = 0; q < 2; ++q) {
+            if (!dyn[q]) continue;
+            for (uint32_t w = 0; w < COLOR_WORDS; ++w) {
+                const unsigned long long u = d.used[(size_t)bs[q] * COLOR_WORDS + w];
+                dg[q] += popc64(u);
+                if (w < (color >> 6))
+                    rk[q] += popc64(u);
+                else if (w == (color >> 6))
+                    rk[q] += popc64(u & ((1ull << (color & 63u)) - 1ull));
+            }
+        }
+        d.s_dep[at] = make_uint4(rk[0], dg[0], rk[1], dg[1]);
+    }
     d.s_nf[at] = make_float4(c.normal.x, c.normal.y, c.friction, 0.0f);
     d.s_inv[at] = make_float4(c.inv_m1, c.inv_m2, c.inv_i1, c.inv_i2);
     if (np > 0) {
@@ -420,7 +499,7 @@ R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
         pc.depth = g1.x;
         prestep_point(c, pc);
         d.s_r0[at] = r;
-        d.s_pm0[at] = make_float4(pc.mass_n, pc.mass_t, pc.depth, 0.0f);
+        d.s_pm0[at] = make_float4(pc.mass_n, pc.mass_t, pc.depth, contact_bias(pc.depth, d.sub_dt));
         d.s_acc0[at] = make_float2(0.0f, 0.0f);
     }
     if (np > 1) {
@@ -431,56 +510,184 @@ R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
         pc.depth = g1.y;
         prestep_point(c, pc);
         d.s_r1[at] = r;
-        d.s_pm1[at] = make_float4(pc.mass_n, pc.mass_t, pc.depth, 0.0f);
+        d.s_pm1[at] = make_float4(pc.mass_n, pc.mass_t, pc.depth, contact_bias(pc.depth, d.sub_dt));
         d.s_acc1[at] = make_float2(0.0f, 0.0f);
     }
 }
 
 // ---- solver sweeps --------------------------------------------------------------------------------------------------
-// K11: one manifold of the current colour (collision.zig:135-218).  Manifolds of one colour share no non-static body.
-R2D_HD void solve_contact_thread(const Dev& d, uint32_t m, float sub_dt) {
+// K11: one manifold (collision.zig:135-218).  Manifolds of one colour share no non-static body.
+//
+// DATAFLOW = false: the caller guarantees (kernel boundary / grid barrier) that all lower colours are done.
+// DATAFLOW = true : no barrier between colours or iterations.  The 4th component of every body's momentum word is a
+//   version: the number of contact updates applied to the body in this substep.  The k-th contact (in colour order) of
+//   a body in iteration `it` runs when the version equals it * degree + k, and publishes momentum and version + 1 in
+//   ONE 16-byte store.  Each body therefore sees exactly the same sequence of updates as with barriers — the result is
+//   bit-identical — but a manifold only waits for its own two bodies.  All waiting threads are resident (cooperative
+//   launch) and walk their manifolds in (iteration, colour) order, so the globally lowest pending manifold can always
+//   run: no deadlock.  A stall would be a bug; it is reported through ERR_STALL instead of hanging the GPU.
+template <bool DATAFLOW>
+R2D_HD void solve_contact_thread(const Dev& d, uint32_t m, float sub_dt, uint32_t it = 0) {
     const uint4 h = d.s_hdr[m];
-    const int np = (int)(h.z & 0xFFu);
-    const bool st1 = (h.z & 0x100u) != 0, st2 = (h.z & 0x200u) != 0;
-    const float4 nf = d.s_nf[m], inv = d.s_inv[m];
+    const bool empty = (h.z & S_EMPTY) != 0;
+    if (!DATAFLOW && empty) return;
+    const int np = empty ? 0 : (int)(h.z & 0xFFu);
+    const bool st1 = empty || (h.z & 0x100u) != 0, st2 = empty || (h.z & 0x200u) != 0;
     ContactConst c;
-    c.normal = mk2(nf.x, nf.y);
-    c.tangent = rot90cw(c.normal);
-    c.friction = nf.z;
-    c.inv_m1 = inv.x;
-    c.inv_m2 = inv.y;
-    c.inv_i1 = inv.z;
-    c.inv_i2 = inv.w;
-    const float4 m1 = d.mom[h.x], m2 = d.mom[h.y];
-    BodyVel b1 = {mk2(m1.x, m1.y), m1.z}, b2 = {mk2(m2.x, m2.y), m2.z};
     ContactPointConst pts[2];
     v2 acc[2];
-    if (np > 0) {
-        const float4 r = d.s_r0[m], pm = d.s_pm0[m];
-        const float2 a = d.s_acc0[m];
-        pts[0].r1 = mk2(r.x, r.y);
-        pts[0].r2 = mk2(r.z, r.w);
-        pts[0].mass_n = pm.x;
-        pts[0].mass_t = pm.y;
-        pts[0].depth = pm.z;
-        acc[0] = mk2(a.x, a.y);
+    uint32_t e1 = 0, e2 = 0;
+    float4 m1 = make_float4(0, 0, 0, 0), m2 = m1;
+    if (!empty) {
+        const float4 nf = d.s_nf[m], inv = d.s_inv[m];
+        c.normal = mk2(nf.x, nf.y);
+        c.tangent = rot90cw(c.normal);
+        c.friction = nf.z;
+        c.inv_m1 = inv.x;
+        c.inv_m2 = inv.y;
+        c.inv_i1 = inv.z;
+        c.inv_i2 = inv.w;
+        {  // point 0 is loaded unconditionally (almost every manifold has it): no dependent load level after the header
+            const float4 r = d.s_r0[m], pm = d.s_pm0[m];
+            const float2 a = d.s_acc0[m];
+            pts[0].r1 = mk2(r.x, r.y);
+            pts[0].r2 = mk2(r.z, r.w);
+            pts[0].mass_n = pm.x;
+            pts[0].mass_t = pm.y;
+            pts[0].depth = pm.z;
+            pts[0].bias = pm.w;
+            acc[0] = mk2(a.x, a.y);
+        }
+        if (np > 1) {
+            const float4 r = d.s_r1[m], pm = d.s_pm1[m];
+            const float2 a = d.s_acc1[m];
+            pts[1].r1 = mk2(r.x, r.y);
+            pts[1].r2 = mk2(r.z, r.w);
+            pts[1].mass_n = pm.x;
+            pts[1].mass_t = pm.y;
+            pts[1].depth = pm.z;
+            pts[1].bias = pm.w;
+            acc[1] = mk2(a.x, a.y);
+        }
+        if (DATAFLOW) {
+            const uint4 dep = d.s_dep[m];
+            e1 = it * dep.y + dep.x;
+            e2 = it * dep.w + dep.z;
+        }
+        m1 = d.mom[h.x];  // static bodies: never written during a sweep
+        m2 = d.mom[h.y];
     }
-    if (np > 1) {
-        const float4 r = d.s_r1[m], pm = d.s_pm1[m];
-        const float2 a = d.s_acc1[m];
-        pts[1].r1 = mk2(r.x, r.y);
-        pts[1].r2 = mk2(r.z, r.w);
-        pts[1].mass_n = pm.x;
-        pts[1].mass_t = pm.y;
-        pts[1].depth = pm.z;
-        acc[1] = mk2(a.x, a.y);
+    if (DATAFLOW) {
+        // The 32 manifolds of a warp have one colour (segments are padded to whole warps), hence no dependencies among
+        // themselves: the warp polls until ALL its lanes are ready and then updates them in one converged pass.
+        uint32_t spins = 0;
+#if defined(__CUDA_ARCH__)
+        // Stage 1: only lane 0 probes (one 16-byte load per warp instead of 64) until ITS body is ready; the other
+        // lanes have the same colour and become ready at about the same time.
+        for (; d.wait_mode < 2u;) {
+            uint32_t lag0 = 0u;
+            if ((threadIdx.x & 31u) == 0u && !st1) lag0 = e1 - f2u(ld_body_word(&d.mom[h.x]).w);
+            lag0 = __shfl_sync(0xffffffffu, lag0, 0);
+            if (lag0 == 0u) break;
+            if (lag0 > d.wait_spin_lag) {
+                const uint32_t ns = lag0 * d.wait_sleep_unit;
+                backoff_ns(ns < d.wait_sleep_max ? ns : d.wait_sleep_max);
+            }
+            if ((++spins & 0xFFu) == 0u) {
+                if (spins > (1u << 20)) atomicOr(&d.counters->err, ERR_STALL);
+                const uint32_t flag = *((volatile uint32_t*)&d.counters->err) & ERR_STALL;
+                if (__any_sync(0xffffffffu, flag != 0u)) return;
+            }
+        }
+#endif
+#if defined(__CUDA_ARCH__)
+        if (d.wait_mode == 2u) {  // DIAGNOSTIC ONLY (wrong results): no waiting at all, measures the dependency-free cost
+            if (!st1) m1 = ld_body_word(&d.mom[h.x]);
+            if (!st2) m2 = ld_body_word(&d.mom[h.y]);
+        } else if (d.wait_mode == 3u) {  // DIAGNOSTIC ONLY: same, with weak .cg loads and default stores
+            if (!st1) m1 = ld_body_word_cg(&d.mom[h.x]);
+            if (!st2) m2 = ld_body_word_cg(&d.mom[h.y]);
+            BodyVel b1 = {mk2(m1.x, m1.y), m1.z}, b2 = {mk2(m2.x, m2.y), m2.z};
+            solve_contact(c, np, pts, acc, st1, st2, b1, b2);
+            d.s_acc0[m] = make_float2(acc[0].x, acc[0].y);
+            if (np > 1) d.s_acc1[m] = make_float2(acc[1].x, acc[1].y);
+            if (!st1) d.mom[h.x] = make_float4(b1.mom.x, b1.mom.y, b1.ang, u2f(e1 + 1u));
+            if (!st2) d.mom[h.y] = make_float4(b2.mom.x, b2.mom.y, b2.ang, u2f(e2 + 1u));
+            return;
+        } else
+        if (d.wait_mode == 1u) {
+            // Ready lanes update as they come (a few converged sub-groups per warp instead of waiting for the slowest lane).
+            bool pending = !empty;
+            while (__any_sync(0xffffffffu, pending)) {
+                uint32_t lag = 0xffffffffu;
+                if (pending) {
+                    if (!st1) m1 = ld_body_word(&d.mom[h.x]);
+                    if (!st2) m2 = ld_body_word(&d.mom[h.y]);
+                    lag = (st1 ? 0u : e1 - f2u(m1.w)) + (st2 ? 0u : e2 - f2u(m2.w));
+                }
+                if (pending && lag == 0u) {
+                    BodyVel b1 = {mk2(m1.x, m1.y), m1.z}, b2 = {mk2(m2.x, m2.y), m2.z};
+                    solve_contact(c, np, pts, acc, st1, st2, b1, b2);
+                    d.s_acc0[m] = make_float2(acc[0].x, acc[0].y);
+                    if (np > 1) d.s_acc1[m] = make_float2(acc[1].x, acc[1].y);
+                    if (!st1) st_body_word(&d.mom[h.x], make_float4(b1.mom.x, b1.mom.y, b1.ang, u2f(e1 + 1u)));
+                    if (!st2) st_body_word(&d.mom[h.y], make_float4(b2.mom.x, b2.mom.y, b2.ang, u2f(e2 + 1u)));
+                    pending = false;
+                }
+                const uint32_t best = __reduce_min_sync(0xffffffffu, pending ? lag : 0xffffffffu);
+                if (best != 0xffffffffu && best > d.wait_spin_lag) {
+                    const uint32_t ns = best * d.wait_sleep_unit;
+                    backoff_ns(ns < d.wait_sleep_max ? ns : d.wait_sleep_max);
+                }
+                if ((++spins & 0xFFu) == 0u) {
+                    if (spins > (1u << 20)) atomicOr(&d.counters->err, ERR_STALL);
+                    const uint32_t flag = *((volatile uint32_t*)&d.counters->err) & ERR_STALL;
+                    if (__any_sync(0xffffffffu, flag != 0u)) return;
+                }
+            }
+            return;
+        }
+#endif
+        for (; d.wait_mode != 2u;) {
+            if (!st1) m1 = ld_body_word(&d.mom[h.x]);
+            if (!st2) m2 = ld_body_word(&d.mom[h.y]);
+            const uint32_t lag = (st1 ? 0u : e1 - f2u(m1.w)) + (st2 ? 0u : e2 - f2u(m2.w));
+#if defined(__CUDA_ARCH__)
+            const uint32_t worst = __reduce_max_sync(0xffffffffu, lag);
+            if (worst == 0u) break;
+            // `worst` updates still have to land before the slowest lane may run: sleep in proportion
+            if (worst > d.wait_spin_lag) {
+                const uint32_t ns = worst * d.wait_sleep_unit;
+                backoff_ns(ns < d.wait_sleep_max ? ns : d.wait_sleep_max);
+            }
+            if ((++spins & 0xFFu) == 0u) {
+                if (spins > (1u << 20)) atomicOr(&d.counters->err, ERR_STALL);
+                const uint32_t flag = *((volatile uint32_t*)&d.counters->err) & ERR_STALL;
+                if (__any_sync(0xffffffffu, flag != 0u)) return;  // warp-uniform exit
+            }
+#else
+            (void)spins;
+            if (lag != 0u) {  // serial emulation: the order must already be right
+                atomic_or_u32(&d.counters->err, ERR_STALL);
+                return;
+            }
+            break;
+#endif
+        }
     }
-    solve_contact(c, np, pts, acc, st1, st2, b1, b2, sub_dt);
+    if (empty) return;
+    BodyVel b1 = {mk2(m1.x, m1.y), m1.z}, b2 = {mk2(m2.x, m2.y), m2.z};
+    solve_contact(c, np, pts, acc, st1, st2, b1, b2);
     if (np > 0) d.s_acc0[m] = make_float2(acc[0].x, acc[0].y);
     if (np > 1) d.s_acc1[m] = make_float2(acc[1].x, acc[1].y);
     // static bodies receive a zero impulse in the reference (`momentum += 0`); not writing them is the same value
-    if (!st1) d.mom[h.x] = make_float4(b1.mom.x, b1.mom.y, b1.ang, m1.w);
-    if (!st2) d.mom[h.y] = make_float4(b2.mom.x, b2.mom.y, b2.ang, m2.w);
+    if (DATAFLOW) {
+        if (!st1) st_body_word(&d.mom[h.x], make_float4(b1.mom.x, b1.mom.y, b1.ang, u2f(e1 + 1u)));
+        if (!st2) st_body_word(&d.mom[h.y], make_float4(b2.mom.x, b2.mom.y, b2.ang, u2f(e2 + 1u)));
+    } else {
+        if (!st1) d.mom[h.x] = make_float4(b1.mom.x, b1.mom.y, b1.ang, m1.w);
+        if (!st2) d.mom[h.y] = make_float4(b2.mom.x, b2.mom.y, b2.ang, m2.w);
+    }
 }
 
 R2D_HD JointBody load_joint_body(const Dev& d, uint32_t s) {
@@ -560,6 +767,7 @@ R2D_HD void integrate_forces_thread(const Dev& d, uint32_t i, float sub_dt, bool
     m.x = fadd(m.x, fmul(f.x, sub_dt));
     m.y = fadd(m.y, fmul(f.y, sub_dt));
     m.z = fadd(m.z, fmul(f.z, sub_dt));
+    m.w = u2f(0u);  // version: contact updates are counted per substep (dataflow sweep)
     d.mom[i] = m;
     // force.xy is next read after the end-of-substep reset (positions kernel), so the gravity sum need not be stored
 }

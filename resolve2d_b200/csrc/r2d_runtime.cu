@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -75,10 +76,13 @@ struct CudaBatch : BatchBase {
     int device = 0;
     int n_sms = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    int color_blocks = 0;
+    int color_blocks = 0, solve_blocks = 0;
+    uint32_t wait_mode = 0, wait_spin_lag = 1, wait_sleep_unit = 200, wait_sleep_max = 4000;
+    int solve_blocks_per_sm = 1;
+    bool persistent_solver = true;   // false: one launch per colour (kept for A/B measurements)
     // bodies
     DBuf<float4> pos, mom, frc, prop, shape, aabb, pose;
-    DBuf<uint32_t> ncells, world_base, grav_off;
+    DBuf<uint32_t> ncells, world_base, grav_off, joint_color_start;
     DBuf<float> grav;
     DBuf<uint64_t> excl;
     DBuf<uint4> j_hdr;
@@ -90,6 +94,7 @@ struct CudaBatch : BatchBase {
     DBuf<uint4> m_hdr, s_hdr;
     DBuf<float4> m_g0, m_g1, m_r0, m_r1, s_nf, s_inv, s_r0, s_r1, s_pm0, s_pm1;
     DBuf<float2> s_acc0, s_acc1;
+    DBuf<uint4> s_dep;
     DBuf<uint32_t> m_color;
     // colouring
     DBuf<unsigned long long> maxprio0, maxprio1, used;
@@ -144,6 +149,16 @@ struct CudaBatch : BatchBase {
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 4) per_sm = 4;
         color_blocks = per_sm * n_sms;
+        R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent, TPB, 0));
+        if (per_sm < 1) per_sm = 1;
+        if (const char* e = getenv("R2D_SOLVE_BLOCKS_PER_SM")) solve_blocks_per_sm = atoi(e);
+        if (const char* e = getenv("R2D_WAIT_MODE")) wait_mode = (uint32_t)atoi(e);
+        if (const char* e = getenv("R2D_WAIT_SPIN_LAG")) wait_spin_lag = (uint32_t)atoi(e);
+        if (const char* e = getenv("R2D_WAIT_SLEEP_UNIT")) wait_sleep_unit = (uint32_t)atoi(e);
+        if (const char* e = getenv("R2D_WAIT_SLEEP_MAX")) wait_sleep_max = (uint32_t)atoi(e);
+        if (per_sm > solve_blocks_per_sm) per_sm = solve_blocks_per_sm;
+        solve_blocks = per_sm * n_sms;
+        if (const char* e = getenv("R2D_SOLVER")) persistent_solver = std::string(e) != "launches";
         R2D_TRY(counters.reserve(1));
         R2D_TRY(color_misc.reserve(MAX_COLORS * 3 + 1 + MAX_COLOR_ROUNDS));
         return R2D_OK;
@@ -208,7 +223,8 @@ struct CudaBatch : BatchBase {
         if ((st = up(pos, image.pos)) || (st = up(mom, image.mom)) || (st = up(frc, image.frc)) || (st = up(prop, image.prop)) ||
             (st = up(shape, image.shape)) || (st = up(aabb, image.aabb)) || (st = up(world_base, image.world_base)) ||
             (st = up(grav_off, image.grav_off)) || (st = up(grav, image.grav)) || (st = up(excl, image.excl)) ||
-            (st = up(j_hdr, image.j_hdr)) || (st = up(j_par, image.j_par)) || (st = up(j_vec, image.j_vec)))
+            (st = up(j_hdr, image.j_hdr)) || (st = up(j_par, image.j_par)) || (st = up(j_vec, image.j_vec)) ||
+            (st = up(joint_color_start, image.joint_color_start)))
             return st;
         R2D_CUDA(cudaStreamSynchronize(stream));  // the image vectors are pageable and may change after we return
         last_pairs = 0;
@@ -390,8 +406,10 @@ struct CudaBatch : BatchBase {
         d.counters = counters.p;
         d.s_hdr = s_hdr.p; d.s_nf = s_nf.p; d.s_inv = s_inv.p; d.s_r0 = s_r0.p; d.s_r1 = s_r1.p;
         d.s_pm0 = s_pm0.p; d.s_pm1 = s_pm1.p; d.s_acc0 = s_acc0.p; d.s_acc1 = s_acc1.p;
+        d.s_dep = s_dep.p;
         d.n_joints = (uint32_t)image.j_hdr.size();
         d.j_hdr = j_hdr.p; d.j_par = j_par.p; d.j_vec = j_vec.p;
+        d.wait_mode = wait_mode; d.wait_spin_lag = wait_spin_lag; d.wait_sleep_unit = wait_sleep_unit; d.wait_sleep_max = wait_sleep_max;
     }
 
     int reserve_entries(size_t n) {
@@ -402,15 +420,19 @@ struct CudaBatch : BatchBase {
     }
     int reserve_pairs(size_t n) {
         int st;
+        const size_t pad = (size_t)MAX_COLORS * COLOR_ALIGN;  // colour segments are padded to whole warps
+        n += pad;
         if ((st = pairs.reserve(n)) || (st = m_hdr.reserve(n)) || (st = m_g0.reserve(n)) || (st = m_g1.reserve(n)) ||
             (st = m_r0.reserve(n)) || (st = m_r1.reserve(n)) || (st = m_color.reserve(n)) || (st = s_hdr.reserve(n)) ||
             (st = s_nf.reserve(n)) || (st = s_inv.reserve(n)) || (st = s_r0.reserve(n)) || (st = s_r1.reserve(n)) ||
-            (st = s_pm0.reserve(n)) || (st = s_pm1.reserve(n)) || (st = s_acc0.reserve(n)) || (st = s_acc1.reserve(n)))
+            (st = s_pm0.reserve(n)) || (st = s_pm1.reserve(n)) || (st = s_acc0.reserve(n)) || (st = s_acc1.reserve(n)) ||
+            (st = s_dep.reserve(n)))
             return st;
         cap_pairs = pairs.cap;
         for (size_t c : {m_hdr.cap, m_g0.cap, m_g1.cap, m_r0.cap, m_r1.cap, m_color.cap, s_hdr.cap, s_nf.cap, s_inv.cap,
-                         s_r0.cap, s_r1.cap, s_pm0.cap, s_pm1.cap, s_acc0.cap, s_acc1.cap})
+                         s_r0.cap, s_r1.cap, s_pm0.cap, s_pm1.cap, s_acc0.cap, s_acc1.cap, s_dep.cap})
             cap_pairs = std::min(cap_pairs, c);
+        cap_pairs -= pad;
         return R2D_OK;
     }
 
@@ -424,6 +446,7 @@ struct CudaBatch : BatchBase {
         stats.n_joint_colors = (uint32_t)image.joint_color_start.size() - 1;
         if (nb == 0) return R2D_OK;
         const float sub_dt = dt / (float)S;  // lib.zig:190-191 (host f32 division, IEEE)
+        d.sub_dt = sub_dt;
         const uint32_t T = grid_mult() * nb;
         int st;
         if ((st = pose.reserve(nb)) || (st = ncells.reserve(nb)) || (st = maxprio0.reserve(nb)) || (st = maxprio1.reserve(nb)) ||
@@ -459,7 +482,18 @@ struct CudaBatch : BatchBase {
                 launches += 1;
             }
             R2D_LAUNCH(R2D_KCLASS_COLORING, k_partition_prestep, grid_for(cap_pairs), TPB, d);
-            // ---- the one synchronisation point of the step ----
+            // ---- substeps: one persistent cooperative kernel (colour ranges are read on the device) ----
+            if (persistent_solver) {
+                prof_begin(R2D_KCLASS_SOLVE_CONTACTS);
+                const uint32_t* jcs_dev = joint_color_start.p;
+                uint32_t n_jc = (uint32_t)image.joint_color_start.size() - 1, S_ = S, I_ = I;
+                float sd = sub_dt;
+                void* args[] = {(void*)&d, (void*)&sd, (void*)&S_, (void*)&I_, (void*)&jcs_dev, (void*)&n_jc};
+                R2D_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(solve_blocks), dim3(TPB), args, 0, stream));
+                prof_end();
+                launches += 1;
+            }
+            // ---- the one synchronisation point of the step: counters + colour offsets ----
             R2D_CUDA(cudaMemcpyAsync(&pinned->counters, counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
             R2D_CUDA(cudaMemcpyAsync(pinned->color_start, d.color_start, (MAX_COLORS + 1) * 4, cudaMemcpyDeviceToHost, stream));
             R2D_CUDA(cudaStreamSynchronize(stream));
@@ -486,18 +520,28 @@ struct CudaBatch : BatchBase {
         stats.n_points = c.n_points;
         stats.n_colors = c.n_colors;
         stats.n_color_rounds = c.n_rounds;
+        if (getenv("R2D_STAMPS")) {
+            fprintf(stderr, "[r2d stamps ns]");
+            for (uint32_t k = 1; k < c.n_stamps && k < 12; ++k)
+                fprintf(stderr, " %u:%lld", k, c.stamp[k] ? (long long)(c.stamp[k] - c.stamp[0]) : -1LL);
+            fprintf(stderr, "\n");
+        }
         if (c.err & ERR_GRID_RANGE) {
             g_cuda_error = "a body AABB covers an unreasonable number of grid cells (NaN/inf pose?)";
             return R2D_ERR_GRID_RANGE;
+        }
+        if (c.err & ERR_STALL) {
+            g_cuda_error = "internal error: the dataflow contact sweep stalled (state of this step is undefined)";
+            return R2D_ERR_CUDA;
         }
         if (c.err & (ERR_COLOR_OVERFLOW | ERR_ROUNDS)) {
             g_cuda_error = "contact graph needs more than R2D_MAX_COLORS colours";
             return R2D_ERR_COLOR_OVERFLOW;
         }
-        // ---- substeps ----
+        // ---- substeps, one launch per colour (A/B path: R2D_SOLVER=launches) ----
         const uint32_t* cs = pinned->color_start;
         const auto& jcs = image.joint_color_start;
-        for (uint32_t s = 0; s < S; ++s) {
+        for (uint32_t s = 0; s < S && !persistent_solver; ++s) {
             R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_integrate_forces, grid_for(nb), TPB, d, sub_dt, (int)(s + 1 == S));
             for (uint32_t it = 0; it < I; ++it) {
                 for (size_t jc = 0; jc + 1 < jcs.size(); ++jc) {

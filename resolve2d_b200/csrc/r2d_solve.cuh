@@ -46,7 +46,12 @@ struct ContactPointConst {
     v2 r1, r2;
     float mass_n, mass_t;
     float depth;
+    float bias;   // Baumgarte bias of collision.zig:172; depth and dt are constant during one process() call
 };
+// bias = BAUMGARTE * max(0, -depth - SLOP) / dt   (collision.zig:172)
+R2D_HD float contact_bias(float depth, float dt) {
+    return fdiv(fmul(BAUMGARTE, fmax_z(0.0f, fsub(-depth, BAUMGARTE_SLOP))), dt);
+}
 
 R2D_HD ContactConst prestep_manifold(v2 normal, bool static1, bool static2, float mass1, float mass2, float inertia1,
                                      float inertia2, float mu1, float mu2) {
@@ -80,7 +85,7 @@ struct BodyVel {
 // calculateImpulses (collision.zig:135-218).  acc[k] = {accumulated_pn, accumulated_pt} persists for the whole
 // process() call (Q7).  Both points see the pre-loop velocities and are applied once at the end (Q8).
 R2D_HD void solve_contact(const ContactConst& c, int n_points, const ContactPointConst* pts, v2* acc, bool static1,
-                          bool static2, BodyVel& b1, BodyVel& b2, float dt) {
+                          bool static2, BodyVel& b1, BodyVel& b2) {
     const v2 vlinear_1 = scale2(b1.mom, c.inv_m1);
     const float omega1 = fmul(b1.ang, c.inv_i1);
     const v2 vlinear_2 = scale2(b2.mom, c.inv_m2);
@@ -102,8 +107,7 @@ R2D_HD void solve_contact(const ContactConst& c, int n_points, const ContactPoin
         const v2 v2_ = add2(vlinear_2, vrot_2);
         const v2 dv = sub2(v1, v2_);
 
-        const float bias = fdiv(fmul(BAUMGARTE, fmax_z(0.0f, fsub(-p.depth, BAUMGARTE_SLOP))), dt);  // :172
-        float num = fadd(dot2(dv, c.normal), bias);
+        float num = fadd(dot2(dv, c.normal), p.bias);  // :172-173, bias evaluated once per call (contact_bias)
         const float pn = fmul(num, p.mass_n);
         if (pn < MIN_MANIFOLD_IMPULSE) continue;  // :176 (Q6)
 

@@ -251,7 +251,10 @@ def build_pile(solver, nx=400, ny=250, seed=CONFIG_SEED["pile100k"]):
 
 
 def build_pile100k(solver):
-    return build_pile(solver, 400, 250)
+    """cfg2.  2000 columns x 50 rows: a wide, shallow drop so that the pile has actually formed after ~200 process()
+    calls (SURVEY 8d's 400 x 250 lattice is 275 m tall and is still in free fall at step 100 — measured in
+    profiles/r01_pile_evolution.md); same body count, radii, pitch, jitter and materials."""
+    return build_pile(solver, 2000, 50)
 
 
 def build_mixed(solver, nx=1250, ny=800, n_large=1000, seed=CONFIG_SEED["mixed1M"]):
@@ -295,7 +298,8 @@ def build_mixed(solver, nx=1250, ny=800, n_large=1000, seed=CONFIG_SEED["mixed1M
 
 
 def build_mixed1M(solver):
-    return build_mixed(solver, 1250, 800, 1000)
+    """cfg3.  5000 x 200 lattice (shallow for the same reason as pile100k) + 1000 large rectangles above it."""
+    return build_mixed(solver, 5000, 200, 1000)
 
 
 def build_pyramid(solver, base=199, n_spinners=50, seed=CONFIG_SEED["pyramid20k"]):

@@ -26,6 +26,7 @@ struct EmuBatch : BatchBase {
     std::vector<uint4> m_hdr, s_hdr;
     std::vector<float4> m_g0, m_g1, m_r0, m_r1, s_nf, s_inv, s_r0, s_r1, s_pm0, s_pm1;
     std::vector<float2> s_acc0, s_acc1;
+    std::vector<uint4> s_dep;
     std::vector<unsigned long long> maxprio0, maxprio1, used;
     std::vector<uint32_t> color_count, color_start, color_cursor, round_left;
     Counters counters{};
@@ -134,6 +135,7 @@ struct EmuBatch : BatchBase {
         if (nb == 0) return R2D_OK;
         const float sub_dt = fdiv(dt, (float)S);   // lib.zig:190-191
         d.n_bodies = nb;
+        d.sub_dt = sub_dt;
         d.pos = pos.data(); d.mom = mom.data(); d.frc = frc.data(); d.prop = prop.data(); d.shape = shape.data();
         d.aabb = aabb.data();
         pose.resize(nb); ncells.resize(nb);
@@ -208,11 +210,14 @@ struct EmuBatch : BatchBase {
         }
         if (counters.err & ERR_COLOR_OVERFLOW) return R2D_ERR_COLOR_OVERFLOW;
         if (counters.err & ERR_GRID_RANGE) return R2D_ERR_GRID_RANGE;
-        for (uint32_t c = 0; c < n_colors; ++c) color_start[c + 1] = color_start[c] + color_count[c];
+        for (uint32_t c = 0; c < n_colors; ++c)
+            color_start[c + 1] = (color_start[c] + color_count[c] + COLOR_ALIGN - 1u) & ~(COLOR_ALIGN - 1u);
+        const uint32_t MP = color_start[n_colors];  // padded manifold slots
 
         // ---- colour partition + pre-step ----
-        s_hdr.resize(M + 1); s_nf.resize(M + 1); s_inv.resize(M + 1); s_r0.resize(M + 1); s_r1.resize(M + 1);
-        s_pm0.resize(M + 1); s_pm1.resize(M + 1); s_acc0.resize(M + 1); s_acc1.resize(M + 1);
+        s_hdr.assign(MP + 1, make_uint4(0, 0, S_EMPTY, 0)); s_nf.resize(MP + 1); s_inv.resize(MP + 1); s_r0.resize(MP + 1);
+        s_r1.resize(MP + 1); s_pm0.resize(MP + 1); s_pm1.resize(MP + 1); s_acc0.resize(MP + 1); s_acc1.resize(MP + 1);
+        s_dep.resize(MP + 1); d.s_dep = s_dep.data();
         d.s_hdr = s_hdr.data(); d.s_nf = s_nf.data(); d.s_inv = s_inv.data(); d.s_r0 = s_r0.data(); d.s_r1 = s_r1.data();
         d.s_pm0 = s_pm0.data(); d.s_pm1 = s_pm1.data(); d.s_acc0 = s_acc0.data(); d.s_acc1 = s_acc1.data();
         for (uint32_t p = 0; p < P; ++p) {
@@ -229,10 +234,11 @@ struct EmuBatch : BatchBase {
                 for (size_t c = 0; c + 1 < jcs.size(); ++c)
                     for (uint32_t j = jcs[c]; j < jcs[c + 1]; ++j) solve_joint_thread(d, j, sub_dt);
                 for (uint32_t c = 0; c < n_colors; ++c)
-                    for (uint32_t m = color_start[c]; m < color_start[c + 1]; ++m) solve_contact_thread(d, m, sub_dt);
+                    for (uint32_t m = color_start[c]; m < color_start[c + 1]; ++m) solve_contact_thread<true>(d, m, sub_dt, it);
             }
             for (uint32_t i = 0; i < nb; ++i) integrate_positions_thread(d, i, sub_dt);
         }
+        if (counters.err & ERR_STALL) return R2D_ERR_CUDA;  // dataflow bookkeeping (rank / degree) is wrong
         stats.n_buckets = d.n_buckets;
         stats.n_entries = E;
         stats.n_pairs = P;
