@@ -140,6 +140,11 @@ int r2d_destroy(r2d_solver* s);
 int r2d_clear(r2d_solver* s);                     /* keeps exclusions and the id counter, like lib.zig:181-187 (Q16) */
 int r2d_set_mode(r2d_solver* s, int mode);        /* R2D_MODE_*; default PARITY */
 int r2d_set_stream(r2d_solver* s, void* cuda_stream); /* run on the caller's cudaStream_t (default: own stream) */
+/* Device memory keeps the bodies in a spatial (Morton) order so that bodies in contact are neighbours in HBM; ids,
+ * iteration order and results are unaffected.  The order is re-derived from the current positions every `steps`
+ * process() calls (default 256, 0 = only when the scene is edited) or on demand. */
+int r2d_set_reorder_interval(r2d_solver* s, uint32_t steps);
+int r2d_reorder(r2d_solver* s);
 
 /* ---- EntityFactory (lib.zig:73-129) ------------------------------------------------------------------ */
 int r2d_make_disc(r2d_solver* s, const r2d_body_opts* o, float radius, uint32_t* out_id);            /* makeDiscBody :73 */
@@ -195,6 +200,8 @@ int r2d_batch_world(r2d_batch* b, uint32_t world, r2d_solver** out);   /* borrow
 int r2d_batch_num_worlds(r2d_batch* b, uint32_t* out);
 int r2d_batch_set_mode(r2d_batch* b, int mode);
 int r2d_batch_set_stream(r2d_batch* b, void* cuda_stream);
+int r2d_batch_set_reorder_interval(r2d_batch* b, uint32_t steps);
+int r2d_batch_reorder(r2d_batch* b);
 int r2d_batch_process(r2d_batch* b, float dt, uint32_t sub_steps, uint32_t collision_iters);
 int r2d_batch_synchronize(r2d_batch* b);
 int r2d_batch_num_bodies(r2d_batch* b, size_t* out);                   /* total over worlds */

@@ -21,7 +21,7 @@ _lib = None
 _ORACLE_SYMBOLS = [
     "create", "destroy", "clear", "set_mode", "make_disc", "make_rect", "make_bodies", "make_gravity",
     "make_distance_joint", "make_offset_distance_joint", "make_fixed_position_joint", "make_motor_joint",
-    "exclude_pair", "remove_body", "process", "step", "synchronize", "num_bodies", "body_id_at", "body_get",
+    "exclude_pair", "remove_body", "process", "step", "synchronize", "reorder", "set_reorder_interval", "num_bodies", "body_id_at", "body_get",
     "body_set_static", "body_set_pos", "body_set_angle", "body_set_momentum", "body_set_ang_momentum",
     "body_set_force", "body_set_torque", "read_bodies", "write_forces", "read_pairs", "read_manifolds",
     "read_joint_order", "get_stats",

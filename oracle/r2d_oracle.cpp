@@ -1262,6 +1262,8 @@ int orc_remove_body(void* h, uint32_t id) { return ((Solver*)h)->removeRigidBody
 int orc_process(void* h, float dt, uint32_t sub_steps, uint32_t iters) { return ((Solver*)h)->process(dt, sub_steps, iters); }
 int orc_step(void* h, float dt, uint32_t sub_steps, uint32_t iters) { return orc_process(h, dt, sub_steps, iters); }
 int orc_synchronize(void*) { return 0; }
+int orc_reorder(void*) { return 0; }                       // memory order is not a concept of the oracle
+int orc_set_reorder_interval(void*, uint32_t) { return 0; }
 
 int orc_num_bodies(void* h, size_t* out) {
     *out = ((Solver*)h)->bodies.size();

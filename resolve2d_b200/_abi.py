@@ -123,6 +123,8 @@ SIGNATURES = {
     "r2d_clear": (C.c_int, [_P]),
     "r2d_set_mode": (C.c_int, [_P, C.c_int]),
     "r2d_set_stream": (C.c_int, [_P, _P]),
+    "r2d_set_reorder_interval": (C.c_int, [_P, _U32]),
+    "r2d_reorder": (C.c_int, [_P]),
     "r2d_make_disc": (C.c_int, [_P, C.POINTER(BodyOpts), _F, _UP]),
     "r2d_make_rect": (C.c_int, [_P, C.POINTER(BodyOpts), _F, _F, _UP]),
     "r2d_make_bodies": (C.c_int, [_P, _P, _SZ, _UP]),
@@ -158,6 +160,8 @@ SIGNATURES = {
     "r2d_batch_num_worlds": (C.c_int, [_P, _UP]),
     "r2d_batch_set_mode": (C.c_int, [_P, C.c_int]),
     "r2d_batch_set_stream": (C.c_int, [_P, _P]),
+    "r2d_batch_set_reorder_interval": (C.c_int, [_P, _U32]),
+    "r2d_batch_reorder": (C.c_int, [_P]),
     "r2d_batch_process": (C.c_int, [_P, _F, _U32, _U32]),
     "r2d_batch_synchronize": (C.c_int, [_P]),
     "r2d_batch_num_bodies": (C.c_int, [_P, C.POINTER(_SZ)]),

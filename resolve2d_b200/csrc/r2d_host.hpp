@@ -131,7 +131,26 @@ struct Image {
     std::vector<uint32_t> joint_color_start;   // n_joint_colors + 1
     std::vector<uint32_t> joint_world, joint_local_index, joint_color;  // per sorted joint
     uint32_t n_bodies = 0;
+    // Device slots are a spatial (Morton) permutation of the host's insertion-order slots inside every world, so that
+    // bodies that touch are neighbours in memory (the gathers of the colouring and of the contact sweep coalesce).
+    // Nothing observable depends on it: pairs, colours and the sweep order are functions of ids and geometry only.
+    std::vector<uint32_t> dev_of_host;   // host global slot (world-major, insertion order) -> device slot
+    std::vector<uint32_t> host_of_dev;   // device slot -> host global slot
+    uint32_t dev_id(uint32_t dev) const { return f2u(shape[dev].w); }
+    uint32_t dev_world(uint32_t dev) const { return f2u(shape[dev].z) >> FLAG_WORLD_SHIFT; }
 };
+
+inline uint32_t morton16(uint32_t x, uint32_t y) {
+    auto spread = [](uint32_t v) {
+        v &= 0xFFFFu;
+        v = (v | (v << 8)) & 0x00FF00FFu;
+        v = (v | (v << 4)) & 0x0F0F0F0Fu;
+        v = (v | (v << 2)) & 0x33333333u;
+        v = (v | (v << 1)) & 0x55555555u;
+        return v;
+    };
+    return spread(x) | (spread(y) << 1);
+}
 
 inline float4 mkf4(float x, float y, float z, float w) { return make_float4(x, y, z, w); }
 
@@ -160,6 +179,39 @@ inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image&
     }
     const size_t nb = im.world_base[nw];
     im.n_bodies = (uint32_t)nb;
+    im.dev_of_host.resize(nb);
+    im.host_of_dev.resize(nb);
+    {
+        std::vector<std::pair<uint64_t, uint32_t>> keyed;
+        for (size_t w = 0; w < nw; ++w) {
+            const World& W = *worlds[w];
+            const uint32_t base = im.world_base[w];
+            const size_t n = W.bodies.size();
+            float minx = 0, miny = 0;
+            bool any = false;
+            for (const Body& b : W.bodies) {
+                if (!(b.pos_x == b.pos_x) || !(b.pos_y == b.pos_y)) continue;
+                if (!any || b.pos_x < minx) minx = b.pos_x;
+                if (!any || b.pos_y < miny) miny = b.pos_y;
+                any = true;
+            }
+            keyed.resize(n);
+            for (size_t k = 0; k < n; ++k) {
+                const Body& b = W.bodies[k];
+                float fx = (b.pos_x - minx) * 0.5f, fy = (b.pos_y - miny) * 0.5f;  // 2 m quantum
+                if (!(fx >= 0.0f)) fx = 0.0f;
+                if (!(fy >= 0.0f)) fy = 0.0f;
+                if (fx > 65535.0f) fx = 65535.0f;
+                if (fy > 65535.0f) fy = 65535.0f;
+                keyed[k] = {morton16((uint32_t)fx, (uint32_t)fy), (uint32_t)k};
+            }
+            std::stable_sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+            for (size_t k = 0; k < n; ++k) {
+                im.host_of_dev[base + k] = base + keyed[k].second;
+                im.dev_of_host[base + keyed[k].second] = base + (uint32_t)k;
+            }
+        }
+    }
     im.pos.resize(nb);
     im.mom.resize(nb);
     im.frc.resize(nb);
@@ -175,11 +227,12 @@ inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image&
     for (size_t w = 0; w < nw; ++w) {
         const World& W = *worlds[w];
         const uint32_t base = im.world_base[w];
-        for (size_t s = 0; s < W.bodies.size(); ++s) body_to_image(W.bodies[s], (uint32_t)w, im, base + s);
+        for (size_t s = 0; s < W.bodies.size(); ++s) body_to_image(W.bodies[s], (uint32_t)w, im, im.dev_of_host[base + s]);
         for (const auto& pr : W.excluded) {
             const int s1 = W.find(pr.first), s2 = W.find(pr.second);
             if (s1 < 0 || s2 < 0 || s1 == s2) continue;
-            const uint64_t lo = base + (uint32_t)std::min(s1, s2), hi = base + (uint32_t)std::max(s1, s2);
+            const uint32_t d1 = im.dev_of_host[base + (uint32_t)s1], d2 = im.dev_of_host[base + (uint32_t)s2];
+            const uint64_t lo = std::min(d1, d2), hi = std::max(d1, d2);
             im.excl.push_back((lo << 32) | hi);
         }
         for (size_t k = 0; k < W.joints.size(); ++k) {
@@ -187,7 +240,7 @@ inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image&
             const int s1 = W.find(j.id1);
             const int s2 = joint_has_two_bodies(j) ? W.find(j.id2) : s1;
             if (s1 < 0 || s2 < 0) return R2D_ERR_INVALID_BODY_ID;
-            gj.push_back({j, (uint32_t)w, (uint32_t)k, base + (uint32_t)s1, base + (uint32_t)s2, 0u});
+            gj.push_back({j, (uint32_t)w, (uint32_t)k, im.dev_of_host[base + (uint32_t)s1], im.dev_of_host[base + (uint32_t)s2], 0u});
         }
     }
     std::sort(im.excl.begin(), im.excl.end());
@@ -312,10 +365,24 @@ struct BatchBase {
             float* dst[3][3] = {{&b.pos_x, &b.pos_y, &b.angle}, {&b.mom_x, &b.mom_y, &b.ang_mom}, {&b.force_x, &b.force_y, &b.torque}};
             for (int k = 0; k < n; ++k) *dst[f][comp + k] = v[k];
         }
-        if (dev_fresh) return backend_write(image.world_base[w->index] + (uint32_t)s, f, comp, n, v);
+        if (dev_fresh) return backend_write(image.dev_of_host[image.world_base[w->index] + (uint32_t)s], f, comp, n, v);
+        return R2D_OK;
+    }
+    uint32_t reorder_interval = 256;   // process() calls between spatial re-sorts of the device order (0 = never)
+    uint32_t steps_since_upload = 0;
+    int reorder() {  // re-derive the device order from the current positions (download, sort, upload)
+        const int st = ensure_host();
+        if (st != R2D_OK) return st;
+        dev_fresh = false;
         return R2D_OK;
     }
     int process(float dt, uint32_t sub_steps, uint32_t iters) {
+        if (dev_fresh && reorder_interval && steps_since_upload >= reorder_interval) {
+            const int sr = reorder();
+            if (sr != R2D_OK) return sr;
+        }
+        if (!dev_fresh) steps_since_upload = 0;
+        steps_since_upload += 1;
         const int st = ensure_device();
         if (st != R2D_OK) return st;
         const int st2 = backend_process(dt, sub_steps, iters);

@@ -178,23 +178,134 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_down(const uint32_t* in, uint
     }
 }
 
-// ---- K4b: per-bucket sort (deterministic bucket order) -----------------------------------------------------------------------
+// ---- K4b / K5: one WARP per bucket ------------------------------------------------------------------------------------------
+// The bucket's entries are staged in shared memory.  k_sort_buckets rank-sorts them (ascending slot, duplicates
+// adjacent) so that the bucket order — and with it the pair list — does not depend on the order the atomics of the
+// fill landed in, and so that membership tests can bisect.  k_bucket_pairs then lets the lanes split the (a, b) tests
+// of the bucket; a pair is counted (WRITE = false) or written at the bucket's scanned offset (WRITE = true) in
+// (a, b) order, which makes the candidate list deterministic.
+constexpr int BUCKET_WARPS = TPB / 32;
+constexpr int BUCKET_CAP = 128;  // entries staged per warp; larger buckets take the (rare) serial path
+
 __global__ void __launch_bounds__(TPB) k_sort_buckets(Dev d) {
-    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < d.n_buckets; b += gridDim.x * blockDim.x)
-        sort_bucket_thread(d, b);
+    __shared__ uint32_t s_in[BUCKET_WARPS][BUCKET_CAP];
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = warp; b < d.n_buckets; b += n_warps) {
+        const uint32_t bs = d.bucket_start[b], be = bucket_end(d, b);
+        const uint32_t n = be > bs ? be - bs : 0u;
+        if (lane == 0) {
+            d.ent_off[b] = 0u;
+            if (n >= 2u) d.work[atomicAdd(&d.counters->n_work, 1u)] = b;  // the pair kernels visit only these
+        }
+        if (n < 2u) continue;  // warp-uniform
+        if (n > BUCKET_CAP) {
+            if (lane == 0) sort_bucket_thread(d, b);
+            continue;
+        }
+        for (uint32_t k = lane; k < n; k += 32) s_in[wib][k] = d.ent_body[bs + k];
+        __syncwarp();
+        for (uint32_t k = lane; k < n; k += 32) {
+            const uint32_t v = s_in[wib][k];
+            uint32_t rank = 0;
+            for (uint32_t q = 0; q < n; ++q) {
+                const uint32_t u = s_in[wib][q];
+                rank += (u < v || (u == v && q < k)) ? 1u : 0u;
+            }
+            d.ent_body[bs + rank] = v;
+        }
+        __syncwarp();
+    }
 }
 
-// ---- K5: candidate pairs per grid entry; WRITE = false counts, true writes at the scanned offsets ----------------------------
+// (a, b), a < b, of the p-th pair in row-major order over the strict upper triangle of an n x n matrix
+__device__ __forceinline__ void tri_decode(uint32_t p, uint32_t n, uint32_t& a, uint32_t& b) {
+    const float fn = (float)(2 * n - 1);
+    int ia = (int)((fn - sqrtf(fn * fn - 8.0f * (float)p)) * 0.5f);
+    if (ia < 0) ia = 0;
+    // row a starts at a*(2n-a-1)/2; correct the float estimate
+    while ((uint32_t)(ia + 1) * (2 * n - (uint32_t)(ia + 1) - 1) / 2 <= p) ++ia;
+    while ((uint32_t)ia * (2 * n - (uint32_t)ia - 1) / 2 > p) --ia;
+    a = (uint32_t)ia;
+    b = p - a * (2 * n - a - 1) / 2 + a + 1;
+}
+
 template <bool WRITE>
-__global__ void __launch_bounds__(TPB) k_pairs(Dev d) {
-    const uint32_t n = live_entries(d);
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        if (!WRITE) {
-            d.ent_off[e] = entry_pairs_thread(d, e, nullptr);
-        } else {
-            const uint32_t off = d.ent_off[e], cnt = d.ent_off[e + 1] - off;
-            if (cnt && off + cnt <= d.cap_pairs) entry_pairs_thread(d, e, d.pairs + off);
+__global__ void __launch_bounds__(TPB) k_bucket_pairs(Dev d) {
+    __shared__ uint32_t s_body[BUCKET_WARPS][BUCKET_CAP];
+    __shared__ uint32_t s_meta[BUCKET_WARPS][BUCKET_CAP];  // flags (bit 0 static) | first-occurrence << 1 | ncells << 2
+    __shared__ float4 s_aabb[BUCKET_WARPS][BUCKET_CAP];
+    __shared__ uint4 s_bkt[BUCKET_WARPS][BUCKET_CAP];
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const bool dead = d.counters->n_entries > d.cap_entries;  // the fill dropped entries: this attempt is redone
+    const uint32_t n_work = d.counters->n_work;
+    for (uint32_t w = warp; w < n_work; w += n_warps) {
+        const uint32_t b = d.work[w];
+        const uint32_t bs = d.bucket_start[b], be = bucket_end(d, b);
+        const uint32_t n = (be > bs && !dead) ? be - bs : 0u;
+        const uint32_t out_at = WRITE ? d.ent_off[b] : 0u;  // ent_off is indexed by BUCKET here
+        uint32_t total = 0;
+        if (n >= 2u && n <= BUCKET_CAP) {
+            for (uint32_t k = lane; k < n; k += 32) {
+                const uint32_t body = d.ent_body[bs + k];
+                const bool first = k == 0 || d.ent_body[bs + k - 1] != body;
+                s_body[wib][k] = body;
+                s_aabb[wib][k] = d.aabb[body];
+                s_bkt[wib][k] = d.bkt[body];
+                uint32_t nc = d.ncells[body];
+                if (nc > 0x3FFFFFFFu) nc = 0x3FFFFFFFu;
+                s_meta[wib][k] = (body_flags(d, body) & FLAG_STATIC) | (first ? 2u : 0u) | (nc << 2);
+            }
+            __syncwarp();
+            const uint32_t n_pairs = n * (n - 1u) / 2u;
+            for (uint32_t base = 0; base < n_pairs; base += 32) {  // lanes split the (a, b) tests in row-major order
+                const uint32_t p = base + lane;
+                bool hit = false;
+                uint2 pr = make_uint2(0u, 0u);
+                if (p < n_pairs) {
+                    uint32_t a, k;
+                    tri_decode(p, n, a, k);
+                    const uint32_t ma = s_meta[wib][a], mb = s_meta[wib][k];
+                    const uint32_t i = s_body[wib][a], j = s_body[wib][k];
+                    if ((ma & mb & 2u) && i != j)
+                        hit = pair_candidate(d, b, i, j, s_aabb[wib][a], s_aabb[wib][k], ma & 1u, mb & 1u, ma >> 2, mb >> 2,
+                                             s_bkt[wib][a], s_bkt[wib][k], &pr);
+                }
+                const uint32_t votes = __ballot_sync(0xffffffffu, hit);
+                if (WRITE && hit) {
+                    const uint32_t at = out_at + total + (uint32_t)__popc(votes & ((1u << lane) - 1u));
+                    if (at < d.cap_pairs) d.pairs[at] = pr;
+                }
+                total += (uint32_t)__popc(votes);
+            }
+            __syncwarp();
+        } else if (n > BUCKET_CAP) {  // oversized bucket: same tests, entries read from global memory
+            for (uint32_t a = 0; a + 1 < n; ++a) {
+                const uint32_t i = d.ent_body[bs + a];
+                if (a > 0 && d.ent_body[bs + a - 1] == i) continue;
+                const float4 ai = d.aabb[i];
+                const uint32_t fi = body_flags(d, i), nci = d.ncells[i];
+                const uint4 bi = d.bkt[i];
+                for (uint32_t base = a + 1; base < n; base += 32) {
+                    const uint32_t k = base + lane;
+                    bool hit = false;
+                    uint2 pr = make_uint2(0u, 0u);
+                    if (k < n) {
+                        const uint32_t j = d.ent_body[bs + k];
+                        if (j != i && d.ent_body[bs + k - 1] != j)
+                            hit = pair_candidate(d, b, i, j, ai, d.aabb[j], fi, body_flags(d, j), nci, d.ncells[j], bi, d.bkt[j], &pr);
+                    }
+                    const uint32_t votes = __ballot_sync(0xffffffffu, hit);
+                    if (WRITE && hit) {
+                        const uint32_t at = out_at + total + (uint32_t)__popc(votes & ((1u << lane) - 1u));
+                        if (at < d.cap_pairs) d.pairs[at] = pr;
+                    }
+                    total += (uint32_t)__popc(votes);
+                }
+            }
         }
+        if (!WRITE && lane == 0) d.ent_off[b] = total;
     }
 }
 
@@ -210,11 +321,19 @@ __global__ void __launch_bounds__(TPB) k_narrow(Dev d) {
             my_k += (uint32_t)np;
         }
     }
+    __shared__ uint32_t s_m, s_k;  // one pair of global atomics per CTA (same-address atomics serialise in L2)
+    if (threadIdx.x == 0) s_m = s_k = 0u;
+    __syncthreads();
     my_m = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), my_m, cg::plus<uint32_t>());
     my_k = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), my_k, cg::plus<uint32_t>());
     if ((threadIdx.x & 31u) == 0 && (my_m | my_k)) {
-        atomicAdd(&d.counters->n_manifolds, my_m);
-        atomicAdd(&d.counters->n_points, my_k);
+        atomicAdd(&s_m, my_m);
+        atomicAdd(&s_k, my_k);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && (s_m | s_k)) {
+        atomicAdd(&d.counters->n_manifolds, s_m);
+        atomicAdd(&d.counters->n_points, s_k);
     }
 }
 
@@ -230,68 +349,69 @@ __global__ void __launch_bounds__(TPB) k_color(Dev d) {
     for (uint32_t p = tid; p < n; p += nth) {
         if (d.m_color[p] != COLOR_PENDING) continue;
         const uint4 h = d.m_hdr[p];
-        color_post(d, h.x, h.y, !(body_flags(d, h.x) & FLAG_STATIC), !(body_flags(d, h.y) & FLAG_STATIC),
-                   manifold_priority(d, h.x, h.y), 1u);
+        color_post(d, h.x, h.y, (h.w & 1u) != 0, (h.w & 2u) != 0, d.m_prio[p], 1u);
     }
+    // Same-address global atomics serialise in L2, so the per-colour populations are histogrammed in shared memory
+    // for the whole kernel and the "anything left?" flag costs at most one global atomic per CTA and round.
+    __shared__ uint32_t s_hist[MAX_COLORS];
+    for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x) s_hist[c] = 0u;
     grid.sync();
     uint32_t round = 1;
     for (; round < MAX_COLOR_ROUNDS; ++round) {
-        uint32_t left = 0;
+        int left = 0;
         for (uint32_t p = tid; p < n; p += nth) {
             const int r = color_round_thread(d, p, round);
-            if (r == 2) {
-                left += 1;
-            } else if (r == 1) {
-                // per-colour population, aggregated over the lanes of the warp that won the same colour
-                const uint32_t c = d.m_color[p];
-                const uint32_t peers = __match_any_sync(__activemask(), c);
-                if ((threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) {
-                    atomicAdd(&d.color_count[c], (uint32_t)__popc(peers));
-                    atomicMax(&d.counters->n_colors, c + 1u);
-                }
-            }
+            if (r == 2)
+                left = 1;
+            else if (r == 1)
+                atomicAdd(&s_hist[d.m_color[p]], 1u);
         }
-        left = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), left, cg::plus<uint32_t>());
-        if ((threadIdx.x & 31u) == 0 && left) atomicAdd(&d.round_left[round], left);
+        if (__syncthreads_or(left) && threadIdx.x == 0) atomicAdd(&d.round_left[round], 1u);
         grid.sync();
         if (__ldcg(&d.round_left[round]) == 0) break;
     }
+    for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x)
+        if (s_hist[c]) atomicAdd(&d.color_count[c], s_hist[c]);
+    grid.sync();
     if (tid == 0) {
         d.counters->n_rounds = round;
         if (round >= MAX_COLOR_ROUNDS) atomicOr(&d.counters->err, ERR_ROUNDS);
-        const uint32_t nc = __ldcg(&d.counters->n_colors);
-        uint32_t run = 0;
-        for (uint32_t c = 0; c < nc; ++c) {  // colour segments start on warp boundaries (dataflow sweep)
-            d.color_start[c] = run;
-            run = (run + __ldcg(&d.color_count[c]) + COLOR_ALIGN - 1u) & ~(COLOR_ALIGN - 1u);
-        }
-        d.color_start[nc] = run;
+        uint32_t nc = 0;
+        for (uint32_t c = 0; c < MAX_COLORS; ++c)
+            if (__ldcg(&d.color_count[c])) nc = c + 1u;
+        d.counters->n_colors = nc;
+        d.counters->n_own_scan = nc * (d.own_words + 1u);
     }
+}
+
+// ---- K9a: owner bitmaps and their popcounts (the scan of which places every manifold, see manifold_owner) ----------------------
+__global__ void __launch_bounds__(TPB) k_owner_bits(Dev d) {
+    if (overflowed(d)) return;
+    const uint32_t n = live_pairs(d);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) owner_bit_thread(d, p);
+}
+__global__ void __launch_bounds__(TPB) k_owner_count(Dev d) {
+    const uint32_t n = d.counters->n_own_scan;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) owner_count_thread(d, k);
 }
 
 // ---- K9: group the manifolds by colour and evaluate the pre-step (collision.zig:102-133) ---------------------------------------
 __global__ void __launch_bounds__(TPB) k_partition_prestep(Dev d) {
     if (overflowed(d)) return;
     const uint32_t n = live_pairs(d);
-    if (blockIdx.x == 0) {  // mark the padding slots at the end of every colour segment
-        const uint32_t nc = d.counters->n_colors;
+    const uint32_t nc = d.counters->n_colors, stride = d.own_words + 1u;
+    if (blockIdx.x == 0) {
+        // colour segment starts (each begins on a warp boundary) and the padding slots at the end of every segment
+        for (uint32_t c = threadIdx.x; c <= nc; c += blockDim.x) d.color_start[c] = d.own_pos[(size_t)c * stride];
         for (uint32_t k = threadIdx.x; k < nc * COLOR_ALIGN; k += blockDim.x) {
             const uint32_t c = k / COLOR_ALIGN;
-            const uint32_t at = d.color_start[c] + d.color_count[c] + (k % COLOR_ALIGN);
-            if (at < d.color_start[c + 1]) d.s_hdr[at] = make_uint4(0u, 0u, S_EMPTY, 0u);
+            const uint32_t at = d.own_pos[(size_t)c * stride + d.own_words] + (k % COLOR_ALIGN);
+            if (at < d.own_pos[(size_t)(c + 1u) * stride]) d.s_hdr[at] = make_uint4(0u, 0u, S_EMPTY, 0u);
         }
     }
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        const uint32_t c = d.m_color[p];
-        if (c >= MAX_COLORS) continue;
-        // one cursor bump per (warp, colour)
-        const uint32_t peers = __match_any_sync(__activemask(), c);
-        const uint32_t lane = threadIdx.x & 31u, leader = (uint32_t)(__ffs(peers) - 1);
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(&d.color_cursor[c], (uint32_t)__popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        const uint32_t at = d.color_start[c] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-        gather_prestep_thread(d, p, at);
+        if (d.m_color[p] >= MAX_COLORS) continue;
+        gather_prestep_thread(d, p, manifold_slot(d, p));
     }
 }
 
@@ -322,20 +442,64 @@ __global__ void __launch_bounds__(SOLVE_TPB) k_solve_joints(Dev d, uint32_t begi
 // Colour ranges and counts are read from device memory, so the host never has to learn them before launching.
 // An abandoned attempt (buffer overflow, colouring error) leaves the body state untouched.
 __device__ __forceinline__ void stamp(const Dev& d, uint32_t slot) {
-    if (blockIdx.x == 0 && threadIdx.x == 0 && slot < 12) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && slot < 10) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         d.counters->stamp[slot] = t;
         d.counters->n_stamps = slot + 1;
     }
 }
+// Shared-memory cache of the solver records: thread t owns manifolds t, t + nth, ... for the whole kernel, so the first
+// SOLVE_SMEM_SLOTS of them are copied once into shared memory (record k of thread x at index k * TPB + x of each array)
+// and every sweep reads its constants — and keeps its accumulated impulses — there; only the two body words of a
+// manifold go through L2.  Records beyond the cache (worlds with more than ~245k manifolds) stream from global memory.
+constexpr int SOLVE_SMEM_SLOTS = 6;
+constexpr int SOLVE_SMEM_BYTES_PER_RECORD = 6 * 16 + 8 + 2 * 16 + 8;  // hdr nf inv dep r0 pm0 | acc0 | r1 pm1 | acc1 = 144
+constexpr size_t SOLVE_SMEM_BYTES = (size_t)SOLVE_SMEM_SLOTS * TPB * SOLVE_SMEM_BYTES_PER_RECORD;
+
 __global__ void __launch_bounds__(TPB) k_solve_persistent(Dev d, float sub_dt, uint32_t S, uint32_t I,
-                                                          const uint32_t* __restrict__ joint_color_start, uint32_t n_joint_colors) {
+                                                          const uint32_t* __restrict__ joint_color_start, uint32_t n_joint_colors,
+                                                          uint32_t smem_slots) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::grid_group grid = cg::this_grid();
     if (overflowed(d) || d.counters->err != 0u) return;  // uniform across the grid
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const uint32_t n_manifolds = d.color_start[d.counters->n_colors];
     stamp(d, 0);
+    // ---- stage my records ----
+    Dev ds = d;  // same code path, record arrays redirected to shared memory
+    {
+        const size_t n = (size_t)SOLVE_SMEM_SLOTS * TPB;
+        unsigned char* q = smem_raw;
+        ds.s_hdr = (uint4*)q;    q += n * 16;
+        ds.s_nf = (float4*)q;    q += n * 16;
+        ds.s_inv = (float4*)q;   q += n * 16;
+        ds.s_dep = (uint4*)q;    q += n * 16;
+        ds.s_r0 = (float4*)q;    q += n * 16;
+        ds.s_pm0 = (float4*)q;   q += n * 16;
+        ds.s_r1 = (float4*)q;    q += n * 16;
+        ds.s_pm1 = (float4*)q;   q += n * 16;
+        ds.s_acc0 = (float2*)q;  q += n * 8;
+        ds.s_acc1 = (float2*)q;
+        for (uint32_t k = 0; k < smem_slots; ++k) {
+            const uint32_t m = tid + k * nth, l = k * TPB + threadIdx.x;
+            if (m >= n_manifolds) break;
+            const uint4 h = d.s_hdr[m];
+            ds.s_hdr[l] = h;
+            if (h.z & S_EMPTY) continue;
+            ds.s_nf[l] = d.s_nf[m];
+            ds.s_inv[l] = d.s_inv[m];
+            ds.s_dep[l] = d.s_dep[m];
+            ds.s_r0[l] = d.s_r0[m];
+            ds.s_pm0[l] = d.s_pm0[m];
+            ds.s_acc0[l] = d.s_acc0[m];
+            if ((h.z & 0xFFu) > 1u) {
+                ds.s_r1[l] = d.s_r1[m];
+                ds.s_pm1[l] = d.s_pm1[m];
+                ds.s_acc1[l] = d.s_acc1[m];
+            }
+        }
+    }
     for (uint32_t s = 0; s < S; ++s) {
         if (s == 0)
             for (uint32_t i = tid; i < d.n_bodies; i += nth) integrate_forces_thread(d, i, sub_dt, S == 1);
@@ -348,7 +512,13 @@ __global__ void __launch_bounds__(TPB) k_solve_persistent(Dev d, float sub_dt, u
                 for (uint32_t j = b + tid; j < e; j += nth) solve_joint_thread(d, j, sub_dt);
                 grid.sync();
             }
-            for (uint32_t m = tid; m < n_manifolds; m += nth) solve_contact_thread<true>(d, m, sub_dt, it);
+            uint32_t k = 0;
+            for (uint32_t m = tid; m < n_manifolds; m += nth, ++k) {
+                if (k < smem_slots)
+                    solve_contact_thread<true>(ds, k * TPB + threadIdx.x, sub_dt, it);  // cached record
+                else
+                    solve_contact_thread<true>(d, m, sub_dt, it);
+            }
             if (s == 0) stamp(d, 3 + it);     // block 0 finished its part of sweep `it`
             if (n_joint_colors) grid.sync();  // joints of the next iteration read what the contacts wrote
         }
@@ -365,10 +535,11 @@ __global__ void __launch_bounds__(TPB) k_solve_persistent(Dev d, float sub_dt, u
 }
 
 // ---- boundary kernels: SoA export for bulk readback, force import ---------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_export_bodies(Dev d, uint32_t first, uint32_t n, uint32_t* ids, float2* pos, float* angle,
-                                                       float2* mom, float* ang_mom, float4* aabb) {
+// `slot_of[k]` = device slot of the k-th requested body (host order): the device order is a spatial permutation
+__global__ void __launch_bounds__(TPB) k_export_bodies(Dev d, const uint32_t* __restrict__ slot_of, uint32_t n, uint32_t* ids,
+                                                       float2* pos, float* angle, float2* mom, float* ang_mom, float4* aabb) {
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const uint32_t s = first + k;
+        const uint32_t s = slot_of[k];
         if (ids) ids[k] = body_id(d, s);
         if (pos || angle) {
             const float4 p = d.pos[s];
@@ -383,9 +554,10 @@ __global__ void __launch_bounds__(TPB) k_export_bodies(Dev d, uint32_t first, ui
         if (aabb) aabb[k] = d.aabb[s];
     }
 }
-__global__ void __launch_bounds__(TPB) k_import_forces(Dev d, uint32_t first, uint32_t n, const float* __restrict__ fxy_t) {
+__global__ void __launch_bounds__(TPB) k_import_forces(Dev d, const uint32_t* __restrict__ slot_of, uint32_t n,
+                                                       const float* __restrict__ fxy_t) {
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const uint32_t s = first + k;
+        const uint32_t s = slot_of[k];
         d.frc[s] = make_float4(fxy_t[3 * k], fxy_t[3 * k + 1], fxy_t[3 * k + 2], d.frc[s].w);
     }
 }

@@ -51,8 +51,11 @@ struct Counters {
     uint32_t n_colors;
     uint32_t n_rounds;
     uint32_t err;
+    uint32_t n_own_scan;     // n_colors * (W + 1): length of the owner-position scan
+    uint32_t n_work;         // buckets holding at least two entries (work list of the pair kernels)
     uint32_t n_stamps;
-    unsigned long long stamp[12];   // %globaltimer at phase boundaries of the persistent solver (block 0; diagnostics)
+    uint32_t pad0;
+    unsigned long long stamp[10];   // %globaltimer at phase boundaries of the persistent solver (block 0; diagnostics)
 };
 
 // Everything the kernels need, passed by value.
@@ -67,6 +70,7 @@ struct Dev {
     float4* aabb;     // centre.x, centre.y, half_w, half_h   (as of the last refresh — stale on purpose, Q3)
     float4* pose;     // x, y, cos(angle), sin(angle)  (scratch of one process())
     uint32_t* ncells; // grid cells covered by the body's AABB
+    uint4* bkt;       // the body's bucket ids when it covers <= 4 cells (0xFFFFFFFF padded); scratch of one process()
     // ---- worlds ----------------------------------------------------------------------------------------------------
     uint32_t n_worlds;
     const uint32_t* world_base;   // n_worlds + 1
@@ -81,13 +85,15 @@ struct Dev {
     uint32_t cap_entries;
     uint32_t* ent_body;           // E
     uint32_t* ent_key;            // E
-    uint32_t* ent_off;            // E + 1: pairs emitted per entry, then its exclusive scan ([E] = P)
+    uint32_t* ent_off;            // T + 1: pairs emitted per BUCKET, then its exclusive scan ([T] = P)
+    uint32_t* work;               // T: ids of the buckets with >= 2 entries (order irrelevant)
     const uint64_t* excl;         // sorted (lo_slot << 32 | hi_slot)
     uint32_t n_excl;
     // ---- candidate pairs / raw manifolds (P slots) ------------------------------------------------------------------
     uint32_t cap_pairs;
     uint2* pairs;                 // (owner slot, other slot)
-    uint4* m_hdr;                 // ref slot, inc slot, n_points | normal_id << 8, -
+    uint4* m_hdr;                 // ref slot, inc slot, n_points | normal_id << 8, dynamic mask (bit 0 ref, bit 1 inc)
+    unsigned long long* m_prio;   // colouring priority of the manifold (contact_priority of the two ids)
     float4* m_g0;                 // normal.x, normal.y, p0.pos.x, p0.pos.y
     float4* m_g1;                 // p0.depth, p1.depth, p1.pos.x, p1.pos.y
     float4* m_r0;                 // p0: ref_r.x, ref_r.y, inc_r.x, inc_r.y
@@ -101,6 +107,10 @@ struct Dev {
     uint32_t* color_start;        // MAX_COLORS + 1
     uint32_t* color_cursor;       // MAX_COLORS
     uint32_t* round_left;         // MAX_COLOR_ROUNDS
+    uint32_t own_words;           // W = ceil(NB / 32)
+    uint32_t* own_bits;           // MAX_COLORS x W: bit (c, b) set iff body b owns a manifold of colour c (at most one)
+    uint32_t* own_pos;            // MAX_COLORS x (W + 1) + 1: popcounts per word (+ the warp padding of the colour), then
+                                  // their exclusive scan = slot of the first owner of each word in the colour-sorted array
     Counters* counters;
     // ---- solver records, grouped by colour (M slots) -----------------------------------------------------------------
     uint4* s_hdr;                 // ref slot, inc slot, n_points | static1 << 8 | static2 << 9 | S_EMPTY, pair slot
@@ -275,8 +285,16 @@ R2D_HD CellRange count_body_thread(const Dev& d, uint32_t i, bool count_inline) 
     d.pose[i] = make_float4(p.x, p.y, cos_ref(p.z), sin_ref(p.z));
     const CellRange r = cell_range(d, i);
     d.ncells[i] = r.count;
-    if (count_inline)
+    uint32_t bk[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    if (r.count <= 4u) {  // small body: remember its buckets (pair de-duplication without touching the grid again)
+        for (uint32_t k = 0; k < r.count; ++k) {
+            bk[k] = cell_bucket(r, k);
+            if (count_inline) atomic_add_u32(&d.bucket_cnt[bk[k]], 1u);
+        }
+    } else if (count_inline) {
         for (uint32_t k = 0; k < r.count; ++k) atomic_add_u32(&d.bucket_cnt[cell_bucket(r, k)], 1u);
+    }
+    d.bkt[i] = make_uint4(bk[0], bk[1], bk[2], bk[3]);
     return r;
 }
 // K4: fill (SpatialHash.zig:62-68): decrement-then-store; leaves bucket_cnt all zero again.
@@ -338,10 +356,42 @@ R2D_HD bool bucket_contains(const Dev& d, uint32_t bucket, uint32_t j) {
     return false;
 }
 
-// K5: candidate pairs owned by grid entry e = (bucket h, body i).  A pair {i, j} sharing several buckets is emitted
-// exactly once: by the body with fewer cells (ties: lower slot), in the lowest-numbered bucket they share.  Filters
-// are the reference's (lib.zig:273-282): both static, self, excluded, AABB — duplicates removed by construction instead
-// of by manifold-map probes.  `out` == nullptr counts only.
+// The candidate test for two distinct bodies i, j that both list bucket h (lib.zig:273-282 + de-duplication).
+// A pair {i, j} sharing several buckets is accepted exactly once: in the lowest-numbered bucket they share; the test
+// walks the cells of the body with fewer cells (the "owner"; ties: lower slot).  Filters are the reference's: both
+// static, excluded, AABB — duplicates are removed by construction instead of by manifold-map probes.
+// On success *out = (owner slot, other slot).
+R2D_HD bool pair_candidate(const Dev& d, uint32_t h, uint32_t i, uint32_t j, const float4& ai, const float4& aj,
+                           uint32_t fi, uint32_t fj, uint32_t nci, uint32_t ncj, const uint4& bi, const uint4& bj, uint2* out) {
+    if (fi & fj & FLAG_STATIC) return false;                                               // :273
+    if (!aabb_intersects(ai.x, ai.y, ai.z, ai.w, aj.x, aj.y, aj.z, aj.w)) return false;    // :282
+    if (pair_excluded(d, i, j)) return false;                                              // :275-276
+    const bool i_owns = nci < ncj || (nci == ncj && i < j);
+    const uint32_t o = i_owns ? i : j, q = i_owns ? j : i;
+    if (nci <= 4u && ncj <= 4u) {
+        // both small: the lowest shared bucket follows from the two remembered bucket lists (pure ALU)
+        const uint32_t a[4] = {bi.x, bi.y, bi.z, bi.w}, b[4] = {bj.x, bj.y, bj.z, bj.w};
+        uint32_t lowest = 0xFFFFFFFFu;
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y)
+                if (a[x] == b[y] && a[x] < lowest) lowest = a[x];
+        if (lowest != h) return false;
+    } else if ((i_owns ? nci : ncj) > 1) {  // a multi-cell body is involved: walk the owner's cells, bisect the buckets
+        const CellRange r = cell_range(d, o);
+        for (uint32_t k = 0; k < r.count; ++k) {
+            const uint32_t h2 = cell_bucket(r, k);
+            if (h2 < h && bucket_contains(d, h2, q)) return false;
+        }
+    }
+    *out = make_uint2(o, q);
+    return true;
+}
+
+// K5, one-thread-per-grid-entry form (used by the serial test emulator; the GPU uses the warp-per-bucket kernels of
+// r2d_kernels.cuh, which accept exactly the same pairs): pairs of entry e = (bucket h, body i) that i owns.
+// `out` == nullptr counts only.
 R2D_HD uint32_t entry_pairs_thread(const Dev& d, uint32_t e, uint2* out) {
     const uint32_t h = d.ent_key[e], i = d.ent_body[e];
     const uint32_t bs = d.bucket_start[h], be = bucket_end(d, h);
@@ -357,20 +407,9 @@ R2D_HD uint32_t entry_pairs_thread(const Dev& d, uint32_t e, uint2* out) {
         if (j == i) continue;                                        // :274
         const uint32_t ncj = d.ncells[j];
         if (!(nci < ncj || (nci == ncj && i < j))) continue;         // j owns this pair
-        if (fi & body_flags(d, j) & FLAG_STATIC) continue;          // :273
-        const float4 aj = d.aabb[j];
-        if (!aabb_intersects(ai.x, ai.y, ai.z, ai.w, aj.x, aj.y, aj.z, aj.w)) continue;  // :282
-        if (pair_excluded(d, i, j)) continue;                        // :275-276
-        if (nci > 1) {  // is h the lowest bucket shared with j?
-            const CellRange r = cell_range(d, i);
-            bool lower = false;
-            for (uint32_t k = 0; k < r.count && !lower; ++k) {
-                const uint32_t h2 = cell_bucket(r, k);
-                if (h2 < h && bucket_contains(d, h2, j)) lower = true;
-            }
-            if (lower) continue;
-        }
-        if (out) out[n] = make_uint2(i, j);
+        uint2 pr;
+        if (!pair_candidate(d, h, i, j, ai, d.aabb[j], fi, body_flags(d, j), nci, ncj, d.bkt[i], d.bkt[j], &pr)) continue;
+        if (out) out[n] = pr;
         ++n;
     }
     return n;
@@ -394,7 +433,10 @@ R2D_HD int narrow_pair_thread(const Dev& d, uint32_t p) {
     }
     const uint32_t lo_slot = a_lo ? pr.x : pr.y, hi_slot = a_lo ? pr.y : pr.x;
     const uint32_t ref = m.ref_is_lo ? lo_slot : hi_slot, inc = m.ref_is_lo ? hi_slot : lo_slot;
-    d.m_hdr[p] = make_uint4(ref, inc, (uint32_t)m.n_points | ((uint32_t)m.normal_id << 8), 0u);
+    const uint32_t f_ref = (m.ref_is_lo == a_lo) ? va.flags : vb.flags, f_inc = (m.ref_is_lo == a_lo) ? vb.flags : va.flags;
+    const uint32_t dyn = ((f_ref & FLAG_STATIC) ? 0u : 1u) | ((f_inc & FLAG_STATIC) ? 0u : 2u);
+    d.m_hdr[p] = make_uint4(ref, inc, (uint32_t)m.n_points | ((uint32_t)m.normal_id << 8), dyn);
+    d.m_prio[p] = contact_priority(a_lo ? va.id : vb.id, a_lo ? vb.id : va.id);  // (lower id, higher id)
     const ContactPoint z = {mk2(0, 0), 0.0f, mk2(0, 0), mk2(0, 0)};
     const ContactPoint p0 = m.n_points > 0 ? m.pt[0] : z, p1 = m.n_points > 1 ? m.pt[1] : z;
     d.m_g0[p] = make_float4(m.normal.x, m.normal.y, p0.pos.x, p0.pos.y);
@@ -406,10 +448,6 @@ R2D_HD int narrow_pair_thread(const Dev& d, uint32_t p) {
 }
 
 // ---- graph colouring (Jones-Plassmann with id-derived priorities; see contact_priority in r2d_solve.cuh) -----------------
-R2D_HD uint64_t manifold_priority(const Dev& d, uint32_t ref, uint32_t inc) {
-    const uint32_t ia = body_id(d, ref), ib = body_id(d, inc);
-    return contact_priority(ia < ib ? ia : ib, ia < ib ? ib : ia);
-}
 R2D_HD void color_post(const Dev& d, uint32_t ref, uint32_t inc, bool dyn1, bool dyn2, uint64_t prio, uint32_t round) {
     unsigned long long* mp = (round & 1u) ? d.maxprio1 : d.maxprio0;
     const unsigned long long v = ((unsigned long long)round << PRIO_ROUND_SHIFT) | prio;
@@ -420,8 +458,8 @@ R2D_HD void color_post(const Dev& d, uint32_t ref, uint32_t inc, bool dyn1, bool
 R2D_HD int color_round_thread(const Dev& d, uint32_t p, uint32_t round) {
     if (d.m_color[p] != COLOR_PENDING) return 0;
     const uint4 h = d.m_hdr[p];
-    const bool dyn1 = !(body_flags(d, h.x) & FLAG_STATIC), dyn2 = !(body_flags(d, h.y) & FLAG_STATIC);
-    const uint64_t prio = manifold_priority(d, h.x, h.y);
+    const bool dyn1 = (h.w & 1u) != 0, dyn2 = (h.w & 2u) != 0;
+    const uint64_t prio = d.m_prio[p];
     const unsigned long long mine = ((unsigned long long)round << PRIO_ROUND_SHIFT) | prio;
     const unsigned long long* mp = (round & 1u) ? d.maxprio1 : d.maxprio0;
     const bool win = (!dyn1 || ld_shared_u64(&mp[h.x]) == mine) && (!dyn2 || ld_shared_u64(&mp[h.y]) == mine);
@@ -457,6 +495,40 @@ R2D_HD int color_round_thread(const Dev& d, uint32_t p, uint32_t round) {
     }
     d.m_color[p] = color;
     return 1;
+}
+
+// The "owner" of a manifold orders the colour-sorted solver records: the lower device slot of its non-static bodies.
+// Colours on one body are pairwise distinct, so a body owns at most one manifold per colour and the position of a
+// manifold inside its colour is the number of owners of that colour with a lower slot — a prefix popcount over a
+// bitmap.  Device slots are in spatial (Morton) order, hence so are the records of every colour: a warp of the sweep
+// touches bodies that are neighbours in memory.
+R2D_HD uint32_t manifold_owner(const uint4& h) {
+    const bool dyn1 = (h.w & 1u) != 0, dyn2 = (h.w & 2u) != 0;
+    if (dyn1 && dyn2) return h.x < h.y ? h.x : h.y;
+    return dyn1 ? h.x : h.y;
+}
+R2D_HD void owner_bit_thread(const Dev& d, uint32_t p) {
+    const uint32_t c = d.m_color[p];
+    if (c >= MAX_COLORS) return;
+    const uint32_t o = manifold_owner(d.m_hdr[p]);
+    atomic_or_u32(&d.own_bits[(size_t)c * d.own_words + (o >> 5)], 1u << (o & 31u));
+}
+// scan input: popcount per bitmap word, and one extra entry per colour that pads its segment to a whole warp
+R2D_HD void owner_count_thread(const Dev& d, uint32_t k) {
+    const uint32_t stride = d.own_words + 1u;
+    const uint32_t c = k / stride, w = k % stride;
+    if (w < d.own_words) {
+        d.own_pos[k] = popc64(d.own_bits[(size_t)c * d.own_words + w]);
+    } else {
+        const uint32_t n = d.color_count[c];
+        d.own_pos[k] = (COLOR_ALIGN - (n % COLOR_ALIGN)) % COLOR_ALIGN;
+    }
+}
+R2D_HD uint32_t manifold_slot(const Dev& d, uint32_t p) {
+    const uint32_t c = d.m_color[p];
+    const uint32_t o = manifold_owner(d.m_hdr[p]);
+    const uint32_t word = d.own_bits[(size_t)c * d.own_words + (o >> 5)];
+    return d.own_pos[(size_t)c * (d.own_words + 1u) + (o >> 5)] + popc64(word & ((1u << (o & 31u)) - 1u));
 }
 
 // ---- colour partition + pre-step (collision.zig:102-133, evaluated once per process(): inputs are constant, Q5) -----------

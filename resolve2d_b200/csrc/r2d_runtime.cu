@@ -76,19 +76,20 @@ struct CudaBatch : BatchBase {
     int device = 0;
     int n_sms = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    int color_blocks = 0, solve_blocks = 0;
-    uint32_t wait_mode = 0, wait_spin_lag = 1, wait_sleep_unit = 200, wait_sleep_max = 4000;
+    int color_blocks = 0, solve_blocks = 0, pair_blocks = 0;
+    uint32_t wait_mode = 1, wait_spin_lag = 1, wait_sleep_unit = 200, wait_sleep_max = 4000;
     int solve_blocks_per_sm = 1;
+    uint32_t solve_smem_slots = SOLVE_SMEM_SLOTS;
     bool persistent_solver = true;   // false: one launch per colour (kept for A/B measurements)
     // bodies
     DBuf<float4> pos, mom, frc, prop, shape, aabb, pose;
-    DBuf<uint32_t> ncells, world_base, grav_off, joint_color_start;
+    DBuf<uint32_t> ncells, world_base, grav_off, joint_color_start, dev_of_host;
     DBuf<float> grav;
     DBuf<uint64_t> excl;
-    DBuf<uint4> j_hdr;
+    DBuf<uint4> j_hdr, bkt;
     DBuf<float4> j_par, j_vec;
     // grid
-    DBuf<uint32_t> bucket_cnt, bucket_start, ent_body, ent_key, ent_off, tile_sums;
+    DBuf<uint32_t> bucket_cnt, bucket_start, ent_body, ent_key, ent_off, tile_sums, work;
     // pairs / manifolds
     DBuf<uint2> pairs;
     DBuf<uint4> m_hdr, s_hdr;
@@ -97,7 +98,8 @@ struct CudaBatch : BatchBase {
     DBuf<uint4> s_dep;
     DBuf<uint32_t> m_color;
     // colouring
-    DBuf<unsigned long long> maxprio0, maxprio1, used;
+    DBuf<unsigned long long> maxprio0, maxprio1, used, m_prio;
+    DBuf<uint32_t> own_bits, own_pos;
     DBuf<uint32_t> color_misc;   // color_count[256] | color_start[257] | color_cursor[256] | round_left[MAX_COLOR_ROUNDS]
     DBuf<Counters> counters;
     // staging for the boundary copies
@@ -147,17 +149,25 @@ struct CudaBatch : BatchBase {
         int per_sm = 0;
         R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_color, TPB, 0));
         if (per_sm < 1) per_sm = 1;
-        if (per_sm > 4) per_sm = 4;
+        {
+            int want = 4;
+            if (const char* e = getenv("R2D_COLOR_BLOCKS_PER_SM")) want = atoi(e);
+            if (per_sm > want) per_sm = want;
+        }
         color_blocks = per_sm * n_sms;
-        R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent, TPB, 0));
+        R2D_CUDA(cudaFuncSetAttribute(k_solve_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_BYTES));
+        R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent, TPB, SOLVE_SMEM_BYTES));
         if (per_sm < 1) per_sm = 1;
         if (const char* e = getenv("R2D_SOLVE_BLOCKS_PER_SM")) solve_blocks_per_sm = atoi(e);
+        if (const char* e = getenv("R2D_SOLVE_SMEM_SLOTS")) solve_smem_slots = std::min<uint32_t>((uint32_t)atoi(e), SOLVE_SMEM_SLOTS);
         if (const char* e = getenv("R2D_WAIT_MODE")) wait_mode = (uint32_t)atoi(e);
         if (const char* e = getenv("R2D_WAIT_SPIN_LAG")) wait_spin_lag = (uint32_t)atoi(e);
         if (const char* e = getenv("R2D_WAIT_SLEEP_UNIT")) wait_sleep_unit = (uint32_t)atoi(e);
         if (const char* e = getenv("R2D_WAIT_SLEEP_MAX")) wait_sleep_max = (uint32_t)atoi(e);
         if (per_sm > solve_blocks_per_sm) per_sm = solve_blocks_per_sm;
         solve_blocks = per_sm * n_sms;
+        R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bucket_pairs<false>, TPB, 0));
+        pair_blocks = (per_sm < 1 ? 1 : per_sm) * n_sms;  // resident CTAs: one warp per listed bucket, grid-stride
         if (const char* e = getenv("R2D_SOLVER")) persistent_solver = std::string(e) != "launches";
         R2D_TRY(counters.reserve(1));
         R2D_TRY(color_misc.reserve(MAX_COLORS * 3 + 1 + MAX_COLOR_ROUNDS));
@@ -185,6 +195,12 @@ struct CudaBatch : BatchBase {
         if (!profiling) return;
         cudaEventRecord(events.back().b, stream);
     }
+    int grid_warp_per(size_t n_items) const {  // one warp per item (bucket): short dependent chains, idle warps exit
+        size_t blocks = (n_items * 32 + TPB - 1) / TPB;
+        if (blocks < 1) blocks = 1;
+        if (blocks > (size_t)1 << 30) blocks = (size_t)1 << 30;
+        return (int)blocks;
+    }
     int grid_for(size_t n, int tpb = TPB) const {  // fixed-shape grids: a multiple of the SM count, grid-stride inside
         size_t blocks = (n + tpb - 1) / tpb;
         const size_t cap = (size_t)n_sms * 8;
@@ -201,12 +217,13 @@ struct CudaBatch : BatchBase {
     } while (0)
 
     // exclusive scan of in[0..n) into out[0..n), out[n] = total (also *total_out); n = min(*n_ptr, n_max) if n_ptr
-    int scan(const uint32_t* in, uint32_t* out, const uint32_t* n_ptr, uint32_t n_max, uint32_t* total_out) {
+    int scan(const uint32_t* in, uint32_t* out, const uint32_t* n_ptr, uint32_t n_max, uint32_t* total_out,
+             int kclass = R2D_KCLASS_BROADPHASE) {
         const uint32_t tiles = (n_max + SCAN_TILE - 1) / SCAN_TILE;
         R2D_TRY(tile_sums.reserve(tiles + 1));
-        R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_scan_reduce, tiles ? tiles : 1, SCAN_TPB, in, tile_sums.p, n_ptr, n_max);
-        R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_scan_spine, 1, SCAN_TPB, tile_sums.p, n_ptr, n_max, out, total_out);
-        R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_scan_down, tiles ? tiles : 1, SCAN_TPB, in, out, tile_sums.p, n_ptr, n_max);
+        R2D_LAUNCH(kclass, k_scan_reduce, tiles ? tiles : 1, SCAN_TPB, in, tile_sums.p, n_ptr, n_max);
+        R2D_LAUNCH(kclass, k_scan_spine, 1, SCAN_TPB, tile_sums.p, n_ptr, n_max, out, total_out);
+        R2D_LAUNCH(kclass, k_scan_down, tiles ? tiles : 1, SCAN_TPB, in, out, tile_sums.p, n_ptr, n_max);
         return R2D_OK;
     }
 
@@ -224,7 +241,7 @@ struct CudaBatch : BatchBase {
             (st = up(shape, image.shape)) || (st = up(aabb, image.aabb)) || (st = up(world_base, image.world_base)) ||
             (st = up(grav_off, image.grav_off)) || (st = up(grav, image.grav)) || (st = up(excl, image.excl)) ||
             (st = up(j_hdr, image.j_hdr)) || (st = up(j_par, image.j_par)) || (st = up(j_vec, image.j_vec)) ||
-            (st = up(joint_color_start, image.joint_color_start)))
+            (st = up(joint_color_start, image.joint_color_start)) || (st = up(dev_of_host, image.dev_of_host)))
             return st;
         R2D_CUDA(cudaStreamSynchronize(stream));  // the image vectors are pageable and may change after we return
         last_pairs = 0;
@@ -244,7 +261,8 @@ struct CudaBatch : BatchBase {
             const uint32_t base = image.world_base[w->index];
             for (size_t s = 0; s < w->bodies.size(); ++s) {
                 host::Body& b = w->bodies[s];
-                const float4 p = hp[base + s], m = hm[base + s], f = hf[base + s], a = ha[base + s];
+                const uint32_t ds = image.dev_of_host[base + s];
+                const float4 p = hp[ds], m = hm[ds], f = hf[ds], a = ha[ds];
                 b.pos_x = p.x; b.pos_y = p.y; b.angle = p.z;
                 b.mom_x = m.x; b.mom_y = m.y; b.ang_mom = m.z;
                 b.force_x = f.x; b.force_y = f.y; b.torque = f.z;
@@ -280,7 +298,7 @@ struct CudaBatch : BatchBase {
         float* d_l = (float*)carve((size_t)n * 4);
         float4* d_aabb = (float4*)carve((size_t)n * 16);
         fill_dev();
-        R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_export_bodies, grid_for(n), TPB, d, first, n, ids ? d_ids : nullptr,
+        R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_export_bodies, grid_for(n), TPB, d, (const uint32_t*)dev_of_host.p + first, n, ids ? d_ids : nullptr,
                    pos_xy ? d_pos : nullptr, angle ? d_ang : nullptr, momentum_xy ? d_mom : nullptr,
                    ang_momentum ? d_l : nullptr, aabb_xywh ? d_aabb : nullptr);
         if (ids) R2D_CUDA(cudaMemcpyAsync(ids, d_ids, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
@@ -297,7 +315,7 @@ struct CudaBatch : BatchBase {
         R2D_TRY(staging.reserve((size_t)n * 44 + 256));
         R2D_CUDA(cudaMemcpyAsync(staging.p, f, (size_t)n * 12, cudaMemcpyHostToDevice, stream));
         fill_dev();
-        R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_import_forces, grid_for(n), TPB, d, first, n, (const float*)staging.p);
+        R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_import_forces, grid_for(n), TPB, d, (const uint32_t*)dev_of_host.p + first, n, (const float*)staging.p);
         // pageable source buffers are consumed before cudaMemcpyAsync returns; pinned ones must stay valid until the
         // next synchronising call (r2d_process synchronises once per step)
         return R2D_OK;
@@ -386,24 +404,25 @@ struct CudaBatch : BatchBase {
     void fill_dev() {
         d.n_bodies = image.n_bodies;
         d.pos = pos.p; d.mom = mom.p; d.frc = frc.p; d.prop = prop.p; d.shape = shape.p; d.aabb = aabb.p;
-        d.pose = pose.p; d.ncells = ncells.p;
+        d.pose = pose.p; d.ncells = ncells.p; d.bkt = bkt.p;
         d.n_worlds = (uint32_t)worlds.size();
         d.world_base = world_base.p; d.grav_off = grav_off.p; d.grav = grav.p;
         d.cell = grid_cell(); d.table_mult = grid_mult();
         d.n_buckets = d.table_mult * d.n_bodies;
         d.bucket_cnt = bucket_cnt.p; d.bucket_start = bucket_start.p;
         d.cap_entries = (uint32_t)cap_entries;
-        d.ent_body = ent_body.p; d.ent_key = ent_key.p; d.ent_off = ent_off.p;
+        d.ent_body = ent_body.p; d.ent_key = ent_key.p; d.ent_off = ent_off.p; d.work = work.p;
         d.excl = (const uint64_t*)excl.p; d.n_excl = (uint32_t)image.excl.size();
         d.cap_pairs = (uint32_t)cap_pairs;
         d.pairs = pairs.p; d.m_hdr = m_hdr.p; d.m_g0 = m_g0.p; d.m_g1 = m_g1.p; d.m_r0 = m_r0.p; d.m_r1 = m_r1.p;
-        d.m_color = m_color.p;
+        d.m_color = m_color.p; d.m_prio = m_prio.p;
         d.maxprio0 = maxprio0.p; d.maxprio1 = maxprio1.p; d.used = used.p;
         d.color_count = color_misc.p;
         d.color_start = color_misc.p + MAX_COLORS;
         d.color_cursor = color_misc.p + 2 * MAX_COLORS + 1;
         d.round_left = color_misc.p + 3 * MAX_COLORS + 1;
         d.counters = counters.p;
+        d.own_words = (d.n_bodies + 31u) / 32u; d.own_bits = own_bits.p; d.own_pos = own_pos.p;
         d.s_hdr = s_hdr.p; d.s_nf = s_nf.p; d.s_inv = s_inv.p; d.s_r0 = s_r0.p; d.s_r1 = s_r1.p;
         d.s_pm0 = s_pm0.p; d.s_pm1 = s_pm1.p; d.s_acc0 = s_acc0.p; d.s_acc1 = s_acc1.p;
         d.s_dep = s_dep.p;
@@ -414,8 +433,8 @@ struct CudaBatch : BatchBase {
 
     int reserve_entries(size_t n) {
         int st;
-        if ((st = ent_body.reserve(n)) || (st = ent_key.reserve(n)) || (st = ent_off.reserve(n + 2))) return st;
-        cap_entries = std::min(std::min(ent_body.cap, ent_key.cap), ent_off.cap - 2);
+        if ((st = ent_body.reserve(n)) || (st = ent_key.reserve(n))) return st;
+        cap_entries = std::min(ent_body.cap, ent_key.cap);
         return R2D_OK;
     }
     int reserve_pairs(size_t n) {
@@ -423,13 +442,13 @@ struct CudaBatch : BatchBase {
         const size_t pad = (size_t)MAX_COLORS * COLOR_ALIGN;  // colour segments are padded to whole warps
         n += pad;
         if ((st = pairs.reserve(n)) || (st = m_hdr.reserve(n)) || (st = m_g0.reserve(n)) || (st = m_g1.reserve(n)) ||
-            (st = m_r0.reserve(n)) || (st = m_r1.reserve(n)) || (st = m_color.reserve(n)) || (st = s_hdr.reserve(n)) ||
+            (st = m_r0.reserve(n)) || (st = m_r1.reserve(n)) || (st = m_color.reserve(n)) || (st = m_prio.reserve(n)) || (st = s_hdr.reserve(n)) ||
             (st = s_nf.reserve(n)) || (st = s_inv.reserve(n)) || (st = s_r0.reserve(n)) || (st = s_r1.reserve(n)) ||
             (st = s_pm0.reserve(n)) || (st = s_pm1.reserve(n)) || (st = s_acc0.reserve(n)) || (st = s_acc1.reserve(n)) ||
             (st = s_dep.reserve(n)))
             return st;
         cap_pairs = pairs.cap;
-        for (size_t c : {m_hdr.cap, m_g0.cap, m_g1.cap, m_r0.cap, m_r1.cap, m_color.cap, s_hdr.cap, s_nf.cap, s_inv.cap,
+        for (size_t c : {m_prio.cap, m_hdr.cap, m_g0.cap, m_g1.cap, m_r0.cap, m_r1.cap, m_color.cap, s_hdr.cap, s_nf.cap, s_inv.cap,
                          s_r0.cap, s_r1.cap, s_pm0.cap, s_pm1.cap, s_acc0.cap, s_acc1.cap, s_dep.cap})
             cap_pairs = std::min(cap_pairs, c);
         cap_pairs -= pad;
@@ -449,9 +468,11 @@ struct CudaBatch : BatchBase {
         d.sub_dt = sub_dt;
         const uint32_t T = grid_mult() * nb;
         int st;
-        if ((st = pose.reserve(nb)) || (st = ncells.reserve(nb)) || (st = maxprio0.reserve(nb)) || (st = maxprio1.reserve(nb)) ||
+        const size_t own_w = ((size_t)nb + 31) / 32;
+        if ((st = own_bits.reserve(own_w * MAX_COLORS)) || (st = own_pos.reserve((own_w + 1) * MAX_COLORS + 2)) ||
+            (st = pose.reserve(nb)) || (st = ncells.reserve(nb)) || (st = bkt.reserve(nb)) || (st = maxprio0.reserve(nb)) || (st = maxprio1.reserve(nb)) ||
             (st = used.reserve((size_t)nb * COLOR_WORDS)) || (st = bucket_cnt.reserve((size_t)T + 1, true, stream)) ||
-            (st = bucket_start.reserve((size_t)T + 1)))
+            (st = bucket_start.reserve((size_t)T + 1)) || (st = ent_off.reserve((size_t)T + 2)) || (st = work.reserve((size_t)T + 1)))
             return st;
         if (cap_entries == 0 && (st = reserve_entries((size_t)nb * 3 + 4096))) return st;
         if (cap_pairs == 0 && (st = reserve_pairs((size_t)nb * 6 + 4096))) return st;
@@ -463,14 +484,16 @@ struct CudaBatch : BatchBase {
             R2D_CUDA(cudaMemsetAsync(maxprio0.p, 0, (size_t)nb * 8, stream));
             R2D_CUDA(cudaMemsetAsync(maxprio1.p, 0, (size_t)nb * 8, stream));
             R2D_CUDA(cudaMemsetAsync(used.p, 0, (size_t)nb * COLOR_WORDS * 8, stream));
+            R2D_CUDA(cudaMemsetAsync(own_bits.p, 0, own_w * MAX_COLORS * 4, stream));
             // ---- broadphase ----
             R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_grid_cells<false>, grid_for(nb), TPB, d);
             if ((st = scan(d.bucket_cnt, d.bucket_start, nullptr, T, &d.counters->n_entries))) return st;
             R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_grid_cells<true>, grid_for(nb), TPB, d);
-            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_sort_buckets, grid_for(T), TPB, d);
-            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_pairs<false>, grid_for(cap_entries), TPB, d);
-            if ((st = scan(d.ent_off, d.ent_off, &d.counters->n_entries, (uint32_t)cap_entries, &d.counters->n_pairs))) return st;
-            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_pairs<true>, grid_for(cap_entries), TPB, d);
+            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_sort_buckets, grid_warp_per(T), TPB, d);
+            // pairs per BUCKET (one warp each) -> scan over the T buckets -> write at the scanned offsets
+            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_bucket_pairs<false>, pair_blocks, TPB, d);
+            if ((st = scan(d.ent_off, d.ent_off, nullptr, T, &d.counters->n_pairs))) return st;
+            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_bucket_pairs<true>, pair_blocks, TPB, d);
             // ---- narrowphase ----
             R2D_LAUNCH(R2D_KCLASS_NARROWPHASE, k_narrow, grid_for(cap_pairs), TPB, d);
             // ---- colouring + partition + pre-step ----
@@ -481,6 +504,10 @@ struct CudaBatch : BatchBase {
                 prof_end();
                 launches += 1;
             }
+            // owner bitmaps -> popcounts -> scan = position of every manifold in the colour-sorted, spatially ordered records
+            R2D_LAUNCH(R2D_KCLASS_COLORING, k_owner_bits, grid_for(cap_pairs), TPB, d);
+            R2D_LAUNCH(R2D_KCLASS_COLORING, k_owner_count, grid_for((own_w + 1) * 64), TPB, d);
+            if ((st = scan(d.own_pos, d.own_pos, &d.counters->n_own_scan, (uint32_t)((own_w + 1) * MAX_COLORS), nullptr, R2D_KCLASS_COLORING))) return st;
             R2D_LAUNCH(R2D_KCLASS_COLORING, k_partition_prestep, grid_for(cap_pairs), TPB, d);
             // ---- substeps: one persistent cooperative kernel (colour ranges are read on the device) ----
             if (persistent_solver) {
@@ -488,8 +515,9 @@ struct CudaBatch : BatchBase {
                 const uint32_t* jcs_dev = joint_color_start.p;
                 uint32_t n_jc = (uint32_t)image.joint_color_start.size() - 1, S_ = S, I_ = I;
                 float sd = sub_dt;
-                void* args[] = {(void*)&d, (void*)&sd, (void*)&S_, (void*)&I_, (void*)&jcs_dev, (void*)&n_jc};
-                R2D_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(solve_blocks), dim3(TPB), args, 0, stream));
+                uint32_t slots = solve_smem_slots;
+                void* args[] = {(void*)&d, (void*)&sd, (void*)&S_, (void*)&I_, (void*)&jcs_dev, (void*)&n_jc, (void*)&slots};
+                R2D_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(solve_blocks), dim3(TPB), args, SOLVE_SMEM_BYTES, stream));
                 prof_end();
                 launches += 1;
             }
@@ -522,7 +550,7 @@ struct CudaBatch : BatchBase {
         stats.n_color_rounds = c.n_rounds;
         if (getenv("R2D_STAMPS")) {
             fprintf(stderr, "[r2d stamps ns]");
-            for (uint32_t k = 1; k < c.n_stamps && k < 12; ++k)
+            for (uint32_t k = 1; k < c.n_stamps && k < 10; ++k)
                 fprintf(stderr, " %u:%lld", k, c.stamp[k] ? (long long)(c.stamp[k] - c.stamp[0]) : -1LL);
             fprintf(stderr, "\n");
         }

@@ -94,7 +94,9 @@ R2D_HD void solve_contact(const ContactConst& c, int n_points, const ContactPoin
     v2 lin1 = mk2(0.0f, 0.0f), lin2 = mk2(0.0f, 0.0f);
     float rot1 = 0.0f, rot2 = 0.0f;
 
-    for (int k = 0; k < n_points; ++k) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {  // fully unrolled: pts[] / acc[] stay in registers (no local-memory arrays)
+        if (k >= n_points) break;
         const ContactPointConst& p = pts[k];
         if (p.depth >= 0.0f) {  // :154-158
             acc[k] = mk2(0.0f, 0.0f);

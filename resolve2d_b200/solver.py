@@ -231,6 +231,13 @@ class Solver:
     def set_stream(self, cuda_stream: int):
         self._check(self._fn("set_stream")(self._h, C.c_void_p(cuda_stream)), "set_stream")
 
+    def reorder(self):
+        """Re-derive the spatial device order from the current positions (results are unaffected)."""
+        self._check(self._fn("reorder")(self._h), "reorder")
+
+    def set_reorder_interval(self, steps: int):
+        self._check(self._fn("set_reorder_interval")(self._h, steps), "set_reorder_interval")
+
     def process(self, dt: float, sub_steps: int, collision_iters: int):  # lib.zig:189
         self._check(self._fn("process")(self._h, dt, sub_steps, collision_iters), "process")
 
@@ -348,6 +355,12 @@ class Batch:
 
     def set_stream(self, cuda_stream: int):
         _abi.check(self._lib, self._lib.r2d_batch_set_stream(self._h, C.c_void_p(cuda_stream)), "batch_set_stream")
+
+    def reorder(self):
+        _abi.check(self._lib, self._lib.r2d_batch_reorder(self._h), "batch_reorder")
+
+    def set_reorder_interval(self, steps: int):
+        _abi.check(self._lib, self._lib.r2d_batch_set_reorder_interval(self._h, steps), "batch_set_reorder_interval")
 
     def process(self, dt: float, sub_steps: int, collision_iters: int):
         _abi.check(self._lib, self._lib.r2d_batch_process(self._h, dt, sub_steps, collision_iters), "batch_process")

@@ -23,12 +23,12 @@ struct EmuBatch : BatchBase {
     std::vector<float4> pos, mom, frc, prop, shape, aabb, pose;
     std::vector<uint32_t> ncells, bucket_cnt, bucket_start, ent_body, ent_key, ent_off, m_color;
     std::vector<uint2> pairs;
-    std::vector<uint4> m_hdr, s_hdr;
+    std::vector<uint4> m_hdr, s_hdr, bkt;
     std::vector<float4> m_g0, m_g1, m_r0, m_r1, s_nf, s_inv, s_r0, s_r1, s_pm0, s_pm1;
     std::vector<float2> s_acc0, s_acc1;
     std::vector<uint4> s_dep;
-    std::vector<unsigned long long> maxprio0, maxprio1, used;
-    std::vector<uint32_t> color_count, color_start, color_cursor, round_left;
+    std::vector<unsigned long long> maxprio0, maxprio1, used, m_prio;
+    std::vector<uint32_t> color_count, color_start, color_cursor, round_left, own_bits, own_pos;
     Counters counters{};
     uint32_t n_pairs_last = 0;
 
@@ -47,7 +47,8 @@ struct EmuBatch : BatchBase {
             const uint32_t base = image.world_base[w->index];
             for (size_t s = 0; s < w->bodies.size(); ++s) {
                 host::Body& b = w->bodies[s];
-                const float4 p = pos[base + s], m = mom[base + s], f = frc[base + s], a = aabb[base + s];
+                const uint32_t ds = image.dev_of_host[base + s];
+                const float4 p = pos[ds], m = mom[ds], f = frc[ds], a = aabb[ds];
                 b.pos_x = p.x; b.pos_y = p.y; b.angle = p.z;
                 b.mom_x = m.x; b.mom_y = m.y; b.ang_mom = m.z;
                 b.force_x = f.x; b.force_y = f.y; b.torque = f.z;
@@ -65,7 +66,7 @@ struct EmuBatch : BatchBase {
     int backend_read_bodies(uint32_t first, uint32_t n, uint32_t* ids, float* pos_xy, float* angle, float* momentum_xy,
                             float* ang_momentum, float* aabb_xywh) override {
         for (uint32_t k = 0; k < n; ++k) {
-            const uint32_t s = first + k;
+            const uint32_t s = image.dev_of_host[first + k];
             if (ids) ids[k] = f2u(shape[s].w);
             if (pos_xy) { pos_xy[2 * k] = pos[s].x; pos_xy[2 * k + 1] = pos[s].y; }
             if (angle) angle[k] = pos[s].z;
@@ -77,9 +78,10 @@ struct EmuBatch : BatchBase {
     }
     int backend_write_forces(uint32_t first, uint32_t n, const float* f) override {
         for (uint32_t k = 0; k < n; ++k) {
-            frc[first + k].x = f[3 * k];
-            frc[first + k].y = f[3 * k + 1];
-            frc[first + k].z = f[3 * k + 2];
+            const uint32_t s = image.dev_of_host[first + k];
+            frc[s].x = f[3 * k];
+            frc[s].y = f[3 * k + 1];
+            frc[s].z = f[3 * k + 2];
         }
         return R2D_OK;
     }
@@ -138,8 +140,8 @@ struct EmuBatch : BatchBase {
         d.sub_dt = sub_dt;
         d.pos = pos.data(); d.mom = mom.data(); d.frc = frc.data(); d.prop = prop.data(); d.shape = shape.data();
         d.aabb = aabb.data();
-        pose.resize(nb); ncells.resize(nb);
-        d.pose = pose.data(); d.ncells = ncells.data();
+        pose.resize(nb); ncells.resize(nb); bkt.resize(nb);
+        d.pose = pose.data(); d.ncells = ncells.data(); d.bkt = bkt.data();
         d.n_worlds = (uint32_t)worlds.size();
         d.world_base = image.world_base.data(); d.grav_off = image.grav_off.data(); d.grav = image.grav.data();
         d.cell = grid_cell(); d.table_mult = grid_mult();
@@ -177,6 +179,7 @@ struct EmuBatch : BatchBase {
         m_g0.resize(P + 1); m_g1.resize(P + 1); m_r0.resize(P + 1); m_r1.resize(P + 1);
         d.m_hdr = m_hdr.data(); d.m_g0 = m_g0.data(); d.m_g1 = m_g1.data(); d.m_r0 = m_r0.data(); d.m_r1 = m_r1.data();
         d.m_color = m_color.data();
+        m_prio.assign(P + 1, 0); d.m_prio = m_prio.data();
         uint32_t M = 0, K = 0;
         for (uint32_t p = 0; p < P; ++p) {
             const int np = narrow_pair_thread(d, p);
@@ -191,8 +194,7 @@ struct EmuBatch : BatchBase {
         for (uint32_t p = 0; p < P; ++p) {
             if (m_color[p] != COLOR_PENDING) continue;
             const uint4 h = m_hdr[p];
-            color_post(d, h.x, h.y, !(body_flags(d, h.x) & FLAG_STATIC), !(body_flags(d, h.y) & FLAG_STATIC),
-                       manifold_priority(d, h.x, h.y), 1);
+            color_post(d, h.x, h.y, (h.w & 1u) != 0, (h.w & 2u) != 0, d.m_prio[p], 1);
         }
         uint32_t rounds = 0, n_colors = 0;
         for (uint32_t round = 1; round < MAX_COLOR_ROUNDS; ++round) {
@@ -210,20 +212,32 @@ struct EmuBatch : BatchBase {
         }
         if (counters.err & ERR_COLOR_OVERFLOW) return R2D_ERR_COLOR_OVERFLOW;
         if (counters.err & ERR_GRID_RANGE) return R2D_ERR_GRID_RANGE;
-        for (uint32_t c = 0; c < n_colors; ++c)
-            color_start[c + 1] = (color_start[c] + color_count[c] + COLOR_ALIGN - 1u) & ~(COLOR_ALIGN - 1u);
+        // ---- owner bitmaps -> positions (colour-sorted, owner-slot order) + pre-step ----
+        counters.n_colors = n_colors;
+        d.own_words = (nb + 31u) / 32u;
+        own_bits.assign((size_t)MAX_COLORS * d.own_words, 0u);
+        own_pos.assign((size_t)MAX_COLORS * (d.own_words + 1u) + 2u, 0u);
+        d.own_bits = own_bits.data(); d.own_pos = own_pos.data();
+        for (uint32_t p = 0; p < P; ++p) owner_bit_thread(d, p);
+        const uint32_t n_scan = n_colors * (d.own_words + 1u);
+        for (uint32_t k = 0; k < n_scan; ++k) owner_count_thread(d, k);
+        exclusive_scan(own_pos.data(), n_scan);
+        for (uint32_t c = 0; c <= n_colors; ++c) color_start[c] = own_pos[(size_t)c * (d.own_words + 1u)];
         const uint32_t MP = color_start[n_colors];  // padded manifold slots
-
-        // ---- colour partition + pre-step ----
         s_hdr.assign(MP + 1, make_uint4(0, 0, S_EMPTY, 0)); s_nf.resize(MP + 1); s_inv.resize(MP + 1); s_r0.resize(MP + 1);
         s_r1.resize(MP + 1); s_pm0.resize(MP + 1); s_pm1.resize(MP + 1); s_acc0.resize(MP + 1); s_acc1.resize(MP + 1);
         s_dep.resize(MP + 1); d.s_dep = s_dep.data();
         d.s_hdr = s_hdr.data(); d.s_nf = s_nf.data(); d.s_inv = s_inv.data(); d.s_r0 = s_r0.data(); d.s_r1 = s_r1.data();
         d.s_pm0 = s_pm0.data(); d.s_pm1 = s_pm1.data(); d.s_acc0 = s_acc0.data(); d.s_acc1 = s_acc1.data();
-        for (uint32_t p = 0; p < P; ++p) {
-            if (m_color[p] >= MAX_COLORS) continue;
-            const uint32_t at = color_start[m_color[p]] + color_cursor[m_color[p]]++;
-            gather_prestep_thread(d, p, at);
+        {
+            std::vector<char> taken(MP + 1, 0);
+            for (uint32_t p = 0; p < P; ++p) {
+                if (m_color[p] >= MAX_COLORS) continue;
+                const uint32_t at = manifold_slot(d, p);
+                if (at >= MP || taken[at] || at < color_start[m_color[p]] || at >= color_start[m_color[p] + 1]) return R2D_ERR_CUDA;
+                taken[at] = 1;
+                gather_prestep_thread(d, p, at);
+            }
         }
 
         // ---- substeps (lib.zig:199-250) ----
