@@ -178,6 +178,60 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_down(const uint32_t* in, uint
     }
 }
 
+// Single-pass chained scan (decoupled look-back): one launch instead of three.  Tile ids come from an atomic ticket,
+// so a CTA only ever waits for tiles that started before it; every tile publishes (flag, value) as ONE 64-bit word
+// (flag 1 = aggregate of the tile, 2 = inclusive prefix), which needs no fence.  `state` (n_tiles + 1 words, the last
+// one is the ticket) must be zero on entry.  in == out is allowed.
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_chained(const uint32_t* in, uint32_t* out, const uint32_t* n_ptr, uint32_t n_max,
+                                                           unsigned long long* state, uint32_t state_tiles, uint32_t* total_out) {
+    __shared__ uint32_t s_tile, s_prefix;
+    const uint32_t n = scan_count(n_ptr, n_max);
+    if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd(&state[state_tiles], 1ull);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t n_tiles = n ? (n + SCAN_TILE - 1) / SCAN_TILE : 1u;
+    if (tile >= n_tiles) return;
+    const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_IPT;
+    uint32_t v[SCAN_IPT];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0u;
+        sum += v[k];
+    }
+    uint32_t aggregate;
+    const uint32_t local = block_exclusive_scan(sum, &aggregate);
+    if (threadIdx.x == 0) {
+        uint32_t prefix = 0;
+        if (tile == 0) {
+            atomicExch(&state[0], (2ull << 32) | aggregate);
+        } else {
+            atomicExch(&state[tile], (1ull << 32) | aggregate);
+            for (uint32_t t = tile; t-- > 0;) {
+                unsigned long long w;
+                do {
+                    w = *((volatile unsigned long long*)&state[t]);
+                } while ((w >> 32) == 0ull);
+                prefix += (uint32_t)w;
+                if ((w >> 32) == 2ull) break;
+            }
+            atomicExch(&state[tile], (2ull << 32) | (unsigned long long)(uint32_t)(prefix + aggregate));
+        }
+        s_prefix = prefix;
+        if (tile == n_tiles - 1) {
+            out[n] = prefix + aggregate;
+            if (total_out) *total_out = prefix + aggregate;
+        }
+    }
+    __syncthreads();
+    uint32_t run = s_prefix + local;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+}
+
 // ---- K4b / K5: one WARP per bucket ------------------------------------------------------------------------------------------
 // The bucket's entries are staged in shared memory.  k_sort_buckets rank-sorts them (ascending slot, duplicates
 // adjacent) so that the bucket order — and with it the pair list — does not depend on the order the atomics of the
@@ -185,7 +239,8 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_down(const uint32_t* in, uint
 // of the bucket; a pair is counted (WRITE = false) or written at the bucket's scanned offset (WRITE = true) in
 // (a, b) order, which makes the candidate list deterministic.
 constexpr int BUCKET_WARPS = TPB / 32;
-constexpr int BUCKET_CAP = 128;  // entries staged per warp; larger buckets take the (rare) serial path
+constexpr int BUCKET_CAP = 128;    // entries staged in shared memory; larger buckets read their entries from global memory
+constexpr int HEAVY_BUCKET = 40;   // buckets with more entries get a whole CTA instead of a warp (n^2 pair tests)
 
 __global__ void __launch_bounds__(TPB) k_sort_buckets(Dev d) {
     __shared__ uint32_t s_in[BUCKET_WARPS][BUCKET_CAP];
@@ -196,7 +251,10 @@ __global__ void __launch_bounds__(TPB) k_sort_buckets(Dev d) {
         const uint32_t n = be > bs ? be - bs : 0u;
         if (lane == 0) {
             d.ent_off[b] = 0u;
-            if (n >= 2u) d.work[atomicAdd(&d.counters->n_work, 1u)] = b;  // the pair kernels visit only these
+            if (n > (uint32_t)HEAVY_BUCKET)
+                d.work[d.n_buckets - 1u - atomicAdd(&d.counters->n_heavy, 1u)] = b;
+            else if (n >= 2u)
+                d.work[atomicAdd(&d.counters->n_work, 1u)] = b;  // the pair kernels visit only listed buckets
         }
         if (n < 2u) continue;  // warp-uniform
         if (n > BUCKET_CAP) {
@@ -230,82 +288,103 @@ __device__ __forceinline__ void tri_decode(uint32_t p, uint32_t n, uint32_t& a, 
     b = p - a * (2 * n - a - 1) / 2 + a + 1;
 }
 
-template <bool WRITE>
+// One bucket, worked on by a TEAM of lanes: a warp (light buckets, 8 buckets per CTA) or the whole CTA (heavy buckets).
+// Pair tests are taken in row-major order of the strict upper triangle; every warp of the team owns a contiguous range
+// of pair indices, so concatenating the warps' hits in warp order keeps the (a, b) order deterministic.
+template <bool WRITE, bool HEAVY>
 __global__ void __launch_bounds__(TPB) k_bucket_pairs(Dev d) {
-    __shared__ uint32_t s_body[BUCKET_WARPS][BUCKET_CAP];
-    __shared__ uint32_t s_meta[BUCKET_WARPS][BUCKET_CAP];  // flags (bit 0 static) | first-occurrence << 1 | ncells << 2
-    __shared__ float4 s_aabb[BUCKET_WARPS][BUCKET_CAP];
-    __shared__ uint4 s_bkt[BUCKET_WARPS][BUCKET_CAP];
-    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    constexpr int TEAMS = HEAVY ? 1 : BUCKET_WARPS;       // teams per CTA
+    constexpr uint32_t TEAM = HEAVY ? TPB : 32;           // lanes per team
+    constexpr uint32_t TEAM_WARPS = TEAM / 32;
+    __shared__ uint32_t s_body[TEAMS][BUCKET_CAP];
+    __shared__ uint32_t s_meta[TEAMS][BUCKET_CAP];  // flags (bit 0 static) | first-occurrence << 1 | ncells << 2
+    __shared__ float4 s_aabb[TEAMS][BUCKET_CAP];
+    __shared__ uint4 s_bkt[TEAMS][BUCKET_CAP];
+    __shared__ uint32_t s_warp_total[BUCKET_WARPS];
+    const uint32_t lane = threadIdx.x & 31u, warp_in_cta = threadIdx.x >> 5;
+    const uint32_t team_in_cta = HEAVY ? 0u : warp_in_cta;
+    const uint32_t tl = HEAVY ? threadIdx.x : lane;                  // lane inside the team
+    const uint32_t tw = HEAVY ? warp_in_cta : 0u;                    // warp inside the team
+    const uint32_t team = HEAVY ? blockIdx.x : (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_teams = HEAVY ? gridDim.x : (gridDim.x * blockDim.x) >> 5;
     const bool dead = d.counters->n_entries > d.cap_entries;  // the fill dropped entries: this attempt is redone
-    const uint32_t n_work = d.counters->n_work;
-    for (uint32_t w = warp; w < n_work; w += n_warps) {
-        const uint32_t b = d.work[w];
+    const uint32_t n_items = HEAVY ? d.counters->n_heavy : d.counters->n_work;
+    for (uint32_t w = team; w < n_items; w += n_teams) {
+        const uint32_t b = HEAVY ? d.work[d.n_buckets - 1u - w] : d.work[w];
         const uint32_t bs = d.bucket_start[b], be = bucket_end(d, b);
         const uint32_t n = (be > bs && !dead) ? be - bs : 0u;
-        const uint32_t out_at = WRITE ? d.ent_off[b] : 0u;  // ent_off is indexed by BUCKET here
-        uint32_t total = 0;
-        if (n >= 2u && n <= BUCKET_CAP) {
-            for (uint32_t k = lane; k < n; k += 32) {
+        const bool staged = n <= BUCKET_CAP;
+        if (staged) {
+            for (uint32_t k = tl; k < n; k += TEAM) {
                 const uint32_t body = d.ent_body[bs + k];
                 const bool first = k == 0 || d.ent_body[bs + k - 1] != body;
-                s_body[wib][k] = body;
-                s_aabb[wib][k] = d.aabb[body];
-                s_bkt[wib][k] = d.bkt[body];
+                s_body[team_in_cta][k] = body;
+                s_aabb[team_in_cta][k] = d.aabb[body];
+                s_bkt[team_in_cta][k] = d.bkt[body];
                 uint32_t nc = d.ncells[body];
                 if (nc > 0x3FFFFFFFu) nc = 0x3FFFFFFFu;
-                s_meta[wib][k] = (body_flags(d, body) & FLAG_STATIC) | (first ? 2u : 0u) | (nc << 2);
+                s_meta[team_in_cta][k] = (body_flags(d, body) & FLAG_STATIC) | (first ? 2u : 0u) | (nc << 2);
             }
-            __syncwarp();
-            const uint32_t n_pairs = n * (n - 1u) / 2u;
-            for (uint32_t base = 0; base < n_pairs; base += 32) {  // lanes split the (a, b) tests in row-major order
+        }
+        if (HEAVY) __syncthreads(); else __syncwarp();
+        const uint32_t n_pairs = n >= 2u ? n * (n - 1u) / 2u : 0u;
+        // contiguous range of pair indices of this warp (multiple of 32 so that ballots stay aligned)
+        const uint32_t per_warp = ((n_pairs + TEAM_WARPS * 32u - 1u) / (TEAM_WARPS * 32u)) * 32u;
+        const uint32_t p_begin = tw * per_warp, p_end = (p_begin + per_warp < n_pairs) ? p_begin + per_warp : n_pairs;
+        uint32_t out_at = (WRITE && !HEAVY) ? d.ent_off[b] : 0u;  // ent_off is indexed by BUCKET (scanned for the write pass)
+        // HEAVY + WRITE: count first (pass 0) to learn the offsets of the warps, then write (pass 1)
+        for (int pass = (HEAVY && WRITE) ? 0 : 1; pass < 2; ++pass) {
+            const bool writing = WRITE && pass == 1;
+            uint32_t total = 0;
+            for (uint32_t base = p_begin; base < p_end; base += 32) {
                 const uint32_t p = base + lane;
                 bool hit = false;
                 uint2 pr = make_uint2(0u, 0u);
-                if (p < n_pairs) {
+                if (p < p_end) {
                     uint32_t a, k;
                     tri_decode(p, n, a, k);
-                    const uint32_t ma = s_meta[wib][a], mb = s_meta[wib][k];
-                    const uint32_t i = s_body[wib][a], j = s_body[wib][k];
-                    if ((ma & mb & 2u) && i != j)
-                        hit = pair_candidate(d, b, i, j, s_aabb[wib][a], s_aabb[wib][k], ma & 1u, mb & 1u, ma >> 2, mb >> 2,
-                                             s_bkt[wib][a], s_bkt[wib][k], &pr);
+                    if (staged) {
+                        const uint32_t ma = s_meta[team_in_cta][a], mb = s_meta[team_in_cta][k];
+                        const uint32_t i = s_body[team_in_cta][a], j = s_body[team_in_cta][k];
+                        if ((ma & mb & 2u) && i != j)
+                            hit = pair_candidate(d, b, i, j, s_aabb[team_in_cta][a], s_aabb[team_in_cta][k], ma & 1u, mb & 1u,
+                                                 ma >> 2, mb >> 2, s_bkt[team_in_cta][a], s_bkt[team_in_cta][k], &pr);
+                    } else {  // oversized bucket: entries straight from global memory
+                        const uint32_t i = d.ent_body[bs + a], j = d.ent_body[bs + k];
+                        const bool fa = a == 0 || d.ent_body[bs + a - 1] != i, fb = d.ent_body[bs + k - 1] != j;
+                        if (fa && fb && i != j)
+                            hit = pair_candidate(d, b, i, j, d.aabb[i], d.aabb[j], body_flags(d, i), body_flags(d, j), d.ncells[i],
+                                                 d.ncells[j], d.bkt[i], d.bkt[j], &pr);
+                    }
                 }
                 const uint32_t votes = __ballot_sync(0xffffffffu, hit);
-                if (WRITE && hit) {
+                if (writing && hit) {
                     const uint32_t at = out_at + total + (uint32_t)__popc(votes & ((1u << lane) - 1u));
                     if (at < d.cap_pairs) d.pairs[at] = pr;
                 }
                 total += (uint32_t)__popc(votes);
             }
-            __syncwarp();
-        } else if (n > BUCKET_CAP) {  // oversized bucket: same tests, entries read from global memory
-            for (uint32_t a = 0; a + 1 < n; ++a) {
-                const uint32_t i = d.ent_body[bs + a];
-                if (a > 0 && d.ent_body[bs + a - 1] == i) continue;
-                const float4 ai = d.aabb[i];
-                const uint32_t fi = body_flags(d, i), nci = d.ncells[i];
-                const uint4 bi = d.bkt[i];
-                for (uint32_t base = a + 1; base < n; base += 32) {
-                    const uint32_t k = base + lane;
-                    bool hit = false;
-                    uint2 pr = make_uint2(0u, 0u);
-                    if (k < n) {
-                        const uint32_t j = d.ent_body[bs + k];
-                        if (j != i && d.ent_body[bs + k - 1] != j)
-                            hit = pair_candidate(d, b, i, j, ai, d.aabb[j], fi, body_flags(d, j), nci, d.ncells[j], bi, d.bkt[j], &pr);
+            if (!HEAVY) {
+                if (!WRITE && lane == 0) d.ent_off[b] = total;
+            } else if (pass == 0 || !WRITE) {
+                if (lane == 0) s_warp_total[tw] = total;
+                __syncthreads();
+                if (!WRITE) {
+                    if (threadIdx.x == 0) {
+                        uint32_t sum = 0;
+                        for (uint32_t q = 0; q < TEAM_WARPS; ++q) sum += s_warp_total[q];
+                        d.ent_off[b] = sum;
                     }
-                    const uint32_t votes = __ballot_sync(0xffffffffu, hit);
-                    if (WRITE && hit) {
-                        const uint32_t at = out_at + total + (uint32_t)__popc(votes & ((1u << lane) - 1u));
-                        if (at < d.cap_pairs) d.pairs[at] = pr;
-                    }
-                    total += (uint32_t)__popc(votes);
+                } else {
+                    out_at = d.ent_off[b];
+                    for (uint32_t q = 0; q < tw; ++q) out_at += s_warp_total[q];
                 }
+                __syncthreads();
             }
+            if (!HEAVY && WRITE) break;
+            if (!HEAVY && !WRITE) break;
         }
-        if (!WRITE && lane == 0) d.ent_off[b] = total;
+        if (HEAVY) __syncthreads(); else __syncwarp();
     }
 }
 
@@ -341,25 +420,53 @@ __global__ void __launch_bounds__(TPB) k_narrow(Dev d) {
 // Jones-Plassmann rounds over the pending manifolds with one grid barrier per round.  Round r reads the priorities
 // posted for r in maxprio[r & 1] and posts those of the losers for r + 1 into the other array.  The result equals a
 // sequential greedy colouring in descending priority, so it is a pure function of the contact graph and the body ids.
+constexpr int COLOR_REG_SLOTS = 2;  // pending manifolds a thread keeps in registers across the rounds
+
 __global__ void __launch_bounds__(TPB) k_color(Dev d) {
     cg::grid_group grid = cg::this_grid();
     const bool dead = overflowed(d);
     const uint32_t n = dead ? 0u : live_pairs(d);
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    for (uint32_t p = tid; p < n; p += nth) {
-        if (d.m_color[p] != COLOR_PENDING) continue;
-        const uint4 h = d.m_hdr[p];
-        color_post(d, h.x, h.y, (h.w & 1u) != 0, (h.w & 2u) != 0, d.m_prio[p], 1u);
-    }
     // Same-address global atomics serialise in L2, so the per-colour populations are histogrammed in shared memory
     // for the whole kernel and the "anything left?" flag costs at most one global atomic per CTA and round.
     __shared__ uint32_t s_hist[MAX_COLORS];
     for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x) s_hist[c] = 0u;
+    // The first COLOR_REG_SLOTS slots of a thread (p = tid + k * nth) live in registers for all rounds: header and
+    // priority are read once, a round costs only the gathers of the two body words and the atomics.
+    uint4 rh[COLOR_REG_SLOTS];
+    unsigned long long rp[COLOR_REG_SLOTS];
+    bool pend[COLOR_REG_SLOTS];
+#pragma unroll
+    for (int k = 0; k < COLOR_REG_SLOTS; ++k) {
+        const uint32_t p = tid + (uint32_t)k * nth;
+        pend[k] = p < n && d.m_color[p] == COLOR_PENDING;
+        if (pend[k]) {
+            rh[k] = d.m_hdr[p];
+            rp[k] = d.m_prio[p];
+            color_post(d, rh[k].x, rh[k].y, (rh[k].w & 1u) != 0, (rh[k].w & 2u) != 0, rp[k], 1u);
+        }
+    }
+    for (uint32_t p = tid + COLOR_REG_SLOTS * nth; p < n; p += nth) {
+        if (d.m_color[p] != COLOR_PENDING) continue;
+        const uint4 h = d.m_hdr[p];
+        color_post(d, h.x, h.y, (h.w & 1u) != 0, (h.w & 2u) != 0, d.m_prio[p], 1u);
+    }
     grid.sync();
     uint32_t round = 1;
     for (; round < MAX_COLOR_ROUNDS; ++round) {
         int left = 0;
-        for (uint32_t p = tid; p < n; p += nth) {
+#pragma unroll
+        for (int k = 0; k < COLOR_REG_SLOTS; ++k) {
+            if (!pend[k]) continue;
+            uint32_t c;
+            if (color_round_core(d, tid + (uint32_t)k * nth, rh[k], rp[k], round, &c) == 1) {
+                atomicAdd(&s_hist[c], 1u);
+                pend[k] = false;
+            } else {
+                left = 1;
+            }
+        }
+        for (uint32_t p = tid + COLOR_REG_SLOTS * nth; p < n; p += nth) {
             const int r = color_round_thread(d, p, round);
             if (r == 2)
                 left = 1;

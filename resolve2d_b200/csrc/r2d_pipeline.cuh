@@ -52,9 +52,9 @@ struct Counters {
     uint32_t n_rounds;
     uint32_t err;
     uint32_t n_own_scan;     // n_colors * (W + 1): length of the owner-position scan
-    uint32_t n_work;         // buckets holding at least two entries (work list of the pair kernels)
+    uint32_t n_work;         // buckets holding 2..HEAVY_BUCKET entries (work list of the warp-per-bucket pair kernels)
+    uint32_t n_heavy;        // buckets holding more (CTA-per-bucket pair kernels)
     uint32_t n_stamps;
-    uint32_t pad0;
     unsigned long long stamp[10];   // %globaltimer at phase boundaries of the persistent solver (block 0; diagnostics)
 };
 
@@ -86,7 +86,8 @@ struct Dev {
     uint32_t* ent_body;           // E
     uint32_t* ent_key;            // E
     uint32_t* ent_off;            // T + 1: pairs emitted per BUCKET, then its exclusive scan ([T] = P)
-    uint32_t* work;               // T: ids of the buckets with >= 2 entries (order irrelevant)
+    uint32_t* work;               // T: ids of the light buckets (2..HEAVY_BUCKET entries) from the front, of the heavy ones
+                                  // from the back (work[T - 1 - k]); order irrelevant
     const uint64_t* excl;         // sorted (lo_slot << 32 | hi_slot)
     uint32_t n_excl;
     // ---- candidate pairs / raw manifolds (P slots) ------------------------------------------------------------------
@@ -454,12 +455,10 @@ R2D_HD void color_post(const Dev& d, uint32_t ref, uint32_t inc, bool dyn1, bool
     if (dyn1) atomic_max_u64(&mp[ref], v);
     if (dyn2) atomic_max_u64(&mp[inc], v);
 }
-// One colouring round for pair slot p.  Returns: 0 nothing pending, 1 coloured now, 2 still pending (re-posted).
-R2D_HD int color_round_thread(const Dev& d, uint32_t p, uint32_t round) {
-    if (d.m_color[p] != COLOR_PENDING) return 0;
-    const uint4 h = d.m_hdr[p];
+// One colouring round for a pending manifold whose header / priority the caller holds (registers across rounds).
+// Returns 1 coloured now (colour in *out_color), 2 still pending (re-posted for round + 1).
+R2D_HD int color_round_core(const Dev& d, uint32_t p, const uint4& h, uint64_t prio, uint32_t round, uint32_t* out_color) {
     const bool dyn1 = (h.w & 1u) != 0, dyn2 = (h.w & 2u) != 0;
-    const uint64_t prio = d.m_prio[p];
     const unsigned long long mine = ((unsigned long long)round << PRIO_ROUND_SHIFT) | prio;
     const unsigned long long* mp = (round & 1u) ? d.maxprio1 : d.maxprio0;
     const bool win = (!dyn1 || ld_shared_u64(&mp[h.x]) == mine) && (!dyn2 || ld_shared_u64(&mp[h.y]) == mine);
@@ -494,7 +493,14 @@ R2D_HD int color_round_thread(const Dev& d, uint32_t p, uint32_t round) {
         *u = ld_shared_u64(u) | bit;
     }
     d.m_color[p] = color;
+    *out_color = color;
     return 1;
+}
+// Same, reading everything from memory.  Returns 0 if slot p holds nothing pending.
+R2D_HD int color_round_thread(const Dev& d, uint32_t p, uint32_t round) {
+    if (d.m_color[p] != COLOR_PENDING) return 0;
+    uint32_t c;
+    return color_round_core(d, p, d.m_hdr[p], d.m_prio[p], round, &c);
 }
 
 // The "owner" of a manifold orders the colour-sorted solver records: the lower device slot of its non-static bodies.

@@ -76,7 +76,7 @@ struct CudaBatch : BatchBase {
     int device = 0;
     int n_sms = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    int color_blocks = 0, solve_blocks = 0, pair_blocks = 0;
+    int color_blocks = 0, solve_blocks = 0, pair_blocks = 0, heavy_blocks = 0;
     uint32_t wait_mode = 1, wait_spin_lag = 1, wait_sleep_unit = 200, wait_sleep_max = 4000;
     int solve_blocks_per_sm = 1;
     uint32_t solve_smem_slots = SOLVE_SMEM_SLOTS;
@@ -98,10 +98,13 @@ struct CudaBatch : BatchBase {
     DBuf<uint4> s_dep;
     DBuf<uint32_t> m_color;
     // colouring
-    DBuf<unsigned long long> maxprio0, maxprio1, used, m_prio;
-    DBuf<uint32_t> own_bits, own_pos;
-    DBuf<uint32_t> color_misc;   // color_count[256] | color_start[257] | color_cursor[256] | round_left[MAX_COLOR_ROUNDS]
-    DBuf<Counters> counters;
+    DBuf<unsigned long long> m_prio;
+    // everything that must be zero at the start of a step lives in ONE allocation (one memset per step)
+    DBuf<unsigned char> zeroed;
+    size_t zeroed_bytes = 0, scan_state_cap = 0;
+    size_t off_counters = 0, off_color_misc = 0, off_scan = 0, off_maxprio0 = 0, off_maxprio1 = 0, off_used = 0, off_own_bits = 0;
+    unsigned long long* scan_state(int which) { return (unsigned long long*)(zeroed.p + off_scan) + (size_t)which * scan_state_cap; }
+    DBuf<uint32_t> own_pos;
     // staging for the boundary copies
     DBuf<unsigned char> staging;
     PinnedStep* pinned = nullptr;
@@ -166,11 +169,11 @@ struct CudaBatch : BatchBase {
         if (const char* e = getenv("R2D_WAIT_SLEEP_MAX")) wait_sleep_max = (uint32_t)atoi(e);
         if (per_sm > solve_blocks_per_sm) per_sm = solve_blocks_per_sm;
         solve_blocks = per_sm * n_sms;
-        R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bucket_pairs<false>, TPB, 0));
+        R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_bucket_pairs<false, false>), TPB, 0));
         pair_blocks = (per_sm < 1 ? 1 : per_sm) * n_sms;  // resident CTAs: one warp per listed bucket, grid-stride
+        R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_bucket_pairs<false, true>), TPB, 0));
+        heavy_blocks = (per_sm < 1 ? 1 : per_sm) * n_sms;  // one CTA per heavy bucket, grid-stride
         if (const char* e = getenv("R2D_SOLVER")) persistent_solver = std::string(e) != "launches";
-        R2D_TRY(counters.reserve(1));
-        R2D_TRY(color_misc.reserve(MAX_COLORS * 3 + 1 + MAX_COLOR_ROUNDS));
         return R2D_OK;
     }
 
@@ -216,14 +219,13 @@ struct CudaBatch : BatchBase {
         launches += 1;                                          \
     } while (0)
 
-    // exclusive scan of in[0..n) into out[0..n), out[n] = total (also *total_out); n = min(*n_ptr, n_max) if n_ptr
-    int scan(const uint32_t* in, uint32_t* out, const uint32_t* n_ptr, uint32_t n_max, uint32_t* total_out,
-             int kclass = R2D_KCLASS_BROADPHASE) {
-        const uint32_t tiles = (n_max + SCAN_TILE - 1) / SCAN_TILE;
-        R2D_TRY(tile_sums.reserve(tiles + 1));
-        R2D_LAUNCH(kclass, k_scan_reduce, tiles ? tiles : 1, SCAN_TPB, in, tile_sums.p, n_ptr, n_max);
-        R2D_LAUNCH(kclass, k_scan_spine, 1, SCAN_TPB, tile_sums.p, n_ptr, n_max, out, total_out);
-        R2D_LAUNCH(kclass, k_scan_down, tiles ? tiles : 1, SCAN_TPB, in, out, tile_sums.p, n_ptr, n_max);
+    // exclusive scan of in[0..n) into out[0..n), out[n] = total (also *total_out); n = min(*n_ptr, n_max) if n_ptr.
+    // One chained-scan launch; `which` selects one of the pre-zeroed state regions of this step.
+    int scan(const uint32_t* in, uint32_t* out, const uint32_t* n_ptr, uint32_t n_max, uint32_t* total_out, int kclass, int which) {
+        const uint32_t tiles = (n_max + SCAN_TILE - 1) / SCAN_TILE + 1;
+        if (tiles + 1 > scan_state_cap) return R2D_ERR_CUDA;
+        unsigned long long* st = scan_state(which);
+        R2D_LAUNCH(kclass, k_scan_chained, tiles, SCAN_TPB, in, out, n_ptr, n_max, st, (uint32_t)(scan_state_cap - 1), total_out);
         return R2D_OK;
     }
 
@@ -416,13 +418,18 @@ struct CudaBatch : BatchBase {
         d.cap_pairs = (uint32_t)cap_pairs;
         d.pairs = pairs.p; d.m_hdr = m_hdr.p; d.m_g0 = m_g0.p; d.m_g1 = m_g1.p; d.m_r0 = m_r0.p; d.m_r1 = m_r1.p;
         d.m_color = m_color.p; d.m_prio = m_prio.p;
-        d.maxprio0 = maxprio0.p; d.maxprio1 = maxprio1.p; d.used = used.p;
-        d.color_count = color_misc.p;
-        d.color_start = color_misc.p + MAX_COLORS;
-        d.color_cursor = color_misc.p + 2 * MAX_COLORS + 1;
-        d.round_left = color_misc.p + 3 * MAX_COLORS + 1;
-        d.counters = counters.p;
-        d.own_words = (d.n_bodies + 31u) / 32u; d.own_bits = own_bits.p; d.own_pos = own_pos.p;
+        d.maxprio0 = (unsigned long long*)(zeroed.p + off_maxprio0);
+        d.maxprio1 = (unsigned long long*)(zeroed.p + off_maxprio1);
+        d.used = (unsigned long long*)(zeroed.p + off_used);
+        uint32_t* color_misc = (uint32_t*)(zeroed.p + off_color_misc);
+        d.color_count = color_misc;
+        d.color_start = color_misc + MAX_COLORS;
+        d.color_cursor = color_misc + 2 * MAX_COLORS + 1;
+        d.round_left = color_misc + 3 * MAX_COLORS + 1;
+        d.counters = (Counters*)(zeroed.p + off_counters);
+        d.own_words = (d.n_bodies + 31u) / 32u;
+        d.own_bits = (uint32_t*)(zeroed.p + off_own_bits);
+        d.own_pos = own_pos.p;
         d.s_hdr = s_hdr.p; d.s_nf = s_nf.p; d.s_inv = s_inv.p; d.s_r0 = s_r0.p; d.s_r1 = s_r1.p;
         d.s_pm0 = s_pm0.p; d.s_pm1 = s_pm1.p; d.s_acc0 = s_acc0.p; d.s_acc1 = s_acc1.p;
         d.s_dep = s_dep.p;
@@ -469,9 +476,23 @@ struct CudaBatch : BatchBase {
         const uint32_t T = grid_mult() * nb;
         int st;
         const size_t own_w = ((size_t)nb + 31) / 32;
-        if ((st = own_bits.reserve(own_w * MAX_COLORS)) || (st = own_pos.reserve((own_w + 1) * MAX_COLORS + 2)) ||
-            (st = pose.reserve(nb)) || (st = ncells.reserve(nb)) || (st = bkt.reserve(nb)) || (st = maxprio0.reserve(nb)) || (st = maxprio1.reserve(nb)) ||
-            (st = used.reserve((size_t)nb * COLOR_WORDS)) || (st = bucket_cnt.reserve((size_t)T + 1, true, stream)) ||
+        {   // layout of the zeroed arena for this body count
+            auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+            const size_t max_scan = std::max<size_t>((size_t)T + 1, (own_w + 1) * MAX_COLORS + 2);
+            scan_state_cap = (max_scan + SCAN_TILE - 1) / SCAN_TILE + 4;
+            size_t o = 0;
+            off_counters = o; o = align(o + sizeof(Counters));
+            off_color_misc = o; o = align(o + (MAX_COLORS * 3 + 1 + MAX_COLOR_ROUNDS) * 4);
+            off_scan = o; o = align(o + 3 * scan_state_cap * 8);
+            off_maxprio0 = o; o = align(o + (size_t)nb * 8);
+            off_maxprio1 = o; o = align(o + (size_t)nb * 8);
+            off_used = o; o = align(o + (size_t)nb * COLOR_WORDS * 8);
+            off_own_bits = o; o = align(o + own_w * MAX_COLORS * 4);
+            zeroed_bytes = o;
+            if ((st = zeroed.reserve(zeroed_bytes))) return st;
+        }
+        if ((st = own_pos.reserve((own_w + 1) * MAX_COLORS + 2)) ||
+            (st = pose.reserve(nb)) || (st = ncells.reserve(nb)) || (st = bkt.reserve(nb)) ||  (st = bucket_cnt.reserve((size_t)T + 1, true, stream)) ||
             (st = bucket_start.reserve((size_t)T + 1)) || (st = ent_off.reserve((size_t)T + 2)) || (st = work.reserve((size_t)T + 1)))
             return st;
         if (cap_entries == 0 && (st = reserve_entries((size_t)nb * 3 + 4096))) return st;
@@ -479,21 +500,18 @@ struct CudaBatch : BatchBase {
 
         for (int attempt = 0;; ++attempt) {
             fill_dev();
-            R2D_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(Counters), stream));
-            R2D_CUDA(cudaMemsetAsync(color_misc.p, 0, (MAX_COLORS * 3 + 1 + MAX_COLOR_ROUNDS) * 4, stream));
-            R2D_CUDA(cudaMemsetAsync(maxprio0.p, 0, (size_t)nb * 8, stream));
-            R2D_CUDA(cudaMemsetAsync(maxprio1.p, 0, (size_t)nb * 8, stream));
-            R2D_CUDA(cudaMemsetAsync(used.p, 0, (size_t)nb * COLOR_WORDS * 8, stream));
-            R2D_CUDA(cudaMemsetAsync(own_bits.p, 0, own_w * MAX_COLORS * 4, stream));
+            R2D_CUDA(cudaMemsetAsync(zeroed.p, 0, zeroed_bytes, stream));  // counters, colour tables, scan states, masks
             // ---- broadphase ----
             R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_grid_cells<false>, grid_for(nb), TPB, d);
-            if ((st = scan(d.bucket_cnt, d.bucket_start, nullptr, T, &d.counters->n_entries))) return st;
+            if ((st = scan(d.bucket_cnt, d.bucket_start, nullptr, T, &d.counters->n_entries, R2D_KCLASS_BROADPHASE, 0))) return st;
             R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_grid_cells<true>, grid_for(nb), TPB, d);
             R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_sort_buckets, grid_warp_per(T), TPB, d);
             // pairs per BUCKET (one warp each) -> scan over the T buckets -> write at the scanned offsets
-            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_bucket_pairs<false>, pair_blocks, TPB, d);
-            if ((st = scan(d.ent_off, d.ent_off, nullptr, T, &d.counters->n_pairs))) return st;
-            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_bucket_pairs<true>, pair_blocks, TPB, d);
+            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, (k_bucket_pairs<false, false>), pair_blocks, TPB, d);
+            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, (k_bucket_pairs<false, true>), heavy_blocks, TPB, d);
+            if ((st = scan(d.ent_off, d.ent_off, nullptr, T, &d.counters->n_pairs, R2D_KCLASS_BROADPHASE, 1))) return st;
+            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, (k_bucket_pairs<true, false>), pair_blocks, TPB, d);
+            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, (k_bucket_pairs<true, true>), heavy_blocks, TPB, d);
             // ---- narrowphase ----
             R2D_LAUNCH(R2D_KCLASS_NARROWPHASE, k_narrow, grid_for(cap_pairs), TPB, d);
             // ---- colouring + partition + pre-step ----
@@ -507,7 +525,7 @@ struct CudaBatch : BatchBase {
             // owner bitmaps -> popcounts -> scan = position of every manifold in the colour-sorted, spatially ordered records
             R2D_LAUNCH(R2D_KCLASS_COLORING, k_owner_bits, grid_for(cap_pairs), TPB, d);
             R2D_LAUNCH(R2D_KCLASS_COLORING, k_owner_count, grid_for((own_w + 1) * 64), TPB, d);
-            if ((st = scan(d.own_pos, d.own_pos, &d.counters->n_own_scan, (uint32_t)((own_w + 1) * MAX_COLORS), nullptr, R2D_KCLASS_COLORING))) return st;
+            if ((st = scan(d.own_pos, d.own_pos, &d.counters->n_own_scan, (uint32_t)((own_w + 1) * MAX_COLORS), nullptr, R2D_KCLASS_COLORING, 2))) return st;
             R2D_LAUNCH(R2D_KCLASS_COLORING, k_partition_prestep, grid_for(cap_pairs), TPB, d);
             // ---- substeps: one persistent cooperative kernel (colour ranges are read on the device) ----
             if (persistent_solver) {
@@ -522,7 +540,7 @@ struct CudaBatch : BatchBase {
                 launches += 1;
             }
             // ---- the one synchronisation point of the step: counters + colour offsets ----
-            R2D_CUDA(cudaMemcpyAsync(&pinned->counters, counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+            R2D_CUDA(cudaMemcpyAsync(&pinned->counters, d.counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
             R2D_CUDA(cudaMemcpyAsync(pinned->color_start, d.color_start, (MAX_COLORS + 1) * 4, cudaMemcpyDeviceToHost, stream));
             R2D_CUDA(cudaStreamSynchronize(stream));
             R2D_CUDA(cudaGetLastError());
