@@ -393,12 +393,33 @@ __global__ void __launch_bounds__(TPB) k_narrow(Dev d) {
     if (overflowed(d)) return;
     const uint32_t n = live_pairs(d);
     uint32_t my_m = 0, my_k = 0;
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        const int np = narrow_pair_thread(d, p);
-        if (np >= 0) {
-            my_m += 1;
-            my_k += (uint32_t)np;
+    // Each CTA takes 256 consecutive pairs and re-deals them to its threads sorted by shape combination (disc-disc,
+    // disc-rect, rect-rect), so that a warp runs one SAT flavour instead of all three (mixed scenes diverge 3-way
+    // otherwise).  The result of a pair does not depend on which thread computes it.
+    __shared__ uint32_t s_idx[TPB];
+    __shared__ uint32_t s_cnt[3];
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t p = base + threadIdx.x;
+        uint32_t t = 3;
+        if (p < n) {
+            const uint2 pr = d.pairs[p];
+            t = ((body_flags(d, pr.x) & FLAG_RECT) ? 1u : 0u) + ((body_flags(d, pr.y) & FLAG_RECT) ? 1u : 0u);
         }
+        if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0u;
+        __syncthreads();
+        const uint32_t rank = t < 3 ? atomicAdd(&s_cnt[t], 1u) : 0u;
+        __syncthreads();
+        const uint32_t c0 = s_cnt[0], c1 = s_cnt[1], c2 = s_cnt[2];
+        if (t < 3) s_idx[(t == 0 ? 0u : (t == 1 ? c0 : c0 + c1)) + rank] = p;
+        __syncthreads();
+        if (threadIdx.x < c0 + c1 + c2) {
+            const int np = narrow_pair_thread(d, s_idx[threadIdx.x]);
+            if (np >= 0) {
+                my_m += 1;
+                my_k += (uint32_t)np;
+            }
+        }
+        __syncthreads();
     }
     __shared__ uint32_t s_m, s_k;  // one pair of global atomics per CTA (same-address atomics serialise in L2)
     if (threadIdx.x == 0) s_m = s_k = 0u;
@@ -639,6 +660,55 @@ __global__ void __launch_bounds__(TPB) k_solve_persistent(Dev d, float sub_dt, u
         if (s == 0) stamp(d, 9);
     }
     stamp(d, 10);
+}
+
+// ---- K13: worlds that fit in shared memory — one CTA per world, no inter-CTA synchronisation at all --------------------------------
+// A batch of small independent worlds (cfg5: 4,096 x 256 bodies) needs no grid barrier and no dataflow: world w's
+// manifolds of colour c are the contiguous range [slot(c, base_w), slot(c, base_{w+1})) of the colour-sorted records
+// (owner order is world-major), its momentum words live in shared memory for the whole substep loop, and colours are
+// separated by __syncthreads().  The per-body update sequence is the colour order, as everywhere else: bit-identical.
+constexpr int WORLD_TPB = 128;
+constexpr uint32_t WORLD_MAX_BODIES = 1024;   // 16 KB of momentum words
+
+__device__ __forceinline__ uint32_t owner_rank(const Dev& d, uint32_t c, uint32_t slot) {  // owners of colour c below `slot`
+    const uint32_t word = d.own_bits[(size_t)c * d.own_words + (slot >> 5)];
+    return d.own_pos[(size_t)c * (d.own_words + 1u) + (slot >> 5)] + (uint32_t)__popc(word & ((1u << (slot & 31u)) - 1u));
+}
+
+__global__ void __launch_bounds__(WORLD_TPB) k_solve_worlds(Dev d, float sub_dt, uint32_t S, uint32_t I) {
+    __shared__ float4 s_mom[WORLD_MAX_BODIES];
+    __shared__ uint32_t s_begin[MAX_COLORS], s_end[MAX_COLORS];
+    if (overflowed(d) || d.counters->err != 0u) return;
+    const uint32_t nc = d.counters->n_colors;
+    for (uint32_t w = blockIdx.x; w < d.n_worlds; w += gridDim.x) {
+        const uint32_t b0 = d.world_base[w], b1 = d.world_base[w + 1], nb = b1 - b0;
+        for (uint32_t c = threadIdx.x; c < nc; c += blockDim.x) {
+            s_begin[c] = owner_rank(d, c, b0);
+            // the last world's range ends where the colour's padding begins
+            s_end[c] = (b1 < d.n_bodies) ? owner_rank(d, c, b1) : d.own_pos[(size_t)c * (d.own_words + 1u) + d.own_words];
+        }
+        Dev ds = d;
+        ds.mom = s_mom - b0;  // ds.mom[global slot] addresses the shared copy of this world's momentum words
+        for (uint32_t s = 0; s < S; ++s) {
+            for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+                if (s > 0) integrate_positions_thread(d, b0 + i, sub_dt);
+                integrate_forces_thread(d, b0 + i, sub_dt, s + 1 == S);
+                s_mom[i] = d.mom[b0 + i];
+            }
+            __syncthreads();
+            for (uint32_t it = 0; it < I; ++it)
+                for (uint32_t c = 0; c < nc; ++c) {
+                    for (uint32_t m = s_begin[c] + threadIdx.x; m < s_end[c]; m += blockDim.x) solve_contact_thread<false>(ds, m, sub_dt);
+                    __syncthreads();
+                }
+            for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+                const float4 m = s_mom[i];
+                if (!(body_flags(d, b0 + i) & FLAG_STATIC)) d.mom[b0 + i] = m;
+                if (s + 1 == S) integrate_positions_thread(d, b0 + i, sub_dt);
+            }
+            __syncthreads();
+        }
+    }
 }
 
 // ---- boundary kernels: SoA export for bulk readback, force import ---------------------------------------------------------------

@@ -24,6 +24,8 @@ struct BodyView {
     uint32_t flags;
     uint32_t id;
     v2 wv[4];        // rectangle: world vertices rot(local[k]) + pos, local = (-w,-h),(-w,h),(w,h),(w,-h) (Rectangle.zig:38-40)
+    v2 en[4];        // rectangle: outward edge normals rot90ccw(normalize(wv[k+1] - wv[k])) — what getNormal (Rectangle.zig:132-151)
+                     // and clipAgainstEdge (:220-227) both evaluate, always from the same vertices, so once is bit-identical
 };
 
 R2D_HD bool is_rect(const BodyView& b) { return (b.flags & FLAG_RECT) != 0; }
@@ -45,10 +47,13 @@ R2D_HD BodyView make_view(float px, float py, float c, float s, float shape_a, f
         v.wv[1] = add2(rotate_cs(mk2(-w, h), c, s), v.pos);
         v.wv[2] = add2(rotate_cs(mk2(w, h), c, s), v.pos);
         v.wv[3] = add2(rotate_cs(mk2(w, -h), c, s), v.pos);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v.en[k] = rot90ccw(normalize2(sub2(v.wv[(k + 1) & 3], v.wv[k])));
     } else {
         v.a = shape_a;
         v.b = 0.0f;
         v.wv[0] = v.wv[1] = v.wv[2] = v.wv[3] = v.pos;
+        v.en[0] = v.en[1] = v.en[2] = v.en[3] = mk2(0.0f, 0.0f);
     }
     return v;
 }
@@ -84,16 +89,14 @@ struct Edge {
     v2 ea, eb;   // rectangle: the edge itself (world)
 };
 
-// getNormal: Disc.zig:86-90 (axis toward the other body's closest point), Rectangle.zig:132-151
+// getNormal: Disc.zig:86-90 (axis toward the other body's closest point), Rectangle.zig:132-151.
+// k is a compile-time-unrollable index wherever this is called, so wv[] / en[] stay in registers.
 R2D_HD Edge get_normal(const BodyView& self, const BodyView& other, int k) {
     Edge e;
     if (is_rect(self)) {
-        const int kn = (k == 3) ? 0 : k + 1;
-        const v2 a1 = self.wv[k], a2 = self.wv[kn];
-        const v2 dir = normalize2(sub2(a2, a1));
-        e.dir = rot90ccw(dir);
-        e.ea = a1;
-        e.eb = a2;
+        e.dir = self.en[k];
+        e.ea = self.wv[k];
+        e.eb = self.wv[(k + 1) & 3];
     } else {
         const v2 closest = closest_point(other, self.pos);
         e.dir = normalize2(sub2(closest, self.pos));
@@ -137,7 +140,9 @@ R2D_HD bool normal_should_flip(v2 n, const BodyView& ref, const BodyView& inc) {
 R2D_HD bool overlap_sat(SatResult& ret, const BodyView& R, const BodyView& I, int ref_tag) {
     const float EPS = SAT_OVERLAP_THRESHOLD;
     const int nn = is_rect(R) ? 4 : 1;
-    for (int k = 0; k < nn; ++k) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // unrolled: static indices into wv[] / en[]
+        if (k >= nn) break;
         v2 normal = get_normal(R, I, k).dir;
         bool flipped = false;
         if (normal_should_flip(normal, R, I)) {
@@ -247,7 +252,11 @@ R2D_HD void identify_points(Manifold& m, const BodyView& ref, const BodyView& in
         m.n_points = 1;
         return;
     }
-    const Edge n = get_normal(ref, inc, normal_id);  // UNFLIPPED outward normal + edge (Q13)
+    Edge n;  // UNFLIPPED outward normal + edge of the reference face (Q13); selected without dynamic indexing
+    n = get_normal(ref, inc, 0);
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+        if (k == normal_id) n = get_normal(ref, inc, k);
     if (is_rect(inc)) {
         // Rectangle.clipAgainstEdge: incident edge = argmin_k dot(normal, outward_normal_k), strict <
         v2 best_a = inc.wv[0], best_b = inc.wv[0];
@@ -257,8 +266,7 @@ R2D_HD void identify_points(Manifold& m, const BodyView& ref, const BodyView& in
         for (int i = 0; i < 4; ++i) {
             const int ni = (i == 3) ? 0 : i + 1;
             const v2 next = inc.wv[ni];
-            const v2 tangent = normalize2(sub2(next, curr));
-            const v2 tentative = rot90ccw(tangent);
+            const v2 tentative = inc.en[i];  // rot90ccw(normalize(next - curr)), Rectangle.zig:224-225
             const float d = dot2(n.dir, tentative);
             if (d < best_dot) {
                 best_a = curr;

@@ -80,7 +80,9 @@ struct CudaBatch : BatchBase {
     uint32_t wait_mode = 1, wait_spin_lag = 1, wait_sleep_unit = 200, wait_sleep_max = 4000;
     int solve_blocks_per_sm = 1;
     uint32_t solve_smem_slots = SOLVE_SMEM_SLOTS;
-    bool persistent_solver = true;   // false: one launch per colour (kept for A/B measurements)
+    bool persistent_solver = true;
+    bool world_solver = true;       // CTA-per-world shared-memory solver when every world is small and there are no joints
+    uint32_t max_world_bodies = 0;   // false: one launch per colour (kept for A/B measurements)
     // bodies
     DBuf<float4> pos, mom, frc, prop, shape, aabb, pose;
     DBuf<uint32_t> ncells, world_base, grav_off, joint_color_start, dev_of_host;
@@ -174,6 +176,7 @@ struct CudaBatch : BatchBase {
         R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_bucket_pairs<false, true>), TPB, 0));
         heavy_blocks = (per_sm < 1 ? 1 : per_sm) * n_sms;  // one CTA per heavy bucket, grid-stride
         if (const char* e = getenv("R2D_SOLVER")) persistent_solver = std::string(e) != "launches";
+        if (const char* e = getenv("R2D_WORLD_SOLVER")) world_solver = atoi(e) != 0;
         return R2D_OK;
     }
 
@@ -247,6 +250,9 @@ struct CudaBatch : BatchBase {
             return st;
         R2D_CUDA(cudaStreamSynchronize(stream));  // the image vectors are pageable and may change after we return
         last_pairs = 0;
+        max_world_bodies = 0;
+        for (size_t w = 0; w + 1 < image.world_base.size(); ++w)
+            max_world_bodies = std::max(max_world_bodies, image.world_base[w + 1] - image.world_base[w]);
         return R2D_OK;
     }
     int backend_download() override {
@@ -528,7 +534,12 @@ struct CudaBatch : BatchBase {
             if ((st = scan(d.own_pos, d.own_pos, &d.counters->n_own_scan, (uint32_t)((own_w + 1) * MAX_COLORS), nullptr, R2D_KCLASS_COLORING, 2))) return st;
             R2D_LAUNCH(R2D_KCLASS_COLORING, k_partition_prestep, grid_for(cap_pairs), TPB, d);
             // ---- substeps: one persistent cooperative kernel (colour ranges are read on the device) ----
-            if (persistent_solver) {
+            const bool use_world_solver = persistent_solver && world_solver && image.j_hdr.empty() &&
+                                          max_world_bodies <= WORLD_MAX_BODIES;
+            if (use_world_solver) {
+                const uint32_t blocks = (uint32_t)std::min<size_t>(worlds.size(), (size_t)n_sms * 16);
+                R2D_LAUNCH(R2D_KCLASS_SOLVE_CONTACTS, k_solve_worlds, blocks, WORLD_TPB, d, sub_dt, S, I);
+            } else if (persistent_solver) {
                 prof_begin(R2D_KCLASS_SOLVE_CONTACTS);
                 const uint32_t* jcs_dev = joint_color_start.p;
                 uint32_t n_jc = (uint32_t)image.joint_color_start.size() - 1, S_ = S, I_ = I;
