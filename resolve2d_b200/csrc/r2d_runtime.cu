@@ -535,7 +535,8 @@ struct CudaBatch : BatchBase {
             R2D_LAUNCH(R2D_KCLASS_COLORING, k_partition_prestep, grid_for(cap_pairs), TPB, d);
             // ---- substeps: one persistent cooperative kernel (colour ranges are read on the device) ----
             const bool use_world_solver = persistent_solver && world_solver && image.j_hdr.empty() &&
-                                          max_world_bodies <= WORLD_MAX_BODIES;
+                                          max_world_bodies <= WORLD_MAX_BODIES &&
+                                          worlds.size() >= (size_t)n_sms / 2;  // enough worlds to fill the GPU with one CTA each
             if (use_world_solver) {
                 const uint32_t blocks = (uint32_t)std::min<size_t>(worlds.size(), (size_t)n_sms * 16);
                 R2D_LAUNCH(R2D_KCLASS_SOLVE_CONTACTS, k_solve_worlds, blocks, WORLD_TPB, d, sub_dt, S, I);

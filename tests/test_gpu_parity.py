@@ -123,6 +123,45 @@ def test_gpu_batch_matches_standalone_worlds():
         at += n
 
 
+def test_gpu_large_batch_uses_world_solver_and_matches_oracle():
+    """>= 74 worlds switches the substep loop to the CTA-per-world shared-memory kernel; sampled worlds must still match
+    the oracle bit for bit (the other batch test, with 24 worlds, goes through the persistent dataflow kernel)."""
+    n_worlds, steps = 96, 60
+    batch = Batch(n_worlds, 2.0, 4)
+    sample = (0, 1, 37, 95)
+    oracles = {}
+    for w in range(n_worlds):
+        scenes.build_batch_world(batch.world(w), w)
+        if w in sample:
+            o = OracleSolver(2.0, 4, order=ORDER_COLORED)
+            scenes.build_batch_world(o, w)
+            oracles[w] = o
+    for step in range(steps):
+        batch.process(scenes.DT, 4, 4)
+        for o in oracles.values():
+            o.process(scenes.DT, 4, 4)
+    for w, o in oracles.items():
+        ws = batch.world(w)
+        assert np.array_equal(ws.read_pairs(), o.read_pairs()), w
+        assert_manifolds_equal(ws.read_manifolds(), o.read_manifolds(), f"world {w}")
+        assert_bodies_equal(ws.read_bodies(), o.read_bodies(), f"world {w}")
+
+
+def test_gpu_reorder_does_not_change_results():
+    """The spatial device order is invisible: forcing a re-sort every step gives the same bits as never re-sorting."""
+    a, b = Solver(2.0, 4), Solver(2.0, 4)
+    a.set_reorder_interval(1)
+    b.set_reorder_interval(0)
+    for s in (a, b):
+        scenes.build_box1k(s)
+    for _ in range(40):
+        a.process(scenes.DT, 4, 4)
+        b.process(scenes.DT, 4, 4)
+    assert_bodies_equal(a.read_bodies(), b.read_bodies(), "reorder")
+    assert np.array_equal(a.read_pairs(), b.read_pairs())
+    assert_manifolds_equal(a.read_manifolds(), b.read_manifolds(), "reorder")
+
+
 def test_gpu_fast_mode_grid_parameters():
     """MODE_FAST honours cell_width / table_mult (the reference stores but ignores them, lib.zig:254-255); the oracle
     in the same mode must agree bit for bit, and the candidate set must equal the parity-mode one on this scene."""
