@@ -36,6 +36,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Libraries (NCCL, the CUDA runtime) may print to fd 1; the contract is ONE JSON line on stdout.  Everything except the
+# final line is therefore sent to stderr: fd 1 is pointed at stderr for the whole run and the line goes to the saved fd.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 # ---- workloads -------------------------------------------------------------------------------------------------------
 def workload_table():
     from resolve2d_b200 import scenes
@@ -153,7 +163,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.time() - t0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- our arm ------------------------------------------------------------------------------------------------------------------
@@ -344,7 +354,7 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "batched": batched,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def main():
