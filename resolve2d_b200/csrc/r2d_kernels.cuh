@@ -19,6 +19,7 @@ namespace cg = cooperative_groups;
 constexpr int TPB = 256;            // threads per CTA of the streaming kernels
 constexpr int SOLVE_TPB = 128;      // colour sweeps: small CTAs spread thin colours over all SMs
 constexpr int BIG_LIST = 32;        // big bodies a CTA can defer per pass
+constexpr int WORLD_TPB = 128;      // CTA-per-world kernels (batches of small worlds)
 
 __device__ __forceinline__ uint32_t live_entries(const Dev& d) {
     const uint32_t e = d.counters->n_entries;
@@ -242,20 +243,28 @@ constexpr int BUCKET_WARPS = TPB / 32;
 constexpr int BUCKET_CAP = 128;    // entries staged in shared memory; larger buckets read their entries from global memory
 constexpr int HEAVY_BUCKET = 40;   // buckets with more entries get a whole CTA instead of a warp (n^2 pair tests)
 
+// one THREAD per bucket: clear its pair counter and list it if it can produce pairs (light: a warp, heavy: a CTA)
+__global__ void __launch_bounds__(TPB) k_list_buckets(Dev d) {
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < d.n_buckets; b += gridDim.x * blockDim.x) {
+        const uint32_t bs = d.bucket_start[b], be = bucket_end(d, b);
+        const uint32_t n = be > bs ? be - bs : 0u;
+        d.ent_off[b] = 0u;
+        if (n > (uint32_t)HEAVY_BUCKET)
+            d.work[d.n_buckets - 1u - atomicAdd(&d.counters->n_heavy, 1u)] = b;
+        else if (n >= 2u)
+            d.work[atomicAdd(&d.counters->n_work, 1u)] = b;
+    }
+}
+// one WARP per listed bucket (light ones from the front of the list, heavy ones from the back)
 __global__ void __launch_bounds__(TPB) k_sort_buckets(Dev d) {
     __shared__ uint32_t s_in[BUCKET_WARPS][BUCKET_CAP];
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t b = warp; b < d.n_buckets; b += n_warps) {
+    const uint32_t n_light = d.counters->n_work, n_items = n_light + d.counters->n_heavy;
+    for (uint32_t w = warp; w < n_items; w += n_warps) {
+        const uint32_t b = w < n_light ? d.work[w] : d.work[d.n_buckets - 1u - (w - n_light)];
         const uint32_t bs = d.bucket_start[b], be = bucket_end(d, b);
         const uint32_t n = be > bs ? be - bs : 0u;
-        if (lane == 0) {
-            d.ent_off[b] = 0u;
-            if (n > (uint32_t)HEAVY_BUCKET)
-                d.work[d.n_buckets - 1u - atomicAdd(&d.counters->n_heavy, 1u)] = b;
-            else if (n >= 2u)
-                d.work[atomicAdd(&d.counters->n_work, 1u)] = b;  // the pair kernels visit only listed buckets
-        }
         if (n < 2u) continue;  // warp-uniform
         if (n > BUCKET_CAP) {
             if (lane == 0) sort_bucket_thread(d, b);
@@ -512,6 +521,97 @@ __global__ void __launch_bounds__(TPB) k_color(Dev d) {
     }
 }
 
+// ---- K8 for batches of small worlds: one CTA colours one world with the per-body words in shared memory -------------------------
+// World w's candidate pairs are the contiguous slots [ent_off[first bucket of w], ent_off[first bucket of w + 1]) (the
+// pair list is bucket-major and a world owns a contiguous bucket range), and its conflict graph is closed, so the
+// Jones-Plassmann rounds need only __syncthreads().  Same rounds, same priorities, same colours as k_color.
+constexpr uint32_t COLOR_WORLD_MAX_BODIES = 512;
+
+__global__ void __launch_bounds__(WORLD_TPB) k_color_worlds(Dev d) {
+    __shared__ unsigned long long s_mp0[COLOR_WORLD_MAX_BODIES], s_mp1[COLOR_WORLD_MAX_BODIES];
+    __shared__ unsigned long long s_used[COLOR_WORLD_MAX_BODIES * COLOR_WORDS];
+    __shared__ uint32_t s_hist[MAX_COLORS];
+    if (overflowed(d)) return;
+    for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x) s_hist[c] = 0u;
+    uint32_t max_round = 0;
+    for (uint32_t w = blockIdx.x; w < d.n_worlds; w += gridDim.x) {
+        const uint32_t b0 = d.world_base[w], b1 = d.world_base[w + 1], nb = b1 - b0;
+        const uint32_t p0 = d.ent_off[d.table_mult * b0], p1 = d.ent_off[d.table_mult * b1];
+        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+            s_mp0[i] = 0ull;
+            s_mp1[i] = 0ull;
+#pragma unroll
+            for (uint32_t q = 0; q < COLOR_WORDS; ++q) s_used[i * COLOR_WORDS + q] = 0ull;
+        }
+        __syncthreads();
+        Dev ds = d;
+        ds.color_smem = 1u;
+        ds.maxprio0 = s_mp0 - b0;
+        ds.maxprio1 = s_mp1 - b0;
+        ds.used = s_used - (size_t)b0 * COLOR_WORDS;
+        // the first WORLD_REG_SLOTS slots of a thread stay in registers for all rounds (header + priority read once)
+        constexpr int WORLD_REG_SLOTS = 6;
+        uint4 rh[WORLD_REG_SLOTS];
+        unsigned long long rp[WORLD_REG_SLOTS];
+        bool pend[WORLD_REG_SLOTS];
+#pragma unroll
+        for (int k = 0; k < WORLD_REG_SLOTS; ++k) {
+            const uint32_t p = p0 + threadIdx.x + (uint32_t)k * blockDim.x;
+            pend[k] = p < p1 && d.m_color[p] == COLOR_PENDING;
+            if (pend[k]) {
+                rh[k] = d.m_hdr[p];
+                rp[k] = d.m_prio[p];
+                color_post(ds, rh[k].x, rh[k].y, (rh[k].w & 1u) != 0, (rh[k].w & 2u) != 0, rp[k], 1u);
+            }
+        }
+        for (uint32_t p = p0 + threadIdx.x + WORLD_REG_SLOTS * blockDim.x; p < p1; p += blockDim.x) {
+            if (d.m_color[p] != COLOR_PENDING) continue;
+            const uint4 h = d.m_hdr[p];
+            color_post(ds, h.x, h.y, (h.w & 1u) != 0, (h.w & 2u) != 0, d.m_prio[p], 1u);
+        }
+        __syncthreads();
+        uint32_t round = 1;
+        for (; round < MAX_COLOR_ROUNDS; ++round) {
+            int left = 0;
+#pragma unroll
+            for (int k = 0; k < WORLD_REG_SLOTS; ++k) {
+                if (!pend[k]) continue;
+                uint32_t c;
+                if (color_round_core(ds, p0 + threadIdx.x + (uint32_t)k * blockDim.x, rh[k], rp[k], round, &c) == 1) {
+                    atomicAdd(&s_hist[c], 1u);
+                    pend[k] = false;
+                } else {
+                    left = 1;
+                }
+            }
+            for (uint32_t p = p0 + threadIdx.x + WORLD_REG_SLOTS * blockDim.x; p < p1; p += blockDim.x) {
+                const int r = color_round_thread(ds, p, round);
+                if (r == 2)
+                    left = 1;
+                else if (r == 1)
+                    atomicAdd(&s_hist[d.m_color[p]], 1u);
+            }
+            if (!__syncthreads_or(left)) break;
+        }
+        if (round >= MAX_COLOR_ROUNDS && threadIdx.x == 0) atomicOr(&d.counters->err, ERR_ROUNDS);
+        max_round = round > max_round ? round : max_round;
+        __syncthreads();
+    }
+    for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x)
+        if (s_hist[c]) atomicAdd(&d.color_count[c], s_hist[c]);
+    if (threadIdx.x == 0) atomicMax(&d.counters->n_rounds, max_round);
+}
+// closes the per-world colouring: number of colours and the length of the owner-position scan
+__global__ void k_color_finish(Dev d) {
+    if (threadIdx.x == 0) {
+        uint32_t nc = 0;
+        for (uint32_t c = 0; c < MAX_COLORS; ++c)
+            if (d.color_count[c]) nc = c + 1u;
+        d.counters->n_colors = nc;
+        d.counters->n_own_scan = nc * (d.own_words + 1u);
+    }
+}
+
 // ---- K9a: owner bitmaps and their popcounts (the scan of which places every manifold, see manifold_owner) ----------------------
 __global__ void __launch_bounds__(TPB) k_owner_bits(Dev d) {
     if (overflowed(d)) return;
@@ -667,7 +767,6 @@ __global__ void __launch_bounds__(TPB) k_solve_persistent(Dev d, float sub_dt, u
 // manifolds of colour c are the contiguous range [slot(c, base_w), slot(c, base_{w+1})) of the colour-sorted records
 // (owner order is world-major), its momentum words live in shared memory for the whole substep loop, and colours are
 // separated by __syncthreads().  The per-body update sequence is the colour order, as everywhere else: bit-identical.
-constexpr int WORLD_TPB = 128;
 constexpr uint32_t WORLD_MAX_BODIES = 1024;   // 16 KB of momentum words
 
 __device__ __forceinline__ uint32_t owner_rank(const Dev& d, uint32_t c, uint32_t slot) {  // owners of colour c below `slot`

@@ -132,6 +132,7 @@ struct Dev {
     const float4* j_vec;          // r1.x, r1.y, r2.x, r2.y  |  target.x, target.y, -, -
     float sub_dt;                 // dt / sub_steps of the current process() call
     // ---- dataflow sweep tuning (wait policy only; never affects results) ------------------------------------------------
+    uint32_t color_smem;          // 1: maxprio / used point into shared memory (per-world colouring kernel)
     uint32_t wait_mode;           // 0: the warp updates when all its lanes are ready; 1: ready lanes update as they come
     uint32_t wait_spin_lag;       // lag <= this: poll again immediately
     uint32_t wait_sleep_unit;     // otherwise sleep lag * unit ns ...
@@ -230,10 +231,12 @@ R2D_HD void backoff_ns(uint32_t ns) {
 }
 
 // Loads of words that OTHER CTAs update inside the same cooperative kernel (between grid barriers): served from L2.
-R2D_HD unsigned long long ld_shared_u64(const unsigned long long* p) {
+R2D_HD unsigned long long ld_shared_u64(const unsigned long long* p, bool in_smem = false) {
 #if defined(__CUDA_ARCH__)
+    if (in_smem) return *((const volatile unsigned long long*)p);  // per-world colouring: the words live in shared memory
     return __ldcg(p);
 #else
+    (void)in_smem;
     return *p;
 #endif
 }
@@ -461,7 +464,8 @@ R2D_HD int color_round_core(const Dev& d, uint32_t p, const uint4& h, uint64_t p
     const bool dyn1 = (h.w & 1u) != 0, dyn2 = (h.w & 2u) != 0;
     const unsigned long long mine = ((unsigned long long)round << PRIO_ROUND_SHIFT) | prio;
     const unsigned long long* mp = (round & 1u) ? d.maxprio1 : d.maxprio0;
-    const bool win = (!dyn1 || ld_shared_u64(&mp[h.x]) == mine) && (!dyn2 || ld_shared_u64(&mp[h.y]) == mine);
+    const bool sm = d.color_smem != 0u;
+    const bool win = (!dyn1 || ld_shared_u64(&mp[h.x], sm) == mine) && (!dyn2 || ld_shared_u64(&mp[h.y], sm) == mine);
     if (!win) {
         color_post(d, h.x, h.y, dyn1, dyn2, prio, round + 1);
         return 2;
@@ -469,8 +473,8 @@ R2D_HD int color_round_core(const Dev& d, uint32_t p, const uint4& h, uint64_t p
     uint32_t color = MAX_COLORS;
     for (uint32_t w = 0; w < COLOR_WORDS; ++w) {
         unsigned long long u = 0;
-        if (dyn1) u |= ld_shared_u64(&d.used[(size_t)h.x * COLOR_WORDS + w]);
-        if (dyn2) u |= ld_shared_u64(&d.used[(size_t)h.y * COLOR_WORDS + w]);
+        if (dyn1) u |= ld_shared_u64(&d.used[(size_t)h.x * COLOR_WORDS + w], sm);
+        if (dyn2) u |= ld_shared_u64(&d.used[(size_t)h.y * COLOR_WORDS + w], sm);
         if (~u) {
             uint32_t b = 0;
             while ((u >> b) & 1ull) ++b;
@@ -486,11 +490,11 @@ R2D_HD int color_round_core(const Dev& d, uint32_t p, const uint4& h, uint64_t p
     // unique winner per body and round: a plain read-modify-write cannot race
     if (dyn1) {
         unsigned long long* u = &d.used[(size_t)h.x * COLOR_WORDS + (color >> 6)];
-        *u = ld_shared_u64(u) | bit;
+        *u = ld_shared_u64(u, sm) | bit;
     }
     if (dyn2) {
         unsigned long long* u = &d.used[(size_t)h.y * COLOR_WORDS + (color >> 6)];
-        *u = ld_shared_u64(u) | bit;
+        *u = ld_shared_u64(u, sm) | bit;
     }
     d.m_color[p] = color;
     *out_color = color;

@@ -441,7 +441,7 @@ struct CudaBatch : BatchBase {
         d.s_dep = s_dep.p;
         d.n_joints = (uint32_t)image.j_hdr.size();
         d.j_hdr = j_hdr.p; d.j_par = j_par.p; d.j_vec = j_vec.p;
-        d.wait_mode = wait_mode; d.wait_spin_lag = wait_spin_lag; d.wait_sleep_unit = wait_sleep_unit; d.wait_sleep_max = wait_sleep_max;
+        d.color_smem = 0; d.wait_mode = wait_mode; d.wait_spin_lag = wait_spin_lag; d.wait_sleep_unit = wait_sleep_unit; d.wait_sleep_max = wait_sleep_max;
     }
 
     int reserve_entries(size_t n) {
@@ -511,7 +511,8 @@ struct CudaBatch : BatchBase {
             R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_grid_cells<false>, grid_for(nb), TPB, d);
             if ((st = scan(d.bucket_cnt, d.bucket_start, nullptr, T, &d.counters->n_entries, R2D_KCLASS_BROADPHASE, 0))) return st;
             R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_grid_cells<true>, grid_for(nb), TPB, d);
-            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_sort_buckets, grid_warp_per(T), TPB, d);
+            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_list_buckets, grid_for(T), TPB, d);
+            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_sort_buckets, pair_blocks, TPB, d);
             // pairs per BUCKET (one warp each) -> scan over the T buckets -> write at the scanned offsets
             R2D_LAUNCH(R2D_KCLASS_BROADPHASE, (k_bucket_pairs<false, false>), pair_blocks, TPB, d);
             R2D_LAUNCH(R2D_KCLASS_BROADPHASE, (k_bucket_pairs<false, true>), heavy_blocks, TPB, d);
@@ -521,7 +522,12 @@ struct CudaBatch : BatchBase {
             // ---- narrowphase ----
             R2D_LAUNCH(R2D_KCLASS_NARROWPHASE, k_narrow, grid_for(cap_pairs), TPB, d);
             // ---- colouring + partition + pre-step ----
-            {
+            const bool many_small_worlds = world_solver && worlds.size() >= (size_t)n_sms / 2;
+            if (many_small_worlds && max_world_bodies <= COLOR_WORLD_MAX_BODIES) {
+                const uint32_t blocks = (uint32_t)std::min<size_t>(worlds.size(), (size_t)n_sms * 8);
+                R2D_LAUNCH(R2D_KCLASS_COLORING, k_color_worlds, blocks, WORLD_TPB, d);
+                R2D_LAUNCH(R2D_KCLASS_COLORING, k_color_finish, 1, 32, d);
+            } else {
                 prof_begin(R2D_KCLASS_COLORING);
                 void* args[] = {(void*)&d};
                 R2D_CUDA(cudaLaunchCooperativeKernel((void*)k_color, dim3(color_blocks), dim3(TPB), args, 0, stream));

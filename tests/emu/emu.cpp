@@ -137,6 +137,7 @@ struct EmuBatch : BatchBase {
         if (nb == 0) return R2D_OK;
         const float sub_dt = fdiv(dt, (float)S);   // lib.zig:190-191
         d.n_bodies = nb;
+        d.color_smem = 0;
         d.sub_dt = sub_dt;
         d.pos = pos.data(); d.mom = mom.data(); d.frc = frc.data(); d.prop = prop.data(); d.shape = shape.data();
         d.aabb = aabb.data();
