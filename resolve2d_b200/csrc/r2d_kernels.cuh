@@ -797,7 +797,7 @@ __global__ void __launch_bounds__(WORLD_TPB) k_solve_worlds(Dev d, float sub_dt,
             __syncthreads();
             for (uint32_t it = 0; it < I; ++it)
                 for (uint32_t c = 0; c < nc; ++c) {
-                    for (uint32_t m = s_begin[c] + threadIdx.x; m < s_end[c]; m += blockDim.x) solve_contact_thread<false>(ds, m, sub_dt);
+                    for (uint32_t m = s_begin[c] + threadIdx.x; m < s_end[c]; m += blockDim.x) solve_contact_thread<false, true>(ds, m, sub_dt);
                     __syncthreads();
                 }
             for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {

@@ -608,10 +608,12 @@ R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
 //   bit-identical — but a manifold only waits for its own two bodies.  All waiting threads are resident (cooperative
 //   launch) and walk their manifolds in (iteration, colour) order, so the globally lowest pending manifold can always
 //   run: no deadlock.  A stall would be a bug; it is reported through ERR_STALL instead of hanging the GPU.
-template <bool DATAFLOW>
+// DENSE = true: the caller guarantees that slot m is a real record (no padding), so every array is fetched at once
+// instead of after the header has arrived (one memory round trip per manifold instead of two).
+template <bool DATAFLOW, bool DENSE = false>
 R2D_HD void solve_contact_thread(const Dev& d, uint32_t m, float sub_dt, uint32_t it = 0) {
     const uint4 h = d.s_hdr[m];
-    const bool empty = (h.z & S_EMPTY) != 0;
+    const bool empty = !DENSE && (h.z & S_EMPTY) != 0;
     if (!DATAFLOW && empty) return;
     const int np = empty ? 0 : (int)(h.z & 0xFFu);
     const bool st1 = empty || (h.z & 0x100u) != 0, st2 = empty || (h.z & 0x200u) != 0;
