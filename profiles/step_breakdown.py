@@ -5,7 +5,10 @@ from resolve2d_b200 import Solver, scenes
 import bench
 name = sys.argv[1] if len(sys.argv) > 1 else "pile100k"
 build, preroll = bench.workload_table()[name]
-s = Solver(2.0, 4); cfg = build(s)
+import os
+s = Solver(float(os.environ.get("R2D_CELL", "2.0")), int(os.environ.get("R2D_MULT", "4")))
+if os.environ.get("R2D_FAST"): s.set_mode(1)
+cfg = build(s)
 S, I = cfg["sub_steps"], cfg["iters"]
 for _ in range(preroll + 50): s.process(scenes.DT, S, I)
 s.synchronize(); t = time.perf_counter()
