@@ -4,9 +4,11 @@
 // the parity checker for the CUDA path and the CPU baseline of bench.py.  Only tests/, __graft_entry__.smoke() and
 // bench.py's cpu_baseline / --impl reference legs may load it; nothing under resolve2d_b200/ does.
 //
-// Pinning: tests/test_oracle_golden.py checks this file against the golden per-step hashes and raw values taken from
-// the reference's own prebuilt binary (demos/web/public/resolve2d.wasm; SURVEY.md Appendix F, tests/golden/) for the
-// scenes 0_1_car_platformer, its driven variant and 0_3_many_boxes, bit for bit.
+// Pinning: this file is checked bit for bit against outputs of the reference itself — its prebuilt binary
+// demos/web/public/resolve2d.wasm executed by oracle/wasm_interp.cpp (tests/golden/make_wasm_golden.py ->
+// tests/golden/wasm_golden.json, tests/test_oracle_wasm_golden.py: every step of six runs incl. body removal and
+// other dt/sub_steps/iters) and against the survey's vectors (tests/golden/appendix_f.json,
+// tests/test_oracle_golden.py: also candidate-pair sets and manifold lists).
 //
 // Every block cites the Zig source it restates (paths relative to /root/reference/src/core).  Build with
 // -ffp-contract=off: all arithmetic is IEEE f32, one rounding per operation, no FMA (wasm semantics).
