@@ -47,6 +47,8 @@ def load():
         lib.orc_set_gs_order.argtypes = [C.c_void_p, C.c_int]
         lib.orc_timed_steps.restype = C.c_double
         lib.orc_timed_steps.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32]
+        lib.orc_load_state.restype = C.c_int
+        lib.orc_load_state.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 5
         lib.orc_raw_candidates.restype = C.c_uint64
         lib.orc_raw_candidates.argtypes = [C.c_void_p]
         lib.orc_sinf.restype = C.c_float
@@ -77,6 +79,14 @@ class OracleSolver(Solver):
 
     def set_stream(self, cuda_stream):  # no device
         raise NotImplementedError
+
+    def load_state(self, bodies: dict):
+        """Overwrite pos/angle/momentum/ang_momentum/aabb of all bodies (iteration order) from a read_bodies() dict."""
+        import numpy as np
+        a = {k: np.ascontiguousarray(bodies[k], dtype=np.float32) for k in ("pos", "angle", "momentum", "ang_momentum", "aabb")}
+        st = self._lib.orc_load_state(self._h, len(a["angle"]), a["pos"].ctypes.data, a["angle"].ctypes.data,
+                                      a["momentum"].ctypes.data, a["ang_momentum"].ctypes.data, a["aabb"].ctypes.data)
+        assert st == 0, st
 
     def timed_steps(self, dt: float, sub_steps: int, iters: int, steps: int) -> float:
         return self._lib.orc_timed_steps(self._h, dt, sub_steps, iters, steps)

@@ -1352,6 +1352,24 @@ int orc_write_forces(void* h, const float* fxy_t, size_t n) {
     }
     return 0;
 }
+// Test helper: overwrite the dynamic state of all bodies (iteration order) — lets a full-size scene that was settled on
+// the GPU be handed to the oracle for a bit-exact comparison of the following steps.
+int orc_load_state(void* h, size_t n, const float* pos_xy, const float* angle, const float* momentum_xy, const float* ang_momentum,
+                   const float* aabb_xywh) {
+    Solver* s = (Solver*)h;
+    if (n != s->bodies.size()) return -4;
+    for (size_t i = 0; i < n; ++i) {
+        RigidBody& b = s->bodies[i];
+        b.props.pos = Vector2(pos_xy[2 * i], pos_xy[2 * i + 1]);
+        b.props.angle = angle[i];
+        b.props.momentum = Vector2(momentum_xy[2 * i], momentum_xy[2 * i + 1]);
+        b.props.ang_momentum = ang_momentum[i];
+        b.aabb.pos = Vector2(aabb_xywh[4 * i], aabb_xywh[4 * i + 1]);
+        b.aabb.half_width = aabb_xywh[4 * i + 2];
+        b.aabb.half_height = aabb_xywh[4 * i + 3];
+    }
+    return 0;
+}
 int orc_read_pairs(void* h, uint32_t* lo, uint32_t* hi, size_t capacity, size_t* out_n) {
     Solver* s = (Solver*)h;
     if (out_n) *out_n = s->candidate_pairs.size();

@@ -253,3 +253,78 @@ def test_gpu_ordering_effect_is_reported_not_asserted():
         if first is None and d > 1e-3:
             first = step
     print(f"ordering effect on 0_3: max |dpos| first exceeds 1e-3 at step {first}; at step 120 it is {d:.3g} m")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json's FULL sizes.  The scene is settled on the GPU, its state handed to the oracle, and the following
+# process() calls are compared bit for bit (pairs, manifolds, colours, state); plus size-independent properties.
+# ---------------------------------------------------------------------------------------------------------------------
+def _full_size_handoff(build, settle_steps, check_steps, what):
+    gpu = Solver(2.0, 4)
+    cfg = build(gpu)
+    S, I = cfg["sub_steps"], cfg["iters"]
+    for _ in range(settle_steps):
+        gpu.process(scenes.DT, S, I)
+    orc = OracleSolver(2.0, 4, order=ORDER_COLORED)
+    build(orc)
+    state = gpu.read_bodies()
+    assert np.array_equal(state["id"], orc.read_bodies()["id"])
+    orc.load_state(state)
+    for k in range(check_steps):
+        gpu.process(scenes.DT, S, I)
+        orc.process(scenes.DT, S, I)
+        tag = f"{what} step {settle_steps + k + 1}"
+        assert np.array_equal(gpu.read_pairs(), orc.read_pairs()), f"{tag}: candidate pairs"
+        assert_manifolds_equal(gpu.read_manifolds(), orc.read_manifolds(), tag)
+        assert_bodies_equal(gpu.read_bodies(), orc.read_bodies(), tag)
+    return gpu
+
+
+def test_gpu_full_size_pile100k():
+    gpu = _full_size_handoff(scenes.build_pile100k, 180, 2, "pile100k")
+    st = gpu.stats()
+    assert st.n_bodies == 100003 and st.n_manifolds > 150000
+
+
+def test_gpu_full_size_pyramid20k():
+    gpu = _full_size_handoff(scenes.build_pyramid20k, 40, 2, "pyramid20k")
+    st = gpu.stats()
+    assert st.n_bodies == 19951 and st.n_joints > 1500
+
+
+def test_gpu_full_size_mixed1M():
+    gpu = _full_size_handoff(scenes.build_mixed1M, 90, 1, "mixed1M")
+    st = gpu.stats()
+    assert st.n_bodies == 1001003 and st.n_manifolds > 100000
+
+
+def test_gpu_full_size_batch4096_sampled_worlds_and_determinism():
+    """cfg5 at full size: sampled worlds vs the oracle, and two identical batches stay bit-identical (no dependence
+    on thread timing anywhere: atomics only ever feed order-independent results)."""
+    n_worlds, steps = 4096, 70
+    a, b = Batch(n_worlds, 2.0, 4), Batch(n_worlds, 2.0, 4)
+    sample = (0, 1234, 4095)
+    oracles = {}
+    for w in range(n_worlds):
+        d = scenes.descs_batch_world(w)
+        for x in (a, b):
+            fac = x.world(w).entity_factory()
+            fac.make_downwards_gravity(scenes.GRAVITY)
+            fac.make_bodies(d)
+        if w in sample:
+            o = OracleSolver(2.0, 4, order=ORDER_COLORED)
+            scenes.build_batch_world(o, w)
+            oracles[w] = o
+    for _ in range(steps):
+        a.process(scenes.DT, 4, 4)
+        b.process(scenes.DT, 4, 4)
+        for o in oracles.values():
+            o.process(scenes.DT, 4, 4)
+    ba, bb = a.read_bodies(), b.read_bodies()
+    assert_bodies_equal(ba, bb, "two identical batches")
+    assert a.stats().n_manifolds == b.stats().n_manifolds > 500000
+    for w, o in oracles.items():
+        ws = a.world(w)
+        assert np.array_equal(ws.read_pairs(), o.read_pairs()), w
+        assert_manifolds_equal(ws.read_manifolds(), o.read_manifolds(), f"world {w}")
+        assert_bodies_equal(ws.read_bodies(), o.read_bodies(), f"world {w}")
