@@ -240,8 +240,9 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_chained(const uint32_t* in, u
 // of the bucket; a pair is counted (WRITE = false) or written at the bucket's scanned offset (WRITE = true) in
 // (a, b) order, which makes the candidate list deterministic.
 constexpr int BUCKET_WARPS = TPB / 32;
-constexpr int BUCKET_CAP = 128;    // entries staged in shared memory; larger buckets read their entries from global memory
-constexpr int HEAVY_BUCKET = 40;   // buckets with more entries get a whole CTA instead of a warp (n^2 pair tests)
+constexpr int BUCKET_CAP = 256;    // entries staged in shared memory; larger buckets read their entries from global memory
+constexpr int HEAVY_BUCKET = 16;   // buckets with more entries get a whole CTA instead of a warp (n^2 pair tests)
+constexpr uint32_t HIT_WORDS_PER_ENTRY = 4;  // ballot words kept per grid entry: n (n - 1) / 64 <= 4 n for n <= 257
 
 // one THREAD per bucket: clear its pair counter and list it if it can produce pairs (light: a warp, heavy: a CTA)
 __global__ void __launch_bounds__(TPB) k_list_buckets(Dev d) {
@@ -297,21 +298,78 @@ __device__ __forceinline__ void tri_decode(uint32_t p, uint32_t n, uint32_t& a, 
     b = p - a * (2 * n - a - 1) / 2 + a + 1;
 }
 
+// advance (a, b) by `step` positions in that order (the caller guarantees the target index is < n(n-1)/2)
+__device__ __forceinline__ void tri_advance(uint32_t n, uint32_t step, uint32_t& a, uint32_t& b) {
+    b += step;
+    while (b >= n) {
+        b -= n;
+        a += 1u;
+        b += a + 1u;
+    }
+}
+
 // One bucket, worked on by a TEAM of lanes: a warp (light buckets, 8 buckets per CTA) or the whole CTA (heavy buckets).
-// Pair tests are taken in row-major order of the strict upper triangle; every warp of the team owns a contiguous range
-// of pair indices, so concatenating the warps' hits in warp order keeps the (a, b) order deterministic.
-template <bool WRITE, bool HEAVY>
-__global__ void __launch_bounds__(TPB) k_bucket_pairs(Dev d) {
+// Pair tests are taken in row-major order of the strict upper triangle, 32 consecutive tests per warp iteration; every
+// warp of the team owns a contiguous range of test indices.  The COUNT pass evaluates the tests, stores the bucket's
+// hit count in ent_off[b] and — for buckets staged in shared memory (n <= BUCKET_CAP) — the 32-test ballots in
+// hit_bits[4 * bucket_start + test / 32]  (n (n - 1) / 64 <= 4 n words for n <= 257).  After the scan of ent_off the
+// WRITE pass only has to expand those ballots: one word per team lane, a team-wide exclusive scan of the popcounts,
+// and a tri_decode per HIT instead of per test (hits are ~6 % of the tests in a dense pile).  Oversized buckets
+// (n > BUCKET_CAP) keep no ballots and repeat their tests in the write pass.
+struct BucketItem {
+    uint32_t b, bs, n;
+};
+template <bool HEAVY>
+__device__ __forceinline__ BucketItem bucket_item(const Dev& d, uint32_t w, bool dead) {
+    BucketItem it;
+    it.b = HEAVY ? d.work[d.n_buckets - 1u - w] : d.work[w];
+    it.bs = d.bucket_start[it.b];
+    const uint32_t be = bucket_end(d, it.b);
+    it.n = (be > it.bs && !dead) ? be - it.bs : 0u;
+    return it;
+}
+
+// tests [p_begin, p_end) of an oversized bucket straight from global memory; returns the warp's hit count and, when
+// `out_at` is valid, writes the hits at out_at, out_at + 1, ... in test order
+__device__ __forceinline__ uint32_t bucket_tests_global(const Dev& d, const BucketItem& it, uint32_t p_begin, uint32_t p_end,
+                                                        uint32_t lane, bool writing, uint32_t out_at) {
+    uint32_t total = 0;
+    for (uint32_t base = p_begin; base < p_end; base += 32) {
+        const uint32_t p = base + lane;
+        bool hit = false;
+        uint2 pr = make_uint2(0u, 0u);
+        if (p < p_end) {
+            uint32_t a, k;
+            tri_decode(p, it.n, a, k);
+            const uint32_t i = d.ent_body[it.bs + a], j = d.ent_body[it.bs + k];
+            const bool fa = a == 0 || d.ent_body[it.bs + a - 1] != i, fb = d.ent_body[it.bs + k - 1] != j;
+            if (fa && fb && i != j)
+                hit = pair_candidate(d, it.b, i, j, d.aabb[i], d.aabb[j], body_flags(d, i), body_flags(d, j), d.ncells[i],
+                                     d.ncells[j], d.bkt[i], d.bkt[j], &pr);
+        }
+        const uint32_t votes = __ballot_sync(0xffffffffu, hit);
+        if (writing && hit) {
+            const uint32_t at = out_at + total + (uint32_t)__popc(votes & ((1u << lane) - 1u));
+            if (at < d.cap_pairs) d.pairs[at] = pr;
+        }
+        total += (uint32_t)__popc(votes);
+    }
+    return total;
+}
+
+template <bool HEAVY>
+__device__ __forceinline__ void bucket_count_part(const Dev& d) {
     constexpr int TEAMS = HEAVY ? 1 : BUCKET_WARPS;       // teams per CTA
     constexpr uint32_t TEAM = HEAVY ? TPB : 32;           // lanes per team
     constexpr uint32_t TEAM_WARPS = TEAM / 32;
-    __shared__ uint32_t s_body[TEAMS][BUCKET_CAP];
-    __shared__ uint32_t s_meta[TEAMS][BUCKET_CAP];  // flags (bit 0 static) | first-occurrence << 1 | ncells << 2
-    __shared__ float4 s_aabb[TEAMS][BUCKET_CAP];
-    __shared__ uint4 s_bkt[TEAMS][BUCKET_CAP];
+    constexpr int CAP = HEAVY ? BUCKET_CAP : HEAVY_BUCKET;  // entries a team can stage (light buckets are small by definition)
+    __shared__ uint32_t s_body[TEAMS][CAP];
+    __shared__ uint32_t s_meta[TEAMS][CAP];  // flags (bit 0 static) | first-occurrence << 1 | ncells << 2
+    __shared__ float4 s_aabb[TEAMS][CAP];
+    __shared__ uint4 s_bkt[TEAMS][CAP];
     __shared__ uint32_t s_warp_total[BUCKET_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp_in_cta = threadIdx.x >> 5;
-    const uint32_t team_in_cta = HEAVY ? 0u : warp_in_cta;
+    const uint32_t tc = HEAVY ? 0u : warp_in_cta;                    // team inside the CTA
     const uint32_t tl = HEAVY ? threadIdx.x : lane;                  // lane inside the team
     const uint32_t tw = HEAVY ? warp_in_cta : 0u;                    // warp inside the team
     const uint32_t team = HEAVY ? blockIdx.x : (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -319,82 +377,160 @@ __global__ void __launch_bounds__(TPB) k_bucket_pairs(Dev d) {
     const bool dead = d.counters->n_entries > d.cap_entries;  // the fill dropped entries: this attempt is redone
     const uint32_t n_items = HEAVY ? d.counters->n_heavy : d.counters->n_work;
     for (uint32_t w = team; w < n_items; w += n_teams) {
-        const uint32_t b = HEAVY ? d.work[d.n_buckets - 1u - w] : d.work[w];
-        const uint32_t bs = d.bucket_start[b], be = bucket_end(d, b);
-        const uint32_t n = (be > bs && !dead) ? be - bs : 0u;
+        const BucketItem it = bucket_item<HEAVY>(d, w, dead);
+        const uint32_t n = it.n;
         const bool staged = n <= BUCKET_CAP;
         if (staged) {
             for (uint32_t k = tl; k < n; k += TEAM) {
-                const uint32_t body = d.ent_body[bs + k];
-                const bool first = k == 0 || d.ent_body[bs + k - 1] != body;
-                s_body[team_in_cta][k] = body;
-                s_aabb[team_in_cta][k] = d.aabb[body];
-                s_bkt[team_in_cta][k] = d.bkt[body];
+                const uint32_t body = d.ent_body[it.bs + k];
+                const bool first = k == 0 || d.ent_body[it.bs + k - 1] != body;
+                s_body[tc][k] = body;
+                s_aabb[tc][k] = d.aabb[body];
+                s_bkt[tc][k] = d.bkt[body];
                 uint32_t nc = d.ncells[body];
                 if (nc > 0x3FFFFFFFu) nc = 0x3FFFFFFFu;
-                s_meta[team_in_cta][k] = (body_flags(d, body) & FLAG_STATIC) | (first ? 2u : 0u) | (nc << 2);
+                s_meta[tc][k] = (body_flags(d, body) & FLAG_STATIC) | (first ? 2u : 0u) | (nc << 2);
             }
         }
         if (HEAVY) __syncthreads(); else __syncwarp();
         const uint32_t n_pairs = n >= 2u ? n * (n - 1u) / 2u : 0u;
-        // contiguous range of pair indices of this warp (multiple of 32 so that ballots stay aligned)
+        // contiguous range of test indices of this warp (a multiple of 32, so that ballot words stay aligned)
         const uint32_t per_warp = ((n_pairs + TEAM_WARPS * 32u - 1u) / (TEAM_WARPS * 32u)) * 32u;
         const uint32_t p_begin = tw * per_warp, p_end = (p_begin + per_warp < n_pairs) ? p_begin + per_warp : n_pairs;
-        uint32_t out_at = (WRITE && !HEAVY) ? d.ent_off[b] : 0u;  // ent_off is indexed by BUCKET (scanned for the write pass)
-        // HEAVY + WRITE: count first (pass 0) to learn the offsets of the warps, then write (pass 1)
-        for (int pass = (HEAVY && WRITE) ? 0 : 1; pass < 2; ++pass) {
-            const bool writing = WRITE && pass == 1;
-            uint32_t total = 0;
+        uint32_t total = 0;
+        if (!staged) {
+            total = bucket_tests_global(d, it, p_begin, p_end, lane, false, 0u);
+        } else if (p_begin < p_end) {
+            uint32_t* bits = d.hit_bits + HIT_WORDS_PER_ENTRY * (size_t)it.bs;
+            uint32_t a = 0, k = 0;
+            if (p_begin + lane < p_end) tri_decode(p_begin + lane, n, a, k);
             for (uint32_t base = p_begin; base < p_end; base += 32) {
                 const uint32_t p = base + lane;
                 bool hit = false;
-                uint2 pr = make_uint2(0u, 0u);
                 if (p < p_end) {
-                    uint32_t a, k;
-                    tri_decode(p, n, a, k);
-                    if (staged) {
-                        const uint32_t ma = s_meta[team_in_cta][a], mb = s_meta[team_in_cta][k];
-                        const uint32_t i = s_body[team_in_cta][a], j = s_body[team_in_cta][k];
-                        if ((ma & mb & 2u) && i != j)
-                            hit = pair_candidate(d, b, i, j, s_aabb[team_in_cta][a], s_aabb[team_in_cta][k], ma & 1u, mb & 1u,
-                                                 ma >> 2, mb >> 2, s_bkt[team_in_cta][a], s_bkt[team_in_cta][k], &pr);
-                    } else {  // oversized bucket: entries straight from global memory
-                        const uint32_t i = d.ent_body[bs + a], j = d.ent_body[bs + k];
-                        const bool fa = a == 0 || d.ent_body[bs + a - 1] != i, fb = d.ent_body[bs + k - 1] != j;
-                        if (fa && fb && i != j)
-                            hit = pair_candidate(d, b, i, j, d.aabb[i], d.aabb[j], body_flags(d, i), body_flags(d, j), d.ncells[i],
-                                                 d.ncells[j], d.bkt[i], d.bkt[j], &pr);
-                    }
+                    const uint32_t ma = s_meta[tc][a], mb = s_meta[tc][k];
+                    const uint32_t i = s_body[tc][a], j = s_body[tc][k];
+                    uint2 pr;
+                    if ((ma & mb & 2u) && i != j)
+                        hit = pair_candidate(d, it.b, i, j, s_aabb[tc][a], s_aabb[tc][k], ma & 1u, mb & 1u, ma >> 2, mb >> 2,
+                                             s_bkt[tc][a], s_bkt[tc][k], &pr);
+                    if (p + 32u < p_end) tri_advance(n, 32u, a, k);
                 }
                 const uint32_t votes = __ballot_sync(0xffffffffu, hit);
-                if (writing && hit) {
-                    const uint32_t at = out_at + total + (uint32_t)__popc(votes & ((1u << lane) - 1u));
-                    if (at < d.cap_pairs) d.pairs[at] = pr;
-                }
+                if (lane == 0) bits[base >> 5] = votes;
                 total += (uint32_t)__popc(votes);
             }
-            if (!HEAVY) {
-                if (!WRITE && lane == 0) d.ent_off[b] = total;
-            } else if (pass == 0 || !WRITE) {
-                if (lane == 0) s_warp_total[tw] = total;
-                __syncthreads();
-                if (!WRITE) {
-                    if (threadIdx.x == 0) {
-                        uint32_t sum = 0;
-                        for (uint32_t q = 0; q < TEAM_WARPS; ++q) sum += s_warp_total[q];
-                        d.ent_off[b] = sum;
-                    }
-                } else {
-                    out_at = d.ent_off[b];
-                    for (uint32_t q = 0; q < tw; ++q) out_at += s_warp_total[q];
-                }
-                __syncthreads();
+        }
+        if (!HEAVY) {
+            if (lane == 0) d.ent_off[it.b] = total;
+        } else {
+            if (lane == 0) s_warp_total[tw] = total;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t sum = 0;
+                for (uint32_t q = 0; q < TEAM_WARPS; ++q) sum += s_warp_total[q];
+                d.ent_off[it.b] = sum;
             }
-            if (!HEAVY && WRITE) break;
-            if (!HEAVY && !WRITE) break;
         }
         if (HEAVY) __syncthreads(); else __syncwarp();
     }
+}
+
+// heavy buckets first (a CTA each: the long poles), then the light ones (a warp each) fill the tail of the same launch
+__global__ void __launch_bounds__(TPB) k_bucket_count(Dev d) {
+    bucket_count_part<true>(d);
+    __syncthreads();
+    bucket_count_part<false>(d);
+}
+
+template <bool HEAVY>
+__device__ __forceinline__ void bucket_write_part(const Dev& d) {
+    constexpr int TEAMS = HEAVY ? 1 : BUCKET_WARPS;
+    constexpr uint32_t TEAM = HEAVY ? TPB : 32;
+    constexpr uint32_t TEAM_WARPS = TEAM / 32;
+    constexpr int CAP = HEAVY ? BUCKET_CAP : HEAVY_BUCKET;
+    __shared__ uint32_t s_body[TEAMS][CAP];
+    __shared__ uint32_t s_nc[TEAMS][CAP];
+    __shared__ uint32_t s_warp_total[BUCKET_WARPS];
+    const uint32_t lane = threadIdx.x & 31u, warp_in_cta = threadIdx.x >> 5;
+    const uint32_t tc = HEAVY ? 0u : warp_in_cta;
+    const uint32_t tl = HEAVY ? threadIdx.x : lane;
+    const uint32_t tw = HEAVY ? warp_in_cta : 0u;
+    const uint32_t team = HEAVY ? blockIdx.x : (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_teams = HEAVY ? gridDim.x : (gridDim.x * blockDim.x) >> 5;
+    const bool dead = d.counters->n_entries > d.cap_entries;
+    const uint32_t n_items = HEAVY ? d.counters->n_heavy : d.counters->n_work;
+    for (uint32_t w = team; w < n_items; w += n_teams) {
+        const BucketItem it = bucket_item<HEAVY>(d, w, dead);
+        const uint32_t n = it.n;
+        const uint32_t n_pairs = n >= 2u ? n * (n - 1u) / 2u : 0u;
+        const uint32_t out_base = d.ent_off[it.b];  // scanned: first pair slot of this bucket
+        if (n <= BUCKET_CAP) {
+            for (uint32_t k = tl; k < n; k += TEAM) {
+                const uint32_t body = d.ent_body[it.bs + k];
+                s_body[tc][k] = body;
+                s_nc[tc][k] = d.ncells[body];
+            }
+            // one ballot word per team lane and chunk (light buckets: <= 4 words; heavy ones: <= 1020, 256 per chunk)
+            const uint32_t n_words = (n_pairs + 31u) >> 5;
+            uint32_t running = out_base;
+            for (uint32_t w0 = 0; w0 < n_words; w0 += TEAM) {
+                const uint32_t wi = w0 + tl;
+                const uint32_t word = wi < n_words ? d.hit_bits[HIT_WORDS_PER_ENTRY * (size_t)it.bs + wi] : 0u;
+                const uint32_t cnt = (uint32_t)__popc(word);
+                uint32_t at = cnt;  // inclusive scan over the team, then made exclusive
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, at, o);
+                    if (lane >= (uint32_t)o) at += t;
+                }
+                uint32_t chunk_total = 0;
+                if (HEAVY) {
+                    if (lane == 31) s_warp_total[tw] = at;
+                    __syncthreads();  // also orders the staging of s_body / s_nc before the first expansion
+                    for (uint32_t q = 0; q < TEAM_WARPS; ++q) {
+                        if (q < tw) at += s_warp_total[q];
+                        chunk_total += s_warp_total[q];
+                    }
+                } else {
+                    __syncwarp();
+                }
+                at = running + at - cnt;
+                uint32_t rest = word;
+                while (rest) {
+                    const uint32_t bit = (uint32_t)__ffs((int)rest) - 1u;
+                    rest &= rest - 1u;
+                    uint32_t a, k;
+                    tri_decode(wi * 32u + bit, n, a, k);
+                    const uint32_t i = s_body[tc][a], j = s_body[tc][k];
+                    const uint32_t nci = s_nc[tc][a], ncj = s_nc[tc][k];
+                    const bool i_owns = nci < ncj || (nci == ncj && i < j);  // same orientation as pair_candidate
+                    if (at < d.cap_pairs) d.pairs[at] = i_owns ? make_uint2(i, j) : make_uint2(j, i);
+                    ++at;
+                }
+                running += chunk_total;
+                if (HEAVY) __syncthreads();  // s_warp_total is reused by the next chunk
+            }
+        } else {
+            const uint32_t per_warp = ((n_pairs + TEAM_WARPS * 32u - 1u) / (TEAM_WARPS * 32u)) * 32u;
+            const uint32_t p_begin = tw * per_warp, p_end = (p_begin + per_warp < n_pairs) ? p_begin + per_warp : n_pairs;
+            uint32_t out_at = out_base;
+            if (HEAVY) {  // count first to learn where the warps of the team write
+                const uint32_t total = bucket_tests_global(d, it, p_begin, p_end, lane, false, 0u);
+                if (lane == 0) s_warp_total[tw] = total;
+                __syncthreads();
+                for (uint32_t q = 0; q < tw; ++q) out_at += s_warp_total[q];
+            }
+            bucket_tests_global(d, it, p_begin, p_end, lane, true, out_at);
+        }
+        if (HEAVY) __syncthreads(); else __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_bucket_write(Dev d) {
+    bucket_write_part<true>(d);
+    __syncthreads();
+    bucket_write_part<false>(d);
 }
 
 // ---- K6: narrowphase, one thread per candidate pair --------------------------------------------------------------------------
@@ -451,8 +587,9 @@ __global__ void __launch_bounds__(TPB) k_narrow(Dev d) {
 // posted for r in maxprio[r & 1] and posts those of the losers for r + 1 into the other array.  The result equals a
 // sequential greedy colouring in descending priority, so it is a pure function of the contact graph and the body ids.
 constexpr int COLOR_REG_SLOTS = 2;  // pending manifolds a thread keeps in registers across the rounds
+constexpr int FLOW_SLOTS = 8;       // manifolds per thread the dataflow colouring can hold (registers)
 
-__global__ void __launch_bounds__(TPB) k_color(Dev d) {
+__global__ void __launch_bounds__(TPB, 4) k_color(Dev d) {
     cg::grid_group grid = cg::this_grid();
     const bool dead = overflowed(d);
     const uint32_t n = dead ? 0u : live_pairs(d);
@@ -461,6 +598,95 @@ __global__ void __launch_bounds__(TPB) k_color(Dev d) {
     // for the whole kernel and the "anything left?" flag costs at most one global atomic per CTA and round.
     __shared__ uint32_t s_hist[MAX_COLORS];
     for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x) s_hist[c] = 0u;
+    __syncthreads();
+    // ---- dataflow colouring: no rounds, no barriers (see flow_try) ----
+    // Every thread holds its manifolds p = tid + k * nth in registers and probes them round-robin; all threads are
+    // resident (cooperative launch) and every pending manifold keeps being probed, so the pending manifold with the
+    // globally highest priority — which is always ready — always gets its turn: no deadlock.
+    // (flow_abort is only written by the narrowphase, so the decision is the same for every thread of the grid)
+    const bool flow = d.flow != 0u && d.counters->flow_abort == 0u && n <= (uint32_t)FLOW_SLOTS * nth;
+    if (flow) {
+        uint32_t fa[FLOW_SLOTS], fb[FLOW_SLOTS], fm[FLOW_SLOTS];  // ref slot, inc slot, dyn mask | ranks << 2 | pending << 31
+        uint32_t n_pending = 0;
+#pragma unroll
+        for (int k = 0; k < FLOW_SLOTS; ++k) {
+            const uint32_t p = tid + (uint32_t)k * nth;
+            fm[k] = 0u;
+            fa[k] = fb[k] = 0u;
+            if (p < n && d.m_color[p] == COLOR_PENDING) {
+                const uint4 h = d.m_hdr[p];
+                fa[k] = h.x;
+                fb[k] = h.y;
+                fm[k] = (h.w & 3u) | (flow_ranks(d, h, d.m_prio[p]) << 2) | 0x80000000u;
+                n_pending += 1u;
+            }
+        }
+        // The warp stays converged: every pass ends in a warp vote, so a lane that waits for a manifold held by a
+        // sibling lane (neighbouring pairs share bodies) can never spin ahead of the lane it waits for.
+        uint32_t idle = 0;
+        for (;;) {
+            bool progress = false;
+            uint32_t min_lag = 0xFFFFFFFFu;
+#pragma unroll
+            for (int k = 0; k < FLOW_SLOTS; ++k) {
+                if (!(fm[k] & 0x80000000u)) continue;
+                uint32_t c = 0, lag = 0;
+                const int r = flow_try(d, tid + (uint32_t)k * nth, fa[k], fb[k], fm[k] & 3u, (fm[k] >> 2) & 0xFFFFu, &c, &lag);
+                if (r == 1) {
+                    atomicAdd(&s_hist[c], 1u);
+                    fm[k] = 0u;
+                    n_pending -= 1u;
+                    progress = true;
+                } else if (r == 0) {
+                    min_lag = lag < min_lag ? lag : min_lag;
+                } else {
+                    n_pending = 0u;  // colour overflow: flow_fail is set, everybody leaves
+                }
+            }
+            if (!__any_sync(0xffffffffu, n_pending != 0u)) break;
+            if (__any_sync(0xffffffffu, progress)) {
+                idle = 0;
+                continue;
+            }
+            const uint32_t warp_lag = __reduce_min_sync(0xffffffffu, min_lag);
+            if (warp_lag > 1u) backoff_ns((warp_lag < 8u ? warp_lag - 1u : 7u) * d.flow_sleep_unit);
+            if ((++idle & 63u) == 0u) {
+                if (*((volatile uint32_t*)&d.counters->flow_fail)) break;
+                if (idle > (1u << 20)) {  // a stall would be a bug; report it instead of hanging the GPU
+                    atomicOr(&d.counters->err, ERR_FLOW_STALL);
+                    atomicOr(&d.counters->flow_fail, 1u);
+                    break;
+                }
+            }
+        }
+    }
+    if (flow) {
+        __syncthreads();
+        for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x)
+            if (s_hist[c]) atomicAdd(&d.color_count[c], s_hist[c]);
+        grid.sync();
+        if (__ldcg(&d.counters->flow_fail) == 0u) {
+            if (tid == 0) {
+                uint32_t nc = 0;
+                for (uint32_t c = 0; c < FLOW_COLORS; ++c)
+                    if (__ldcg(&d.color_count[c])) nc = c + 1u;
+                d.counters->n_colors = nc;
+                d.counters->n_own_scan = nc * (d.own_words + 1u);
+                d.counters->n_rounds = 0u;
+                d.counters->flow_used = 1u;
+            }
+            return;
+        }
+        // abandoned: forget the partial result and colour by rounds (maxprio / used are still zero)
+        for (uint32_t p = tid; p < n; p += nth)
+            if (d.m_color[p] < MAX_COLORS) d.m_color[p] = COLOR_PENDING;
+        if (blockIdx.x == 0)
+            for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x) d.color_count[c] = 0u;
+        for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x) s_hist[c] = 0u;
+        __syncthreads();
+        grid.sync();
+    }
+    // ---- Jones-Plassmann rounds ----
     // The first COLOR_REG_SLOTS slots of a thread (p = tid + k * nth) live in registers for all rounds: header and
     // priority are read once, a round costs only the gathers of the two body words and the atomics.
     uint4 rh[COLOR_REG_SLOTS];

@@ -33,6 +33,8 @@ constexpr uint32_t MAX_COLORS = 256;
 constexpr uint32_t S_EMPTY = 0x400u;              // s_hdr.z: padding slot (colour segments are padded to whole warps)
 constexpr uint32_t COLOR_ALIGN = 32;
 constexpr uint32_t COLOR_WORDS = MAX_COLORS / 64;
+constexpr uint32_t ADJ_CAP = 32;                   // manifolds a non-static body can list for the dataflow colouring
+constexpr uint32_t FLOW_COLORS = 96;               // colours the 16-byte colouring word of a body can hold
 constexpr uint32_t MAX_COLOR_ROUNDS = 4000;        // < 2^12 (round tag field of the priority word)
 constexpr uint32_t BIG_BODY_CELLS = 64;            // bodies covering more cells are walked by a whole CTA
 constexpr int64_t MAX_BODY_CELLS = 1 << 22;        // beyond this the pose is garbage (NaN/inf): R2D_ERR_GRID_RANGE
@@ -40,6 +42,7 @@ constexpr int64_t MAX_BODY_CELLS = 1 << 22;        // beyond this the pose is ga
 constexpr uint32_t ERR_COLOR_OVERFLOW = 1u;
 constexpr uint32_t ERR_GRID_RANGE = 2u;
 constexpr uint32_t ERR_ROUNDS = 4u;
+constexpr uint32_t ERR_FLOW_STALL = 16u;       // dataflow colouring stalled (same: a bug, reported)
 constexpr uint32_t ERR_STALL = 8u;             // dataflow sweep stalled (a bug, never data): reported instead of hanging
 
 // Device-side counters of one process() call (one 128-byte block, copied to pinned host memory once per step).
@@ -55,6 +58,9 @@ struct Counters {
     uint32_t n_work;         // buckets holding 2..HEAVY_BUCKET entries (work list of the warp-per-bucket pair kernels)
     uint32_t n_heavy;        // buckets holding more (CTA-per-bucket pair kernels)
     uint32_t n_stamps;
+    uint32_t flow_abort;     // set by the narrowphase: a body has more than ADJ_CAP manifolds, colour by rounds
+    uint32_t flow_fail;      // set inside the dataflow colouring: more than FLOW_COLORS colours needed (or a stall)
+    uint32_t flow_used;      // the colours of this step come from the dataflow colouring (masks in cstate, not in used)
     unsigned long long stamp[10];   // %globaltimer at phase boundaries of the persistent solver (block 0; diagnostics)
 };
 
@@ -88,6 +94,7 @@ struct Dev {
     uint32_t* ent_off;            // T + 1: pairs emitted per BUCKET, then its exclusive scan ([T] = P)
     uint32_t* work;               // T: ids of the light buckets (2..HEAVY_BUCKET entries) from the front, of the heavy ones
                                   // from the back (work[T - 1 - k]); order irrelevant
+    uint32_t* hit_bits;           // 4 * cap_entries: 32-test ballots of the count pass, bucket b's words at 4 * bucket_start[b]
     const uint64_t* excl;         // sorted (lo_slot << 32 | hi_slot)
     uint32_t n_excl;
     // ---- candidate pairs / raw manifolds (P slots) ------------------------------------------------------------------
@@ -108,6 +115,12 @@ struct Dev {
     uint32_t* color_start;        // MAX_COLORS + 1
     uint32_t* color_cursor;       // MAX_COLORS
     uint32_t* round_left;         // MAX_COLOR_ROUNDS
+    // dataflow colouring (single worlds): the manifolds of a body, and one 16-byte word per body that is both the wait
+    // target and the data — {96-bit colour mask, manifolds coloured so far}
+    uint32_t flow;                // 1: k_narrow lists every manifold on its non-static bodies (adj_*), k_color may use them
+    uint32_t* adj_cnt;            // NB: manifolds on the body (may exceed ADJ_CAP: then the colouring falls back to rounds)
+    unsigned long long* adj_prio; // NB * ADJ_CAP: their priorities, in arrival order
+    uint4* cstate;                // NB
     uint32_t own_words;           // W = ceil(NB / 32)
     uint32_t* own_bits;           // MAX_COLORS x W: bit (c, b) set iff body b owns a manifold of colour c (at most one)
     uint32_t* own_pos;            // MAX_COLORS x (W + 1) + 1: popcounts per word (+ the warp padding of the colour), then
@@ -131,6 +144,7 @@ struct Dev {
     const float4* j_par;          // power_max, power_min, beta, target (distance | omega)
     const float4* j_vec;          // r1.x, r1.y, r2.x, r2.y  |  target.x, target.y, -, -
     float sub_dt;                 // dt / sub_steps of the current process() call
+    uint32_t flow_sleep_unit;     // dataflow colouring wait policy: ns of back-off per manifold still ahead
     // ---- dataflow sweep tuning (wait policy only; never affects results) ------------------------------------------------
     uint32_t color_smem;          // 1: maxprio / used point into shared memory (per-world colouring kernel)
     uint32_t wait_mode;           // 0: the warp updates when all its lanes are ready; 1: ready lanes update as they come
@@ -425,6 +439,14 @@ R2D_HD BodyView load_view(const Dev& d, uint32_t i) {
     const float4 s = d.shape[i];
     return make_view(p.x, p.y, p.z, p.w, s.x, s.y, f2u(s.z), f2u(s.w));
 }
+// the manifold lists of the dataflow colouring (arrival order is irrelevant: only "how many have a higher priority" is used)
+R2D_HD void adj_append(const Dev& d, uint32_t body, unsigned long long prio) {
+    const uint32_t k = atomic_add_u32(&d.adj_cnt[body], 1u);
+    if (k < ADJ_CAP)
+        d.adj_prio[(size_t)body * ADJ_CAP + k] = prio;
+    else
+        atomic_or_u32(&d.counters->flow_abort, 1u);
+}
 // K6: one candidate pair -> raw manifold slot.  Returns the number of contact points, or -1 if SAT finds a gap.
 R2D_HD int narrow_pair_thread(const Dev& d, uint32_t p) {
     const uint2 pr = d.pairs[p];
@@ -440,7 +462,12 @@ R2D_HD int narrow_pair_thread(const Dev& d, uint32_t p) {
     const uint32_t f_ref = (m.ref_is_lo == a_lo) ? va.flags : vb.flags, f_inc = (m.ref_is_lo == a_lo) ? vb.flags : va.flags;
     const uint32_t dyn = ((f_ref & FLAG_STATIC) ? 0u : 1u) | ((f_inc & FLAG_STATIC) ? 0u : 2u);
     d.m_hdr[p] = make_uint4(ref, inc, (uint32_t)m.n_points | ((uint32_t)m.normal_id << 8), dyn);
-    d.m_prio[p] = contact_priority(a_lo ? va.id : vb.id, a_lo ? vb.id : va.id);  // (lower id, higher id)
+    const unsigned long long prio = contact_priority(a_lo ? va.id : vb.id, a_lo ? vb.id : va.id);  // (lower id, higher id)
+    d.m_prio[p] = prio;
+    if (d.flow) {
+        if (dyn & 1u) adj_append(d, ref, prio);
+        if (dyn & 2u) adj_append(d, inc, prio);
+    }
     const ContactPoint z = {mk2(0, 0), 0.0f, mk2(0, 0), mk2(0, 0)};
     const ContactPoint p0 = m.n_points > 0 ? m.pt[0] : z, p1 = m.n_points > 1 ? m.pt[1] : z;
     d.m_g0[p] = make_float4(m.normal.x, m.normal.y, p0.pos.x, p0.pos.y);
@@ -507,6 +534,94 @@ R2D_HD int color_round_thread(const Dev& d, uint32_t p, uint32_t round) {
     return color_round_core(d, p, d.m_hdr[p], d.m_prio[p], round, &c);
 }
 
+// ---- dataflow form of the same colouring ----------------------------------------------------------------------------
+// Greedy colouring in descending priority means: a manifold takes the lowest colour free on both bodies once every
+// manifold with a HIGHER priority on either body has taken its own.  With r_b = the number of such manifolds on body
+// b (counted in the body's list), that is "wait until body b has coloured exactly r_b manifolds" — no rounds, no
+// barriers, a manifold only waits for its own two bodies, exactly like the solver sweep.  The per-body word
+// {mask[0..95], coloured} is read and written as ONE 16-byte relaxed access (see ld_body_word), and only one manifold
+// per body is ever allowed to write, so there is no atomic and no fence.  Result: identical to the rounds above.
+R2D_HD uint4 ld_cstate(const uint4* p) {
+    const float4 v = ld_body_word(reinterpret_cast<const float4*>(p));
+    return make_uint4(f2u(v.x), f2u(v.y), f2u(v.z), f2u(v.w));
+}
+R2D_HD void st_cstate(uint4* p, uint4 v) {
+    st_body_word(reinterpret_cast<float4*>(p), make_float4(u2f(v.x), u2f(v.y), u2f(v.z), u2f(v.w)));
+}
+// ranks of a manifold on its two bodies: r1 | r2 << 8  (0 for a static body)
+R2D_HD uint32_t flow_ranks(const Dev& d, const uint4& h, unsigned long long prio) {
+    uint32_t r[2] = {0u, 0u};
+    const uint32_t bs[2] = {h.x, h.y};
+    for (int q = 0; q < 2; ++q) {
+        if (!(h.w & (1u << q))) continue;
+        uint32_t n = d.adj_cnt[bs[q]];
+        if (n > ADJ_CAP) n = ADJ_CAP;  // overflow: the colouring is abandoned anyway
+        const unsigned long long* list = d.adj_prio + (size_t)bs[q] * ADJ_CAP;
+        for (uint32_t k = 0; k < n; ++k) r[q] += list[k] > prio ? 1u : 0u;
+    }
+    return r[0] | (r[1] << 8);
+}
+// One probe.  Returns 1 (coloured, colour in *out), 0 (not ready; *lag = how many manifolds the slower body still
+// has to colour first) or -1 (more than FLOW_COLORS colours needed: flow_fail is raised).
+R2D_HD int flow_try(const Dev& d, uint32_t p, uint32_t ref, uint32_t inc, uint32_t dyn, uint32_t ranks, uint32_t* out, uint32_t* lag) {
+    const bool dyn1 = (dyn & 1u) != 0, dyn2 = (dyn & 2u) != 0;
+    uint4 w1 = make_uint4(0u, 0u, 0u, 0u), w2 = w1;
+    if (dyn1) w1 = ld_cstate(&d.cstate[ref]);
+    if (dyn2) w2 = ld_cstate(&d.cstate[inc]);
+    const uint32_t lag1 = dyn1 ? (ranks & 0xFFu) - w1.w : 0u, lag2 = dyn2 ? (ranks >> 8) - w2.w : 0u;
+    if (lag1 | lag2) {
+        *lag = lag1 > lag2 ? lag1 : lag2;
+        return 0;
+    }
+    const uint32_t u[3] = {w1.x | w2.x, w1.y | w2.y, w1.z | w2.z};
+    uint32_t color = FLOW_COLORS;
+    for (uint32_t w = 0; w < 3; ++w)
+        if (~u[w]) {
+            uint32_t b = 0;
+            while ((u[w] >> b) & 1u) ++b;
+            color = w * 32u + b;
+            break;
+        }
+    if (color >= FLOW_COLORS) {
+        atomic_or_u32(&d.counters->flow_fail, 1u);
+        return -1;
+    }
+    const uint32_t bit = 1u << (color & 31u), word = color >> 5;
+    if (dyn1) st_cstate(&d.cstate[ref], make_uint4(w1.x | (word == 0 ? bit : 0u), w1.y | (word == 1 ? bit : 0u),
+                                                   w1.z | (word == 2 ? bit : 0u), w1.w + 1u));
+    if (dyn2) st_cstate(&d.cstate[inc], make_uint4(w2.x | (word == 0 ? bit : 0u), w2.y | (word == 1 ? bit : 0u),
+                                                   w2.z | (word == 2 ? bit : 0u), w2.w + 1u));
+    d.m_color[p] = color;
+    *out = color;
+    return 1;
+}
+// colours below `color` on body b and colours used on it at all (the dataflow order of the solver sweep)
+R2D_HD void body_color_rank(const Dev& d, bool from_flow, uint32_t b, uint32_t color, uint32_t* rank, uint32_t* degree) {
+    uint32_t rk = 0, dg = 0;
+    if (from_flow) {
+        const uint4 w = d.cstate[b];
+        const uint32_t u[3] = {w.x, w.y, w.z};
+        for (uint32_t k = 0; k < 3; ++k) {
+            dg += popc64(u[k]);
+            if (k < (color >> 5))
+                rk += popc64(u[k]);
+            else if (k == (color >> 5))
+                rk += popc64(u[k] & ((1u << (color & 31u)) - 1u));
+        }
+    } else {
+        for (uint32_t w = 0; w < COLOR_WORDS; ++w) {
+            const unsigned long long u = d.used[(size_t)b * COLOR_WORDS + w];
+            dg += popc64(u);
+            if (w < (color >> 6))
+                rk += popc64(u);
+            else if (w == (color >> 6))
+                rk += popc64(u & ((1ull << (color & 63u)) - 1ull));
+        }
+    }
+    *rank = rk;
+    *degree = dg;
+}
+
 // The "owner" of a manifold orders the colour-sorted solver records: the lower device slot of its non-static bodies.
 // Colours on one body are pairwise distinct, so a body owns at most one manifold per colour and the position of a
 // manifold inside its colour is the number of owners of that colour with a lower slot — a prefix popcount over a
@@ -555,20 +670,10 @@ R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
     // rank = colours below mine, degree = colours used.
     {
         const uint32_t color = d.m_color[p];
+        const bool from_flow = d.counters->flow_used != 0u;
         uint32_t rk[2] = {0, 0}, dg[2] = {0, 0};
-        const uint32_t bs[2] = {h.x, h.y};
-        const bool dyn[2] = {!st1, !st2};
-        for (int q = 0; q < 2; ++q) {
-            if (!dyn[q]) continue;
-            for (uint32_t w = 0; w < COLOR_WORDS; ++w) {
-                const unsigned long long u = d.used[(size_t)bs[q] * COLOR_WORDS + w];
-                dg[q] += popc64(u);
-                if (w < (color >> 6))
-                    rk[q] += popc64(u);
-                else if (w == (color >> 6))
-                    rk[q] += popc64(u & ((1ull << (color & 63u)) - 1ull));
-            }
-        }
+        if (!st1) body_color_rank(d, from_flow, h.x, color, &rk[0], &dg[0]);
+        if (!st2) body_color_rank(d, from_flow, h.y, color, &rk[1], &dg[1]);
         d.s_dep[at] = make_uint4(rk[0], dg[0], rk[1], dg[1]);
     }
     d.s_nf[at] = make_float4(c.normal.x, c.normal.y, c.friction, 0.0f);

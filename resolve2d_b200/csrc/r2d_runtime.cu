@@ -76,7 +76,7 @@ struct CudaBatch : BatchBase {
     int device = 0;
     int n_sms = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    int color_blocks = 0, solve_blocks = 0, pair_blocks = 0, heavy_blocks = 0;
+    int color_blocks = 0, solve_blocks = 0, pair_blocks = 0;
     uint32_t wait_mode = 1, wait_spin_lag = 1, wait_sleep_unit = 200, wait_sleep_max = 4000;
     int solve_blocks_per_sm = 1;
     uint32_t solve_smem_slots = SOLVE_SMEM_SLOTS;
@@ -91,7 +91,7 @@ struct CudaBatch : BatchBase {
     DBuf<uint4> j_hdr, bkt;
     DBuf<float4> j_par, j_vec;
     // grid
-    DBuf<uint32_t> bucket_cnt, bucket_start, ent_body, ent_key, ent_off, tile_sums, work;
+    DBuf<uint32_t> bucket_cnt, bucket_start, ent_body, ent_key, ent_off, tile_sums, work, hit_bits;
     // pairs / manifolds
     DBuf<uint2> pairs;
     DBuf<uint4> m_hdr, s_hdr;
@@ -105,6 +105,10 @@ struct CudaBatch : BatchBase {
     DBuf<unsigned char> zeroed;
     size_t zeroed_bytes = 0, scan_state_cap = 0;
     size_t off_counters = 0, off_color_misc = 0, off_scan = 0, off_maxprio0 = 0, off_maxprio1 = 0, off_used = 0, off_own_bits = 0;
+    size_t off_adj_cnt = 0, off_cstate = 0;
+    DBuf<unsigned long long> adj_prio;
+    bool flow_coloring = true, flow_now = false;   // dataflow colouring of single worlds (R2D_FLOW_COLORING=0: rounds only)
+    uint32_t flow_sleep_unit = 150;
     unsigned long long* scan_state(int which) { return (unsigned long long*)(zeroed.p + off_scan) + (size_t)which * scan_state_cap; }
     DBuf<uint32_t> own_pos;
     // staging for the boundary copies
@@ -171,12 +175,12 @@ struct CudaBatch : BatchBase {
         if (const char* e = getenv("R2D_WAIT_SLEEP_MAX")) wait_sleep_max = (uint32_t)atoi(e);
         if (per_sm > solve_blocks_per_sm) per_sm = solve_blocks_per_sm;
         solve_blocks = per_sm * n_sms;
-        R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_bucket_pairs<false, false>), TPB, 0));
-        pair_blocks = (per_sm < 1 ? 1 : per_sm) * n_sms;  // resident CTAs: one warp per listed bucket, grid-stride
-        R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_bucket_pairs<false, true>), TPB, 0));
-        heavy_blocks = (per_sm < 1 ? 1 : per_sm) * n_sms;  // one CTA per heavy bucket, grid-stride
+        R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bucket_count, TPB, 0));
+        pair_blocks = (per_sm < 1 ? 1 : per_sm) * n_sms;  // resident CTAs: a CTA per heavy bucket, a warp per light one, grid-stride
         if (const char* e = getenv("R2D_SOLVER")) persistent_solver = std::string(e) != "launches";
         if (const char* e = getenv("R2D_WORLD_SOLVER")) world_solver = atoi(e) != 0;
+        if (const char* e = getenv("R2D_FLOW_COLORING")) flow_coloring = atoi(e) != 0;
+        if (const char* e = getenv("R2D_FLOW_SLEEP_UNIT")) flow_sleep_unit = (uint32_t)atoi(e);
         return R2D_OK;
     }
 
@@ -419,7 +423,7 @@ struct CudaBatch : BatchBase {
         d.n_buckets = d.table_mult * d.n_bodies;
         d.bucket_cnt = bucket_cnt.p; d.bucket_start = bucket_start.p;
         d.cap_entries = (uint32_t)cap_entries;
-        d.ent_body = ent_body.p; d.ent_key = ent_key.p; d.ent_off = ent_off.p; d.work = work.p;
+        d.ent_body = ent_body.p; d.ent_key = ent_key.p; d.ent_off = ent_off.p; d.work = work.p; d.hit_bits = hit_bits.p;
         d.excl = (const uint64_t*)excl.p; d.n_excl = (uint32_t)image.excl.size();
         d.cap_pairs = (uint32_t)cap_pairs;
         d.pairs = pairs.p; d.m_hdr = m_hdr.p; d.m_g0 = m_g0.p; d.m_g1 = m_g1.p; d.m_r0 = m_r0.p; d.m_r1 = m_r1.p;
@@ -433,6 +437,11 @@ struct CudaBatch : BatchBase {
         d.color_cursor = color_misc + 2 * MAX_COLORS + 1;
         d.round_left = color_misc + 3 * MAX_COLORS + 1;
         d.counters = (Counters*)(zeroed.p + off_counters);
+        d.flow = flow_now ? 1u : 0u;
+        d.adj_cnt = (uint32_t*)(zeroed.p + off_adj_cnt);
+        d.cstate = (uint4*)(zeroed.p + off_cstate);
+        d.adj_prio = adj_prio.p;
+        d.flow_sleep_unit = flow_sleep_unit;
         d.own_words = (d.n_bodies + 31u) / 32u;
         d.own_bits = (uint32_t*)(zeroed.p + off_own_bits);
         d.own_pos = own_pos.p;
@@ -448,6 +457,7 @@ struct CudaBatch : BatchBase {
         int st;
         if ((st = ent_body.reserve(n)) || (st = ent_key.reserve(n))) return st;
         cap_entries = std::min(ent_body.cap, ent_key.cap);
+        if ((st = hit_bits.reserve(HIT_WORDS_PER_ENTRY * cap_entries + 64))) return st;  // ballots of the staged buckets
         return R2D_OK;
     }
     int reserve_pairs(size_t n) {
@@ -494,6 +504,8 @@ struct CudaBatch : BatchBase {
             off_maxprio1 = o; o = align(o + (size_t)nb * 8);
             off_used = o; o = align(o + (size_t)nb * COLOR_WORDS * 8);
             off_own_bits = o; o = align(o + own_w * MAX_COLORS * 4);
+            off_adj_cnt = o; o = align(o + (size_t)nb * 4);
+            off_cstate = o; o = align(o + (size_t)nb * 16);
             zeroed_bytes = o;
             if ((st = zeroed.reserve(zeroed_bytes))) return st;
         }
@@ -504,6 +516,13 @@ struct CudaBatch : BatchBase {
         if (cap_entries == 0 && (st = reserve_entries((size_t)nb * 3 + 4096))) return st;
         if (cap_pairs == 0 && (st = reserve_pairs((size_t)nb * 6 + 4096))) return st;
 
+        // colouring flavour: CTA-per-world rounds in shared memory for batches of small worlds, else the dataflow
+        // colouring while the candidate pairs fit its register slots (decided again on the device), else grid-wide rounds
+        const bool many_small_worlds = world_solver && worlds.size() >= (size_t)n_sms / 2;
+        const bool color_per_world = many_small_worlds && max_world_bodies <= COLOR_WORLD_MAX_BODIES;
+        const size_t pairs_guess = last_pairs ? (size_t)last_pairs : (size_t)nb * 3;
+        flow_now = flow_coloring && !color_per_world && pairs_guess <= (size_t)FLOW_SLOTS * color_blocks * TPB;
+        if (flow_now && (st = adj_prio.reserve((size_t)nb * ADJ_CAP))) return st;
         for (int attempt = 0;; ++attempt) {
             fill_dev();
             R2D_CUDA(cudaMemsetAsync(zeroed.p, 0, zeroed_bytes, stream));  // counters, colour tables, scan states, masks
@@ -514,16 +533,13 @@ struct CudaBatch : BatchBase {
             R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_list_buckets, grid_for(T), TPB, d);
             R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_sort_buckets, pair_blocks, TPB, d);
             // pairs per BUCKET (one warp each) -> scan over the T buckets -> write at the scanned offsets
-            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, (k_bucket_pairs<false, false>), pair_blocks, TPB, d);
-            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, (k_bucket_pairs<false, true>), heavy_blocks, TPB, d);
+            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_bucket_count, pair_blocks, TPB, d);
             if ((st = scan(d.ent_off, d.ent_off, nullptr, T, &d.counters->n_pairs, R2D_KCLASS_BROADPHASE, 1))) return st;
-            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, (k_bucket_pairs<true, false>), pair_blocks, TPB, d);
-            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, (k_bucket_pairs<true, true>), heavy_blocks, TPB, d);
+            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_bucket_write, pair_blocks, TPB, d);
             // ---- narrowphase ----
             R2D_LAUNCH(R2D_KCLASS_NARROWPHASE, k_narrow, grid_for(cap_pairs), TPB, d);
             // ---- colouring + partition + pre-step ----
-            const bool many_small_worlds = world_solver && worlds.size() >= (size_t)n_sms / 2;
-            if (many_small_worlds && max_world_bodies <= COLOR_WORLD_MAX_BODIES) {
+            if (color_per_world) {
                 const uint32_t blocks = (uint32_t)std::min<size_t>(worlds.size(), (size_t)n_sms * 8);
                 R2D_LAUNCH(R2D_KCLASS_COLORING, k_color_worlds, blocks, WORLD_TPB, d);
                 R2D_LAUNCH(R2D_KCLASS_COLORING, k_color_finish, 1, 32, d);
@@ -593,6 +609,10 @@ struct CudaBatch : BatchBase {
         if (c.err & ERR_GRID_RANGE) {
             g_cuda_error = "a body AABB covers an unreasonable number of grid cells (NaN/inf pose?)";
             return R2D_ERR_GRID_RANGE;
+        }
+        if (c.err & ERR_FLOW_STALL) {
+            g_cuda_error = "internal error: the dataflow colouring stalled (state of this step is undefined)";
+            return R2D_ERR_CUDA;
         }
         if (c.err & ERR_STALL) {
             g_cuda_error = "internal error: the dataflow contact sweep stalled (state of this step is undefined)";

@@ -302,6 +302,24 @@ def build_mixed1M(solver):
     return build_mixed(solver, 5000, 200, 1000)
 
 
+def build_hub(solver, n_discs=48):
+    """A plank resting on a row of `n_discs` discs: ONE non-static body with n_discs manifolds (as many colours), the
+    case the per-body manifold lists of the dataflow colouring cannot hold (they fall back to colouring by rounds)."""
+    fac = solver.entity_factory()
+    fac.make_downwards_gravity(GRAVITY)
+    pitch, r = 0.85, 0.4
+    width = n_discs * pitch
+    d = _descs(n_discs)
+    d["pos_x"] = (np.arange(n_discs, dtype=np.float32) - f32((n_discs - 1) / 2.0)) * f32(pitch)
+    d["pos_y"] = f32(r)
+    d["shape"], d["a"] = SHAPE_DISC, f32(r)
+    plank = _descs(1)
+    plank["pos_x"], plank["pos_y"] = 0.0, 2 * r + 0.3
+    plank["shape"], plank["a"], plank["b"] = SHAPE_RECT, width, 0.6
+    fac.make_bodies(np.concatenate([_static_rect((0, -1), width + 8, 2), d, plank]))
+    return {"sub_steps": 4, "iters": 4}
+
+
 def build_pyramid(solver, base=199, n_spinners=50, seed=CONFIG_SEED["pyramid20k"]):
     """cfg4: rectangle pyramid (1.0 x 0.5, base row `base`), distance joints between horizontal neighbours on every
     10th row, fixed-position joints on both ends of the base row, `n_spinners` motor-driven bars beside it

@@ -27,7 +27,9 @@ struct EmuBatch : BatchBase {
     std::vector<float4> m_g0, m_g1, m_r0, m_r1, s_nf, s_inv, s_r0, s_r1, s_pm0, s_pm1;
     std::vector<float2> s_acc0, s_acc1;
     std::vector<uint4> s_dep;
-    std::vector<unsigned long long> maxprio0, maxprio1, used, m_prio;
+    std::vector<unsigned long long> maxprio0, maxprio1, used, m_prio, adj_prio;
+    std::vector<uint32_t> adj_cnt;
+    std::vector<uint4> cstate;
     std::vector<uint32_t> color_count, color_start, color_cursor, round_left, own_bits, own_pos;
     Counters counters{};
     uint32_t n_pairs_last = 0;
@@ -181,6 +183,10 @@ struct EmuBatch : BatchBase {
         d.m_hdr = m_hdr.data(); d.m_g0 = m_g0.data(); d.m_g1 = m_g1.data(); d.m_r0 = m_r0.data(); d.m_r1 = m_r1.data();
         d.m_color = m_color.data();
         m_prio.assign(P + 1, 0); d.m_prio = m_prio.data();
+        // dataflow colouring inputs (R2D_EMU_FLOW=0 emulates the rounds-only path)
+        d.flow = (getenv("R2D_EMU_FLOW") && atoi(getenv("R2D_EMU_FLOW")) == 0) ? 0u : 1u;
+        adj_cnt.assign(nb, 0); adj_prio.assign((size_t)nb * ADJ_CAP, 0); cstate.assign(nb, make_uint4(0, 0, 0, 0));
+        d.adj_cnt = adj_cnt.data(); d.adj_prio = adj_prio.data(); d.cstate = cstate.data();
         uint32_t M = 0, K = 0;
         for (uint32_t p = 0; p < P; ++p) {
             const int np = narrow_pair_thread(d, p);
@@ -192,13 +198,47 @@ struct EmuBatch : BatchBase {
         color_count.assign(MAX_COLORS, 0); color_start.assign(MAX_COLORS + 1, 0); color_cursor.assign(MAX_COLORS, 0);
         d.maxprio0 = maxprio0.data(); d.maxprio1 = maxprio1.data(); d.used = used.data();
         d.color_count = color_count.data(); d.color_start = color_start.data(); d.color_cursor = color_cursor.data();
-        for (uint32_t p = 0; p < P; ++p) {
+        uint32_t rounds = 0, n_colors = 0;
+        bool flow_done = false;
+        if (d.flow && !counters.flow_abort) {
+            // the dataflow colouring, probed serially: every pass colours what is ready (k_color's flow phase)
+            std::vector<uint32_t> ranks(P, 0);
+            uint32_t pending = 0;
+            for (uint32_t p = 0; p < P; ++p)
+                if (m_color[p] == COLOR_PENDING) {
+                    ranks[p] = flow_ranks(d, m_hdr[p], m_prio[p]);
+                    ++pending;
+                }
+            while (pending && !counters.flow_fail) {
+                uint32_t done = 0;
+                for (uint32_t p = 0; p < P; ++p) {
+                    if (m_color[p] != COLOR_PENDING) continue;
+                    uint32_t c = 0, lag = 0;
+                    if (flow_try(d, p, m_hdr[p].x, m_hdr[p].y, m_hdr[p].w & 3u, ranks[p], &c, &lag) == 1) {
+                        color_count[c] += 1;
+                        n_colors = std::max(n_colors, c + 1);
+                        ++done;
+                    }
+                }
+                if (!done && !counters.flow_fail) return R2D_ERR_CUDA;  // would be a stall on the GPU
+                pending -= done;
+            }
+            if (counters.flow_fail) {  // more than FLOW_COLORS colours: start over with the rounds
+                for (uint32_t p = 0; p < P; ++p)
+                    if (m_color[p] < MAX_COLORS) m_color[p] = COLOR_PENDING;
+                color_count.assign(MAX_COLORS, 0);
+                n_colors = 0;
+            } else {
+                flow_done = true;
+                counters.flow_used = 1;
+            }
+        }
+        for (uint32_t p = 0; p < P && !flow_done; ++p) {
             if (m_color[p] != COLOR_PENDING) continue;
             const uint4 h = m_hdr[p];
             color_post(d, h.x, h.y, (h.w & 1u) != 0, (h.w & 2u) != 0, d.m_prio[p], 1);
         }
-        uint32_t rounds = 0, n_colors = 0;
-        for (uint32_t round = 1; round < MAX_COLOR_ROUNDS; ++round) {
+        for (uint32_t round = 1; round < MAX_COLOR_ROUNDS && !flow_done; ++round) {
             // Serial emulation caveat: a thread of round r must not see round-r writes of `used` by another winner on a
             // shared body — there is none (unique winner per body and round) — nor round r+1 posts, which go to the
             // other maxprio array.  So a plain loop is equivalent to the parallel round.

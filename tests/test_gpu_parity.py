@@ -65,6 +65,16 @@ def test_gpu_box1k():
     assert cand.stats().n_manifolds > 1500
 
 
+def test_gpu_dataflow_colouring_and_its_fallback():
+    """single worlds are coloured by the dataflow kernel phase (no rounds); a body with more manifolds than its list
+    holds (a plank on 48 discs) makes the same launch fall back to Jones-Plassmann rounds — same colours either way"""
+    cand, _ = run_parity(lambda: Solver(2.0, 4), scenes.build_box1k, 60, check_every=10, what="box1k flow")
+    assert cand.stats().n_color_rounds == 0
+    cand, _ = run_parity(lambda: Solver(2.0, 4), scenes.build_hub, 90, check_every=10, what="hub")
+    st = cand.stats()
+    assert st.n_colors >= 40 and st.n_color_rounds > 0
+
+
 def test_gpu_substep_iteration_variants():
     for S, I in ((1, 1), (1, 4), (2, 10), (4, 0)):
         run_parity(lambda: Solver(2.0, 4), scenes.build_box1k, 60, check_every=20, what=f"box1k S{S} I{I}", sub_steps=S,
