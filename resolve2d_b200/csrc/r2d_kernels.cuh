@@ -241,10 +241,23 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_chained(const uint32_t* in, u
 // (a, b) order, which makes the candidate list deterministic.
 constexpr int BUCKET_WARPS = TPB / 32;
 constexpr int BUCKET_CAP = 256;    // entries staged in shared memory; larger buckets read their entries from global memory
-constexpr int HEAVY_BUCKET = 16;   // buckets with more entries get a whole CTA instead of a warp (n^2 pair tests)
+constexpr int SMALL_BUCKET = 16;   // up to here: a warp per bucket
+constexpr int HEAVY_BUCKET = 40;   // above: a whole CTA per bucket (n^2 pair tests).  In between ("medium"): a CTA each when
+                                   // there are too few of them to fill the GPU with warps (a dense pile), else a warp each
+                                   // (thousands of small worlds)
 constexpr uint32_t HIT_WORDS_PER_ENTRY = 4;  // ballot words kept per grid entry: n (n - 1) / 64 <= 4 n for n <= 257
 
-// one THREAD per bucket: clear its pair counter and list it if it can produce pairs (light: a warp, heavy: a CTA)
+// work lists: small buckets from the front of work[0, T), heavy ones from its back, medium ones in work[T, 2T)
+enum { LIST_SMALL = 0, LIST_MEDIUM = 1, LIST_HEAVY = 2 };
+template <int LIST>
+__device__ __forceinline__ uint32_t list_count(const Dev& d) {
+    return LIST == LIST_HEAVY ? d.counters->n_heavy : (LIST == LIST_MEDIUM ? d.counters->n_mid : d.counters->n_work);
+}
+template <int LIST>
+__device__ __forceinline__ uint32_t list_bucket(const Dev& d, uint32_t w) {
+    return LIST == LIST_HEAVY ? d.work[d.n_buckets - 1u - w] : (LIST == LIST_MEDIUM ? d.work[d.n_buckets + w] : d.work[w]);
+}
+// one THREAD per bucket: clear its pair counter and list it if it can produce pairs
 __global__ void __launch_bounds__(TPB) k_list_buckets(Dev d) {
     for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < d.n_buckets; b += gridDim.x * blockDim.x) {
         const uint32_t bs = d.bucket_start[b], be = bucket_end(d, b);
@@ -252,18 +265,22 @@ __global__ void __launch_bounds__(TPB) k_list_buckets(Dev d) {
         d.ent_off[b] = 0u;
         if (n > (uint32_t)HEAVY_BUCKET)
             d.work[d.n_buckets - 1u - atomicAdd(&d.counters->n_heavy, 1u)] = b;
+        else if (n > (uint32_t)SMALL_BUCKET)
+            d.work[d.n_buckets + atomicAdd(&d.counters->n_mid, 1u)] = b;
         else if (n >= 2u)
             d.work[atomicAdd(&d.counters->n_work, 1u)] = b;
     }
 }
-// one WARP per listed bucket (light ones from the front of the list, heavy ones from the back)
+// one WARP per listed bucket
 __global__ void __launch_bounds__(TPB) k_sort_buckets(Dev d) {
     __shared__ uint32_t s_in[BUCKET_WARPS][BUCKET_CAP];
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t n_light = d.counters->n_work, n_items = n_light + d.counters->n_heavy;
+    const uint32_t n_small = d.counters->n_work, n_mid = d.counters->n_mid, n_items = n_small + n_mid + d.counters->n_heavy;
     for (uint32_t w = warp; w < n_items; w += n_warps) {
-        const uint32_t b = w < n_light ? d.work[w] : d.work[d.n_buckets - 1u - (w - n_light)];
+        const uint32_t b = w < n_small ? list_bucket<LIST_SMALL>(d, w)
+                                       : (w < n_small + n_mid ? list_bucket<LIST_MEDIUM>(d, w - n_small)
+                                                              : list_bucket<LIST_HEAVY>(d, w - n_small - n_mid));
         const uint32_t bs = d.bucket_start[b], be = bucket_end(d, b);
         const uint32_t n = be > bs ? be - bs : 0u;
         if (n < 2u) continue;  // warp-uniform
@@ -319,10 +336,10 @@ __device__ __forceinline__ void tri_advance(uint32_t n, uint32_t step, uint32_t&
 struct BucketItem {
     uint32_t b, bs, n;
 };
-template <bool HEAVY>
+template <int LIST>
 __device__ __forceinline__ BucketItem bucket_item(const Dev& d, uint32_t w, bool dead) {
     BucketItem it;
-    it.b = HEAVY ? d.work[d.n_buckets - 1u - w] : d.work[w];
+    it.b = list_bucket<LIST>(d, w);
     it.bs = d.bucket_start[it.b];
     const uint32_t be = bucket_end(d, it.b);
     it.n = (be > it.bs && !dead) ? be - it.bs : 0u;
@@ -357,12 +374,14 @@ __device__ __forceinline__ uint32_t bucket_tests_global(const Dev& d, const Buck
     return total;
 }
 
-template <bool HEAVY>
+// LIST: which work list; HEAVY: the team is the whole CTA (else a warp)
+template <int LIST, bool HEAVY>
 __device__ __forceinline__ void bucket_count_part(const Dev& d) {
     constexpr int TEAMS = HEAVY ? 1 : BUCKET_WARPS;       // teams per CTA
     constexpr uint32_t TEAM = HEAVY ? TPB : 32;           // lanes per team
     constexpr uint32_t TEAM_WARPS = TEAM / 32;
-    constexpr int CAP = HEAVY ? BUCKET_CAP : HEAVY_BUCKET;  // entries a team can stage (light buckets are small by definition)
+    // entries a team can stage (the lists bound the bucket sizes)
+    constexpr int CAP = LIST == LIST_HEAVY ? BUCKET_CAP : (LIST == LIST_MEDIUM ? HEAVY_BUCKET : SMALL_BUCKET);
     __shared__ uint32_t s_body[TEAMS][CAP];
     __shared__ uint32_t s_meta[TEAMS][CAP];  // flags (bit 0 static) | first-occurrence << 1 | ncells << 2
     __shared__ float4 s_aabb[TEAMS][CAP];
@@ -375,11 +394,11 @@ __device__ __forceinline__ void bucket_count_part(const Dev& d) {
     const uint32_t team = HEAVY ? blockIdx.x : (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_teams = HEAVY ? gridDim.x : (gridDim.x * blockDim.x) >> 5;
     const bool dead = d.counters->n_entries > d.cap_entries;  // the fill dropped entries: this attempt is redone
-    const uint32_t n_items = HEAVY ? d.counters->n_heavy : d.counters->n_work;
+    const uint32_t n_items = list_count<LIST>(d);
     for (uint32_t w = team; w < n_items; w += n_teams) {
-        const BucketItem it = bucket_item<HEAVY>(d, w, dead);
+        const BucketItem it = bucket_item<LIST>(d, w, dead);
         const uint32_t n = it.n;
-        const bool staged = n <= BUCKET_CAP;
+        const bool staged = n <= (uint32_t)CAP;
         if (staged) {
             for (uint32_t k = tl; k < n; k += TEAM) {
                 const uint32_t body = d.ent_body[it.bs + k];
@@ -437,18 +456,26 @@ __device__ __forceinline__ void bucket_count_part(const Dev& d) {
 }
 
 // heavy buckets first (a CTA each: the long poles), then the light ones (a warp each) fill the tail of the same launch
+// medium buckets: CTA teams when a warp each would leave most of the GPU idle
+__device__ __forceinline__ bool medium_by_cta(const Dev& d) { return d.counters->n_mid < 4u * gridDim.x; }
+
 __global__ void __launch_bounds__(TPB) k_bucket_count(Dev d) {
-    bucket_count_part<true>(d);
+    bucket_count_part<LIST_HEAVY, true>(d);
     __syncthreads();
-    bucket_count_part<false>(d);
+    if (medium_by_cta(d))
+        bucket_count_part<LIST_MEDIUM, true>(d);
+    else
+        bucket_count_part<LIST_MEDIUM, false>(d);
+    __syncthreads();
+    bucket_count_part<LIST_SMALL, false>(d);
 }
 
-template <bool HEAVY>
+template <int LIST, bool HEAVY>
 __device__ __forceinline__ void bucket_write_part(const Dev& d) {
     constexpr int TEAMS = HEAVY ? 1 : BUCKET_WARPS;
     constexpr uint32_t TEAM = HEAVY ? TPB : 32;
     constexpr uint32_t TEAM_WARPS = TEAM / 32;
-    constexpr int CAP = HEAVY ? BUCKET_CAP : HEAVY_BUCKET;
+    constexpr int CAP = LIST == LIST_HEAVY ? BUCKET_CAP : (LIST == LIST_MEDIUM ? HEAVY_BUCKET : SMALL_BUCKET);
     __shared__ uint32_t s_body[TEAMS][CAP];
     __shared__ uint32_t s_nc[TEAMS][CAP];
     __shared__ uint32_t s_warp_total[BUCKET_WARPS];
@@ -459,13 +486,13 @@ __device__ __forceinline__ void bucket_write_part(const Dev& d) {
     const uint32_t team = HEAVY ? blockIdx.x : (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_teams = HEAVY ? gridDim.x : (gridDim.x * blockDim.x) >> 5;
     const bool dead = d.counters->n_entries > d.cap_entries;
-    const uint32_t n_items = HEAVY ? d.counters->n_heavy : d.counters->n_work;
+    const uint32_t n_items = list_count<LIST>(d);
     for (uint32_t w = team; w < n_items; w += n_teams) {
-        const BucketItem it = bucket_item<HEAVY>(d, w, dead);
+        const BucketItem it = bucket_item<LIST>(d, w, dead);
         const uint32_t n = it.n;
         const uint32_t n_pairs = n >= 2u ? n * (n - 1u) / 2u : 0u;
         const uint32_t out_base = d.ent_off[it.b];  // scanned: first pair slot of this bucket
-        if (n <= BUCKET_CAP) {
+        if (n <= (uint32_t)CAP) {
             for (uint32_t k = tl; k < n; k += TEAM) {
                 const uint32_t body = d.ent_body[it.bs + k];
                 s_body[tc][k] = body;
@@ -528,9 +555,14 @@ __device__ __forceinline__ void bucket_write_part(const Dev& d) {
 }
 
 __global__ void __launch_bounds__(TPB) k_bucket_write(Dev d) {
-    bucket_write_part<true>(d);
+    bucket_write_part<LIST_HEAVY, true>(d);
     __syncthreads();
-    bucket_write_part<false>(d);
+    if (medium_by_cta(d))
+        bucket_write_part<LIST_MEDIUM, true>(d);
+    else
+        bucket_write_part<LIST_MEDIUM, false>(d);
+    __syncthreads();
+    bucket_write_part<LIST_SMALL, false>(d);
 }
 
 // ---- K6: narrowphase, one thread per candidate pair --------------------------------------------------------------------------
@@ -904,14 +936,15 @@ __device__ __forceinline__ void stamp(const Dev& d, uint32_t slot) {
     }
 }
 // Shared-memory cache of the solver records: thread t owns manifolds t, t + nth, ... for the whole kernel, so the first
-// SOLVE_SMEM_SLOTS of them are copied once into shared memory (record k of thread x at index k * TPB + x of each array)
+// SOLVE_SMEM_SLOTS of them are copied once into shared memory (record k of thread x at index k * PSOLVE_TPB + x of each array)
 // and every sweep reads its constants — and keeps its accumulated impulses — there; only the two body words of a
 // manifold go through L2.  Records beyond the cache (worlds with more than ~245k manifolds) stream from global memory.
+constexpr int PSOLVE_TPB = 256;      // threads per CTA of the persistent solver (one CTA per SM; 512 x 3 slots measured the same)
 constexpr int SOLVE_SMEM_SLOTS = 6;
 constexpr int SOLVE_SMEM_BYTES_PER_RECORD = 6 * 16 + 8 + 2 * 16 + 8;  // hdr nf inv dep r0 pm0 | acc0 | r1 pm1 | acc1 = 144
-constexpr size_t SOLVE_SMEM_BYTES = (size_t)SOLVE_SMEM_SLOTS * TPB * SOLVE_SMEM_BYTES_PER_RECORD;
+constexpr size_t SOLVE_SMEM_BYTES = (size_t)SOLVE_SMEM_SLOTS * PSOLVE_TPB * SOLVE_SMEM_BYTES_PER_RECORD;
 
-__global__ void __launch_bounds__(TPB) k_solve_persistent(Dev d, float sub_dt, uint32_t S, uint32_t I,
+__global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float sub_dt, uint32_t S, uint32_t I,
                                                           const uint32_t* __restrict__ joint_color_start, uint32_t n_joint_colors,
                                                           uint32_t smem_slots) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -923,7 +956,7 @@ __global__ void __launch_bounds__(TPB) k_solve_persistent(Dev d, float sub_dt, u
     // ---- stage my records ----
     Dev ds = d;  // same code path, record arrays redirected to shared memory
     {
-        const size_t n = (size_t)SOLVE_SMEM_SLOTS * TPB;
+        const size_t n = (size_t)SOLVE_SMEM_SLOTS * PSOLVE_TPB;
         unsigned char* q = smem_raw;
         ds.s_hdr = (uint4*)q;    q += n * 16;
         ds.s_nf = (float4*)q;    q += n * 16;
@@ -936,7 +969,7 @@ __global__ void __launch_bounds__(TPB) k_solve_persistent(Dev d, float sub_dt, u
         ds.s_acc0 = (float2*)q;  q += n * 8;
         ds.s_acc1 = (float2*)q;
         for (uint32_t k = 0; k < smem_slots; ++k) {
-            const uint32_t m = tid + k * nth, l = k * TPB + threadIdx.x;
+            const uint32_t m = tid + k * nth, l = k * PSOLVE_TPB + threadIdx.x;
             if (m >= n_manifolds) break;
             const uint4 h = d.s_hdr[m];
             ds.s_hdr[l] = h;
@@ -969,7 +1002,7 @@ __global__ void __launch_bounds__(TPB) k_solve_persistent(Dev d, float sub_dt, u
             uint32_t k = 0;
             for (uint32_t m = tid; m < n_manifolds; m += nth, ++k) {
                 if (k < smem_slots)
-                    solve_contact_thread<true>(ds, k * TPB + threadIdx.x, sub_dt, it);  // cached record
+                    solve_contact_thread<true>(ds, k * PSOLVE_TPB + threadIdx.x, sub_dt, it);  // cached record
                 else
                     solve_contact_thread<true>(d, m, sub_dt, it);
             }

@@ -55,8 +55,9 @@ struct Counters {
     uint32_t n_rounds;
     uint32_t err;
     uint32_t n_own_scan;     // n_colors * (W + 1): length of the owner-position scan
-    uint32_t n_work;         // buckets holding 2..HEAVY_BUCKET entries (work list of the warp-per-bucket pair kernels)
-    uint32_t n_heavy;        // buckets holding more (CTA-per-bucket pair kernels)
+    uint32_t n_work;         // buckets holding 2..SMALL_BUCKET entries (a warp each in the pair kernels)
+    uint32_t n_mid;          // SMALL_BUCKET+1..HEAVY_BUCKET entries (a warp or a CTA each, see medium_by_cta)
+    uint32_t n_heavy;        // buckets holding more (a CTA each)
     uint32_t n_stamps;
     uint32_t flow_abort;     // set by the narrowphase: a body has more than ADJ_CAP manifolds, colour by rounds
     uint32_t flow_fail;      // set inside the dataflow colouring: more than FLOW_COLORS colours needed (or a stall)
@@ -92,8 +93,8 @@ struct Dev {
     uint32_t* ent_body;           // E
     uint32_t* ent_key;            // E
     uint32_t* ent_off;            // T + 1: pairs emitted per BUCKET, then its exclusive scan ([T] = P)
-    uint32_t* work;               // T: ids of the light buckets (2..HEAVY_BUCKET entries) from the front, of the heavy ones
-                                  // from the back (work[T - 1 - k]); order irrelevant
+    uint32_t* work;               // 2T: ids of the small buckets from the front of [0, T), of the heavy ones from its back
+                                  // (work[T - 1 - k]), of the medium ones in [T, 2T); order irrelevant
     uint32_t* hit_bits;           // 4 * cap_entries: 32-test ballots of the count pass, bucket b's words at 4 * bucket_start[b]
     const uint64_t* excl;         // sorted (lo_slot << 32 | hi_slot)
     uint32_t n_excl;
@@ -148,6 +149,7 @@ struct Dev {
     // ---- dataflow sweep tuning (wait policy only; never affects results) ------------------------------------------------
     uint32_t color_smem;          // 1: maxprio / used point into shared memory (per-world colouring kernel)
     uint32_t wait_mode;           // 0: the warp updates when all its lanes are ready; 1: ready lanes update as they come
+    uint32_t wait_probe;          // 1: lane 0 probes alone until its bodies are ready, then the whole warp loads
     uint32_t wait_spin_lag;       // lag <= this: poll again immediately
     uint32_t wait_sleep_unit;     // otherwise sleep lag * unit ns ...
     uint32_t wait_sleep_max;      // ... capped at this many ns
@@ -773,7 +775,7 @@ R2D_HD void solve_contact_thread(const Dev& d, uint32_t m, float sub_dt, uint32_
 #if defined(__CUDA_ARCH__)
         // Stage 1: only lane 0 probes (one 16-byte load per warp instead of 64) until ITS body is ready; the other
         // lanes have the same colour and become ready at about the same time.
-        for (; d.wait_mode < 2u;) {
+        for (; d.wait_mode < 2u && d.wait_probe != 0u;) {
             uint32_t lag0 = 0u;
             if ((threadIdx.x & 31u) == 0u && !st1) lag0 = e1 - f2u(ld_body_word(&d.mom[h.x]).w);
             lag0 = __shfl_sync(0xffffffffu, lag0, 0);

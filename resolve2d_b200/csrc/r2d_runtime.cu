@@ -77,7 +77,7 @@ struct CudaBatch : BatchBase {
     int n_sms = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int color_blocks = 0, solve_blocks = 0, pair_blocks = 0;
-    uint32_t wait_mode = 1, wait_spin_lag = 1, wait_sleep_unit = 200, wait_sleep_max = 4000;
+    uint32_t wait_mode = 1, wait_probe = 1, wait_spin_lag = 1, wait_sleep_unit = 200, wait_sleep_max = 4000;
     int solve_blocks_per_sm = 1;
     uint32_t solve_smem_slots = SOLVE_SMEM_SLOTS;
     bool persistent_solver = true;
@@ -165,11 +165,12 @@ struct CudaBatch : BatchBase {
         }
         color_blocks = per_sm * n_sms;
         R2D_CUDA(cudaFuncSetAttribute(k_solve_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_BYTES));
-        R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent, TPB, SOLVE_SMEM_BYTES));
+        R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent, PSOLVE_TPB, SOLVE_SMEM_BYTES));
         if (per_sm < 1) per_sm = 1;
         if (const char* e = getenv("R2D_SOLVE_BLOCKS_PER_SM")) solve_blocks_per_sm = atoi(e);
         if (const char* e = getenv("R2D_SOLVE_SMEM_SLOTS")) solve_smem_slots = std::min<uint32_t>((uint32_t)atoi(e), SOLVE_SMEM_SLOTS);
         if (const char* e = getenv("R2D_WAIT_MODE")) wait_mode = (uint32_t)atoi(e);
+        if (const char* e = getenv("R2D_WAIT_PROBE")) wait_probe = (uint32_t)atoi(e);
         if (const char* e = getenv("R2D_WAIT_SPIN_LAG")) wait_spin_lag = (uint32_t)atoi(e);
         if (const char* e = getenv("R2D_WAIT_SLEEP_UNIT")) wait_sleep_unit = (uint32_t)atoi(e);
         if (const char* e = getenv("R2D_WAIT_SLEEP_MAX")) wait_sleep_max = (uint32_t)atoi(e);
@@ -450,7 +451,7 @@ struct CudaBatch : BatchBase {
         d.s_dep = s_dep.p;
         d.n_joints = (uint32_t)image.j_hdr.size();
         d.j_hdr = j_hdr.p; d.j_par = j_par.p; d.j_vec = j_vec.p;
-        d.color_smem = 0; d.wait_mode = wait_mode; d.wait_spin_lag = wait_spin_lag; d.wait_sleep_unit = wait_sleep_unit; d.wait_sleep_max = wait_sleep_max;
+        d.color_smem = 0; d.wait_mode = wait_mode; d.wait_probe = wait_probe; d.wait_spin_lag = wait_spin_lag; d.wait_sleep_unit = wait_sleep_unit; d.wait_sleep_max = wait_sleep_max;
     }
 
     int reserve_entries(size_t n) {
@@ -511,7 +512,7 @@ struct CudaBatch : BatchBase {
         }
         if ((st = own_pos.reserve((own_w + 1) * MAX_COLORS + 2)) ||
             (st = pose.reserve(nb)) || (st = ncells.reserve(nb)) || (st = bkt.reserve(nb)) ||  (st = bucket_cnt.reserve((size_t)T + 1, true, stream)) ||
-            (st = bucket_start.reserve((size_t)T + 1)) || (st = ent_off.reserve((size_t)T + 2)) || (st = work.reserve((size_t)T + 1)))
+            (st = bucket_start.reserve((size_t)T + 1)) || (st = ent_off.reserve((size_t)T + 2)) || (st = work.reserve(2 * (size_t)T + 2)))
             return st;
         if (cap_entries == 0 && (st = reserve_entries((size_t)nb * 3 + 4096))) return st;
         if (cap_pairs == 0 && (st = reserve_pairs((size_t)nb * 6 + 4096))) return st;
@@ -569,7 +570,7 @@ struct CudaBatch : BatchBase {
                 float sd = sub_dt;
                 uint32_t slots = solve_smem_slots;
                 void* args[] = {(void*)&d, (void*)&sd, (void*)&S_, (void*)&I_, (void*)&jcs_dev, (void*)&n_jc, (void*)&slots};
-                R2D_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(solve_blocks), dim3(TPB), args, SOLVE_SMEM_BYTES, stream));
+                R2D_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(solve_blocks), dim3(PSOLVE_TPB), args, SOLVE_SMEM_BYTES, stream));
                 prof_end();
                 launches += 1;
             }
