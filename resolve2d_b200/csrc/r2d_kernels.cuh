@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(TPB) k_bucket_write(Dev d) {
 }
 
 // ---- K6: narrowphase, one thread per candidate pair --------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_narrow(Dev d) {
+__global__ void __launch_bounds__(TPB, 3) k_narrow(Dev d) {
     if (overflowed(d)) return;
     const uint32_t n = live_pairs(d);
     uint32_t my_m = 0, my_k = 0;
@@ -1026,7 +1026,7 @@ __global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float su
 // manifolds of colour c are the contiguous range [slot(c, base_w), slot(c, base_{w+1})) of the colour-sorted records
 // (owner order is world-major), its momentum words live in shared memory for the whole substep loop, and colours are
 // separated by __syncthreads().  The per-body update sequence is the colour order, as everywhere else: bit-identical.
-constexpr uint32_t WORLD_MAX_BODIES = 1024;   // 16 KB of momentum words
+constexpr uint32_t WORLD_MAX_BODIES = 512;    // 8 KB of momentum words
 
 __device__ __forceinline__ uint32_t owner_rank(const Dev& d, uint32_t c, uint32_t slot) {  // owners of colour c below `slot`
     const uint32_t word = d.own_bits[(size_t)c * d.own_words + (slot >> 5)];

@@ -137,13 +137,16 @@ R2D_HD bool normal_should_flip(v2 n, const BodyView& ref, const BodyView& inc) {
 }
 
 // overlapSAT (collision.zig:228-290).  `ref_tag` is stored into ret.ref_is_first whenever this pass takes the axis.
-R2D_HD bool overlap_sat(SatResult& ret, const BodyView& R, const BodyView& I, int ref_tag) {
+// The axis loop is NOT unrolled (code size: the narrowphase is instruction-fetch bound otherwise).  To keep the
+// vertex / normal arrays in registers without dynamic indexing, R is a private copy whose arrays are rotated by one
+// position per axis: axis k is always en[0] with the edge (wv[0], wv[1]).  project() takes min / max over all four
+// vertices, which does not depend on their order, so every value is the one the indexed form computes.
+R2D_HD bool overlap_sat(SatResult& ret, BodyView R, const BodyView& I, int ref_tag) {
     const float EPS = SAT_OVERLAP_THRESHOLD;
     const int nn = is_rect(R) ? 4 : 1;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {  // unrolled: static indices into wv[] / en[]
-        if (k >= nn) break;
-        v2 normal = get_normal(R, I, k).dir;
+#pragma unroll 1
+    for (int k = 0; k < nn; ++k) {
+        v2 normal = get_normal(R, I, 0).dir;
         bool flipped = false;
         if (normal_should_flip(normal, R, I)) {
             normal = negate_mul(normal);
@@ -182,8 +185,30 @@ R2D_HD bool overlap_sat(SatResult& ret, const BodyView& R, const BodyView& I, in
             ret.normal_id = k;
             ret.ref_is_first = ref_tag;
         }
+        // next axis: rotate the private copy
+        const v2 w0 = R.wv[0], e0 = R.en[0];
+        R.wv[0] = R.wv[1]; R.wv[1] = R.wv[2]; R.wv[2] = R.wv[3]; R.wv[3] = w0;
+        R.en[0] = R.en[1]; R.en[1] = R.en[2]; R.en[2] = R.en[3]; R.en[3] = e0;
     }
     return true;
+}
+
+// a ? x : y, field by field (register selects instead of two copies of the code that follows)
+R2D_HD BodyView select_view(bool a, const BodyView& x, const BodyView& y) {
+    BodyView v;
+    v.pos = a ? x.pos : y.pos;
+    v.c = a ? x.c : y.c;
+    v.s = a ? x.s : y.s;
+    v.a = a ? x.a : y.a;
+    v.b = a ? x.b : y.b;
+    v.flags = a ? x.flags : y.flags;
+    v.id = a ? x.id : y.id;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v.wv[k] = a ? x.wv[k] : y.wv[k];
+        v.en[k] = a ? x.en[k] : y.en[k];
+    }
+    return v;
 }
 
 struct ContactPoint {
@@ -313,16 +338,17 @@ R2D_HD Manifold narrowphase(const BodyView& lo, const BodyView& hi) {
     ret.normal_id = 0;
     ret.ref_is_first = 1;
     m.normal = ret.normal;
-    if (!overlap_sat(ret, lo, hi, 1)) return m;
-    if (!overlap_sat(ret, hi, lo, 0)) return m;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {  // (lo, hi) then (hi, lo): one copy of the axis loop
+        const bool first = pass == 0;
+        if (!overlap_sat(ret, select_view(first, lo, hi), select_view(first, hi, lo), first ? 1 : 0)) return m;
+    }
     m.collides = 1;
     m.ref_is_lo = ret.ref_is_first;
     m.normal_id = ret.normal_id;
     m.normal = ret.normal;
-    if (m.ref_is_lo)
-        identify_points(m, lo, hi, ret.normal_id);
-    else
-        identify_points(m, hi, lo, ret.normal_id);
+    const bool ref_lo = m.ref_is_lo != 0;
+    identify_points(m, select_view(ref_lo, lo, hi), select_view(ref_lo, hi, lo), ret.normal_id);
     return m;
 }
 

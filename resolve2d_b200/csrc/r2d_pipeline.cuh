@@ -76,6 +76,7 @@ struct Dev {
     float4* shape;    // a, b, bits(flags), bits(id)   flags: bit0 static, bit1 rect, bits 8.. world
     float4* aabb;     // centre.x, centre.y, half_w, half_h   (as of the last refresh — stale on purpose, Q3)
     float4* pose;     // x, y, cos(angle), sin(angle)  (scratch of one process())
+    float4* view;     // 4 per body, rectangles only: world vertices 0..3, outward edge normals 0..3 (scratch of one process())
     uint32_t* ncells; // grid cells covered by the body's AABB
     uint4* bkt;       // the body's bucket ids when it covers <= 4 cells (0xFFFFFFFF padded); scratch of one process()
     // ---- worlds ----------------------------------------------------------------------------------------------------
@@ -298,11 +299,49 @@ R2D_HD uint32_t cell_bucket(const CellRange& r, uint32_t k) {
     return r.bucket_base + (uint32_t)cell_hash(xi, yi, (uint64_t)r.table_size);
 }
 
+// The world vertices and edge normals of a rectangle are evaluated once per body and process() call (K2) and
+// fetched here — one body is in several candidate pairs, and the four normalisations dominate make_view.
+R2D_HD BodyView load_view(const Dev& d, uint32_t i) {
+    const float4 p = d.pose[i];
+    const float4 s = d.shape[i];
+    BodyView v;
+    v.pos = mk2(p.x, p.y);
+    v.c = p.z;
+    v.s = p.w;
+    v.flags = f2u(s.z);
+    v.id = f2u(s.w);
+    if (v.flags & FLAG_RECT) {
+        v.a = fdiv(s.x, 2.0f);  // Rectangle.zig:38-39
+        v.b = fdiv(s.y, 2.0f);
+        const float4 q0 = d.view[4 * (size_t)i], q1 = d.view[4 * (size_t)i + 1], q2 = d.view[4 * (size_t)i + 2],
+                     q3 = d.view[4 * (size_t)i + 3];
+        v.wv[0] = mk2(q0.x, q0.y); v.wv[1] = mk2(q0.z, q0.w); v.wv[2] = mk2(q1.x, q1.y); v.wv[3] = mk2(q1.z, q1.w);
+        v.en[0] = mk2(q2.x, q2.y); v.en[1] = mk2(q2.z, q2.w); v.en[2] = mk2(q3.x, q3.y); v.en[3] = mk2(q3.z, q3.w);
+    } else {
+        v.a = s.x;
+        v.b = 0.0f;
+        v.wv[0] = v.wv[1] = v.wv[2] = v.wv[3] = v.pos;
+        v.en[0] = v.en[1] = v.en[2] = v.en[3] = mk2(0.0f, 0.0f);
+    }
+    return v;
+}
+// K2 side of it
+R2D_HD void store_view(const Dev& d, uint32_t i, const float4& pose) {
+    const float4 s = d.shape[i];
+    if (!(f2u(s.z) & FLAG_RECT)) return;
+    const BodyView v = make_view(pose.x, pose.y, pose.z, pose.w, s.x, s.y, f2u(s.z), f2u(s.w));
+    d.view[4 * (size_t)i] = make_float4(v.wv[0].x, v.wv[0].y, v.wv[1].x, v.wv[1].y);
+    d.view[4 * (size_t)i + 1] = make_float4(v.wv[2].x, v.wv[2].y, v.wv[3].x, v.wv[3].y);
+    d.view[4 * (size_t)i + 2] = make_float4(v.en[0].x, v.en[0].y, v.en[1].x, v.en[1].y);
+    d.view[4 * (size_t)i + 3] = make_float4(v.en[2].x, v.en[2].y, v.en[3].x, v.en[3].y);
+}
 // K2: pose cache + cell count (SpatialHash.zig:46-49).  Returns the cell range so the caller can walk big bodies
 // cooperatively; small bodies are counted here.
 R2D_HD CellRange count_body_thread(const Dev& d, uint32_t i, bool count_inline) {
     const float4 p = d.pos[i];
-    d.pose[i] = make_float4(p.x, p.y, cos_ref(p.z), sin_ref(p.z));
+    const float4 pose = make_float4(p.x, p.y, cos_ref(p.z), sin_ref(p.z));
+    d.pose[i] = pose;
+    store_view(d, i, pose);
     const CellRange r = cell_range(d, i);
     d.ncells[i] = r.count;
     uint32_t bk[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
@@ -436,11 +475,6 @@ R2D_HD uint32_t entry_pairs_thread(const Dev& d, uint32_t e, uint2* out) {
 }
 
 // ---- narrowphase ---------------------------------------------------------------------------------------------------
-R2D_HD BodyView load_view(const Dev& d, uint32_t i) {
-    const float4 p = d.pose[i];
-    const float4 s = d.shape[i];
-    return make_view(p.x, p.y, p.z, p.w, s.x, s.y, f2u(s.z), f2u(s.w));
-}
 // the manifold lists of the dataflow colouring (arrival order is irrelevant: only "how many have a higher priority" is used)
 R2D_HD void adj_append(const Dev& d, uint32_t body, unsigned long long prio) {
     const uint32_t k = atomic_add_u32(&d.adj_cnt[body], 1u);

@@ -80,11 +80,12 @@ struct CudaBatch : BatchBase {
     uint32_t wait_mode = 1, wait_probe = 1, wait_spin_lag = 1, wait_sleep_unit = 200, wait_sleep_max = 4000;
     int solve_blocks_per_sm = 1;
     uint32_t solve_smem_slots = SOLVE_SMEM_SLOTS;
+    int world_solve_tpb = WORLD_TPB;
     bool persistent_solver = true;
     bool world_solver = true;       // CTA-per-world shared-memory solver when every world is small and there are no joints
     uint32_t max_world_bodies = 0;   // false: one launch per colour (kept for A/B measurements)
     // bodies
-    DBuf<float4> pos, mom, frc, prop, shape, aabb, pose;
+    DBuf<float4> pos, mom, frc, prop, shape, aabb, pose, view;
     DBuf<uint32_t> ncells, world_base, grav_off, joint_color_start, dev_of_host;
     DBuf<float> grav;
     DBuf<uint64_t> excl;
@@ -180,6 +181,7 @@ struct CudaBatch : BatchBase {
         pair_blocks = (per_sm < 1 ? 1 : per_sm) * n_sms;  // resident CTAs: a CTA per heavy bucket, a warp per light one, grid-stride
         if (const char* e = getenv("R2D_SOLVER")) persistent_solver = std::string(e) != "launches";
         if (const char* e = getenv("R2D_WORLD_SOLVER")) world_solver = atoi(e) != 0;
+        if (const char* e = getenv("R2D_WORLD_SOLVE_TPB")) world_solve_tpb = std::max(32, std::min((int)WORLD_TPB, atoi(e) / 32 * 32));
         if (const char* e = getenv("R2D_FLOW_COLORING")) flow_coloring = atoi(e) != 0;
         if (const char* e = getenv("R2D_FLOW_SLEEP_UNIT")) flow_sleep_unit = (uint32_t)atoi(e);
         return R2D_OK;
@@ -417,7 +419,7 @@ struct CudaBatch : BatchBase {
     void fill_dev() {
         d.n_bodies = image.n_bodies;
         d.pos = pos.p; d.mom = mom.p; d.frc = frc.p; d.prop = prop.p; d.shape = shape.p; d.aabb = aabb.p;
-        d.pose = pose.p; d.ncells = ncells.p; d.bkt = bkt.p;
+        d.pose = pose.p; d.view = view.p; d.ncells = ncells.p; d.bkt = bkt.p;
         d.n_worlds = (uint32_t)worlds.size();
         d.world_base = world_base.p; d.grav_off = grav_off.p; d.grav = grav.p;
         d.cell = grid_cell(); d.table_mult = grid_mult();
@@ -511,7 +513,7 @@ struct CudaBatch : BatchBase {
             if ((st = zeroed.reserve(zeroed_bytes))) return st;
         }
         if ((st = own_pos.reserve((own_w + 1) * MAX_COLORS + 2)) ||
-            (st = pose.reserve(nb)) || (st = ncells.reserve(nb)) || (st = bkt.reserve(nb)) ||  (st = bucket_cnt.reserve((size_t)T + 1, true, stream)) ||
+            (st = pose.reserve(nb)) || (st = view.reserve(4 * (size_t)nb)) || (st = ncells.reserve(nb)) || (st = bkt.reserve(nb)) ||  (st = bucket_cnt.reserve((size_t)T + 1, true, stream)) ||
             (st = bucket_start.reserve((size_t)T + 1)) || (st = ent_off.reserve((size_t)T + 2)) || (st = work.reserve(2 * (size_t)T + 2)))
             return st;
         if (cap_entries == 0 && (st = reserve_entries((size_t)nb * 3 + 4096))) return st;
@@ -562,7 +564,7 @@ struct CudaBatch : BatchBase {
                                           worlds.size() >= (size_t)n_sms / 2;  // enough worlds to fill the GPU with one CTA each
             if (use_world_solver) {
                 const uint32_t blocks = (uint32_t)std::min<size_t>(worlds.size(), (size_t)n_sms * 16);
-                R2D_LAUNCH(R2D_KCLASS_SOLVE_CONTACTS, k_solve_worlds, blocks, WORLD_TPB, d, sub_dt, S, I);
+                R2D_LAUNCH(R2D_KCLASS_SOLVE_CONTACTS, k_solve_worlds, blocks, world_solve_tpb, d, sub_dt, S, I);
             } else if (persistent_solver) {
                 prof_begin(R2D_KCLASS_SOLVE_CONTACTS);
                 const uint32_t* jcs_dev = joint_color_start.p;

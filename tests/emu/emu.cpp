@@ -20,7 +20,7 @@ using host::RawManifold;
 
 struct EmuBatch : BatchBase {
     Dev d{};
-    std::vector<float4> pos, mom, frc, prop, shape, aabb, pose;
+    std::vector<float4> pos, mom, frc, prop, shape, aabb, pose, view;
     std::vector<uint32_t> ncells, bucket_cnt, bucket_start, ent_body, ent_key, ent_off, m_color;
     std::vector<uint2> pairs;
     std::vector<uint4> m_hdr, s_hdr, bkt;
@@ -143,8 +143,8 @@ struct EmuBatch : BatchBase {
         d.sub_dt = sub_dt;
         d.pos = pos.data(); d.mom = mom.data(); d.frc = frc.data(); d.prop = prop.data(); d.shape = shape.data();
         d.aabb = aabb.data();
-        pose.resize(nb); ncells.resize(nb); bkt.resize(nb);
-        d.pose = pose.data(); d.ncells = ncells.data(); d.bkt = bkt.data();
+        pose.resize(nb); view.resize(4 * (size_t)nb); ncells.resize(nb); bkt.resize(nb);
+        d.pose = pose.data(); d.view = view.data(); d.ncells = ncells.data(); d.bkt = bkt.data();
         d.n_worlds = (uint32_t)worlds.size();
         d.world_base = image.world_base.data(); d.grav_off = image.grav_off.data(); d.grav = image.grav.data();
         d.cell = grid_cell(); d.table_mult = grid_mult();
