@@ -1069,6 +1069,256 @@ __global__ void __launch_bounds__(WORLD_TPB) k_solve_worlds(Dev d, float sub_dt,
     }
 }
 
+// ---- K14: one world, one spatial TILE of bodies per SM — the momentum words of a tile live in shared memory ---------------------
+// The dataflow sweep of k_solve_persistent is bound by the rate at which L2 serves scattered 16-byte body words (two
+// loads and two stores per manifold and sweep).  Device slots are in Morton order, so the bodies [t B, (t + 1) B) are a
+// compact patch of the world and most manifolds touch two bodies of the same patch.  CTA t therefore runs ALL
+// manifolds owned by its bodies (per colour a contiguous range of the owner-ordered records, see manifold_owner) and
+// keeps the momentum word of every body that no other CTA touches in shared memory, with its version counter next
+// to it.  Bodies that a foreign CTA touches ("shared": marked by the partition kernel) stay in global memory with the
+// 16-byte version protocol of k_solve_persistent.  Same per-body update sequence as everywhere else: bit-identical.
+//
+// A warp works on tasks of 32 consecutive records of ONE colour (no dependencies inside a warp) and takes its tasks in
+// ascending (iteration, colour) order; all CTAs are resident (cooperative launch), so the lowest unfinished record of
+// the grid can always run: no deadlock.  The first `cache_tasks` tasks of a CTA keep their records (and accumulated
+// impulses) in shared memory for the whole kernel.
+constexpr int TILE_TPB = 512;
+constexpr uint32_t TILE_MAX_BODIES = 1024;
+constexpr uint32_t TILE_MAX_TASKS = 512;
+constexpr uint32_t TILE_LOC1 = 0x1000u, TILE_LOC2 = 0x2000u;  // s_hdr.z of a cached record: body word in shared memory
+constexpr size_t TILE_FIXED_SMEM = (size_t)TILE_MAX_BODIES * 20 + (size_t)TILE_MAX_TASKS * 8 + (size_t)MAX_COLORS * 8;
+constexpr size_t TILE_SMEM_BYTES = 232448 - 1024;  // all of it (the static part of the kernel is tiny)
+constexpr uint32_t TILE_CACHE_TASKS = (uint32_t)((TILE_SMEM_BYTES - TILE_FIXED_SMEM) / (32 * 144));
+
+__device__ __forceinline__ uint32_t ld_volatile_shared_u32(const uint32_t* p) { return *((const volatile uint32_t*)p); }
+__device__ __forceinline__ float4 ld_volatile_shared_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"((uint32_t)__cvta_generic_to_shared(p))
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_shared_f4(float4* p, float4 v) {
+    asm volatile("st.volatile.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(TILE_TPB) k_solve_tiles(Dev d, float sub_dt, uint32_t S, uint32_t I, uint32_t cache_tasks) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::grid_group grid = cg::this_grid();
+    if (overflowed(d) || d.counters->err != 0u) return;  // uniform across the grid
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const uint32_t B = d.tile_bodies;
+    const uint32_t b0 = blockIdx.x * B < d.n_bodies ? blockIdx.x * B : d.n_bodies;
+    const uint32_t b1 = b0 + B < d.n_bodies ? b0 + B : d.n_bodies;
+    const uint32_t nb = b1 - b0, nc = d.counters->n_colors;
+    // ---- shared memory layout ----
+    unsigned char* q = smem_raw;
+    float4* t_mom = (float4*)q;                 q += (size_t)TILE_MAX_BODIES * 16;
+    uint32_t* t_ver = (uint32_t*)q;             q += (size_t)TILE_MAX_BODIES * 4;
+    uint32_t* t_first = (uint32_t*)q;           q += (size_t)TILE_MAX_TASKS * 4;
+    uint32_t* t_count = (uint32_t*)q;           q += (size_t)TILE_MAX_TASKS * 4;
+    uint32_t* t_cbeg = (uint32_t*)q;            q += (size_t)MAX_COLORS * 4;
+    uint32_t* t_cend = (uint32_t*)q;            q += (size_t)MAX_COLORS * 4;
+    Dev ds = d;  // record arrays of the cached tasks
+    {
+        const size_t n = (size_t)cache_tasks * 32;
+        ds.s_hdr = (uint4*)q;    q += n * 16;
+        ds.s_nf = (float4*)q;    q += n * 16;
+        ds.s_inv = (float4*)q;   q += n * 16;
+        ds.s_dep = (uint4*)q;    q += n * 16;
+        ds.s_r0 = (float4*)q;    q += n * 16;
+        ds.s_pm0 = (float4*)q;   q += n * 16;
+        ds.s_r1 = (float4*)q;    q += n * 16;
+        ds.s_pm1 = (float4*)q;   q += n * 16;
+        ds.s_acc0 = (float2*)q;  q += n * 8;
+        ds.s_acc1 = (float2*)q;
+    }
+    __shared__ uint32_t s_n_tasks;
+    // ---- task table: per colour the records owned by this tile, cut into warps ----
+    for (uint32_t c = threadIdx.x; c < nc; c += blockDim.x) {
+        t_cbeg[c] = owner_rank(d, c, b0);
+        t_cend[c] = (b1 < d.n_bodies) ? owner_rank(d, c, b1) : d.own_pos[(size_t)c * (d.own_words + 1u) + d.own_words];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t k = 0;
+        for (uint32_t c = 0; c < nc; ++c)
+            for (uint32_t r = t_cbeg[c]; r < t_cend[c]; r += 32u, ++k)
+                if (k < TILE_MAX_TASKS) {
+                    t_first[k] = r;
+                    t_count[k] = t_cend[c] - r < 32u ? t_cend[c] - r : 32u;
+                }
+        s_n_tasks = k;
+        if (k > TILE_MAX_TASKS || nb > TILE_MAX_BODIES) atomicOr(&d.counters->tile_fallback, 1u);
+    }
+    __syncthreads();
+    const uint32_t n_tasks = s_n_tasks;
+    grid.sync();
+    if (__ldcg(&d.counters->tile_fallback) != 0u) return;  // nothing has been modified: the host runs k_solve_persistent
+    stamp(d, 0);
+    // ---- stage the cached records; remember which body words are tile-local ----
+    for (uint32_t k = warp; k < n_tasks && k < cache_tasks; k += n_warps) {
+        if (lane >= t_count[k]) continue;
+        const uint32_t m = t_first[k] + lane, l = k * 32u + lane;
+        uint4 h = d.s_hdr[m];
+        const bool st1 = (h.z & 0x100u) != 0, st2 = (h.z & 0x200u) != 0;
+        if (!st1 && h.x >= b0 && h.x < b1 && d.body_shared[h.x] == 0u) h.z |= TILE_LOC1;
+        if (!st2 && h.y >= b0 && h.y < b1 && d.body_shared[h.y] == 0u) h.z |= TILE_LOC2;
+        ds.s_hdr[l] = h;
+        ds.s_nf[l] = d.s_nf[m];
+        ds.s_inv[l] = d.s_inv[m];
+        ds.s_dep[l] = d.s_dep[m];
+        ds.s_r0[l] = d.s_r0[m];
+        ds.s_pm0[l] = d.s_pm0[m];
+        ds.s_acc0[l] = d.s_acc0[m];
+        if ((h.z & 0xFFu) > 1u) {
+            ds.s_r1[l] = d.s_r1[m];
+            ds.s_pm1[l] = d.s_pm1[m];
+            ds.s_acc1[l] = d.s_acc1[m];
+        }
+    }
+    for (uint32_t s = 0; s < S; ++s) {
+        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+            if (s == 0) integrate_forces_thread(d, b0 + i, sub_dt, S == 1);
+            t_mom[i] = d.mom[b0 + i];
+            t_ver[i] = 0u;
+        }
+        if (s == 0) stamp(d, 1);
+        __syncthreads();
+        grid.sync();
+        if (s == 0) stamp(d, 2);
+        for (uint32_t it = 0; it < I; ++it) {
+            for (uint32_t k = warp; k < n_tasks; k += n_warps) {
+                const bool cached = k < cache_tasks;
+                const Dev& rd = cached ? ds : d;
+                const uint32_t x = cached ? k * 32u + lane : t_first[k] + lane;
+                bool pending = lane < t_count[k];
+                // ---- record ----
+                uint4 h = make_uint4(0u, 0u, 0u, 0u);
+                ContactConst c;
+                ContactPointConst pts[2];
+                v2 acc[2];
+                int np = 0;
+                bool st1 = true, st2 = true, loc1 = false, loc2 = false;
+                uint32_t e1 = 0, e2 = 0;
+                float4 m1 = make_float4(0, 0, 0, 0), m2 = m1;
+                if (pending) {
+                    h = rd.s_hdr[x];
+                    np = (int)(h.z & 0xFFu);
+                    st1 = (h.z & 0x100u) != 0;
+                    st2 = (h.z & 0x200u) != 0;
+                    if (cached) {
+                        loc1 = (h.z & TILE_LOC1) != 0;
+                        loc2 = (h.z & TILE_LOC2) != 0;
+                    } else {
+                        loc1 = !st1 && h.x >= b0 && h.x < b1 && d.body_shared[h.x] == 0u;
+                        loc2 = !st2 && h.y >= b0 && h.y < b1 && d.body_shared[h.y] == 0u;
+                    }
+                    const float4 nf = rd.s_nf[x], inv = rd.s_inv[x];
+                    c.normal = mk2(nf.x, nf.y);
+                    c.tangent = rot90cw(c.normal);
+                    c.friction = nf.z;
+                    c.inv_m1 = inv.x;
+                    c.inv_m2 = inv.y;
+                    c.inv_i1 = inv.z;
+                    c.inv_i2 = inv.w;
+                    {
+                        const float4 r = rd.s_r0[x], pm = rd.s_pm0[x];
+                        const float2 a = rd.s_acc0[x];
+                        pts[0].r1 = mk2(r.x, r.y);
+                        pts[0].r2 = mk2(r.z, r.w);
+                        pts[0].mass_n = pm.x;
+                        pts[0].mass_t = pm.y;
+                        pts[0].depth = pm.z;
+                        pts[0].bias = pm.w;
+                        acc[0] = mk2(a.x, a.y);
+                    }
+                    if (np > 1) {
+                        const float4 r = rd.s_r1[x], pm = rd.s_pm1[x];
+                        const float2 a = rd.s_acc1[x];
+                        pts[1].r1 = mk2(r.x, r.y);
+                        pts[1].r2 = mk2(r.z, r.w);
+                        pts[1].mass_n = pm.x;
+                        pts[1].mass_t = pm.y;
+                        pts[1].depth = pm.z;
+                        pts[1].bias = pm.w;
+                        acc[1] = mk2(a.x, a.y);
+                    }
+                    const uint4 dep = rd.s_dep[x];
+                    e1 = it * dep.y + dep.x;
+                    e2 = it * dep.w + dep.z;
+                    if (st1) m1 = d.mom[h.x];  // static bodies are never written during a sweep
+                    if (st2) m2 = d.mom[h.y];
+                }
+                // ---- wait for both bodies, update, publish ----
+                uint32_t spins = 0;
+                while (__any_sync(0xffffffffu, pending)) {
+                    if (pending) {
+                        uint32_t lag = 0u;
+                        if (!st1) {
+                            if (loc1) {
+                                lag += e1 - ld_volatile_shared_u32(&t_ver[h.x - b0]);
+                            } else {
+                                m1 = ld_body_word(&d.mom[h.x]);
+                                lag += e1 - f2u(m1.w);
+                            }
+                        }
+                        if (!st2) {
+                            if (loc2) {
+                                lag += e2 - ld_volatile_shared_u32(&t_ver[h.y - b0]);
+                            } else {
+                                m2 = ld_body_word(&d.mom[h.y]);
+                                lag += e2 - f2u(m2.w);
+                            }
+                        }
+                        if (lag == 0u) {
+                            __threadfence_block();  // the version was written after the momentum it announces
+                            if (loc1) m1 = ld_volatile_shared_f4(&t_mom[h.x - b0]);
+                            if (loc2) m2 = ld_volatile_shared_f4(&t_mom[h.y - b0]);
+                            BodyVel v1 = {mk2(m1.x, m1.y), m1.z}, v2_ = {mk2(m2.x, m2.y), m2.z};
+                            solve_contact(c, np, pts, acc, st1, st2, v1, v2_);
+                            rd.s_acc0[x] = make_float2(acc[0].x, acc[0].y);
+                            if (np > 1) rd.s_acc1[x] = make_float2(acc[1].x, acc[1].y);
+                            if (loc1) st_volatile_shared_f4(&t_mom[h.x - b0], make_float4(v1.mom.x, v1.mom.y, v1.ang, 0.0f));
+                            if (loc2) st_volatile_shared_f4(&t_mom[h.y - b0], make_float4(v2_.mom.x, v2_.mom.y, v2_.ang, 0.0f));
+                            if (!st1 && !loc1) st_body_word(&d.mom[h.x], make_float4(v1.mom.x, v1.mom.y, v1.ang, u2f(e1 + 1u)));
+                            if (!st2 && !loc2) st_body_word(&d.mom[h.y], make_float4(v2_.mom.x, v2_.mom.y, v2_.ang, u2f(e2 + 1u)));
+                            if (loc1 || loc2) {
+                                __threadfence_block();
+                                if (loc1) *((volatile uint32_t*)&t_ver[h.x - b0]) = e1 + 1u;
+                                if (loc2) *((volatile uint32_t*)&t_ver[h.y - b0]) = e2 + 1u;
+                            }
+                            pending = false;
+                        }
+                    }
+                    if ((++spins & 0xFFu) == 0u) {
+                        // a stall would be a bug: flag it and let everybody run to the end (a CTA that returned early
+                        // would leave the others waiting at the grid barrier)
+                        if (spins > (1u << 20)) atomicOr(&d.counters->err, ERR_STALL);
+                        if (*((volatile uint32_t*)&d.counters->err) & ERR_STALL) pending = false;
+                    }
+                }
+            }
+            if (s == 0) stamp(d, 3 + it);
+        }
+        __syncthreads();
+        grid.sync();
+        if (s == 0) stamp(d, 8);
+        // end of substep s fused with the start of substep s + 1 (per body, same thread)
+        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+            const uint32_t b = b0 + i;
+            if (!(body_flags(d, b) & FLAG_STATIC) && d.body_shared[b] == 0u) d.mom[b] = t_mom[i];
+            integrate_positions_thread(d, b, sub_dt);
+            if (s + 1 < S) integrate_forces_thread(d, b, sub_dt, s + 2 == S);
+        }
+        if (s == 0) stamp(d, 9);
+    }
+    // accumulated impulses of the cached records are not needed after the call (collision.zig:102-133 re-creates them)
+}
+
 // ---- boundary kernels: SoA export for bulk readback, force import ---------------------------------------------------------------
 // `slot_of[k]` = device slot of the k-th requested body (host order): the device order is a spatial permutation
 __global__ void __launch_bounds__(TPB) k_export_bodies(Dev d, const uint32_t* __restrict__ slot_of, uint32_t n, uint32_t* ids,

@@ -62,6 +62,7 @@ struct Counters {
     uint32_t flow_abort;     // set by the narrowphase: a body has more than ADJ_CAP manifolds, colour by rounds
     uint32_t flow_fail;      // set inside the dataflow colouring: more than FLOW_COLORS colours needed (or a stall)
     uint32_t flow_used;      // the colours of this step come from the dataflow colouring (masks in cstate, not in used)
+    uint32_t tile_fallback;  // k_solve_tiles declined (a tile has too many bodies / tasks): the host runs k_solve_persistent
     unsigned long long stamp[10];   // %globaltimer at phase boundaries of the persistent solver (block 0; diagnostics)
 };
 
@@ -138,6 +139,8 @@ struct Dev {
     float4* s_pm1;
     float2* s_acc0;               // point 0: accumulated_pn, accumulated_pt
     float2* s_acc1;
+    uint32_t tile_bodies;         // B > 0: k_solve_tiles will run with tiles of B consecutive body slots (else 0)
+    uint32_t* body_shared;        // NB: 1 if a manifold owned by a body of ANOTHER tile touches the body (see k_solve_tiles)
     uint4* s_dep;                 // rank of this manifold among the contacts of its ref body, that body's contact count,
                                   // same for the inc body  (dataflow ordering of the sweep, see solve_contact_thread)
     // ---- joints, grouped by colour -----------------------------------------------------------------------------------
@@ -702,6 +705,8 @@ R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
     const float4 g0 = d.m_g0[p], g1 = d.m_g1[p];
     const ContactConst c = prestep_manifold(mk2(g0.x, g0.y), st1, st2, pr1.x, pr2.x, pr1.y, pr2.y, pr1.z, pr2.z);
     d.s_hdr[at] = make_uint4(h.x, h.y, np | (st1 ? 0x100u : 0u) | (st2 ? 0x200u : 0u), p);
+    if (d.tile_bodies && !st1 && !st2 && h.x / d.tile_bodies != h.y / d.tile_bodies)
+        d.body_shared[h.x > h.y ? h.x : h.y] = 1u;  // the owner is the lower slot: the other body is foreign to its tile
     // Colours on one body are pairwise distinct, so the body's sweep sequence is its colour set in ascending order:
     // rank = colours below mine, degree = colours used.
     {

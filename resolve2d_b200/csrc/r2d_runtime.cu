@@ -106,7 +106,10 @@ struct CudaBatch : BatchBase {
     DBuf<unsigned char> zeroed;
     size_t zeroed_bytes = 0, scan_state_cap = 0;
     size_t off_counters = 0, off_color_misc = 0, off_scan = 0, off_maxprio0 = 0, off_maxprio1 = 0, off_used = 0, off_own_bits = 0;
-    size_t off_adj_cnt = 0, off_cstate = 0;
+    size_t off_adj_cnt = 0, off_cstate = 0, off_body_shared = 0;
+    bool tile_solver = true;          // k_solve_tiles for single worlds without joints that fit (R2D_TILE_SOLVER=0: never)
+    uint32_t tile_bodies_now = 0;
+    bool tile_declined = false;
     DBuf<unsigned long long> adj_prio;
     bool flow_coloring = true, flow_now = false;   // dataflow colouring of single worlds (R2D_FLOW_COLORING=0: rounds only)
     uint32_t flow_sleep_unit = 150;
@@ -183,6 +186,8 @@ struct CudaBatch : BatchBase {
         if (const char* e = getenv("R2D_WORLD_SOLVER")) world_solver = atoi(e) != 0;
         if (const char* e = getenv("R2D_WORLD_SOLVE_TPB")) world_solve_tpb = std::max(32, std::min((int)WORLD_TPB, atoi(e) / 32 * 32));
         if (const char* e = getenv("R2D_FLOW_COLORING")) flow_coloring = atoi(e) != 0;
+        if (const char* e = getenv("R2D_TILE_SOLVER")) tile_solver = atoi(e) != 0;
+        R2D_CUDA(cudaFuncSetAttribute(k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES));
         if (const char* e = getenv("R2D_FLOW_SLEEP_UNIT")) flow_sleep_unit = (uint32_t)atoi(e);
         return R2D_OK;
     }
@@ -257,6 +262,7 @@ struct CudaBatch : BatchBase {
             return st;
         R2D_CUDA(cudaStreamSynchronize(stream));  // the image vectors are pageable and may change after we return
         last_pairs = 0;
+        tile_declined = false;
         max_world_bodies = 0;
         for (size_t w = 0; w + 1 < image.world_base.size(); ++w)
             max_world_bodies = std::max(max_world_bodies, image.world_base[w + 1] - image.world_base[w]);
@@ -445,6 +451,8 @@ struct CudaBatch : BatchBase {
         d.cstate = (uint4*)(zeroed.p + off_cstate);
         d.adj_prio = adj_prio.p;
         d.flow_sleep_unit = flow_sleep_unit;
+        d.tile_bodies = tile_bodies_now;
+        d.body_shared = (uint32_t*)(zeroed.p + off_body_shared);
         d.own_words = (d.n_bodies + 31u) / 32u;
         d.own_bits = (uint32_t*)(zeroed.p + off_own_bits);
         d.own_pos = own_pos.p;
@@ -481,6 +489,19 @@ struct CudaBatch : BatchBase {
         return R2D_OK;
     }
 
+    int launch_persistent(float sub_dt, uint32_t S, uint32_t I) {
+        prof_begin(R2D_KCLASS_SOLVE_CONTACTS);
+        const uint32_t* jcs_dev = joint_color_start.p;
+        uint32_t n_jc = (uint32_t)image.joint_color_start.size() - 1, S_ = S, I_ = I;
+        float sd = sub_dt;
+        uint32_t slots = solve_smem_slots;
+        void* args[] = {(void*)&d, (void*)&sd, (void*)&S_, (void*)&I_, (void*)&jcs_dev, (void*)&n_jc, (void*)&slots};
+        R2D_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(solve_blocks), dim3(PSOLVE_TPB), args, SOLVE_SMEM_BYTES, stream));
+        prof_end();
+        launches += 1;
+        return R2D_OK;
+    }
+
     int backend_process(float dt, uint32_t S, uint32_t I) override {
         R2D_CUDA(cudaSetDevice(device));
         const uint32_t nb = image.n_bodies;
@@ -509,6 +530,7 @@ struct CudaBatch : BatchBase {
             off_own_bits = o; o = align(o + own_w * MAX_COLORS * 4);
             off_adj_cnt = o; o = align(o + (size_t)nb * 4);
             off_cstate = o; o = align(o + (size_t)nb * 16);
+            off_body_shared = o; o = align(o + (size_t)nb * 4);
             zeroed_bytes = o;
             if ((st = zeroed.reserve(zeroed_bytes))) return st;
         }
@@ -526,6 +548,15 @@ struct CudaBatch : BatchBase {
         const size_t pairs_guess = last_pairs ? (size_t)last_pairs : (size_t)nb * 3;
         flow_now = flow_coloring && !color_per_world && pairs_guess <= (size_t)FLOW_SLOTS * color_blocks * TPB;
         if (flow_now && (st = adj_prio.reserve((size_t)nb * ADJ_CAP))) return st;
+        // solver flavour: CTA-per-world for batches of small worlds; one spatial tile of bodies per SM for a single world
+        // without joints that fits (k_solve_tiles may still decline on the device); else the persistent dataflow sweep
+        const bool use_world_solver = persistent_solver && world_solver && image.j_hdr.empty() &&
+                                      max_world_bodies <= WORLD_MAX_BODIES &&
+                                      worlds.size() >= (size_t)n_sms / 2;  // enough worlds to fill the GPU with one CTA each
+        const uint32_t tile_b = (nb + (uint32_t)n_sms - 1) / (uint32_t)n_sms;
+        const bool use_tile_solver = persistent_solver && tile_solver && !tile_declined && !use_world_solver && image.j_hdr.empty() &&
+                                     tile_b <= TILE_MAX_BODIES && nb >= (uint32_t)n_sms * 8;
+        tile_bodies_now = use_tile_solver ? tile_b : 0u;
         for (int attempt = 0;; ++attempt) {
             fill_dev();
             R2D_CUDA(cudaMemsetAsync(zeroed.p, 0, zeroed_bytes, stream));  // counters, colour tables, scan states, masks
@@ -559,22 +590,19 @@ struct CudaBatch : BatchBase {
             if ((st = scan(d.own_pos, d.own_pos, &d.counters->n_own_scan, (uint32_t)((own_w + 1) * MAX_COLORS), nullptr, R2D_KCLASS_COLORING, 2))) return st;
             R2D_LAUNCH(R2D_KCLASS_COLORING, k_partition_prestep, grid_for(cap_pairs), TPB, d);
             // ---- substeps: one persistent cooperative kernel (colour ranges are read on the device) ----
-            const bool use_world_solver = persistent_solver && world_solver && image.j_hdr.empty() &&
-                                          max_world_bodies <= WORLD_MAX_BODIES &&
-                                          worlds.size() >= (size_t)n_sms / 2;  // enough worlds to fill the GPU with one CTA each
             if (use_world_solver) {
                 const uint32_t blocks = (uint32_t)std::min<size_t>(worlds.size(), (size_t)n_sms * 16);
                 R2D_LAUNCH(R2D_KCLASS_SOLVE_CONTACTS, k_solve_worlds, blocks, world_solve_tpb, d, sub_dt, S, I);
-            } else if (persistent_solver) {
+            } else if (use_tile_solver) {
                 prof_begin(R2D_KCLASS_SOLVE_CONTACTS);
-                const uint32_t* jcs_dev = joint_color_start.p;
-                uint32_t n_jc = (uint32_t)image.joint_color_start.size() - 1, S_ = S, I_ = I;
+                uint32_t S_ = S, I_ = I, cache = TILE_CACHE_TASKS;
                 float sd = sub_dt;
-                uint32_t slots = solve_smem_slots;
-                void* args[] = {(void*)&d, (void*)&sd, (void*)&S_, (void*)&I_, (void*)&jcs_dev, (void*)&n_jc, (void*)&slots};
-                R2D_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(solve_blocks), dim3(PSOLVE_TPB), args, SOLVE_SMEM_BYTES, stream));
+                void* args[] = {(void*)&d, (void*)&sd, (void*)&S_, (void*)&I_, (void*)&cache};
+                R2D_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_tiles, dim3(n_sms), dim3(TILE_TPB), args, TILE_SMEM_BYTES, stream));
                 prof_end();
                 launches += 1;
+            } else if (persistent_solver) {
+                if ((st = launch_persistent(sub_dt, S, I))) return st;
             }
             // ---- the one synchronisation point of the step: counters + colour offsets ----
             R2D_CUDA(cudaMemcpyAsync(&pinned->counters, d.counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
@@ -591,6 +619,15 @@ struct CudaBatch : BatchBase {
                 // P is only meaningful once all entries fit; grow generously when it is known to be too small
                 if (c.n_pairs > cap_pairs && (st = reserve_pairs((size_t)c.n_pairs + c.n_pairs / 4))) return st;
                 continue;
+            }
+            if (c.tile_fallback && use_tile_solver) {
+                // k_solve_tiles declined before touching anything (a tile with too many bodies or records): run the
+                // persistent sweep on the same records now, and stop trying tiles until the next upload
+                tile_declined = true;
+                if ((st = launch_persistent(sub_dt, S, I))) return st;
+                R2D_CUDA(cudaMemcpyAsync(&pinned->counters, d.counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+                R2D_CUDA(cudaStreamSynchronize(stream));
+                R2D_CUDA(cudaGetLastError());
             }
             break;
         }
