@@ -1105,7 +1105,8 @@ __device__ __forceinline__ void st_volatile_shared_f4(float4* p, float4 v) {
                  : "memory");
 }
 
-__global__ void __launch_bounds__(TILE_TPB) k_solve_tiles(Dev d, float sub_dt, uint32_t S, uint32_t I, uint32_t cache_tasks) {
+__global__ void __launch_bounds__(TILE_TPB) k_solve_tiles(Dev d, float sub_dt, uint32_t S, uint32_t I, uint32_t cache_tasks,
+                                                          uint32_t max_tasks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::grid_group grid = cg::this_grid();
     if (overflowed(d) || d.counters->err != 0u) return;  // uniform across the grid
@@ -1147,12 +1148,12 @@ __global__ void __launch_bounds__(TILE_TPB) k_solve_tiles(Dev d, float sub_dt, u
         uint32_t k = 0;
         for (uint32_t c = 0; c < nc; ++c)
             for (uint32_t r = t_cbeg[c]; r < t_cend[c]; r += 32u, ++k)
-                if (k < TILE_MAX_TASKS) {
+                if (k < max_tasks) {
                     t_first[k] = r;
                     t_count[k] = t_cend[c] - r < 32u ? t_cend[c] - r : 32u;
                 }
         s_n_tasks = k;
-        if (k > TILE_MAX_TASKS || nb > TILE_MAX_BODIES) atomicOr(&d.counters->tile_fallback, 1u);
+        if (k > max_tasks || nb > TILE_MAX_BODIES) atomicOr(&d.counters->tile_fallback, 1u);
     }
     __syncthreads();
     const uint32_t n_tasks = s_n_tasks;

@@ -108,7 +108,7 @@ struct CudaBatch : BatchBase {
     size_t off_counters = 0, off_color_misc = 0, off_scan = 0, off_maxprio0 = 0, off_maxprio1 = 0, off_used = 0, off_own_bits = 0;
     size_t off_adj_cnt = 0, off_cstate = 0, off_body_shared = 0;
     bool tile_solver = true;          // k_solve_tiles for single worlds without joints that fit (R2D_TILE_SOLVER=0: never)
-    uint32_t tile_bodies_now = 0;
+    uint32_t tile_bodies_now = 0, tile_max_tasks = TILE_MAX_TASKS;
     bool tile_declined = false;
     DBuf<unsigned long long> adj_prio;
     bool flow_coloring = true, flow_now = false;   // dataflow colouring of single worlds (R2D_FLOW_COLORING=0: rounds only)
@@ -187,6 +187,7 @@ struct CudaBatch : BatchBase {
         if (const char* e = getenv("R2D_WORLD_SOLVE_TPB")) world_solve_tpb = std::max(32, std::min((int)WORLD_TPB, atoi(e) / 32 * 32));
         if (const char* e = getenv("R2D_FLOW_COLORING")) flow_coloring = atoi(e) != 0;
         if (const char* e = getenv("R2D_TILE_SOLVER")) tile_solver = atoi(e) != 0;
+        if (const char* e = getenv("R2D_TILE_MAX_TASKS")) tile_max_tasks = std::min<uint32_t>((uint32_t)atoi(e), TILE_MAX_TASKS);  // tests
         R2D_CUDA(cudaFuncSetAttribute(k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES));
         if (const char* e = getenv("R2D_FLOW_SLEEP_UNIT")) flow_sleep_unit = (uint32_t)atoi(e);
         return R2D_OK;
@@ -595,9 +596,9 @@ struct CudaBatch : BatchBase {
                 R2D_LAUNCH(R2D_KCLASS_SOLVE_CONTACTS, k_solve_worlds, blocks, world_solve_tpb, d, sub_dt, S, I);
             } else if (use_tile_solver) {
                 prof_begin(R2D_KCLASS_SOLVE_CONTACTS);
-                uint32_t S_ = S, I_ = I, cache = TILE_CACHE_TASKS;
+                uint32_t S_ = S, I_ = I, cache = TILE_CACHE_TASKS, max_tasks = tile_max_tasks;
                 float sd = sub_dt;
-                void* args[] = {(void*)&d, (void*)&sd, (void*)&S_, (void*)&I_, (void*)&cache};
+                void* args[] = {(void*)&d, (void*)&sd, (void*)&S_, (void*)&I_, (void*)&cache, (void*)&max_tasks};
                 R2D_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_tiles, dim3(n_sms), dim3(TILE_TPB), args, TILE_SMEM_BYTES, stream));
                 prof_end();
                 launches += 1;

@@ -75,6 +75,19 @@ def test_gpu_dataflow_colouring_and_its_fallback():
     assert st.n_colors >= 40 and st.n_color_rounds > 0
 
 
+def test_gpu_solver_flavours_agree(monkeypatch):
+    """pile_10k through the tile solver (default for a single world without joints), through the persistent dataflow
+    sweep (R2D_TILE_SOLVER=0) and through the device-side decline of the tile solver (a tile with more record tasks
+    than allowed -> the host re-launches the persistent sweep): all three bit-identical to the oracle"""
+    build = lambda s: scenes.build_pile(s, 200, 50)
+    run_parity(lambda: Solver(2.0, 4), build, 40, check_every=20, what="pile10k tiles")
+    monkeypatch.setenv("R2D_TILE_SOLVER", "0")
+    run_parity(lambda: Solver(2.0, 4), build, 40, check_every=20, what="pile10k persistent")
+    monkeypatch.setenv("R2D_TILE_SOLVER", "1")
+    monkeypatch.setenv("R2D_TILE_MAX_TASKS", "2")
+    run_parity(lambda: Solver(2.0, 4), build, 40, check_every=20, what="pile10k tile solver declines")
+
+
 def test_gpu_substep_iteration_variants():
     for S, I in ((1, 1), (1, 4), (2, 10), (4, 0)):
         run_parity(lambda: Solver(2.0, 4), scenes.build_box1k, 60, check_every=20, what=f"box1k S{S} I{I}", sub_steps=S,
