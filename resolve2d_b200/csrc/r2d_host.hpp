@@ -7,6 +7,7 @@
 // Bodies/Disc.zig:29-56, Bodies/Rectangle.zig:33-64.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -131,6 +132,10 @@ struct Image {
     std::vector<uint32_t> joint_color_start;   // n_joint_colors + 1
     std::vector<uint32_t> joint_world, joint_local_index, joint_color;  // per sorted joint
     uint32_t n_bodies = 0;
+    // Fine broadphase grid (r2d_pipeline.cuh, "fine grid"): cell width chosen from the body sizes of this upload (0 = no
+    // fine grid), the coarse cell it was chosen for, and how many bodies are too wide for it (FLAG_LARGE).
+    float fine_cell = 0.0f, fine_for_cell = 0.0f;
+    uint32_t n_large = 0, n_large_dynamic = 0;
     // Device slots are a spatial (Morton) permutation of the host's insertion-order slots inside every world, so that
     // bodies that touch are neighbours in memory (the gathers of the colouring and of the contact sweep coalesce).
     // Nothing observable depends on it: pairs, colours and the sweep order are functions of ids and geometry only.
@@ -154,9 +159,9 @@ inline uint32_t morton16(uint32_t x, uint32_t y) {
 
 inline float4 mkf4(float x, float y, float z, float w) { return make_float4(x, y, z, w); }
 
-inline void body_to_image(const Body& b, uint32_t world, Image& im, size_t at) {
+inline void body_to_image(const Body& b, uint32_t world, Image& im, size_t at, bool large) {
     const uint32_t flags = (b.is_static ? FLAG_STATIC : 0u) | (b.shape == R2D_SHAPE_RECT ? FLAG_RECT : 0u) |
-                           (world << FLAG_WORLD_SHIFT);
+                           (large ? FLAG_LARGE : 0u) | (world << FLAG_WORLD_SHIFT);
     im.pos[at] = mkf4(b.pos_x, b.pos_y, b.angle, 0.0f);
     im.mom[at] = mkf4(b.mom_x, b.mom_y, b.ang_mom, 0.0f);
     im.frc[at] = mkf4(b.force_x, b.force_y, b.torque, 0.0f);
@@ -167,8 +172,40 @@ inline void body_to_image(const Body& b, uint32_t world, Image& im, size_t at) {
 
 // Returns R2D_OK or R2D_ERR_INVALID_BODY_ID (a joint names a body that no longer exists — the reference fails inside
 // process() with error.InvalidRigidBodyId, DistanceJoint.zig:44-46; here before any state is touched).
-inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image& im) {
+// Width bound of a body's AABB at any angle: disc 2 r, rectangle its diagonal; never below the stored AABB.
+inline float body_width_bound(const Body& b) {
+    float w = (b.shape == R2D_SHAPE_RECT) ? (float)std::sqrt((double)b.a * b.a + (double)b.b * b.b) : 2.0f * b.a;
+    w = std::max(w, std::max(2.0f * b.aabb_hw, 2.0f * b.aabb_hh));
+    return w == w ? w : INFINITY;
+}
+// Fine broadphase cell: the widest body that is at most 4 x the median width, plus a margin that covers
+// AABB_EPS_OVERLAP and float rounding, capped below the coarse cell (a small body then covers <= 2 x 2 coarse cells).
+constexpr float FINE_MARGIN = 0.05f;
+inline void choose_fine_cell(const std::vector<std::unique_ptr<World>>& worlds, float coarse_cell, Image& im) {
+    im.fine_cell = 0.0f;
+    im.fine_for_cell = coarse_cell;
+    std::vector<float> w;
+    for (auto& W : worlds)
+        for (const Body& b : W->bodies) w.push_back(body_width_bound(b));
+    if (w.empty()) return;
+    std::nth_element(w.begin(), w.begin() + w.size() / 2, w.end());
+    const float median = w[w.size() / 2];
+    const float cap = std::min(3.95f, coarse_cell - FINE_MARGIN);
+    const float limit = std::min(4.0f * median, cap - FINE_MARGIN);
+    float widest = 0.0f;
+    for (float x : w)
+        if (x <= limit) widest = std::max(widest, x);
+    if (!(widest > 0.0f) || !(limit > 0.0f)) return;
+    im.fine_cell = widest + FINE_MARGIN;
+}
+inline bool body_is_large(const Body& b, const Image& im) {
+    return !(im.fine_cell > 0.0f && body_width_bound(b) + FINE_MARGIN <= im.fine_cell);
+}
+
+inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image& im, float coarse_cell) {
     const size_t nw = worlds.size();
+    choose_fine_cell(worlds, coarse_cell, im);
+    im.n_large = im.n_large_dynamic = 0;
     im.world_base.assign(nw + 1, 0);
     im.grav_off.assign(nw + 1, 0);
     im.grav.clear();
@@ -227,7 +264,14 @@ inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image&
     for (size_t w = 0; w < nw; ++w) {
         const World& W = *worlds[w];
         const uint32_t base = im.world_base[w];
-        for (size_t s = 0; s < W.bodies.size(); ++s) body_to_image(W.bodies[s], (uint32_t)w, im, im.dev_of_host[base + s]);
+        for (size_t s = 0; s < W.bodies.size(); ++s) {
+            const bool large = body_is_large(W.bodies[s], im);
+            if (large) {
+                im.n_large += 1;
+                if (!W.bodies[s].is_static) im.n_large_dynamic += 1;
+            }
+            body_to_image(W.bodies[s], (uint32_t)w, im, im.dev_of_host[base + s], large);
+        }
         for (const auto& pr : W.excluded) {
             const int s1 = W.find(pr.first), s2 = W.find(pr.second);
             if (s1 < 0 || s2 < 0 || s1 == s2) continue;
@@ -343,7 +387,7 @@ struct BatchBase {
     }
     int ensure_device() {
         if (!dev_fresh) {
-            const int st = build_image(worlds, image);
+            const int st = build_image(worlds, image, grid_cell());
             if (st != R2D_OK) return st;
             const int st2 = backend_upload();
             if (st2 != R2D_OK) return st2;
@@ -378,6 +422,10 @@ struct BatchBase {
     }
     int process(float dt, uint32_t sub_steps, uint32_t iters) {
         if (dev_fresh && reorder_interval && steps_since_upload >= reorder_interval) {
+            const int sr = reorder();
+            if (sr != R2D_OK) return sr;
+        }
+        if (dev_fresh && image.fine_for_cell != grid_cell()) {  // the mode changed: the fine cell depends on the coarse one
             const int sr = reorder();
             if (sr != R2D_OK) return sr;
         }

@@ -45,10 +45,14 @@ __global__ void __launch_bounds__(TPB) k_grid_cells(Dev d) {
         const uint32_t i = base + threadIdx.x;
         if (i < d.n_bodies) {
             CellRange r;
-            if (FILL)
-                r = cell_range(d, i);
-            else
+            if (!FILL) {
                 r = count_body_thread(d, i, false);
+            } else if (body_is_small(d, body_flags(d, i))) {
+                fill_fine(d, i);
+                r.count = 0;
+            } else {
+                r = cell_range(d, i);
+            }
             bool inline_walk = r.count <= BIG_BODY_CELLS;
             if (!inline_walk) {
                 const uint32_t slot = atomicAdd(&n_big, 1u);
@@ -565,6 +569,46 @@ __global__ void __launch_bounds__(TPB) k_bucket_write(Dev d) {
     bucket_write_part<LIST_SMALL, false>(d);
 }
 
+// ---- K5 with the fine grid: one thread per small body (see fine_body_pairs) ------------------------------------------------------
+// WRITE = false counts (pair_cnt[a + 1]); after the scan WRITE = true emits at pair_cnt[a + 1].  The write pass keeps up
+// to 8 partners in registers (the tests run once) and writes them in ascending slot order; a body with more re-runs them.
+template <bool WRITE>
+__global__ void __launch_bounds__(TPB) k_fine_pairs(Dev d) {
+    if (overflowed(d)) return;
+    if (!WRITE && blockIdx.x == 0 && threadIdx.x == 0) d.pair_cnt[0] = d.ll_on ? d.ent_off[d.n_buckets] : 0u;
+    for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < d.n_bodies; a += gridDim.x * blockDim.x) {
+        const bool live = body_is_small(d, body_flags(d, a));
+        uint32_t got[8];
+        const uint32_t n = live ? fine_body_pairs(d, a, WRITE ? got : nullptr, nullptr) : 0u;
+        if (!WRITE) {
+            d.pair_cnt[a + 1] = n;
+        } else if (n) {
+            const uint32_t at = d.pair_cnt[a + 1];
+            if (at + n <= d.cap_pairs) {
+                uint2* out = d.pairs + at;
+                if (n <= 8u) {
+#pragma unroll
+                    for (int x = 1; x < 8; ++x) {  // insertion sort in registers (fixed trip counts: no local memory)
+#pragma unroll
+                        for (int y = x; y > 0; --y)
+                            if ((uint32_t)x < n && got[y - 1] > got[y]) {
+                                const uint32_t t = got[y - 1];
+                                got[y - 1] = got[y];
+                                got[y] = t;
+                            }
+                    }
+#pragma unroll
+                    for (int x = 0; x < 8; ++x)
+                        if ((uint32_t)x < n) out[x] = make_uint2(a, got[x]);
+                } else {
+                    fine_body_pairs(d, a, nullptr, out);
+                    sort_item_pairs(out, n);
+                }
+            }
+        }
+    }
+}
+
 // ---- K6: narrowphase, one thread per candidate pair --------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB, 3) k_narrow(Dev d) {
     if (overflowed(d)) return;
@@ -794,7 +838,9 @@ __global__ void __launch_bounds__(WORLD_TPB) k_color_worlds(Dev d) {
     uint32_t max_round = 0;
     for (uint32_t w = blockIdx.x; w < d.n_worlds; w += gridDim.x) {
         const uint32_t b0 = d.world_base[w], b1 = d.world_base[w + 1], nb = b1 - b0;
-        const uint32_t p0 = d.ent_off[d.table_mult * b0], p1 = d.ent_off[d.table_mult * b1];
+        // fine grid: the pair list is body-major instead (pair_cnt[b + 1] = first pair emitted by body b)
+        const uint32_t p0 = d.fine_on ? d.pair_cnt[b0 + 1] : d.ent_off[d.table_mult * b0];
+        const uint32_t p1 = d.fine_on ? d.pair_cnt[b1 + 1] : d.ent_off[d.table_mult * b1];
         for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
             s_mp0[i] = 0ull;
             s_mp1[i] = 0ull;

@@ -14,6 +14,7 @@ namespace r2d {
 
 constexpr uint32_t FLAG_STATIC = 1u;       // bit 0 of the per-body flags word
 constexpr uint32_t FLAG_RECT = 2u;         // bit 1: shape type (0 disc, 1 rectangle)
+constexpr uint32_t FLAG_LARGE = 4u;        // bit 2: wider than the fine broadphase cell (set by the host at upload)
 constexpr uint32_t FLAG_WORLD_SHIFT = 8u;  // bits 8..31: world index inside a batch
 
 // What the narrowphase needs to know about one body.

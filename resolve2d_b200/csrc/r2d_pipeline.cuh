@@ -18,6 +18,8 @@
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct uint2 { uint32_t x, y; };
+struct int2 { int32_t x, y; };
+static inline int2 make_int2(int32_t x, int32_t y) { int2 r; r.x = x; r.y = y; return r; }
 struct alignas(16) uint4 { uint32_t x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
@@ -43,6 +45,7 @@ constexpr uint32_t ERR_COLOR_OVERFLOW = 1u;
 constexpr uint32_t ERR_GRID_RANGE = 2u;
 constexpr uint32_t ERR_ROUNDS = 4u;
 constexpr uint32_t ERR_FLOW_STALL = 16u;       // dataflow colouring stalled (same: a bug, reported)
+constexpr uint32_t ERR_FINE = 32u;             // a body flagged small covers more than 4 coarse cells (a bug, reported)
 constexpr uint32_t ERR_STALL = 8u;             // dataflow sweep stalled (a bug, never data): reported instead of hanging
 
 // Device-side counters of one process() call (one 128-byte block, copied to pinned host memory once per step).
@@ -100,6 +103,15 @@ struct Dev {
     uint32_t* hit_bits;           // 4 * cap_entries: 32-test ballots of the count pass, bucket b's words at 4 * bucket_start[b]
     const uint64_t* excl;         // sorted (lo_slot << 32 | hi_slot)
     uint32_t n_excl;
+    // ---- fine grid (see "fine grid" below): small bodies list ONE home cell of width 1 / fine_inv in the buckets
+    //      [n_buckets, 2 n_buckets); only FLAG_LARGE bodies are entered in the coarse buckets --------------------------
+    uint32_t fine_on;             // 0: every body goes through the coarse buckets (the original pipeline)
+    uint32_t ll_on;               // 1: the bucket pair kernels ran on the coarse (large-body) buckets, ent_off[T] = their pairs
+    double fine_inv;              // 1 / fine cell width
+    int2* fcell;                  // NB: home cell of a small body (scratch of one process())
+    float4* ent_aabb;             // E: the stored AABB of the body of a FINE entry (its ent_body carries the static flag in bit 31)
+    uint32_t* pair_cnt;           // NB + 2: [0] = pairs of the bucket kernels, [a + 1] = pairs emitted by small body a; then
+                                  // its exclusive scan: [a + 1] = first pair slot of body a, [NB + 1] = P
     // ---- candidate pairs / raw manifolds (P slots) ------------------------------------------------------------------
     uint32_t cap_pairs;
     uint2* pairs;                 // (owner slot, other slot)
@@ -338,34 +350,91 @@ R2D_HD void store_view(const Dev& d, uint32_t i, const float4& pose) {
     d.view[4 * (size_t)i + 2] = make_float4(v.en[0].x, v.en[0].y, v.en[1].x, v.en[1].y);
     d.view[4 * (size_t)i + 3] = make_float4(v.en[2].x, v.en[2].y, v.en[3].x, v.en[3].y);
 }
+// ---- fine grid ---------------------------------------------------------------------------------------------------------
+// The reference's candidate set is {pairs whose stored AABBs intersect} ∩ {pairs that share a hashed 4 m bucket}.  The
+// first factor is geometry and can be found with any grid; the second is a lookup.  Searching it *through* the 4 m
+// buckets costs n^2 tests per bucket (a settled pile puts ~47 bodies in every occupied bucket: 4.3 M tests for 260 k
+// pairs at 100 k bodies).  So: every body that is narrower than the fine cell f (FLAG_LARGE clear; f ~ the widest
+// common body, chosen by the host at upload) lists ONE home cell — floor(aabb centre / f) — in a second table.  Two
+// small bodies whose AABBs intersect have home cells at most one apart, so a body finds its small partners in its own
+// cell and the four "forward" neighbours (each pair exactly once), ~7 AABB tests per body instead of ~43, and accepts
+// them if their remembered coarse bucket lists (d.bkt) share an entry — the reference's condition, hash collisions
+// included.  Only FLAG_LARGE bodies (floor, walls, long bars) are entered in the coarse buckets; a small body looks them
+// up through its own <= 4 coarse buckets, which IS the reference's query.  Large-large pairs come from the bucket
+// kernels of the original pipeline run on the (now nearly empty) coarse buckets, and only when a dynamic large body exists.
+R2D_HD bool body_is_small(const Dev& d, uint32_t flags) { return d.fine_on != 0u && !(flags & FLAG_LARGE); }
+R2D_HD int32_t fine_coord(float v, double inv) {
+    if (!(v == v)) return 0;
+    double t = floor(dmul((double)v, inv));
+    if (t > 1073741824.0) t = 1073741824.0;
+    if (t < -1073741824.0) t = -1073741824.0;
+    return (int32_t)t;
+}
+// bucket of a fine cell: row-major with a long odd stride, so that x-neighbours are neighbours in the table (coalesced
+// lookups for bodies in spatial order); world w owns the fine buckets [T + mult base_w, T + mult base_{w+1})
+R2D_HD uint32_t fine_bucket(const Dev& d, uint32_t world, int32_t cx, int32_t cy) {
+    const uint32_t b0 = d.world_base[world], b1 = d.world_base[world + 1];
+    const uint32_t h = (uint32_t)cx + (uint32_t)cy * 40503u;
+    return d.n_buckets + d.table_mult * b0 + h % (d.table_mult * (b1 - b0));
+}
+R2D_HD uint32_t fine_tag(int32_t cx, int32_t cy) { return ((uint32_t)cx & 0xFFFFu) | ((uint32_t)cy << 16); }
+
 // K2: pose cache + cell count (SpatialHash.zig:46-49).  Returns the cell range so the caller can walk big bodies
-// cooperatively; small bodies are counted here.
+// cooperatively; small bodies are counted here.  With the fine grid a small body counts its home cell instead (and the
+// returned range is empty).
 R2D_HD CellRange count_body_thread(const Dev& d, uint32_t i, bool count_inline) {
     const float4 p = d.pos[i];
     const float4 pose = make_float4(p.x, p.y, cos_ref(p.z), sin_ref(p.z));
     d.pose[i] = pose;
     store_view(d, i, pose);
-    const CellRange r = cell_range(d, i);
+    CellRange r = cell_range(d, i);
     d.ncells[i] = r.count;
+    const uint32_t flags = body_flags(d, i);
+    const bool small = body_is_small(d, flags);
     uint32_t bk[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
     if (r.count <= 4u) {  // small body: remember its buckets (pair de-duplication without touching the grid again)
         for (uint32_t k = 0; k < r.count; ++k) {
             bk[k] = cell_bucket(r, k);
-            if (count_inline) atomic_add_u32(&d.bucket_cnt[bk[k]], 1u);
+            if (count_inline && !small) atomic_add_u32(&d.bucket_cnt[bk[k]], 1u);
         }
+    } else if (small) {
+        atomic_or_u32(&d.counters->err, ERR_FINE);
     } else if (count_inline) {
         for (uint32_t k = 0; k < r.count; ++k) atomic_add_u32(&d.bucket_cnt[cell_bucket(r, k)], 1u);
     }
     d.bkt[i] = make_uint4(bk[0], bk[1], bk[2], bk[3]);
+    if (small) {
+        const float4 a = d.aabb[i];
+        const int2 c = make_int2(fine_coord(a.x, d.fine_inv), fine_coord(a.y, d.fine_inv));
+        d.fcell[i] = c;
+        atomic_add_u32(&d.bucket_cnt[fine_bucket(d, flags >> FLAG_WORLD_SHIFT, c.x, c.y)], 1u);
+        r.count = 0;
+    }
     return r;
 }
 // K4: fill (SpatialHash.zig:62-68): decrement-then-store; leaves bucket_cnt all zero again.
-R2D_HD void fill_cell(const Dev& d, uint32_t i, uint32_t bucket) {
+R2D_HD void fill_cell(const Dev& d, uint32_t i, uint32_t bucket, uint32_t key) {
     const uint32_t left = atomic_sub_u32(&d.bucket_cnt[bucket], 1u) - 1u;
     const uint32_t at = d.bucket_start[bucket] + left;
     if (at < d.cap_entries) {
         d.ent_body[at] = i;
-        d.ent_key[at] = bucket;
+        d.ent_key[at] = key;
+    }
+}
+R2D_HD void fill_cell(const Dev& d, uint32_t i, uint32_t bucket) { fill_cell(d, i, bucket, bucket); }
+// K4, small body with the fine grid: one entry, keyed by the low bits of its home cell, carrying what the pair test
+// needs (AABB, static flag) so that the test does not have to chase the body
+constexpr uint32_t ENT_STATIC = 0x80000000u;
+R2D_HD void fill_fine(const Dev& d, uint32_t i) {
+    const int2 c = d.fcell[i];
+    const uint32_t flags = body_flags(d, i);
+    const uint32_t bucket = fine_bucket(d, flags >> FLAG_WORLD_SHIFT, c.x, c.y);
+    const uint32_t left = atomic_sub_u32(&d.bucket_cnt[bucket], 1u) - 1u;
+    const uint32_t at = d.bucket_start[bucket] + left;
+    if (at < d.cap_entries) {
+        d.ent_body[at] = i | ((flags & FLAG_STATIC) ? ENT_STATIC : 0u);
+        d.ent_key[at] = fine_tag(c.x, c.y);
+        d.ent_aabb[at] = d.aabb[i];
     }
 }
 R2D_HD uint32_t bucket_end(const struct Dev& d, uint32_t bucket);
@@ -475,6 +544,97 @@ R2D_HD uint32_t entry_pairs_thread(const Dev& d, uint32_t e, uint2* out) {
         ++n;
     }
     return n;
+}
+
+// K5 with the fine grid: the pairs emitted by small body a — its small partners from the home cell and the four forward
+// neighbours in the fine table, then its large partners from its own coarse buckets.  The first 8 accepted partners are
+// returned in `got` (if non-null); all of them are written to `out` as (a, partner) if non-null.  Returns how many.
+R2D_HD bool bucket_lists_share(const uint4& x, const uint4& y) {
+    const uint32_t a[4] = {x.x, x.y, x.z, x.w}, b[4] = {y.x, y.y, y.z, y.w};
+    bool share = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) share = share || (a[i] != 0xFFFFFFFFu && a[i] == b[j]);
+    return share;
+}
+R2D_HD uint32_t fine_body_pairs(const Dev& d, uint32_t a, uint32_t* got, uint2* out) {
+    const uint32_t fa = body_flags(d, a);
+    const float4 aa = d.aabb[a];
+    const int2 ca = d.fcell[a];
+    const uint4 ba = d.bkt[a];
+    const uint32_t world = fa >> FLAG_WORLD_SHIFT;
+    const bool a_static = (fa & FLAG_STATIC) != 0;
+    uint32_t n = 0;
+    // ---- small partners: (0,0) (1,0) (-1,1) (0,1) (1,1) ----
+    uint32_t fs[5], fe[5], ft[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {  // all lookups are issued before the first entry is needed
+        const int32_t ox = (k == 0 || k == 3) ? 0 : ((k == 2) ? -1 : 1), oy = k >= 2 ? 1 : 0;
+        const uint32_t h = fine_bucket(d, world, ca.x + ox, ca.y + oy);
+        ft[k] = fine_tag(ca.x + ox, ca.y + oy);
+        fs[k] = d.bucket_start[h];
+        fe[k] = bucket_end(d, h);
+    }
+    const uint32_t bk[4] = {ba.x, ba.y, ba.z, ba.w};
+    uint32_t cs[4], ce[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        bool use = bk[q] != 0xFFFFFFFFu;
+#pragma unroll
+        for (int q2 = 0; q2 < q; ++q2) use = use && bk[q2] != bk[q];  // two cells of a in one bucket: visited once
+        cs[q] = use ? d.bucket_start[bk[q]] : 0u;
+        ce[q] = use ? bucket_end(d, bk[q]) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        for (uint32_t e = fs[k]; e < fe[k]; ++e) {
+            if (d.ent_key[e] != ft[k]) continue;               // another cell of the same bucket
+            const uint32_t bw = d.ent_body[e], b = bw & ~ENT_STATIC;
+            if (k == 0 && b <= a) continue;                    // same home cell: the lower slot emits the pair (:274 for b == a)
+            if (a_static && (bw & ENT_STATIC)) continue;                                            // :273
+            const float4 ab = d.ent_aabb[e];
+            if (!aabb_intersects(aa.x, aa.y, aa.z, aa.w, ab.x, ab.y, ab.z, ab.w)) continue;         // :282
+            if (!bucket_lists_share(ba, d.bkt[b])) continue;   // the reference only sees b through a shared hashed bucket
+            if (pair_excluded(d, a, b)) continue;                                                   // :275-276
+            if (got && n < 8u) got[n] = b;
+            if (out) out[n] = make_uint2(a, b);
+            ++n;
+        }
+    }
+    // ---- large partners: only FLAG_LARGE bodies are entered in the coarse buckets ----
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        for (uint32_t e = cs[q]; e < ce[q]; ++e) {
+            const uint32_t b = d.ent_body[e];
+            bool seen = false;
+            for (uint32_t e2 = cs[q]; e2 < e; ++e2) seen = seen || d.ent_body[e2] == b;   // b lists this bucket twice
+#pragma unroll
+            for (int q2 = 0; q2 < q; ++q2)                                                 // ... or an earlier bucket of a
+                for (uint32_t e2 = cs[q2]; e2 < ce[q2] && !seen; ++e2) seen = seen || d.ent_body[e2] == b;
+            if (seen) continue;
+            if (a_static && (body_flags(d, b) & FLAG_STATIC)) continue;
+            const float4 ab = d.aabb[b];
+            if (!aabb_intersects(aa.x, aa.y, aa.z, aa.w, ab.x, ab.y, ab.z, ab.w)) continue;
+            if (pair_excluded(d, a, b)) continue;
+            if (got && n < 8u) got[n] = b;
+            if (out) out[n] = make_uint2(a, b);
+            ++n;
+        }
+    }
+    return n;
+}
+// makes the order of a body's pairs independent of the order the fill's atomics landed in
+R2D_HD void sort_item_pairs(uint2* out, uint32_t n) {
+    for (uint32_t x = 1; x < n; ++x) {
+        const uint2 v = out[x];
+        uint32_t y = x;
+        while (y > 0 && out[y - 1].y > v.y) {
+            out[y] = out[y - 1];
+            --y;
+        }
+        out[y] = v;
+    }
 }
 
 // ---- narrowphase ---------------------------------------------------------------------------------------------------

@@ -93,6 +93,11 @@ struct CudaBatch : BatchBase {
     DBuf<float4> j_par, j_vec;
     // grid
     DBuf<uint32_t> bucket_cnt, bucket_start, ent_body, ent_key, ent_off, tile_sums, work, hit_bits;
+    DBuf<int2> fcell;                 // fine grid: home cell per small body
+    DBuf<float4> ent_aabb;            // fine grid: AABB copies in entry order
+    DBuf<uint32_t> pair_cnt;          // fine grid: pairs per small body, then their scan
+    bool fine_grid = true;            // R2D_BROADPHASE=buckets: every body through the coarse buckets (the original pipeline)
+    bool fine_now = false, ll_now = false;
     // pairs / manifolds
     DBuf<uint2> pairs;
     DBuf<uint4> m_hdr, s_hdr;
@@ -190,6 +195,7 @@ struct CudaBatch : BatchBase {
         if (const char* e = getenv("R2D_TILE_MAX_TASKS")) tile_max_tasks = std::min<uint32_t>((uint32_t)atoi(e), TILE_MAX_TASKS);  // tests
         R2D_CUDA(cudaFuncSetAttribute(k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES));
         if (const char* e = getenv("R2D_FLOW_SLEEP_UNIT")) flow_sleep_unit = (uint32_t)atoi(e);
+        if (const char* e = getenv("R2D_BROADPHASE")) fine_grid = std::string(e) != "buckets";
         return R2D_OK;
     }
 
@@ -435,6 +441,9 @@ struct CudaBatch : BatchBase {
         d.cap_entries = (uint32_t)cap_entries;
         d.ent_body = ent_body.p; d.ent_key = ent_key.p; d.ent_off = ent_off.p; d.work = work.p; d.hit_bits = hit_bits.p;
         d.excl = (const uint64_t*)excl.p; d.n_excl = (uint32_t)image.excl.size();
+        d.fine_on = fine_now ? 1u : 0u; d.ll_on = ll_now ? 1u : 0u;
+        d.fine_inv = fine_now ? 1.0 / (double)image.fine_cell : 0.0;
+        d.fcell = fcell.p; d.pair_cnt = pair_cnt.p; d.ent_aabb = ent_aabb.p;
         d.cap_pairs = (uint32_t)cap_pairs;
         d.pairs = pairs.p; d.m_hdr = m_hdr.p; d.m_g0 = m_g0.p; d.m_g1 = m_g1.p; d.m_r0 = m_r0.p; d.m_r1 = m_r1.p;
         d.m_color = m_color.p; d.m_prio = m_prio.p;
@@ -467,8 +476,8 @@ struct CudaBatch : BatchBase {
 
     int reserve_entries(size_t n) {
         int st;
-        if ((st = ent_body.reserve(n)) || (st = ent_key.reserve(n))) return st;
-        cap_entries = std::min(ent_body.cap, ent_key.cap);
+        if ((st = ent_body.reserve(n)) || (st = ent_key.reserve(n)) || (st = ent_aabb.reserve(n))) return st;
+        cap_entries = std::min(std::min(ent_body.cap, ent_key.cap), ent_aabb.cap);
         if ((st = hit_bits.reserve(HIT_WORDS_PER_ENTRY * cap_entries + 64))) return st;  // ballots of the staged buckets
         return R2D_OK;
     }
@@ -519,12 +528,12 @@ struct CudaBatch : BatchBase {
         const size_t own_w = ((size_t)nb + 31) / 32;
         {   // layout of the zeroed arena for this body count
             auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
-            const size_t max_scan = std::max<size_t>((size_t)T + 1, (own_w + 1) * MAX_COLORS + 2);
+            const size_t max_scan = std::max<size_t>(2 * (size_t)T + 1, (own_w + 1) * MAX_COLORS + 2);
             scan_state_cap = (max_scan + SCAN_TILE - 1) / SCAN_TILE + 4;
             size_t o = 0;
             off_counters = o; o = align(o + sizeof(Counters));
             off_color_misc = o; o = align(o + (MAX_COLORS * 3 + 1 + MAX_COLOR_ROUNDS) * 4);
-            off_scan = o; o = align(o + 3 * scan_state_cap * 8);
+            off_scan = o; o = align(o + 4 * scan_state_cap * 8);
             off_maxprio0 = o; o = align(o + (size_t)nb * 8);
             off_maxprio1 = o; o = align(o + (size_t)nb * 8);
             off_used = o; o = align(o + (size_t)nb * COLOR_WORDS * 8);
@@ -536,12 +545,18 @@ struct CudaBatch : BatchBase {
             if ((st = zeroed.reserve(zeroed_bytes))) return st;
         }
         if ((st = own_pos.reserve((own_w + 1) * MAX_COLORS + 2)) ||
-            (st = pose.reserve(nb)) || (st = view.reserve(4 * (size_t)nb)) || (st = ncells.reserve(nb)) || (st = bkt.reserve(nb)) ||  (st = bucket_cnt.reserve((size_t)T + 1, true, stream)) ||
-            (st = bucket_start.reserve((size_t)T + 1)) || (st = ent_off.reserve((size_t)T + 2)) || (st = work.reserve(2 * (size_t)T + 2)))
+            (st = pose.reserve(nb)) || (st = view.reserve(4 * (size_t)nb)) || (st = ncells.reserve(nb)) || (st = bkt.reserve(nb)) ||  (st = bucket_cnt.reserve(2 * (size_t)T + 1, true, stream)) ||
+            (st = bucket_start.reserve(2 * (size_t)T + 2)) || (st = fcell.reserve(nb)) || (st = pair_cnt.reserve((size_t)nb + 3)) || (st = ent_off.reserve((size_t)T + 2)) || (st = work.reserve(2 * (size_t)T + 2)))
             return st;
         if (cap_entries == 0 && (st = reserve_entries((size_t)nb * 3 + 4096))) return st;
         if (cap_pairs == 0 && (st = reserve_pairs((size_t)nb * 6 + 4096))) return st;
 
+        // broadphase flavour: the fine grid whenever the upload found a usable fine cell; the bucket pair kernels then
+        // only run for large-large pairs, i.e. when a dynamic large body exists.  Their pairs come first in the list, so
+        // a batch (whose per-world kernels need a world's pairs contiguous) with dynamic large bodies keeps the buckets.
+        fine_now = fine_grid && image.fine_cell > 0.0f && image.fine_for_cell == grid_cell() &&
+                   (image.n_large_dynamic == 0 || worlds.size() == 1);
+        ll_now = fine_now && image.n_large_dynamic > 0;
         // colouring flavour: CTA-per-world rounds in shared memory for batches of small worlds, else the dataflow
         // colouring while the candidate pairs fit its register slots (decided again on the device), else grid-wide rounds
         const bool many_small_worlds = world_solver && worlds.size() >= (size_t)n_sms / 2;
@@ -563,14 +578,22 @@ struct CudaBatch : BatchBase {
             R2D_CUDA(cudaMemsetAsync(zeroed.p, 0, zeroed_bytes, stream));  // counters, colour tables, scan states, masks
             // ---- broadphase ----
             R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_grid_cells<false>, grid_for(nb), TPB, d);
-            if ((st = scan(d.bucket_cnt, d.bucket_start, nullptr, T, &d.counters->n_entries, R2D_KCLASS_BROADPHASE, 0))) return st;
+            if ((st = scan(d.bucket_cnt, d.bucket_start, nullptr, fine_now ? 2 * T : T, &d.counters->n_entries, R2D_KCLASS_BROADPHASE, 0))) return st;
             R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_grid_cells<true>, grid_for(nb), TPB, d);
-            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_list_buckets, grid_for(T), TPB, d);
-            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_sort_buckets, pair_blocks, TPB, d);
-            // pairs per BUCKET (one warp each) -> scan over the T buckets -> write at the scanned offsets
-            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_bucket_count, pair_blocks, TPB, d);
-            if ((st = scan(d.ent_off, d.ent_off, nullptr, T, &d.counters->n_pairs, R2D_KCLASS_BROADPHASE, 1))) return st;
-            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_bucket_write, pair_blocks, TPB, d);
+            if (!fine_now || ll_now) {
+                R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_list_buckets, grid_for(T), TPB, d);
+                R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_sort_buckets, pair_blocks, TPB, d);
+                // pairs per BUCKET (one warp each) -> scan over the T buckets -> write at the scanned offsets
+                R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_bucket_count, pair_blocks, TPB, d);
+                if ((st = scan(d.ent_off, d.ent_off, nullptr, T, &d.counters->n_pairs, R2D_KCLASS_BROADPHASE, 1))) return st;
+                R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_bucket_write, pair_blocks, TPB, d);
+            }
+            if (fine_now) {
+                // pairs per small BODY (8 lanes each) -> scan over the bodies -> write at the scanned offsets
+                R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_fine_pairs<false>, grid_for(nb), TPB, d);
+                if ((st = scan(d.pair_cnt, d.pair_cnt, nullptr, nb + 1, &d.counters->n_pairs, R2D_KCLASS_BROADPHASE, 3))) return st;
+                R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_fine_pairs<true>, grid_for(nb), TPB, d);
+            }
             // ---- narrowphase ----
             R2D_LAUNCH(R2D_KCLASS_NARROWPHASE, k_narrow, grid_for(cap_pairs), TPB, d);
             // ---- colouring + partition + pre-step ----
@@ -650,6 +673,10 @@ struct CudaBatch : BatchBase {
         if (c.err & ERR_GRID_RANGE) {
             g_cuda_error = "a body AABB covers an unreasonable number of grid cells (NaN/inf pose?)";
             return R2D_ERR_GRID_RANGE;
+        }
+        if (c.err & ERR_FINE) {
+            g_cuda_error = "internal error: a body classified as small covers more than 4 coarse cells";
+            return R2D_ERR_CUDA;
         }
         if (c.err & ERR_FLOW_STALL) {
             g_cuda_error = "internal error: the dataflow colouring stalled (state of this step is undefined)";

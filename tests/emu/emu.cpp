@@ -21,7 +21,9 @@ using host::RawManifold;
 struct EmuBatch : BatchBase {
     Dev d{};
     std::vector<float4> pos, mom, frc, prop, shape, aabb, pose, view;
-    std::vector<uint32_t> ncells, bucket_cnt, bucket_start, ent_body, ent_key, ent_off, m_color;
+    std::vector<uint32_t> ncells, bucket_cnt, bucket_start, ent_body, ent_key, ent_off, m_color, pair_cnt;
+    std::vector<int2> fcell;
+    std::vector<float4> ent_aabb;
     std::vector<uint2> pairs;
     std::vector<uint4> m_hdr, s_hdr, bkt;
     std::vector<float4> m_g0, m_g1, m_r0, m_r1, s_nf, s_inv, s_r0, s_r1, s_pm0, s_pm1;
@@ -149,8 +151,6 @@ struct EmuBatch : BatchBase {
         d.world_base = image.world_base.data(); d.grav_off = image.grav_off.data(); d.grav = image.grav.data();
         d.cell = grid_cell(); d.table_mult = grid_mult();
         d.n_buckets = d.table_mult * nb;
-        bucket_cnt.assign(d.n_buckets + 1, 0); bucket_start.assign(d.n_buckets + 1, 0);
-        d.bucket_cnt = bucket_cnt.data(); d.bucket_start = bucket_start.data();
         d.excl = image.excl.data(); d.n_excl = (uint32_t)image.excl.size();
         counters = Counters{};
         d.counters = &counters;
@@ -158,23 +158,64 @@ struct EmuBatch : BatchBase {
         d.j_hdr = image.j_hdr.data(); d.j_par = image.j_par.data(); d.j_vec = image.j_vec.data();
 
         // ---- broadphase (K2..K5) ----
+        // R2D_EMU_BROADPHASE=buckets emulates the original pipeline (every body through the coarse buckets)
+        const bool want_fine = !(getenv("R2D_EMU_BROADPHASE") && std::string(getenv("R2D_EMU_BROADPHASE")) == "buckets");
+        const bool fine = want_fine && image.fine_cell > 0.0f && image.fine_for_cell == grid_cell() &&
+                          (image.n_large_dynamic == 0 || worlds.size() == 1);
+        const bool ll = fine && image.n_large_dynamic > 0;
+        d.fine_on = fine ? 1u : 0u; d.ll_on = ll ? 1u : 0u;
+        d.fine_inv = fine ? 1.0 / (double)image.fine_cell : 0.0;
+        fcell.resize(nb); d.fcell = fcell.data();
+        const uint32_t TT = fine ? 2 * d.n_buckets : d.n_buckets;
+        bucket_cnt.assign(TT + 1, 0); bucket_start.assign(TT + 2, 0);
+        d.bucket_cnt = bucket_cnt.data(); d.bucket_start = bucket_start.data();
         for (uint32_t i = 0; i < nb; ++i) count_body_thread(d, i, true);
-        memcpy(bucket_start.data(), bucket_cnt.data(), (d.n_buckets + 1) * 4);
-        exclusive_scan(bucket_start.data(), d.n_buckets);
-        const uint32_t E = bucket_start[d.n_buckets];
-        ent_body.assign(E + 1, 0); ent_key.assign(E + 1, 0); ent_off.assign(E + 2, 0);
+        memcpy(bucket_start.data(), bucket_cnt.data(), (TT + 1) * 4);
+        exclusive_scan(bucket_start.data(), TT);
+        const uint32_t E = bucket_start[TT];
+        ent_body.assign(E + 1, 0); ent_key.assign(E + 1, 0); ent_aabb.resize(E + 1); d.ent_aabb = ent_aabb.data(); ent_off.assign(std::max(E, d.n_buckets) + 2, 0);
         d.cap_entries = E; d.ent_body = ent_body.data(); d.ent_key = ent_key.data(); d.ent_off = ent_off.data();
         for (uint32_t i = 0; i < nb; ++i) {
+            if (body_is_small(d, body_flags(d, i))) {
+                fill_fine(d, i);
+                continue;
+            }
             const CellRange r = cell_range(d, i);
             for (uint32_t k = 0; k < r.count; ++k) fill_cell(d, i, cell_bucket(r, k));
         }
-        for (uint32_t b = 0; b < d.n_buckets; ++b) sort_bucket_thread(d, b);
-        for (uint32_t e = 0; e < E; ++e) ent_off[e] = entry_pairs_thread(d, e, nullptr);
-        exclusive_scan(ent_off.data(), E);
-        const uint32_t P = ent_off[E];
+        uint32_t P = 0;
+        if (!fine || ll) {
+            const uint32_t EC = bucket_start[d.n_buckets];  // entries of the coarse buckets
+            for (uint32_t b = 0; b < d.n_buckets; ++b) sort_bucket_thread(d, b);
+            for (uint32_t e = 0; e < EC; ++e) ent_off[e] = entry_pairs_thread(d, e, nullptr);
+            exclusive_scan(ent_off.data(), EC);
+            P = ent_off[EC];
+        }
+        const uint32_t P_ll = P;
+        pair_cnt.assign(nb + 2, 0);
+        d.pair_cnt = pair_cnt.data();
+        if (fine) {
+            pair_cnt[0] = P_ll;
+            for (uint32_t a = 0; a < nb; ++a) {
+                if (!body_is_small(d, body_flags(d, a))) continue;
+                pair_cnt[a + 1] = fine_body_pairs(d, a, nullptr, nullptr);
+            }
+            exclusive_scan(pair_cnt.data(), nb + 1);
+            P = pair_cnt[nb + 1];
+        }
         pairs.assign(P + 1, make_uint2(0, 0));
         d.cap_pairs = P; d.pairs = pairs.data();
-        for (uint32_t e = 0; e < E; ++e) entry_pairs_thread(d, e, pairs.data() + ent_off[e]);
+        if (!fine || ll) {
+            const uint32_t EC = bucket_start[d.n_buckets];
+            for (uint32_t e = 0; e < EC; ++e) entry_pairs_thread(d, e, pairs.data() + ent_off[e]);
+        }
+        if (fine) {
+            for (uint32_t a = 0; a < nb; ++a) {
+                if (!body_is_small(d, body_flags(d, a))) continue;
+                const uint32_t at = pair_cnt[a + 1];
+                sort_item_pairs(pairs.data() + at, fine_body_pairs(d, a, nullptr, pairs.data() + at));
+            }
+        }
         n_pairs_last = P;
 
         // ---- narrowphase (K6) ----

@@ -1,4 +1,6 @@
 """Shared parity assertions: a candidate implementation (CUDA path or CPU emulator) against the oracle."""
+import os
+
 import numpy as np
 
 from oracle import ORDER_COLORED, ORDER_REFERENCE, OracleSolver
@@ -71,8 +73,14 @@ def run_parity(make_candidate, build_scene, steps, check_every=1, pre_step=None,
             assert np.array_equal(gp, wp), f"{tag}: candidate pair set differs ({len(gp)} vs {len(wp)})"
             assert_manifolds_equal(cand.read_manifolds(), orc.read_manifolds(), tag)
             gs, ws = cand.stats(), orc.stats()
-            assert (gs.n_entries, gs.n_pairs, gs.n_manifolds, gs.n_points, gs.n_colors) == \
-                   (ws.n_entries, ws.n_pairs, ws.n_manifolds, ws.n_points, ws.n_colors), f"{tag}: stats"
+            assert (gs.n_pairs, gs.n_manifolds, gs.n_points, gs.n_colors) == \
+                   (ws.n_pairs, ws.n_manifolds, ws.n_points, ws.n_colors), f"{tag}: stats"
+            # E (grid entries) is the reference's sum of covered cells only when every body goes through the hashed
+            # buckets; the fine grid enters small bodies once (in their home cell) and never more often than that
+            if os.environ.get("R2D_BROADPHASE") == "buckets" or os.environ.get("R2D_EMU_BROADPHASE") == "buckets":
+                assert gs.n_entries == ws.n_entries, f"{tag}: grid entries"
+            else:
+                assert gs.n_entries <= ws.n_entries, f"{tag}: grid entries"
             gj, wj = cand.read_joint_order(), orc.read_joint_order()
             assert np.array_equal(gj[0], wj[0]) and np.array_equal(gj[1], wj[1]), f"{tag}: joint order"
             assert_bodies_equal(cand.read_bodies(), orc.read_bodies(), tag)

@@ -37,3 +37,67 @@ def test_emu_dataflow_colouring_is_used_and_falls_back_on_hubs():
     cand, _ = run_parity(lambda: EmuSolver(2.0, 4), scenes.build_hub, 60, check_every=10, what="hub")
     st = cand.stats()
     assert st.n_colors >= 40 and st.n_color_rounds > 0
+
+
+# ---- fine-grid broadphase (small bodies in a fine home-cell table, only large bodies in the hashed 4 m buckets) ----------
+def test_emu_fine_grid_is_used_and_buckets_mode_still_matches(monkeypatch):
+    cand, orc = run_parity(lambda: EmuSolver(2.0, 4), scenes.build_box1k, 30, check_every=10, what="box1k fine")
+    assert cand.stats().n_entries < orc.stats().n_entries        # small bodies list one home cell, not their 4 m cells
+    monkeypatch.setenv("R2D_EMU_BROADPHASE", "buckets")
+    cand, orc = run_parity(lambda: EmuSolver(2.0, 4), scenes.build_box1k, 30, check_every=10, what="box1k buckets")
+    assert cand.stats().n_entries == orc.stats().n_entries
+
+
+def test_emu_fine_grid_with_dynamic_large_bodies():
+    """mixed scene: small discs/rects at any angle + DYNAMIC 8-16 m rectangles (large-large pairs come from the bucket
+    kernels, small-large pairs through the small body's own coarse buckets) falling onto the field."""
+    def build(s):
+        return scenes.build_mixed(s, 40, 12, n_large=6)
+    # the large rectangles are stacked in one column above the field: the first lands at step ~120 (small-large
+    # pairs), the next ones on top of it from step ~180 (large-large pairs)
+    cand, orc = run_parity(lambda: EmuSolver(2.0, 4), build, 260, check_every=20, what="mixed fine")
+    assert cand.stats().n_entries < orc.stats().n_entries
+    n = len(cand.read_bodies()["id"])
+    pairs = np.asarray(cand.read_pairs()).reshape(-1, 2)
+    big = pairs >= n - 6
+    assert (big[:, 0] & big[:, 1]).any() and (big[:, 0] ^ big[:, 1]).any()
+
+
+def test_emu_fine_grid_pyramid_with_spinners_and_joints():
+    def build(s):
+        return scenes.build_pyramid(s, base=16, n_spinners=3)
+    run_parity(lambda: EmuSolver(2.0, 4), build, 60, check_every=20, what="pyramid16 fine")
+
+
+def test_emu_fine_grid_far_from_the_origin_and_negative_cells():
+    """bodies at large negative / positive coordinates (cell indices wrap in the tag and in the bucket hash)."""
+    def build(s, shift):
+        fac = s.entity_factory()
+        fac.make_downwards_gravity(scenes.GRAVITY)
+        import numpy as np
+        rng = scenes.SplitMix64(7)
+        d = scenes.descs_box(rng, 12, 6, origin=(shift - 8.0, 2.0))
+        floor = scenes._static_rect((shift, -1), 40, 2)
+        fac.make_bodies(np.concatenate([floor, d]))
+        return {"sub_steps": 4, "iters": 4}
+    for shift in (-70000.0, 65536.0 * 1.05 - 3.0, 3.0e6):
+        run_parity(lambda: EmuSolver(2.0, 4), lambda s: build(s, shift), 50, check_every=25, what=f"shift {shift}")
+
+
+def test_emu_fine_grid_batch_matches_standalone_worlds():
+    n_worlds = 5
+    batch = EmuBatch(n_worlds, 2.0, 4)
+    oracles = []
+    for w in range(n_worlds):
+        scenes.build_batch_world(batch.world(w), w, nx=9, ny=5)
+        o = OracleSolver(2.0, 4, order=ORDER_COLORED)
+        scenes.build_batch_world(o, w, nx=9, ny=5)
+        oracles.append(o)
+    for step in range(60):
+        batch.process(scenes.DT, 4, 4)
+        for o in oracles:
+            o.process(scenes.DT, 4, 4)
+    for w, o in enumerate(oracles):
+        ws = batch.world(w)
+        assert np.array_equal(ws.read_pairs(), o.read_pairs()), w
+        assert_bodies_equal(ws.read_bodies(), o.read_bodies(), f"emu batch world {w}")
