@@ -41,52 +41,46 @@ __global__ void __launch_bounds__(TPB) k_grid_cells(Dev d) {
     __shared__ uint32_t n_big;
     if (threadIdx.x == 0) n_big = 0;
     __syncthreads();
-    for (uint32_t base = blockIdx.x * blockDim.x; base < d.n_bodies; base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        if (i < d.n_bodies) {
-            CellRange r;
-            if (!FILL) {
-                r = count_body_thread(d, i, false);
-            } else if (body_is_small(d, body_flags(d, i))) {
-                fill_fine(d, i);
-                r.count = 0;
-            } else {
-                r = cell_range(d, i);
-            }
-            bool inline_walk = r.count <= BIG_BODY_CELLS;
-            if (!inline_walk) {
-                const uint32_t slot = atomicAdd(&n_big, 1u);
-                if (slot < BIG_LIST)
-                    big_list[slot] = i;
-                else
-                    inline_walk = true;
-            }
-            if (inline_walk) {
-                for (uint32_t k = 0; k < r.count; ++k) {
-                    const uint32_t b = cell_bucket(r, k);
-                    if (FILL)
-                        fill_cell(d, i, b);
-                    else
-                        atomicAdd(&d.bucket_cnt[b], 1u);
-                }
-            }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n_bodies; i += gridDim.x * blockDim.x) {
+        CellRange r;
+        if (!FILL) {
+            r = count_body_thread(d, i, false);
+        } else if (body_is_small(d, body_flags(d, i))) {
+            fill_fine(d, i);
+            r.count = 0;
+        } else {
+            r = cell_range(d, i);
         }
-        __syncthreads();
-        const uint32_t nb = n_big < BIG_LIST ? n_big : BIG_LIST;
-        for (uint32_t q = 0; q < nb; ++q) {  // e.g. the floor: hundreds of cells, walked by the whole CTA
-            const uint32_t bi = big_list[q];
-            const CellRange r = cell_range(d, bi);
-            for (uint32_t k = threadIdx.x; k < r.count; k += blockDim.x) {
+        bool inline_walk = r.count <= BIG_BODY_CELLS;
+        if (!inline_walk) {  // e.g. the floor: hundreds of cells — deferred to the end, walked by the whole CTA
+            const uint32_t slot = atomicAdd(&n_big, 1u);
+            if (slot < BIG_LIST)
+                big_list[slot] = i;
+            else
+                inline_walk = true;
+        }
+        if (inline_walk) {
+            for (uint32_t k = 0; k < r.count; ++k) {
                 const uint32_t b = cell_bucket(r, k);
                 if (FILL)
-                    fill_cell(d, bi, b);
+                    fill_cell(d, i, b);
                 else
                     atomicAdd(&d.bucket_cnt[b], 1u);
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) n_big = 0;
-        __syncthreads();
+    }
+    __syncthreads();
+    const uint32_t nb = n_big < BIG_LIST ? n_big : BIG_LIST;
+    for (uint32_t q = 0; q < nb; ++q) {
+        const uint32_t bi = big_list[q];
+        const CellRange r = cell_range(d, bi);
+        for (uint32_t k = threadIdx.x; k < r.count; k += blockDim.x) {
+            const uint32_t b = cell_bucket(r, k);
+            if (FILL)
+                fill_cell(d, bi, b);
+            else
+                atomicAdd(&d.bucket_cnt[b], 1u);
+        }
     }
 }
 
@@ -904,6 +898,147 @@ __global__ void __launch_bounds__(WORLD_TPB) k_color_worlds(Dev d) {
     for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x)
         if (s_hist[c]) atomicAdd(&d.color_count[c], s_hist[c]);
     if (threadIdx.x == 0) atomicMax(&d.counters->n_rounds, max_round);
+}
+// ---- K8 for batches of small worlds, sorted form ------------------------------------------------------------------------------
+// "Greedy in descending priority" taken literally: the world's pending manifolds are sorted by priority (one bitonic
+// sort of 64-bit keys {priority, pair index} in shared memory) and one warp colours them in that order, 32 at a time —
+// lowest colour free on both bodies, per-body colour masks in shared memory — while the Jones-Plassmann rounds above
+// need ~26 block-wide rounds with 8 of 32 lanes active.  Same colours by construction (JP with unique priorities == sequential greedy; ties are only
+// possible between manifolds that share no body and then the order does not matter).  Worlds with more than
+// SEQ_WORLD_PAIRS candidate pairs take the rounds with the global per-body arrays instead.
+constexpr uint32_t SEQ_WORLD_PAIRS = 1024;
+
+__global__ void __launch_bounds__(WORLD_TPB) k_color_worlds_seq(Dev d, uint32_t smem_bodies, uint32_t export_used) {
+    extern __shared__ unsigned long long s_used_dyn[];   // smem_bodies x COLOR_WORDS
+    __shared__ unsigned long long s_key[SEQ_WORLD_PAIRS];
+    __shared__ uint32_t s_pair[SEQ_WORLD_PAIRS];
+    __shared__ unsigned char s_col[SEQ_WORLD_PAIRS];
+    __shared__ uint32_t s_hist[MAX_COLORS];
+    __shared__ uint32_t s_n;
+    if (overflowed(d)) return;
+    for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x) s_hist[c] = 0u;
+    uint32_t max_round = 0;
+    for (uint32_t w = blockIdx.x; w < d.n_worlds; w += gridDim.x) {
+        const uint32_t b0 = d.world_base[w], b1 = d.world_base[w + 1], nb = b1 - b0;
+        const uint32_t p0 = d.fine_on ? d.pair_cnt[b0 + 1] : d.ent_off[d.table_mult * b0];
+        const uint32_t p1 = d.fine_on ? d.pair_cnt[b1 + 1] : d.ent_off[d.table_mult * b1];
+        const uint32_t np = p1 - p0;
+        __syncthreads();
+        if (np <= SEQ_WORLD_PAIRS && nb <= smem_bodies && nb <= 4096u) {
+            if (threadIdx.x == 0) s_n = 0u;
+            for (uint32_t i = threadIdx.x; i < nb * COLOR_WORDS; i += blockDim.x) s_used_dyn[i] = 0ull;
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) {
+                const uint32_t p = p0 + i;
+                if (d.m_color[p] != COLOR_PENDING) continue;
+                const uint4 h = d.m_hdr[p];
+                s_pair[i] = (h.x - b0) | ((h.y - b0) << 12) | ((h.w & 3u) << 24);
+                s_key[atomicAdd(&s_n, 1u)] = (d.m_prio[p] << 12) | (unsigned long long)i;   // priorities have 52 bits
+            }
+            __syncthreads();
+            const uint32_t n = s_n;
+            uint32_t m = 1;
+            while (m < n) m <<= 1;
+            for (uint32_t i = n + threadIdx.x; i < m; i += blockDim.x) s_key[i] = 0ull;   // below every real key
+            __syncthreads();
+            for (uint32_t k = 2; k <= m; k <<= 1)           // bitonic sort, descending
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                        const uint32_t x = i ^ j;
+                        if (x > i) {
+                            const unsigned long long a = s_key[i], b = s_key[x];
+                            const bool desc = (i & k) == 0;
+                            if (desc ? a < b : a > b) {
+                                s_key[i] = b;
+                                s_key[x] = a;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+            if (threadIdx.x < 32u) {
+                // One warp walks the sorted list 32 manifolds at a time.  Inside a chunk a lane depends on the EARLIER lanes
+                // that share one of its non-static bodies (found once per chunk with shuffles); lanes whose dependencies are
+                // done colour in parallel — they touch disjoint bodies — so a chunk takes 2-3 passes instead of 32 steps.
+                const uint32_t lane = threadIdx.x;
+                for (uint32_t base = 0; base < n; base += 32u) {
+                    const uint32_t k = base + lane;
+                    const bool active = k < n;
+                    const uint32_t i = active ? ((uint32_t)s_key[k] & 0xFFFu) : 0u, pr = active ? s_pair[i] : 0u;
+                    const uint32_t l1 = pr & 0xFFFu, l2 = (pr >> 12) & 0xFFFu;
+                    const bool dyn1 = ((pr >> 24) & 1u) != 0, dyn2 = ((pr >> 25) & 1u) != 0;
+                    const uint32_t a1 = dyn1 ? l1 : 0xFFFF0000u + 2u * lane, a2 = dyn2 ? l2 : 0xFFFF0001u + 2u * lane;
+                    uint32_t dep = 0u;
+#pragma unroll 8
+                    for (uint32_t j = 0; j < 31u; ++j) {
+                        const uint32_t o1 = __shfl_sync(0xffffffffu, a1, j), o2 = __shfl_sync(0xffffffffu, a2, j);
+                        if (j < lane && (o1 == a1 || o1 == a2 || o2 == a1 || o2 == a2)) dep |= 1u << j;
+                    }
+                    bool pending = active;
+                    for (;;) {
+                        const uint32_t pend_mask = __ballot_sync(0xffffffffu, pending);
+                        if (!pend_mask) break;
+                        if (pending && !(dep & pend_mask)) {
+                            uint32_t color = MAX_COLORS;
+                            for (uint32_t q = 0; q < COLOR_WORDS; ++q) {
+                                unsigned long long u = 0ull;
+                                if (dyn1) u |= s_used_dyn[l1 * COLOR_WORDS + q];
+                                if (dyn2) u |= s_used_dyn[l2 * COLOR_WORDS + q];
+                                if (~u) {
+                                    color = q * 64u + (uint32_t)__ffsll((long long)~u) - 1u;
+                                    break;
+                                }
+                            }
+                            if (color >= MAX_COLORS) {
+                                atomicOr(&d.counters->err, ERR_COLOR_OVERFLOW);
+                                color = MAX_COLORS - 1;
+                            }
+                            const unsigned long long bit = 1ull << (color & 63u);
+                            if (dyn1) s_used_dyn[l1 * COLOR_WORDS + (color >> 6)] |= bit;
+                            if (dyn2) s_used_dyn[l2 * COLOR_WORDS + (color >> 6)] |= bit;
+                            s_col[i] = (unsigned char)color;
+                            atomicAdd(&s_hist[color], 1u);
+                            pending = false;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            __syncthreads();
+            for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+                const uint32_t i = (uint32_t)s_key[k] & 0xFFFu;
+                d.m_color[p0 + i] = s_col[i];
+            }
+            if (export_used)   // the dataflow sweep derives rank / degree from the per-body masks (body_color_rank)
+                for (uint32_t i = threadIdx.x; i < nb * COLOR_WORDS; i += blockDim.x) d.used[(size_t)b0 * COLOR_WORDS + i] = s_used_dyn[i];
+        } else {
+            // rounds on the global per-body arrays (zeroed at the start of the step); only this CTA touches this world
+            for (uint32_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+                if (d.m_color[p] != COLOR_PENDING) continue;
+                const uint4 h = d.m_hdr[p];
+                color_post(d, h.x, h.y, (h.w & 1u) != 0, (h.w & 2u) != 0, d.m_prio[p], 1u);
+            }
+            __syncthreads();
+            uint32_t round = 1;
+            for (; round < MAX_COLOR_ROUNDS; ++round) {
+                int left = 0;
+                for (uint32_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+                    const int r = color_round_thread(d, p, round);
+                    if (r == 2)
+                        left = 1;
+                    else if (r == 1)
+                        atomicAdd(&s_hist[d.m_color[p]], 1u);
+                }
+                if (!__syncthreads_or(left)) break;
+            }
+            if (round >= MAX_COLOR_ROUNDS && threadIdx.x == 0) atomicOr(&d.counters->err, ERR_ROUNDS);
+            max_round = round > max_round ? round : max_round;
+        }
+    }
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x)
+        if (s_hist[c]) atomicAdd(&d.color_count[c], s_hist[c]);
+    if (threadIdx.x == 0 && max_round) atomicMax(&d.counters->n_rounds, max_round);
 }
 // closes the per-world colouring: number of colours and the length of the owner-position scan
 __global__ void k_color_finish(Dev d) {

@@ -384,12 +384,14 @@ R2D_HD uint32_t fine_tag(int32_t cx, int32_t cy) { return ((uint32_t)cx & 0xFFFF
 // returned range is empty).
 R2D_HD CellRange count_body_thread(const Dev& d, uint32_t i, bool count_inline) {
     const float4 p = d.pos[i];
-    const float4 pose = make_float4(p.x, p.y, cos_ref(p.z), sin_ref(p.z));
+    const uint32_t flags = body_flags(d, i);
+    // the rotation only enters through a rectangle's vertices and normals (store_view); a disc's pose carries no angle
+    const bool rect = (flags & FLAG_RECT) != 0;
+    const float4 pose = make_float4(p.x, p.y, rect ? cos_ref(p.z) : 1.0f, rect ? sin_ref(p.z) : 0.0f);
     d.pose[i] = pose;
     store_view(d, i, pose);
     CellRange r = cell_range(d, i);
     d.ncells[i] = r.count;
-    const uint32_t flags = body_flags(d, i);
     const bool small = body_is_small(d, flags);
     uint32_t bk[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
     if (r.count <= 4u) {  // small body: remember its buckets (pair de-duplication without touching the grid again)

@@ -76,6 +76,13 @@ struct CudaBatch : BatchBase {
     int device = 0;
     int n_sms = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // r2d_write_forces copies and scatters on a side stream, so that the host->device transfer of a step's inputs
+    // overlaps the broadphase / narrowphase / colouring of that step; the solver launch (the first reader of `frc`)
+    // and every other entry point wait for it
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t forces_ready = nullptr;
+    bool forces_pending = false;
+    DBuf<unsigned char> staging_f;
     int color_blocks = 0, solve_blocks = 0, pair_blocks = 0;
     uint32_t wait_mode = 1, wait_probe = 1, wait_spin_lag = 1, wait_sleep_unit = 200, wait_sleep_max = 4000;
     int solve_blocks_per_sm = 1;
@@ -96,6 +103,7 @@ struct CudaBatch : BatchBase {
     DBuf<int2> fcell;                 // fine grid: home cell per small body
     DBuf<float4> ent_aabb;            // fine grid: AABB copies in entry order
     DBuf<uint32_t> pair_cnt;          // fine grid: pairs per small body, then their scan
+    bool seq_world_coloring = true;   // R2D_WORLD_COLORING=rounds: Jones-Plassmann rounds per world instead of sort + sequential greedy
     bool fine_grid = true;            // R2D_BROADPHASE=buckets: every body through the coarse buckets (the original pipeline)
     bool fine_now = false, ll_now = false;
     // pairs / manifolds
@@ -148,6 +156,8 @@ struct CudaBatch : BatchBase {
         for (auto& e : event_pool) cudaEventDestroy(e);
         if (pinned) cudaFreeHost(pinned);
         if (own_stream) cudaStreamDestroy(own_stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (forces_ready) cudaEventDestroy(forces_ready);
     }
 
     int init(int dev) {
@@ -163,6 +173,8 @@ struct CudaBatch : BatchBase {
         n_sms = prop_.multiProcessorCount;
         R2D_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
         stream = own_stream;
+        R2D_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        R2D_CUDA(cudaEventCreateWithFlags(&forces_ready, cudaEventDisableTiming));
         R2D_CUDA(cudaHostAlloc((void**)&pinned, sizeof(PinnedStep), cudaHostAllocDefault));
         int per_sm = 0;
         R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_color, TPB, 0));
@@ -196,6 +208,15 @@ struct CudaBatch : BatchBase {
         R2D_CUDA(cudaFuncSetAttribute(k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES));
         if (const char* e = getenv("R2D_FLOW_SLEEP_UNIT")) flow_sleep_unit = (uint32_t)atoi(e);
         if (const char* e = getenv("R2D_BROADPHASE")) fine_grid = std::string(e) != "buckets";
+        if (const char* e = getenv("R2D_WORLD_COLORING")) seq_world_coloring = std::string(e) != "rounds";
+        return R2D_OK;
+    }
+
+    int join_forces() {  // the main stream continues after the pending force import
+        if (forces_pending) {
+            R2D_CUDA(cudaStreamWaitEvent(stream, forces_ready, 0));
+            forces_pending = false;
+        }
         return R2D_OK;
     }
 
@@ -260,6 +281,8 @@ struct CudaBatch : BatchBase {
     }
     int backend_upload() override {
         R2D_CUDA(cudaSetDevice(device));
+        R2D_CUDA(cudaStreamSynchronize(copy_stream));  // a pending force import reads buffers that are replaced below
+        forces_pending = false;
         int st;
         if ((st = up(pos, image.pos)) || (st = up(mom, image.mom)) || (st = up(frc, image.frc)) || (st = up(prop, image.prop)) ||
             (st = up(shape, image.shape)) || (st = up(aabb, image.aabb)) || (st = up(world_base, image.world_base)) ||
@@ -280,6 +303,7 @@ struct CudaBatch : BatchBase {
         const size_t nb = image.n_bodies;
         if (nb == 0) return R2D_OK;
         std::vector<float4> hp(nb), hm(nb), hf(nb), ha(nb);
+        R2D_TRY(join_forces());
         R2D_CUDA(cudaMemcpyAsync(hp.data(), pos.p, nb * 16, cudaMemcpyDeviceToHost, stream));
         R2D_CUDA(cudaMemcpyAsync(hm.data(), mom.p, nb * 16, cudaMemcpyDeviceToHost, stream));
         R2D_CUDA(cudaMemcpyAsync(hf.data(), frc.p, nb * 16, cudaMemcpyDeviceToHost, stream));
@@ -301,6 +325,7 @@ struct CudaBatch : BatchBase {
     }
     int backend_write(uint32_t gslot, BodyField f, int comp, int n, const float* v) override {
         R2D_CUDA(cudaSetDevice(device));
+        R2D_TRY(join_forces());
         float4* arr = f == host::FIELD_POS ? pos.p : (f == host::FIELD_MOM ? mom.p : frc.p);
         float* dst = reinterpret_cast<float*>(arr + gslot) + comp;
         R2D_CUDA(cudaMemcpyAsync(dst, v, (size_t)n * 4, cudaMemcpyHostToDevice, stream));
@@ -340,10 +365,18 @@ struct CudaBatch : BatchBase {
     }
     int backend_write_forces(uint32_t first, uint32_t n, const float* f) override {
         R2D_CUDA(cudaSetDevice(device));
-        R2D_TRY(staging.reserve((size_t)n * 44 + 256));
-        R2D_CUDA(cudaMemcpyAsync(staging.p, f, (size_t)n * 12, cudaMemcpyHostToDevice, stream));
+        if (staging_f.cap < (size_t)n * 12 + 256) {
+            R2D_CUDA(cudaStreamSynchronize(copy_stream));  // an earlier import may still read the old buffer
+            R2D_TRY(staging_f.reserve((size_t)n * 12 + 256));
+        }
+        // the main stream is idle here (every entry point synchronises it before returning), so the side stream may
+        // touch `frc` right away; two imports in a row are ordered by the side stream itself
+        R2D_CUDA(cudaMemcpyAsync(staging_f.p, f, (size_t)n * 12, cudaMemcpyHostToDevice, copy_stream));
         fill_dev();
-        R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_import_forces, grid_for(n), TPB, d, (const uint32_t*)dev_of_host.p + first, n, (const float*)staging.p);
+        k_import_forces<<<grid_for(n), TPB, 0, copy_stream>>>(d, (const uint32_t*)dev_of_host.p + first, n, (const float*)staging_f.p);
+        launches += 1;
+        R2D_CUDA(cudaEventRecord(forces_ready, copy_stream));
+        forces_pending = true;
         // pageable source buffers are consumed before cudaMemcpyAsync returns; pinned ones must stay valid until the
         // next synchronising call (r2d_process synchronises once per step)
         return R2D_OK;
@@ -397,6 +430,7 @@ struct CudaBatch : BatchBase {
     }
     int backend_set_stream(void* s) override {
         R2D_CUDA(cudaSetDevice(device));
+        R2D_TRY(join_forces());
         R2D_CUDA(cudaStreamSynchronize(stream));
         stream = s ? (cudaStream_t)s : own_stream;
         return R2D_OK;
@@ -599,7 +633,16 @@ struct CudaBatch : BatchBase {
             // ---- colouring + partition + pre-step ----
             if (color_per_world) {
                 const uint32_t blocks = (uint32_t)std::min<size_t>(worlds.size(), (size_t)n_sms * 8);
-                R2D_LAUNCH(R2D_KCLASS_COLORING, k_color_worlds, blocks, WORLD_TPB, d);
+                if (seq_world_coloring) {
+                    const uint32_t smem_bodies = max_world_bodies;
+                    const uint32_t export_used = use_world_solver ? 0u : 1u;
+                    prof_begin(R2D_KCLASS_COLORING);
+                    k_color_worlds_seq<<<blocks, WORLD_TPB, (size_t)smem_bodies * COLOR_WORDS * 8, stream>>>(d, smem_bodies, export_used);
+                    prof_end();
+                    launches += 1;
+                } else {
+                    R2D_LAUNCH(R2D_KCLASS_COLORING, k_color_worlds, blocks, WORLD_TPB, d);
+                }
                 R2D_LAUNCH(R2D_KCLASS_COLORING, k_color_finish, 1, 32, d);
             } else {
                 prof_begin(R2D_KCLASS_COLORING);
@@ -614,6 +657,7 @@ struct CudaBatch : BatchBase {
             if ((st = scan(d.own_pos, d.own_pos, &d.counters->n_own_scan, (uint32_t)((own_w + 1) * MAX_COLORS), nullptr, R2D_KCLASS_COLORING, 2))) return st;
             R2D_LAUNCH(R2D_KCLASS_COLORING, k_partition_prestep, grid_for(cap_pairs), TPB, d);
             // ---- substeps: one persistent cooperative kernel (colour ranges are read on the device) ----
+            if ((st = join_forces())) return st;  // forces written for this step have arrived (first reader of `frc`)
             if (use_world_solver) {
                 const uint32_t blocks = (uint32_t)std::min<size_t>(worlds.size(), (size_t)n_sms * 16);
                 R2D_LAUNCH(R2D_KCLASS_SOLVE_CONTACTS, k_solve_worlds, blocks, world_solve_tpb, d, sub_dt, S, I);

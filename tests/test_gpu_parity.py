@@ -208,6 +208,49 @@ def test_gpu_large_batch_uses_world_solver_and_matches_oracle():
         assert_bodies_equal(ws.read_bodies(), o.read_bodies(), f"world {w}")
 
 
+def test_gpu_large_batch_with_joints_uses_per_world_colouring_and_dataflow_sweep():
+    """>= 74 small worlds WITH joints: coloured per world (sorted greedy in shared memory), swept by the persistent
+    dataflow kernel, whose per-body ranks come from the exported colour masks."""
+    n_worlds, steps = 80, 40
+    batch = Batch(n_worlds, 2.0, 4)
+    sample = (0, 3, 41, 79)
+    oracles = {}
+    def build(s, w):
+        return scenes.build_pyramid(s, base=6 + w % 3, n_spinners=1 + w % 2)
+    for w in range(n_worlds):
+        build(batch.world(w), w)
+        if w in sample:
+            o = OracleSolver(2.0, 4, order=ORDER_COLORED)
+            build(o, w)
+            oracles[w] = o
+    for step in range(steps):
+        batch.process(scenes.DT, 4, 10)
+        for o in oracles.values():
+            o.process(scenes.DT, 4, 10)
+    for w, o in oracles.items():
+        ws = batch.world(w)
+        assert np.array_equal(ws.read_pairs(), o.read_pairs()), w
+        assert_manifolds_equal(ws.read_manifolds(), o.read_manifolds(), f"world {w}")
+        assert_bodies_equal(ws.read_bodies(), o.read_bodies(), f"world {w}")
+
+
+def test_gpu_per_world_colouring_by_rounds_matches_sorted(monkeypatch):
+    """R2D_WORLD_COLORING=rounds (Jones-Plassmann rounds per world) and the default (sort + sequential greedy) give the
+    same colours, hence the same state."""
+    def run():
+        batch = Batch(96, 2.0, 4)
+        for w in range(96):
+            scenes.build_batch_world(batch.world(w), w)
+        for _ in range(50):
+            batch.process(scenes.DT, 4, 4)
+        return batch.read_bodies(), batch.world(5).read_manifolds()
+    b1, m1 = run()
+    monkeypatch.setenv("R2D_WORLD_COLORING", "rounds")
+    b2, m2 = run()
+    assert_bodies_equal(b1, b2, "world colouring flavours")
+    assert_manifolds_equal(m1, m2, "world colouring flavours")
+
+
 def test_gpu_reorder_does_not_change_results():
     """The spatial device order is invisible: forcing a re-sort every step gives the same bits as never re-sorting."""
     a, b = Solver(2.0, 4), Solver(2.0, 4)
