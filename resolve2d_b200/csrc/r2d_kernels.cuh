@@ -200,26 +200,40 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_chained(const uint32_t* in, u
     }
     uint32_t aggregate;
     const uint32_t local = block_exclusive_scan(sum, &aggregate);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32u) {
+        // decoupled look-back by one warp: lane j inspects tile (first - j); status 2 = inclusive prefix, 1 = aggregate only
+        const uint32_t lane = threadIdx.x;
         uint32_t prefix = 0;
         if (tile == 0) {
-            atomicExch(&state[0], (2ull << 32) | aggregate);
+            if (lane == 0) atomicExch(&state[0], (2ull << 32) | aggregate);
         } else {
-            atomicExch(&state[tile], (1ull << 32) | aggregate);
-            for (uint32_t t = tile; t-- > 0;) {
-                unsigned long long w;
-                do {
-                    w = *((volatile unsigned long long*)&state[t]);
-                } while ((w >> 32) == 0ull);
-                prefix += (uint32_t)w;
-                if ((w >> 32) == 2ull) break;
+            if (lane == 0) atomicExch(&state[tile], (1ull << 32) | aggregate);
+            int first = (int)tile - 1;
+            for (;;) {
+                const int t = first - (int)lane;
+                unsigned long long w = 3ull << 32;  // beyond tile 0: neutral, counts as "ready"
+                if (t >= 0) {
+                    do {
+                        w = *((volatile unsigned long long*)&state[t]);
+                    } while ((w >> 32) == 0ull);
+                }
+                const uint32_t is_prefix = __ballot_sync(0xffffffffu, (w >> 32) == 2ull);
+                const uint32_t upto = is_prefix ? (uint32_t)__ffs((int)is_prefix) - 1u : 31u;  // lanes 0..upto contribute
+                uint32_t v = (t >= 0 && lane <= upto) ? (uint32_t)w : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                prefix += v;
+                if (is_prefix || first < 32) break;
+                first -= 32;
             }
-            atomicExch(&state[tile], (2ull << 32) | (unsigned long long)(uint32_t)(prefix + aggregate));
+            if (lane == 0) atomicExch(&state[tile], (2ull << 32) | (unsigned long long)(uint32_t)(prefix + aggregate));
         }
-        s_prefix = prefix;
-        if (tile == n_tiles - 1) {
-            out[n] = prefix + aggregate;
-            if (total_out) *total_out = prefix + aggregate;
+        if (lane == 0) {
+            s_prefix = prefix;
+            if (tile == n_tiles - 1) {
+                out[n] = prefix + aggregate;
+                if (total_out) *total_out = prefix + aggregate;
+            }
         }
     }
     __syncthreads();
