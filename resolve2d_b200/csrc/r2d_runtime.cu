@@ -82,6 +82,7 @@ struct CudaBatch : BatchBase {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t forces_ready = nullptr;
     bool forces_pending = false;
+    bool zero_copy = true;            // R2D_ZERO_COPY=0: bulk reads always go through the staging buffer
     DBuf<unsigned char> staging_f;
     int color_blocks = 0, solve_blocks = 0, pair_blocks = 0;
     uint32_t wait_mode = 1, wait_probe = 1, wait_spin_lag = 1, wait_sleep_unit = 200, wait_sleep_max = 4000;
@@ -207,6 +208,7 @@ struct CudaBatch : BatchBase {
         if (const char* e = getenv("R2D_TILE_MAX_TASKS")) tile_max_tasks = std::min<uint32_t>((uint32_t)atoi(e), TILE_MAX_TASKS);  // tests
         R2D_CUDA(cudaFuncSetAttribute(k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES));
         if (const char* e = getenv("R2D_FLOW_SLEEP_UNIT")) flow_sleep_unit = (uint32_t)atoi(e);
+        if (const char* e = getenv("R2D_ZERO_COPY")) zero_copy = atoi(e) != 0;
         if (const char* e = getenv("R2D_BROADPHASE")) fine_grid = std::string(e) != "buckets";
         if (const char* e = getenv("R2D_WORLD_COLORING")) seq_world_coloring = std::string(e) != "rounds";
         return R2D_OK;
@@ -351,6 +353,28 @@ struct CudaBatch : BatchBase {
         float* d_l = (float*)carve((size_t)n * 4);
         float4* d_aabb = (float4*)carve((size_t)n * 16);
         fill_dev();
+        // Pinned (page-locked, UVA-mapped) destinations are written by the export kernel itself: the stores stream over
+        // PCIe as the warps finish, instead of one kernel followed by up to six separate DMA copies.  R2D_ZERO_COPY=0 or
+        // any pageable destination: repack into the staging buffer and copy.
+        auto mapped = [&](void* host) -> void* {
+            if (!host || !zero_copy) return nullptr;
+            cudaPointerAttributes a{};
+            if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+        };
+        void* m_ids = mapped(ids); void* m_pos = mapped(pos_xy); void* m_ang = mapped(angle); void* m_mom = mapped(momentum_xy);
+        void* m_l = mapped(ang_momentum); void* m_aabb = mapped(aabb_xywh);
+        const bool direct = (!ids || m_ids) && (!pos_xy || m_pos) && (!angle || m_ang) && (!momentum_xy || m_mom) &&
+                            (!ang_momentum || m_l) && (!aabb_xywh || m_aabb);
+        if (direct) {
+            R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_export_bodies, grid_for(n), TPB, d, (const uint32_t*)dev_of_host.p + first, n, (uint32_t*)m_ids,
+                       (float2*)m_pos, (float*)m_ang, (float2*)m_mom, (float*)m_l, (float4*)m_aabb);
+            R2D_CUDA(cudaStreamSynchronize(stream));
+            return R2D_OK;
+        }
         R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_export_bodies, grid_for(n), TPB, d, (const uint32_t*)dev_of_host.p + first, n, ids ? d_ids : nullptr,
                    pos_xy ? d_pos : nullptr, angle ? d_ang : nullptr, momentum_xy ? d_mom : nullptr,
                    ang_momentum ? d_l : nullptr, aabb_xywh ? d_aabb : nullptr);
