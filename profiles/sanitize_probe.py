@@ -14,4 +14,19 @@ b = Batch(80, 2.0, 4)
 for w in range(80): scenes.build_batch_world(b.world(w), w, nx=8, ny=4)
 for _ in range(80): b.process(scenes.DT, 4, 4)
 b.read_bodies()
+# fine grid with DYNAMIC large bodies: small-large pairs through the coarse buckets, large-large pairs from the bucket kernels
+c = Solver(2.0, 4); scenes.build_mixed(c, 40, 12, n_large=6)
+for _ in range(230): c.process(scenes.DT, 4, 4)
+c.read_pairs()
+# batch with joints: per-world sorted colouring + exported masks + persistent dataflow sweep
+j = Batch(80, 2.0, 4)
+for w in range(80): scenes.build_pyramid(j.world(w), base=6, n_spinners=1)
+for _ in range(20): j.process(scenes.DT, 4, 10)
+# bulk force import on the side stream, zero-copy export into pinned memory
+import numpy as np, torch
+n = m.num_bodies()
+f = torch.zeros((n, 3), dtype=torch.float32).pin_memory().numpy()
+out = {"pos": torch.empty((n, 2), dtype=torch.float32).pin_memory().numpy(), "angle": None, "momentum": None, "ang_momentum": None, "id": None, "aabb": None}
+for _ in range(3):
+    m.write_forces(f); m.process(scenes.DT, 4, 4); m.read_bodies(out)
 print("sanitize probe done", s.stats().n_manifolds, m.stats().n_manifolds, b.stats().n_manifolds)

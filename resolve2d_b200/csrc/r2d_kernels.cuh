@@ -618,31 +618,46 @@ __global__ void __launch_bounds__(TPB) k_fine_pairs(Dev d) {
 }
 
 // ---- K6: narrowphase, one thread per candidate pair --------------------------------------------------------------------------
+template <uint32_t NARROW_PER_THREAD>
 __global__ void __launch_bounds__(TPB, 3) k_narrow(Dev d) {
     if (overflowed(d)) return;
     const uint32_t n = live_pairs(d);
     uint32_t my_m = 0, my_k = 0;
-    // Each CTA takes 256 consecutive pairs and re-deals them to its threads sorted by shape combination (disc-disc,
-    // disc-rect, rect-rect), so that a warp runs one SAT flavour instead of all three (mixed scenes diverge 3-way
-    // otherwise).  The result of a pair does not depend on which thread computes it.
-    __shared__ uint32_t s_idx[TPB];
-    __shared__ uint32_t s_cnt[3];
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t p = base + threadIdx.x;
-        uint32_t t = 3;
-        if (p < n) {
-            const uint2 pr = d.pairs[p];
-            t = ((body_flags(d, pr.x) & FLAG_RECT) ? 1u : 0u) + ((body_flags(d, pr.y) & FLAG_RECT) ? 1u : 0u);
+    // Each CTA takes NARROW_TILE consecutive pairs and re-deals them to its threads sorted by shape combination IN ID
+    // ORDER (disc-disc, disc-rect, rect-disc, rect-rect; "first" = the lower id, whose axes the first SAT pass tests), so
+    // that a warp runs one SAT flavour with the same trip counts in both passes instead of all of them (a disc owns one
+    // axis, a rectangle four: mixing disc-rect with rect-disc halves the lanes in both passes).  The result of a pair
+    // does not depend on which thread computes it.
+    constexpr uint32_t NARROW_TILE = NARROW_PER_THREAD * TPB;   // 1, 2 or 4 pairs per thread: the host picks by pair count
+    __shared__ uint32_t s_idx[NARROW_TILE];
+    __shared__ uint32_t s_cnt[4];
+    for (uint32_t base = blockIdx.x * NARROW_TILE; base < n; base += gridDim.x * NARROW_TILE) {
+        if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
+        __syncthreads();
+        uint32_t t[NARROW_PER_THREAD], rank[NARROW_PER_THREAD];
+#pragma unroll
+        for (uint32_t k = 0; k < NARROW_PER_THREAD; ++k) {
+            const uint32_t p = base + k * TPB + threadIdx.x;
+            t[k] = 4u;
+            if (p < n) {
+                const uint2 pr = d.pairs[p];
+                const float4 sx = d.shape[pr.x], sy = d.shape[pr.y];
+                const uint32_t rx = (f2u(sx.z) & FLAG_RECT) ? 1u : 0u, ry = (f2u(sy.z) & FLAG_RECT) ? 1u : 0u;
+                const bool x_lo = f2u(sx.w) < f2u(sy.w);
+                t[k] = x_lo ? (rx * 2u + ry) : (ry * 2u + rx);
+            }
         }
-        if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < NARROW_PER_THREAD; ++k) rank[k] = t[k] < 4u ? atomicAdd(&s_cnt[t[k]], 1u) : 0u;
         __syncthreads();
-        const uint32_t rank = t < 3 ? atomicAdd(&s_cnt[t], 1u) : 0u;
+        const uint32_t c0 = s_cnt[0], c1 = s_cnt[1], c2 = s_cnt[2], c3 = s_cnt[3];
+#pragma unroll
+        for (uint32_t k = 0; k < NARROW_PER_THREAD; ++k)
+            if (t[k] < 4u) s_idx[(t[k] == 0 ? 0u : (t[k] == 1 ? c0 : (t[k] == 2 ? c0 + c1 : c0 + c1 + c2))) + rank[k]] = base + k * TPB + threadIdx.x;
         __syncthreads();
-        const uint32_t c0 = s_cnt[0], c1 = s_cnt[1], c2 = s_cnt[2];
-        if (t < 3) s_idx[(t == 0 ? 0u : (t == 1 ? c0 : c0 + c1)) + rank] = p;
-        __syncthreads();
-        if (threadIdx.x < c0 + c1 + c2) {
-            const int np = narrow_pair_thread(d, s_idx[threadIdx.x]);
+        const uint32_t total = c0 + c1 + c2 + c3;
+        for (uint32_t x = threadIdx.x; x < total; x += TPB) {
+            const int np = narrow_pair_thread(d, s_idx[x]);
             if (np >= 0) {
                 my_m += 1;
                 my_k += (uint32_t)np;

@@ -88,6 +88,7 @@ R2D_HD v2 closest_point(const BodyView& b, v2 p) {
 struct Edge {
     v2 dir;      // the axis / outward normal
     v2 ea, eb;   // rectangle: the edge itself (world)
+    v2 closest;  // disc: the other body's closest point, which the axis points at
 };
 
 // getNormal: Disc.zig:86-90 (axis toward the other body's closest point), Rectangle.zig:132-151.
@@ -98,10 +99,12 @@ R2D_HD Edge get_normal(const BodyView& self, const BodyView& other, int k) {
         e.dir = self.en[k];
         e.ea = self.wv[k];
         e.eb = self.wv[(k + 1) & 3];
+        e.closest = self.pos;
     } else {
         const v2 closest = closest_point(other, self.pos);
         e.dir = normalize2(sub2(closest, self.pos));
         e.ea = e.eb = self.pos;
+        e.closest = closest;
     }
     return e;
 }
@@ -130,6 +133,9 @@ struct SatResult {
     float penetration;
     int normal_id;
     int ref_is_first;  // 1: key = (first arg of the pass that took it ... ) see overlap_sat
+    // the unflipped axis of the pass that took it and the closest point it was aimed at: identifyCollisionPoints of a disc
+    // reference evaluates getNormal / closestPoint again with the same arguments (Disc.zig:99-123) — same bits, kept here
+    v2 axis_dir, axis_closest;
 };
 
 // normalShouldFlipSAT (collision.zig:221-226)
@@ -147,7 +153,8 @@ R2D_HD bool overlap_sat(SatResult& ret, BodyView R, const BodyView& I, int ref_t
     const int nn = is_rect(R) ? 4 : 1;
 #pragma unroll 1
     for (int k = 0; k < nn; ++k) {
-        v2 normal = get_normal(R, I, 0).dir;
+        const Edge axis = get_normal(R, I, 0);
+        v2 normal = axis.dir;
         bool flipped = false;
         if (normal_should_flip(normal, R, I)) {
             normal = negate_mul(normal);
@@ -169,6 +176,8 @@ R2D_HD bool overlap_sat(SatResult& ret, BodyView R, const BodyView& I, int ref_t
                 ret.normal = normal;
                 ret.normal_id = k;
                 ret.ref_is_first = ref_tag;
+                ret.axis_dir = axis.dir;
+                ret.axis_closest = axis.closest;
             }
         }
         if (!flipped && approx_eql2(normal, negate2(ret.normal), EPS)) {  // :270-279
@@ -178,6 +187,8 @@ R2D_HD bool overlap_sat(SatResult& ret, BodyView R, const BodyView& I, int ref_t
                 ret.normal = normal;
                 ret.normal_id = k;
                 ret.ref_is_first = ref_tag;
+                ret.axis_dir = axis.dir;
+                ret.axis_closest = axis.closest;
             }
         }
         if (fadd(d, EPS) < ret.penetration) {  // :281-286
@@ -185,6 +196,8 @@ R2D_HD bool overlap_sat(SatResult& ret, BodyView R, const BodyView& I, int ref_t
             ret.normal = normal;
             ret.normal_id = k;
             ret.ref_is_first = ref_tag;
+            ret.axis_dir = axis.dir;
+            ret.axis_closest = axis.closest;
         }
         // next axis: rotate the private copy
         const v2 w0 = R.wv[0], e0 = R.en[0];
@@ -266,11 +279,12 @@ R2D_HD void clip_line_to_line(v2 aa, v2 ab, v2 ba, v2 bb, v2& p1, v2& p2) {
 }
 
 // identifyCollisionPoints: Disc.zig:99-123, Rectangle.zig:171-211 (+ clipAgainstEdge Disc.zig:125-130, Rectangle.zig:213-238)
-R2D_HD void identify_points(Manifold& m, const BodyView& ref, const BodyView& inc, int normal_id) {
+R2D_HD void identify_points(Manifold& m, const BodyView& ref, const BodyView& inc, int normal_id, v2 axis_dir, v2 axis_closest) {
     m.n_points = 0;
     if (!is_rect(ref)) {
-        const v2 pos = closest_point(inc, ref.pos);
-        v2 normal = get_normal(ref, inc, normal_id).dir;
+        // closestPoint(inc, ref.pos) and getNormal(ref, inc): exactly what the SAT pass that chose this reference evaluated
+        const v2 pos = axis_closest;
+        v2 normal = axis_dir;
         if (normal_should_flip(normal, ref, inc)) normal = negate_mul(normal);
         const float dot = dot2(normal, sub2(pos, ref.pos));
         const float depth = fsub(dot, ref.a);
@@ -338,6 +352,7 @@ R2D_HD Manifold narrowphase(const BodyView& lo, const BodyView& hi) {
     ret.normal = mk2(u2f(0xAAAAAAAAu), u2f(0xAAAAAAAAu));  // `undefined` in the reference; never decides anything (Q12)
     ret.normal_id = 0;
     ret.ref_is_first = 1;
+    ret.axis_dir = ret.axis_closest = mk2(0.0f, 0.0f);
     m.normal = ret.normal;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {  // (lo, hi) then (hi, lo): one copy of the axis loop
@@ -349,7 +364,7 @@ R2D_HD Manifold narrowphase(const BodyView& lo, const BodyView& hi) {
     m.normal_id = ret.normal_id;
     m.normal = ret.normal;
     const bool ref_lo = m.ref_is_lo != 0;
-    identify_points(m, select_view(ref_lo, lo, hi), select_view(ref_lo, hi, lo), ret.normal_id);
+    identify_points(m, select_view(ref_lo, lo, hi), select_view(ref_lo, hi, lo), ret.normal_id, ret.axis_dir, ret.axis_closest);
     return m;
 }
 

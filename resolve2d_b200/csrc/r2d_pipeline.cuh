@@ -20,6 +20,8 @@ struct alignas(16) float4 { float x, y, z, w; };
 struct uint2 { uint32_t x, y; };
 struct int2 { int32_t x, y; };
 static inline int2 make_int2(int32_t x, int32_t y) { int2 r; r.x = x; r.y = y; return r; }
+struct alignas(16) int4 { int32_t x, y, z, w; };
+static inline int4 make_int4(int32_t x, int32_t y, int32_t z, int32_t w) { int4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 struct alignas(16) uint4 { uint32_t x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
@@ -108,7 +110,7 @@ struct Dev {
     uint32_t fine_on;             // 0: every body goes through the coarse buckets (the original pipeline)
     uint32_t ll_on;               // 1: the bucket pair kernels ran on the coarse (large-body) buckets, ent_off[T] = their pairs
     double fine_inv;              // 1 / fine cell width
-    int2* fcell;                  // NB: home cell of a small body (scratch of one process())
+    int4* fcell;                  // NB: home cell (x, y) of a small body, its fine bucket and its arrival rank in it (scratch of one process())
     float4* ent_aabb;             // E: the stored AABB of the body of a FINE entry (its ent_body carries the static flag in bit 31)
     uint32_t* pair_cnt;           // NB + 2: [0] = pairs of the bucket kernels, [a + 1] = pairs emitted by small body a; then
                                   // its exclusive scan: [a + 1] = first pair slot of body a, [NB + 1] = P
@@ -407,9 +409,11 @@ R2D_HD CellRange count_body_thread(const Dev& d, uint32_t i, bool count_inline) 
     d.bkt[i] = make_uint4(bk[0], bk[1], bk[2], bk[3]);
     if (small) {
         const float4 a = d.aabb[i];
-        const int2 c = make_int2(fine_coord(a.x, d.fine_inv), fine_coord(a.y, d.fine_inv));
-        d.fcell[i] = c;
-        atomic_add_u32(&d.bucket_cnt[fine_bucket(d, flags >> FLAG_WORLD_SHIFT, c.x, c.y)], 1u);
+        const int32_t cx = fine_coord(a.x, d.fine_inv), cy = fine_coord(a.y, d.fine_inv);
+        const uint32_t fb = fine_bucket(d, flags >> FLAG_WORLD_SHIFT, cx, cy);
+        // the count's own atomic hands out the body's place in the bucket: the fill needs no second atomic (and no hash)
+        const uint32_t rank = atomic_add_u32(&d.bucket_cnt[fb], 1u);
+        d.fcell[i] = make_int4(cx, cy, (int32_t)fb, (int32_t)rank);
         r.count = 0;
     }
     return r;
@@ -428,13 +432,11 @@ R2D_HD void fill_cell(const Dev& d, uint32_t i, uint32_t bucket) { fill_cell(d, 
 // needs (AABB, static flag) so that the test does not have to chase the body
 constexpr uint32_t ENT_STATIC = 0x80000000u;
 R2D_HD void fill_fine(const Dev& d, uint32_t i) {
-    const int2 c = d.fcell[i];
-    const uint32_t flags = body_flags(d, i);
-    const uint32_t bucket = fine_bucket(d, flags >> FLAG_WORLD_SHIFT, c.x, c.y);
-    const uint32_t left = atomic_sub_u32(&d.bucket_cnt[bucket], 1u) - 1u;
-    const uint32_t at = d.bucket_start[bucket] + left;
+    const int4 c = d.fcell[i];
+    const uint32_t bucket = (uint32_t)c.z, at = d.bucket_start[bucket] + (uint32_t)c.w;
+    d.bucket_cnt[bucket] = 0u;   // (every body of the bucket writes the same zero) the counts are all zero again after the fill
     if (at < d.cap_entries) {
-        d.ent_body[at] = i | ((flags & FLAG_STATIC) ? ENT_STATIC : 0u);
+        d.ent_body[at] = i | ((body_flags(d, i) & FLAG_STATIC) ? ENT_STATIC : 0u);
         d.ent_key[at] = fine_tag(c.x, c.y);
         d.ent_aabb[at] = d.aabb[i];
     }
@@ -563,7 +565,7 @@ R2D_HD bool bucket_lists_share(const uint4& x, const uint4& y) {
 R2D_HD uint32_t fine_body_pairs(const Dev& d, uint32_t a, uint32_t* got, uint2* out) {
     const uint32_t fa = body_flags(d, a);
     const float4 aa = d.aabb[a];
-    const int2 ca = d.fcell[a];
+    const int4 ca = d.fcell[a];
     const uint4 ba = d.bkt[a];
     const uint32_t world = fa >> FLAG_WORLD_SHIFT;
     const bool a_static = (fa & FLAG_STATIC) != 0;

@@ -101,7 +101,7 @@ struct CudaBatch : BatchBase {
     DBuf<float4> j_par, j_vec;
     // grid
     DBuf<uint32_t> bucket_cnt, bucket_start, ent_body, ent_key, ent_off, tile_sums, work, hit_bits;
-    DBuf<int2> fcell;                 // fine grid: home cell per small body
+    DBuf<int4> fcell;                 // fine grid: home cell per small body
     DBuf<float4> ent_aabb;            // fine grid: AABB copies in entry order
     DBuf<uint32_t> pair_cnt;          // fine grid: pairs per small body, then their scan
     bool seq_world_coloring = true;   // R2D_WORLD_COLORING=rounds: Jones-Plassmann rounds per world instead of sort + sequential greedy
@@ -653,7 +653,13 @@ struct CudaBatch : BatchBase {
                 R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_fine_pairs<true>, grid_for(nb), TPB, d);
             }
             // ---- narrowphase ----
-            R2D_LAUNCH(R2D_KCLASS_NARROWPHASE, k_narrow, grid_for(cap_pairs), TPB, d);
+            // larger re-deal tiles sort the shape classes better; small pair counts keep one pair per thread (more CTAs)
+            if (pairs_guess > (size_t)n_sms * 3 * TPB * 6)
+                R2D_LAUNCH(R2D_KCLASS_NARROWPHASE, k_narrow<4>, grid_for((cap_pairs + 3) / 4), TPB, d);
+            else if (pairs_guess > (size_t)n_sms * 3 * TPB * 3)
+                R2D_LAUNCH(R2D_KCLASS_NARROWPHASE, k_narrow<2>, grid_for((cap_pairs + 1) / 2), TPB, d);
+            else
+                R2D_LAUNCH(R2D_KCLASS_NARROWPHASE, k_narrow<1>, grid_for(cap_pairs), TPB, d);
             // ---- colouring + partition + pre-step ----
             if (color_per_world) {
                 const uint32_t blocks = (uint32_t)std::min<size_t>(worlds.size(), (size_t)n_sms * 8);

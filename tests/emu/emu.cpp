@@ -22,7 +22,7 @@ struct EmuBatch : BatchBase {
     Dev d{};
     std::vector<float4> pos, mom, frc, prop, shape, aabb, pose, view;
     std::vector<uint32_t> ncells, bucket_cnt, bucket_start, ent_body, ent_key, ent_off, m_color, pair_cnt;
-    std::vector<int2> fcell;
+    std::vector<int4> fcell;
     std::vector<float4> ent_aabb;
     std::vector<uint2> pairs;
     std::vector<uint4> m_hdr, s_hdr, bkt;

@@ -101,3 +101,22 @@ def test_emu_fine_grid_batch_matches_standalone_worlds():
         ws = batch.world(w)
         assert np.array_equal(ws.read_pairs(), o.read_pairs()), w
         assert_bodies_equal(ws.read_bodies(), o.read_bodies(), f"emu batch world {w}")
+
+
+def test_emu_fine_grid_in_fast_mode_with_small_coarse_cells():
+    """MODE_FAST honours cell_width: with 1.3 m coarse cells the discs (1.0 wide) are small and the rectangles (diagonal
+    1.41) are LARGE and dynamic — half of the scene goes through the bucket kernels, half through the fine grid, and the
+    mode switch after the upload re-derives the fine cell."""
+    from resolve2d_b200 import MODE_FAST
+    for cell in (2.0, 1.3):
+        cand, orc = EmuSolver(cell, 4), OracleSolver(cell, 4, order=ORDER_COLORED)
+        for s in (cand, orc):
+            scenes.build_box1k(s)
+            s.process(scenes.DT, 4, 4)      # one step in parity mode first
+            s.set_mode(MODE_FAST)
+        for step in range(45):
+            cand.process(scenes.DT, 4, 4)
+            orc.process(scenes.DT, 4, 4)
+            if step % 15 == 14:
+                assert np.array_equal(cand.read_pairs(), orc.read_pairs()), (cell, step)
+        assert_bodies_equal(cand.read_bodies(), orc.read_bodies(), f"fast mode cell {cell}")

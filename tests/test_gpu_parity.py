@@ -287,6 +287,23 @@ def test_gpu_fast_mode_grid_parameters():
     assert_bodies_equal(cand.read_bodies(), orc.read_bodies(), "fast mode")
 
 
+def test_gpu_fast_mode_small_cells_make_rectangles_large():
+    """MODE_FAST with 1.3 m cells: discs (1.0 wide) stay in the fine grid, rectangles (diagonal 1.41) become LARGE and
+    dynamic — half of the scene goes through the bucket kernels; the mode switch after an upload re-derives the fine cell."""
+    cand, orc = Solver(1.3, 4), OracleSolver(1.3, 4, order=ORDER_COLORED)
+    for s in (cand, orc):
+        scenes.build_box1k(s)
+        s.process(scenes.DT, 4, 4)
+        s.set_mode(MODE_FAST)
+    for step in range(60):
+        cand.process(scenes.DT, 4, 4)
+        orc.process(scenes.DT, 4, 4)
+        if step % 20 == 19:
+            assert np.array_equal(cand.read_pairs(), orc.read_pairs()), step
+    assert_manifolds_equal(cand.read_manifolds(), orc.read_manifolds(), "fast 1.3")
+    assert_bodies_equal(cand.read_bodies(), orc.read_bodies(), "fast 1.3")
+
+
 def test_gpu_remove_body_swapremove_and_dangling_joint():
     s, o = Solver(2.0, 4), OracleSolver(2.0, 4, order=ORDER_COLORED)
     for x in (s, o):
