@@ -929,10 +929,10 @@ __global__ void __launch_bounds__(WORLD_TPB) k_color_worlds(Dev d) {
     if (threadIdx.x == 0) atomicMax(&d.counters->n_rounds, max_round);
 }
 // ---- K8 for batches of small worlds, sorted form ------------------------------------------------------------------------------
-// "Greedy in descending priority" taken literally: the world's pending manifolds are sorted by priority (one bitonic
-// sort of 64-bit keys {priority, pair index} in shared memory) and one warp colours them in that order, 32 at a time —
-// lowest colour free on both bodies, per-body colour masks in shared memory — while the Jones-Plassmann rounds above
-// need ~26 block-wide rounds with 8 of 32 lanes active.  Same colours by construction (JP with unique priorities == sequential greedy; ties are only
+// "Greedy in descending priority" taken literally: the world's pending manifolds are sorted by priority (64-bit keys
+// {priority, pair index}: 16 buckets by the top bits, a rank sort by one warp inside each) and one warp colours them
+// in that order, 32 at a time — lowest colour free on both bodies, per-body colour masks in shared memory — while the
+// Jones-Plassmann rounds above need ~26 block-wide rounds with 8 of 32 lanes active.  Same colours by construction (JP with unique priorities == sequential greedy; ties are only
 // possible between manifolds that share no body and then the order does not matter).  Worlds with more than
 // SEQ_WORLD_PAIRS candidate pairs take the rounds with the global per-body arrays instead.
 constexpr uint32_t SEQ_WORLD_PAIRS = 1024;
@@ -943,9 +943,13 @@ __global__ void __launch_bounds__(WORLD_TPB) k_color_worlds_seq(Dev d, uint32_t 
     __shared__ uint32_t s_pair[SEQ_WORLD_PAIRS];
     __shared__ unsigned char s_col[SEQ_WORLD_PAIRS];
     __shared__ uint32_t s_hist[MAX_COLORS];
+    __shared__ uint32_t s_lanes[COLOR_WORLD_MAX_BODIES];   // per body: the lanes of the current chunk that touch it
+    __shared__ unsigned short s_order[SEQ_WORLD_PAIRS];    // pair indices in descending priority
+    __shared__ uint32_t s_bcnt[16], s_bfill[16], s_bstart[16];
     __shared__ uint32_t s_n;
     if (overflowed(d)) return;
     for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x) s_hist[c] = 0u;
+    for (uint32_t c = threadIdx.x; c < COLOR_WORLD_MAX_BODIES; c += blockDim.x) s_lanes[c] = 0u;
     uint32_t max_round = 0;
     for (uint32_t w = blockIdx.x; w < d.n_worlds; w += gridDim.x) {
         const uint32_t b0 = d.world_base[w], b1 = d.world_base[w + 1], nb = b1 - b0;
@@ -953,56 +957,72 @@ __global__ void __launch_bounds__(WORLD_TPB) k_color_worlds_seq(Dev d, uint32_t 
         const uint32_t p1 = d.fine_on ? d.pair_cnt[b1 + 1] : d.ent_off[d.table_mult * b1];
         const uint32_t np = p1 - p0;
         __syncthreads();
-        if (np <= SEQ_WORLD_PAIRS && nb <= smem_bodies && nb <= 4096u) {
-            if (threadIdx.x == 0) s_n = 0u;
+        if (np <= SEQ_WORLD_PAIRS && nb <= smem_bodies && nb <= COLOR_WORLD_MAX_BODIES) {
+            if (threadIdx.x < 16u) s_bcnt[threadIdx.x] = s_bfill[threadIdx.x] = 0u;
             for (uint32_t i = threadIdx.x; i < nb * COLOR_WORDS; i += blockDim.x) s_used_dyn[i] = 0ull;
             __syncthreads();
-            for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) {
-                const uint32_t p = p0 + i;
-                if (d.m_color[p] != COLOR_PENDING) continue;
-                const uint4 h = d.m_hdr[p];
-                s_pair[i] = (h.x - b0) | ((h.y - b0) << 12) | ((h.w & 3u) << 24);
-                s_key[atomicAdd(&s_n, 1u)] = (d.m_prio[p] << 12) | (unsigned long long)i;   // priorities have 52 bits
+            // ---- sort by priority, descending: 16 buckets by the top bits (a hash: uniform), then a rank sort inside each ----
+            constexpr uint32_t PER_THREAD = SEQ_WORLD_PAIRS / WORLD_TPB;
+            unsigned long long key[PER_THREAD];   // {priority (52 bits), pair index in the world (12 bits)}; 0 = not pending
+#pragma unroll
+            for (uint32_t k = 0; k < PER_THREAD; ++k) {
+                const uint32_t i = threadIdx.x + k * WORLD_TPB, p = p0 + i;
+                key[k] = 0ull;
+                if (i < np && d.m_color[p] == COLOR_PENDING) {
+                    const uint4 h = d.m_hdr[p];
+                    s_pair[i] = (h.x - b0) | ((h.y - b0) << 12) | ((h.w & 3u) << 24);
+                    key[k] = (d.m_prio[p] << 12) | (unsigned long long)i;
+                    atomicAdd(&s_bcnt[(uint32_t)(key[k] >> 60)], 1u);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {   // descending: bucket 15 first
+                uint32_t run = 0;
+                for (int b = 15; b >= 0; --b) {
+                    s_bstart[b] = run;
+                    run += s_bcnt[b];
+                }
+                s_n = run;
+            }
+            __syncthreads();
+#pragma unroll
+            for (uint32_t k = 0; k < PER_THREAD; ++k) {
+                if (key[k] != 0ull) {   // (a priority is never 0: its low word is the sum of two distinct ids)
+                    const uint32_t b = (uint32_t)(key[k] >> 60);
+                    s_key[s_bstart[b] + atomicAdd(&s_bfill[b], 1u)] = key[k];
+                }
             }
             __syncthreads();
             const uint32_t n = s_n;
-            uint32_t m = 1;
-            while (m < n) m <<= 1;
-            for (uint32_t i = n + threadIdx.x; i < m; i += blockDim.x) s_key[i] = 0ull;   // below every real key
-            __syncthreads();
-            for (uint32_t k = 2; k <= m; k <<= 1)           // bitonic sort, descending
-                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
-                        const uint32_t x = i ^ j;
-                        if (x > i) {
-                            const unsigned long long a = s_key[i], b = s_key[x];
-                            const bool desc = (i & k) == 0;
-                            if (desc ? a < b : a > b) {
-                                s_key[i] = b;
-                                s_key[x] = a;
-                            }
-                        }
-                    }
-                    __syncthreads();
+            for (uint32_t b = threadIdx.x >> 5; b < 16u; b += blockDim.x >> 5) {   // a warp per bucket
+                const uint32_t st = s_bstart[b], cnt = s_bcnt[b];
+                for (uint32_t e = threadIdx.x & 31u; e < cnt; e += 32u) {
+                    const unsigned long long mine = s_key[st + e];
+                    uint32_t rank = 0;
+                    for (uint32_t j = 0; j < cnt; ++j) rank += s_key[st + j] > mine ? 1u : 0u;   // keys are unique (pair index)
+                    s_order[st + rank] = (unsigned short)((uint32_t)mine & 0xFFFu);
                 }
+            }
+            __syncthreads();
             if (threadIdx.x < 32u) {
                 // One warp walks the sorted list 32 manifolds at a time.  Inside a chunk a lane depends on the EARLIER lanes
-                // that share one of its non-static bodies (found once per chunk with shuffles); lanes whose dependencies are
+                // that share one of its non-static bodies (found once per chunk, see s_lanes); lanes whose dependencies are
                 // done colour in parallel — they touch disjoint bodies — so a chunk takes 2-3 passes instead of 32 steps.
                 const uint32_t lane = threadIdx.x;
                 for (uint32_t base = 0; base < n; base += 32u) {
                     const uint32_t k = base + lane;
                     const bool active = k < n;
-                    const uint32_t i = active ? ((uint32_t)s_key[k] & 0xFFFu) : 0u, pr = active ? s_pair[i] : 0u;
+                    const uint32_t i = active ? (uint32_t)s_order[k] : 0u, pr = active ? s_pair[i] : 0u;
                     const uint32_t l1 = pr & 0xFFFu, l2 = (pr >> 12) & 0xFFFu;
                     const bool dyn1 = ((pr >> 24) & 1u) != 0, dyn2 = ((pr >> 25) & 1u) != 0;
-                    const uint32_t a1 = dyn1 ? l1 : 0xFFFF0000u + 2u * lane, a2 = dyn2 ? l2 : 0xFFFF0001u + 2u * lane;
-                    uint32_t dep = 0u;
-#pragma unroll 8
-                    for (uint32_t j = 0; j < 31u; ++j) {
-                        const uint32_t o1 = __shfl_sync(0xffffffffu, a1, j), o2 = __shfl_sync(0xffffffffu, a2, j);
-                        if (j < lane && (o1 == a1 || o1 == a2 || o2 == a1 || o2 == a2)) dep |= 1u << j;
-                    }
+                    // lanes of this chunk on each body, collected in shared memory (two atomicOr per lane instead of 62 shuffles)
+                    if (dyn1) atomicOr(&s_lanes[l1], 1u << lane);
+                    if (dyn2) atomicOr(&s_lanes[l2], 1u << lane);
+                    __syncwarp();
+                    const uint32_t dep = ((dyn1 ? s_lanes[l1] : 0u) | (dyn2 ? s_lanes[l2] : 0u)) & ((1u << lane) - 1u);
+                    __syncwarp();
+                    if (dyn1) s_lanes[l1] = 0u;
+                    if (dyn2) s_lanes[l2] = 0u;
                     bool pending = active;
                     for (;;) {
                         const uint32_t pend_mask = __ballot_sync(0xffffffffu, pending);
@@ -1035,7 +1055,7 @@ __global__ void __launch_bounds__(WORLD_TPB) k_color_worlds_seq(Dev d, uint32_t 
             }
             __syncthreads();
             for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
-                const uint32_t i = (uint32_t)s_key[k] & 0xFFFu;
+                const uint32_t i = (uint32_t)s_order[k];
                 d.m_color[p0 + i] = s_col[i];
             }
             if (export_used)   // the dataflow sweep derives rank / degree from the per-body masks (body_color_rank)
