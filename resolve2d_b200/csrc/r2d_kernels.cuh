@@ -578,40 +578,47 @@ __global__ void __launch_bounds__(TPB) k_bucket_write(Dev d) {
 }
 
 // ---- K5 with the fine grid: one thread per small body (see fine_body_pairs) ------------------------------------------------------
-// WRITE = false counts (pair_cnt[a + 1]); after the scan WRITE = true emits at pair_cnt[a + 1].  The write pass keeps up
-// to 8 partners in registers (the tests run once) and writes them in ascending slot order; a body with more re-runs them.
+// WRITE = false runs the tests, counts (pair_cnt[a + 1]) and parks the first 8 partners of the body in `fine_cand`; after
+// the scan WRITE = true only sorts the parked partners (ascending slot: the order of the list must not depend on the
+// order the fill's atomics landed in) and emits them at pair_cnt[a + 1].  A body with more than 8 partners re-runs the tests.
 template <bool WRITE>
 __global__ void __launch_bounds__(TPB) k_fine_pairs(Dev d) {
     if (overflowed(d)) return;
     if (!WRITE && blockIdx.x == 0 && threadIdx.x == 0) d.pair_cnt[0] = d.ll_on ? d.ent_off[d.n_buckets] : 0u;
     for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < d.n_bodies; a += gridDim.x * blockDim.x) {
-        const bool live = body_is_small(d, body_flags(d, a));
         uint32_t got[8];
-        const uint32_t n = live ? fine_body_pairs(d, a, WRITE ? got : nullptr, nullptr) : 0u;
         if (!WRITE) {
+            const bool live = body_is_small(d, body_flags(d, a));
+            const uint32_t n = live ? fine_body_pairs(d, a, got, nullptr) : 0u;
             d.pair_cnt[a + 1] = n;
-        } else if (n) {
-            const uint32_t at = d.pair_cnt[a + 1];
-            if (at + n <= d.cap_pairs) {
-                uint2* out = d.pairs + at;
-                if (n <= 8u) {
+            uint4* park = d.fine_cand + 2 * (size_t)a;
+            if (n > 0u) park[0] = make_uint4(got[0], n > 1u ? got[1] : 0u, n > 2u ? got[2] : 0u, n > 3u ? got[3] : 0u);
+            if (n > 4u) park[1] = make_uint4(got[4], n > 5u ? got[5] : 0u, n > 6u ? got[6] : 0u, n > 7u ? got[7] : 0u);
+        } else {
+            const uint32_t at = d.pair_cnt[a + 1], n = d.pair_cnt[a + 2] - at;
+            if (n == 0u || at + n > d.cap_pairs) continue;
+            uint2* out = d.pairs + at;
+            if (n <= 8u) {
+                const uint4* park = d.fine_cand + 2 * (size_t)a;
+                const uint4 q0 = park[0], q1 = n > 4u ? park[1] : make_uint4(0u, 0u, 0u, 0u);
+                got[0] = q0.x; got[1] = q0.y; got[2] = q0.z; got[3] = q0.w;
+                got[4] = q1.x; got[5] = q1.y; got[6] = q1.z; got[7] = q1.w;
 #pragma unroll
-                    for (int x = 1; x < 8; ++x) {  // insertion sort in registers (fixed trip counts: no local memory)
+                for (int x = 1; x < 8; ++x) {  // insertion sort in registers (fixed trip counts: no local memory)
 #pragma unroll
-                        for (int y = x; y > 0; --y)
-                            if ((uint32_t)x < n && got[y - 1] > got[y]) {
-                                const uint32_t t = got[y - 1];
-                                got[y - 1] = got[y];
-                                got[y] = t;
-                            }
-                    }
-#pragma unroll
-                    for (int x = 0; x < 8; ++x)
-                        if ((uint32_t)x < n) out[x] = make_uint2(a, got[x]);
-                } else {
-                    fine_body_pairs(d, a, nullptr, out);
-                    sort_item_pairs(out, n);
+                    for (int y = x; y > 0; --y)
+                        if ((uint32_t)x < n && got[y - 1] > got[y]) {
+                            const uint32_t t = got[y - 1];
+                            got[y - 1] = got[y];
+                            got[y] = t;
+                        }
                 }
+#pragma unroll
+                for (int x = 0; x < 8; ++x)
+                    if ((uint32_t)x < n) out[x] = make_uint2(a, got[x]);
+            } else {
+                fine_body_pairs(d, a, nullptr, out);
+                sort_item_pairs(out, n);
             }
         }
     }

@@ -112,6 +112,7 @@ struct Dev {
     double fine_inv;              // 1 / fine cell width
     int4* fcell;                  // NB: home cell (x, y) of a small body, its fine bucket and its arrival rank in it (scratch of one process())
     float4* ent_aabb;             // E: the stored AABB of the body of a FINE entry (its ent_body carries the static flag in bit 31)
+    uint4* fine_cand;             // 2 NB: the first 8 partners found by small body a (count pass -> write pass)
     uint32_t* pair_cnt;           // NB + 2: [0] = pairs of the bucket kernels, [a + 1] = pairs emitted by small body a; then
                                   // its exclusive scan: [a + 1] = first pair slot of body a, [NB + 1] = P
     // ---- candidate pairs / raw manifolds (P slots) ------------------------------------------------------------------

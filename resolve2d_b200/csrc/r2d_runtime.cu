@@ -103,6 +103,7 @@ struct CudaBatch : BatchBase {
     DBuf<uint32_t> bucket_cnt, bucket_start, ent_body, ent_key, ent_off, tile_sums, work, hit_bits;
     DBuf<int4> fcell;                 // fine grid: home cell per small body
     DBuf<float4> ent_aabb;            // fine grid: AABB copies in entry order
+    DBuf<uint4> fine_cand;            // fine grid: partners parked between the count and the write pass
     DBuf<uint32_t> pair_cnt;          // fine grid: pairs per small body, then their scan
     bool seq_world_coloring = true;   // R2D_WORLD_COLORING=rounds: Jones-Plassmann rounds per world instead of sort + sequential greedy
     bool fine_grid = true;            // R2D_BROADPHASE=buckets: every body through the coarse buckets (the original pipeline)
@@ -501,7 +502,7 @@ struct CudaBatch : BatchBase {
         d.excl = (const uint64_t*)excl.p; d.n_excl = (uint32_t)image.excl.size();
         d.fine_on = fine_now ? 1u : 0u; d.ll_on = ll_now ? 1u : 0u;
         d.fine_inv = fine_now ? 1.0 / (double)image.fine_cell : 0.0;
-        d.fcell = fcell.p; d.pair_cnt = pair_cnt.p; d.ent_aabb = ent_aabb.p;
+        d.fcell = fcell.p; d.pair_cnt = pair_cnt.p; d.ent_aabb = ent_aabb.p; d.fine_cand = fine_cand.p;
         d.cap_pairs = (uint32_t)cap_pairs;
         d.pairs = pairs.p; d.m_hdr = m_hdr.p; d.m_g0 = m_g0.p; d.m_g1 = m_g1.p; d.m_r0 = m_r0.p; d.m_r1 = m_r1.p;
         d.m_color = m_color.p; d.m_prio = m_prio.p;
@@ -604,7 +605,7 @@ struct CudaBatch : BatchBase {
         }
         if ((st = own_pos.reserve((own_w + 1) * MAX_COLORS + 2)) ||
             (st = pose.reserve(nb)) || (st = view.reserve(4 * (size_t)nb)) || (st = ncells.reserve(nb)) || (st = bkt.reserve(nb)) ||  (st = bucket_cnt.reserve(2 * (size_t)T + 1, true, stream)) ||
-            (st = bucket_start.reserve(2 * (size_t)T + 2)) || (st = fcell.reserve(nb)) || (st = pair_cnt.reserve((size_t)nb + 3)) || (st = ent_off.reserve((size_t)T + 2)) || (st = work.reserve(2 * (size_t)T + 2)))
+            (st = bucket_start.reserve(2 * (size_t)T + 2)) || (st = fcell.reserve(nb)) || (st = fine_cand.reserve(2 * (size_t)nb)) || (st = pair_cnt.reserve((size_t)nb + 3)) || (st = ent_off.reserve((size_t)T + 2)) || (st = work.reserve(2 * (size_t)T + 2)))
             return st;
         if (cap_entries == 0 && (st = reserve_entries((size_t)nb * 3 + 4096))) return st;
         if (cap_pairs == 0 && (st = reserve_pairs((size_t)nb * 6 + 4096))) return st;
