@@ -166,6 +166,12 @@ int r2d_remove_body(r2d_solver* s, uint32_t id);  /* removeRigidBody = swapRemov
 /* ---- the hot path: Solver.process (lib.zig:189-251; wasm solverProcess) ------------------------------ */
 int r2d_process(r2d_solver* s, float dt, uint32_t sub_steps, uint32_t collision_iters);
 int r2d_step(r2d_solver* s, float dt, uint32_t sub_steps, uint32_t collision_iters); /* alias (north_star's name) */
+/* process() followed by r2d_read_bodies() of ALL bodies (n = r2d_num_bodies) in one call and ONE host synchronisation: the
+ * export of the new state is enqueued behind the step's last kernel (pinned destinations are written straight over PCIe).
+ * Replaces the per-frame "solverProcess, then 17 getters per body" loop of demos/web/src/wasm_bridge.ts:43-81 /
+ * demos/native/src/Renderer.zig:84-157.  Any output pointer may be NULL. */
+int r2d_process_read(r2d_solver* s, float dt, uint32_t sub_steps, uint32_t collision_iters, uint32_t* ids, float* pos_xy,
+                     float* angle, float* momentum_xy, float* ang_momentum, float* aabb_xywh, size_t n);
 int r2d_synchronize(r2d_solver* s);               /* wait for the solver's stream */
 
 /* ---- state access (replaces raw `*RigidBody`, lib.zig:23-31; wasm getters/setters :88-251) ------------ */
@@ -203,6 +209,8 @@ int r2d_batch_set_stream(r2d_batch* b, void* cuda_stream);
 int r2d_batch_set_reorder_interval(r2d_batch* b, uint32_t steps);
 int r2d_batch_reorder(r2d_batch* b);
 int r2d_batch_process(r2d_batch* b, float dt, uint32_t sub_steps, uint32_t collision_iters);
+int r2d_batch_process_read(r2d_batch* b, float dt, uint32_t sub_steps, uint32_t collision_iters, uint32_t* ids, float* pos_xy,
+                           float* angle, float* momentum_xy, float* ang_momentum, float* aabb_xywh, size_t n);
 int r2d_batch_synchronize(r2d_batch* b);
 int r2d_batch_num_bodies(r2d_batch* b, size_t* out);                   /* total over worlds */
 /* bulk access over all worlds, world-major then slot order */

@@ -137,6 +137,7 @@ SIGNATURES = {
     "r2d_remove_body": (C.c_int, [_P, _U32]),
     "r2d_process": (C.c_int, [_P, _F, _U32, _U32]),
     "r2d_step": (C.c_int, [_P, _F, _U32, _U32]),
+    "r2d_process_read": (C.c_int, [_P, _F, _U32, _U32, _P, _P, _P, _P, _P, _P, _SZ]),
     "r2d_synchronize": (C.c_int, [_P]),
     "r2d_num_bodies": (C.c_int, [_P, C.POINTER(_SZ)]),
     "r2d_body_id_at": (C.c_int, [_P, _SZ, _UP]),
@@ -163,6 +164,7 @@ SIGNATURES = {
     "r2d_batch_set_reorder_interval": (C.c_int, [_P, _U32]),
     "r2d_batch_reorder": (C.c_int, [_P]),
     "r2d_batch_process": (C.c_int, [_P, _F, _U32, _U32]),
+    "r2d_batch_process_read": (C.c_int, [_P, _F, _U32, _U32, _P, _P, _P, _P, _P, _P, _SZ]),
     "r2d_batch_synchronize": (C.c_int, [_P]),
     "r2d_batch_num_bodies": (C.c_int, [_P, C.POINTER(_SZ)]),
     "r2d_batch_read_bodies": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _SZ]),

@@ -412,6 +412,15 @@ struct BatchBase {
         if (dev_fresh) return backend_write(image.dev_of_host[image.world_base[w->index] + (uint32_t)s], f, comp, n, v);
         return R2D_OK;
     }
+    // process() + bulk read of every body in ONE call (r2d_process_read): a backend may enqueue the export behind the
+    // step's last kernel, so that the call has a single host synchronisation (sets readback_done); otherwise the
+    // generic path reads after the step.
+    struct Readback {
+        uint32_t* ids = nullptr;
+        float *pos_xy = nullptr, *angle = nullptr, *momentum_xy = nullptr, *ang_momentum = nullptr, *aabb_xywh = nullptr;
+    };
+    const Readback* readback = nullptr;
+    bool readback_done = false;
     uint32_t reorder_interval = 256;   // process() calls between spatial re-sorts of the device order (0 = never)
     uint32_t steps_since_upload = 0;
     int reorder() {  // re-derive the device order from the current positions (download, sort, upload)
@@ -420,7 +429,7 @@ struct BatchBase {
         dev_fresh = false;
         return R2D_OK;
     }
-    int process(float dt, uint32_t sub_steps, uint32_t iters) {
+    int process(float dt, uint32_t sub_steps, uint32_t iters, const Readback* rb = nullptr) {
         if (dev_fresh && reorder_interval && steps_since_upload >= reorder_interval) {
             const int sr = reorder();
             if (sr != R2D_OK) return sr;
@@ -433,8 +442,13 @@ struct BatchBase {
         steps_since_upload += 1;
         const int st = ensure_device();
         if (st != R2D_OK) return st;
+        readback = rb;
+        readback_done = false;
         const int st2 = backend_process(dt, sub_steps, iters);
+        readback = nullptr;
         if (st2 == R2D_OK || st2 == R2D_ERR_COLOR_OVERFLOW) host_fresh = false;
+        if (st2 == R2D_OK && rb && !readback_done && image.n_bodies)
+            return backend_read_bodies(0, image.n_bodies, rb->ids, rb->pos_xy, rb->angle, rb->momentum_xy, rb->ang_momentum, rb->aabb_xywh);
         return st2;
     }
 };

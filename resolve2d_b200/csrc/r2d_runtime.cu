@@ -335,8 +335,9 @@ struct CudaBatch : BatchBase {
         R2D_CUDA(cudaStreamSynchronize(stream));  // `v` lives on the caller's stack
         return R2D_OK;
     }
-    int backend_read_bodies(uint32_t first, uint32_t n, uint32_t* ids, float* pos_xy, float* angle, float* momentum_xy,
-                            float* ang_momentum, float* aabb_xywh) override {
+    // enqueues the export (kernel + copies) of bodies [first, first + n) on the main stream; the caller synchronises
+    int enqueue_read_bodies(uint32_t first, uint32_t n, uint32_t* ids, float* pos_xy, float* angle, float* momentum_xy,
+                            float* ang_momentum, float* aabb_xywh) {
         R2D_CUDA(cudaSetDevice(device));
         // repack the float4 SoA into the caller's layout on the device, then one copy per requested array
         R2D_TRY(staging.reserve((size_t)n * 44 + 256));
@@ -373,7 +374,6 @@ struct CudaBatch : BatchBase {
         if (direct) {
             R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_export_bodies, grid_for(n), TPB, d, (const uint32_t*)dev_of_host.p + first, n, (uint32_t*)m_ids,
                        (float2*)m_pos, (float*)m_ang, (float2*)m_mom, (float*)m_l, (float4*)m_aabb);
-            R2D_CUDA(cudaStreamSynchronize(stream));
             return R2D_OK;
         }
         R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_export_bodies, grid_for(n), TPB, d, (const uint32_t*)dev_of_host.p + first, n, ids ? d_ids : nullptr,
@@ -385,6 +385,11 @@ struct CudaBatch : BatchBase {
         if (momentum_xy) R2D_CUDA(cudaMemcpyAsync(momentum_xy, d_mom, (size_t)n * 8, cudaMemcpyDeviceToHost, stream));
         if (ang_momentum) R2D_CUDA(cudaMemcpyAsync(ang_momentum, d_l, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
         if (aabb_xywh) R2D_CUDA(cudaMemcpyAsync(aabb_xywh, d_aabb, (size_t)n * 16, cudaMemcpyDeviceToHost, stream));
+        return R2D_OK;
+    }
+    int backend_read_bodies(uint32_t first, uint32_t n, uint32_t* ids, float* pos_xy, float* angle, float* momentum_xy,
+                            float* ang_momentum, float* aabb_xywh) override {
+        R2D_TRY(enqueue_read_bodies(first, n, ids, pos_xy, angle, momentum_xy, ang_momentum, aabb_xywh));
         R2D_CUDA(cudaStreamSynchronize(stream));
         return R2D_OK;
     }
@@ -703,6 +708,16 @@ struct CudaBatch : BatchBase {
             } else if (persistent_solver) {
                 if ((st = launch_persistent(sub_dt, S, I))) return st;
             }
+            // r2d_process_read: the export of the new state rides behind the solver, inside the same synchronisation
+            if (readback && persistent_solver) {
+                const uint32_t keep = launches;
+                if ((st = enqueue_read_bodies(0, nb, readback->ids, readback->pos_xy, readback->angle, readback->momentum_xy,
+                                              readback->ang_momentum, readback->aabb_xywh)))
+                    return st;
+                launches = keep + 1;
+                fill_dev();
+                readback_done = true;
+            }
             // ---- the one synchronisation point of the step: counters + colour offsets ----
             R2D_CUDA(cudaMemcpyAsync(&pinned->counters, d.counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
             R2D_CUDA(cudaMemcpyAsync(pinned->color_start, d.color_start, (MAX_COLORS + 1) * 4, cudaMemcpyDeviceToHost, stream));
@@ -724,6 +739,9 @@ struct CudaBatch : BatchBase {
                 // persistent sweep on the same records now, and stop trying tiles until the next upload
                 tile_declined = true;
                 if ((st = launch_persistent(sub_dt, S, I))) return st;
+                if (readback && (st = enqueue_read_bodies(0, nb, readback->ids, readback->pos_xy, readback->angle, readback->momentum_xy,
+                                                          readback->ang_momentum, readback->aabb_xywh)))
+                    return st;   // the export enqueued above saw the state before this sweep
                 R2D_CUDA(cudaMemcpyAsync(&pinned->counters, d.counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
                 R2D_CUDA(cudaStreamSynchronize(stream));
                 R2D_CUDA(cudaGetLastError());

@@ -243,6 +243,17 @@ class Solver:
 
     step = process  # north_star's name for the same call
 
+    def process_read(self, dt: float, sub_steps: int, collision_iters: int, out: dict) -> dict:
+        """process() + read_bodies(out) in one call and one host synchronisation (r2d_process_read): the export of the
+        new state is enqueued behind the step's last kernel.  `out` holds preallocated (ideally pinned) arrays or None
+        per key, as for read_bodies."""
+        def p(k):
+            a = out.get(k)
+            return None if a is None else C.c_void_p(a.ctypes.data)
+        self._check(self._fn("process_read")(self._h, dt, sub_steps, collision_iters, p("id"), p("pos"), p("angle"),
+                                             p("momentum"), p("ang_momentum"), p("aabb"), self.num_bodies()), "process_read")
+        return out
+
     def synchronize(self):
         self._check(self._fn("synchronize")(self._h), "synchronize")
 
@@ -364,6 +375,16 @@ class Batch:
 
     def process(self, dt: float, sub_steps: int, collision_iters: int):
         _abi.check(self._lib, self._lib.r2d_batch_process(self._h, dt, sub_steps, collision_iters), "batch_process")
+
+    def process_read(self, dt: float, sub_steps: int, collision_iters: int, out: dict) -> dict:
+        """batch_process() + read_bodies(out) of every world in one call and one host synchronisation."""
+        def p(k):
+            a = out.get(k)
+            return None if a is None else C.c_void_p(a.ctypes.data)
+        _abi.check(self._lib, self._lib.r2d_batch_process_read(self._h, dt, sub_steps, collision_iters, p("id"), p("pos"),
+                                                                p("angle"), p("momentum"), p("ang_momentum"), p("aabb"),
+                                                                self.num_bodies()), "batch_process_read")
+        return out
 
     def synchronize(self):
         _abi.check(self._lib, self._lib.r2d_batch_synchronize(self._h), "batch_synchronize")

@@ -120,3 +120,18 @@ def test_emu_fine_grid_in_fast_mode_with_small_coarse_cells():
             if step % 15 == 14:
                 assert np.array_equal(cand.read_pairs(), orc.read_pairs()), (cell, step)
         assert_bodies_equal(cand.read_bodies(), orc.read_bodies(), f"fast mode cell {cell}")
+
+
+def test_emu_process_read_equals_process_then_read():
+    a, b = EmuSolver(2.0, 4), EmuSolver(2.0, 4)
+    for s in (a, b):
+        scenes.setup_0_3_many_boxes(s)
+    n = a.num_bodies()
+    out = {"id": np.empty(n, np.uint32), "pos": np.empty((n, 2), np.float32), "angle": np.empty(n, np.float32),
+           "momentum": np.empty((n, 2), np.float32), "ang_momentum": None, "aabb": np.empty((n, 4), np.float32)}
+    for _ in range(30):
+        a.process_read(scenes.DT, 4, 4, out)
+        b.process(scenes.DT, 4, 4)
+    ref = b.read_bodies()
+    for k in ("id", "pos", "angle", "momentum", "aabb"):
+        assert np.array_equal(out[k].view(np.uint32), ref[k].view(np.uint32)), k

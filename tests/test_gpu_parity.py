@@ -358,6 +358,44 @@ def test_gpu_write_forces_and_bulk_read():
     assert_bodies_equal(s.read_bodies(), o.read_bodies(), "write_forces")
 
 
+def test_gpu_process_read_equals_process_then_read():
+    """r2d_process_read / r2d_batch_process_read (export enqueued behind the step, one synchronisation) == process() followed
+    by read_bodies(), with pinned and with pageable destinations, through the tile solver and through its fallback."""
+    import torch
+    def run(build, steps, pinned, S=4, I=4):
+        a, b = Solver(2.0, 4), Solver(2.0, 4)
+        for s in (a, b):
+            build(s)
+        n = a.num_bodies()
+        mk = (lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()) if pinned else \
+             (lambda shape, dt: torch.empty(shape, dtype=dt).numpy())
+        out = {"id": mk((n,), torch.int32).view(np.uint32), "pos": mk((n, 2), torch.float32), "angle": mk((n,), torch.float32),
+               "momentum": mk((n, 2), torch.float32), "ang_momentum": mk((n,), torch.float32), "aabb": mk((n, 4), torch.float32)}
+        for _ in range(steps):
+            a.process_read(scenes.DT, S, I, out)
+            b.process(scenes.DT, S, I)
+        ref = b.read_bodies()
+        for k in out:
+            assert np.array_equal(out[k].view(np.uint32), ref[k].view(np.uint32)), k
+    run(scenes.setup_0_3_many_boxes, 40, True)
+    run(scenes.setup_0_3_many_boxes, 40, False)
+    run(lambda s: scenes.build_pile(s, 100, 30), 60, True)            # 3,000 bodies: tile solver
+    run(lambda s: scenes.build_pyramid(s, base=16, n_spinners=2), 30, True, 4, 10)   # joints: persistent solver
+    batch, batch2 = Batch(80, 2.0, 4), Batch(80, 2.0, 4)
+    for w in range(80):
+        scenes.build_batch_world(batch.world(w), w, nx=8, ny=4)
+        scenes.build_batch_world(batch2.world(w), w, nx=8, ny=4)
+    n = batch.num_bodies()
+    out = {"id": None, "pos": torch.empty((n, 2), dtype=torch.float32).pin_memory().numpy(), "angle": np.empty(n, np.float32),
+           "momentum": None, "ang_momentum": None, "aabb": None}
+    for _ in range(30):
+        batch.process_read(scenes.DT, 4, 4, out)
+        batch2.process(scenes.DT, 4, 4)
+    ref = batch2.read_bodies()
+    assert np.array_equal(out["pos"].view(np.uint32), ref["pos"].view(np.uint32))
+    assert np.array_equal(out["angle"].view(np.uint32), ref["angle"].view(np.uint32))
+
+
 def test_gpu_ordering_effect_is_reported_not_asserted():
     """Colour order vs the reference's insertion order: identical until real impacts, chaotic afterwards.
     Only the impact-free prefix is asserted; the divergence is printed for the record."""
