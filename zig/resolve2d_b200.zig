@@ -41,6 +41,7 @@ const c = struct {
     pub extern "c" fn r2d_destroy(s: ?*r2d_solver) c_int;
     pub extern "c" fn r2d_clear(s: ?*r2d_solver) c_int;
     pub extern "c" fn r2d_process(s: ?*r2d_solver, dt: f32, sub_steps: u32, collision_iters: u32) c_int;
+    pub extern "c" fn r2d_process_read(s: ?*r2d_solver, dt: f32, sub_steps: u32, collision_iters: u32, ids: ?[*]u32, pos_xy: ?[*]f32, angle: ?[*]f32, momentum_xy: ?[*]f32, ang_momentum: ?[*]f32, aabb_xywh: ?[*]f32, n: usize) c_int;
     pub extern "c" fn r2d_make_disc(s: ?*r2d_solver, o: *const BodyOpts, radius: f32, out_id: *u32) c_int;
     pub extern "c" fn r2d_make_rect(s: ?*r2d_solver, o: *const BodyOpts, width: f32, height: f32, out_id: *u32) c_int;
     pub extern "c" fn r2d_make_gravity(s: ?*r2d_solver, g: f32) c_int;
