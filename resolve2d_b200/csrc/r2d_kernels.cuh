@@ -1229,7 +1229,7 @@ __global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float su
     }
     for (uint32_t s = 0; s < S; ++s) {
         if (s == 0)
-            for (uint32_t i = tid; i < d.n_bodies; i += nth) integrate_forces_thread(d, i, sub_dt, S == 1);
+            for (uint32_t i = tid; i < d.n_bodies; i += 4u * nth) integrate_batch<4>(d, i, nth, sub_dt, false, true, S == 1);
         if (s == 0) stamp(d, 1);
         grid.sync();
         if (s == 0) stamp(d, 2);
@@ -1252,10 +1252,7 @@ __global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float su
         if (!n_joint_colors) grid.sync();
         if (s == 0) stamp(d, 8);
         // end of substep s fused with the start of substep s + 1: both are per-body, same thread, no barrier needed
-        for (uint32_t i = tid; i < d.n_bodies; i += nth) {
-            integrate_positions_thread(d, i, sub_dt);
-            if (s + 1 < S) integrate_forces_thread(d, i, sub_dt, s + 2 == S);
-        }
+        for (uint32_t i = tid; i < d.n_bodies; i += 4u * nth) integrate_batch<4>(d, i, nth, sub_dt, true, s + 1 < S, s + 2 == S);
         if (s == 0) stamp(d, 9);
     }
     stamp(d, 10);
