@@ -142,6 +142,30 @@ def cpu_steps_per_second(workload, steps, preroll):
     return s.num_bodies(), steps / sec, sec, S, I
 
 
+def cpu_batched_world_steps_per_second(n_worlds, steps, preroll):
+    """cfg5 on the host: `n_worlds` independent oracle Solvers (reference sweep order), one world per task on all host
+    cores (the reference is single-threaded per world; independent worlds are the only parallelism it has).
+    ctypes releases the GIL inside orc_timed_steps, so plain threads run the C++ oracle in parallel."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import ORDER_REFERENCE, OracleSolver
+    from resolve2d_b200 import scenes
+    cores = os.cpu_count() or 1
+    worlds = []
+    for w in range(n_worlds):
+        s = OracleSolver(2.0, 4, order=ORDER_REFERENCE)
+        scenes.build_batch_world(s, w)
+        worlds.append(s)
+
+    def run(s, k):
+        return s.timed_steps(scenes.DT, 4, 4, k)
+    with ThreadPoolExecutor(cores) as ex:
+        list(ex.map(lambda s: run(s, preroll), worlds))
+        t0 = time.perf_counter()
+        list(ex.map(lambda s: run(s, steps), worlds))
+        sec = time.perf_counter() - t0
+    return n_worlds * steps / sec, cores, sec
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -331,6 +355,13 @@ def run_ours(args, rank, world, local_rank):
                    "manifolds": bst.n_manifolds, "launches_per_step": bst.n_launches}
         batch.destroy()
 
+    if batched is not None and rank == 0 and world == 1 and not args.no_cpu:
+        n_cpu_worlds = 16 * (os.cpu_count() or 1)
+        wsps, cores, csec = cpu_batched_world_steps_per_second(n_cpu_worlds, 100, args.batch_preroll)
+        batched["cpu_baseline"] = {"value": wsps, "unit": "world-steps/s", "cores": cores, "kind": "port",
+                                   "sample": f"{n_cpu_worlds} worlds x 100 process() calls after {args.batch_preroll} untimed calls, "
+                                             f"one world per task on {cores} threads ({csec:.1f} s timed), oracle/ in the "
+                                             "reference's sweep order"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         t0 = time.time()
