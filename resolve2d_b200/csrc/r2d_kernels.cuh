@@ -1272,6 +1272,7 @@ __device__ __forceinline__ uint32_t owner_rank(const Dev& d, uint32_t c, uint32_
 
 __global__ void __launch_bounds__(WORLD_TPB) k_solve_worlds(Dev d, float sub_dt, uint32_t S, uint32_t I) {
     __shared__ float4 s_mom[WORLD_MAX_BODIES];
+    __shared__ float2 s_invb[WORLD_MAX_BODIES];
     __shared__ uint32_t s_begin[MAX_COLORS], s_end[MAX_COLORS];
     if (overflowed(d) || d.counters->err != 0u) return;
     const uint32_t nc = d.counters->n_colors;
@@ -1284,6 +1285,13 @@ __global__ void __launch_bounds__(WORLD_TPB) k_solve_worlds(Dev d, float sub_dt,
         }
         Dev ds = d;
         ds.mom = s_mom - b0;  // ds.mom[global slot] addresses the shared copy of this world's momentum words
+        ds.inv_body = s_invb - b0;
+        ds.world_slot0 = b0;
+        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+            const float4 pr = d.prop[b0 + i];
+            const bool st = (body_flags(d, b0 + i) & FLAG_STATIC) != 0;
+            s_invb[i] = make_float2(st ? 0.0f : fdiv(1.0f, pr.x), st ? 0.0f : fdiv(1.0f, pr.y));   // prestep_manifold, per body
+        }
         for (uint32_t s = 0; s < S; ++s) {
             for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
                 if (s > 0) integrate_positions_thread(d, b0 + i, sub_dt);

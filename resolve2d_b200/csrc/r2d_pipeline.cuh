@@ -154,6 +154,12 @@ struct Dev {
     float4* s_pm1;
     float2* s_acc0;               // point 0: accumulated_pn, accumulated_pt
     float2* s_acc1;
+    uint2* world_hdr;             // non-null (batches solved per world): compact header {ref | inc << 16 (world-local slots),
+                                  // n_points | static bits} written next to s_hdr; the per-world solver reads these 8 bytes
+                                  // instead of the 16 of s_hdr (lives in the s_dep buffer, which that solver does not use)
+    uint32_t world_slot0;         // first slot of the world a CTA-per-world kernel is working on (base of world_hdr's slots)
+    const float2* inv_body;       // non-null: per-body (1 / mass, 1 / inertia), 0 for static bodies, indexed like `mom` — the
+                                  // CTA-per-world solver keeps it in shared memory and skips the s_inv fetch (16 of 88 bytes)
     uint32_t tile_bodies;         // B > 0: k_solve_tiles will run with tiles of B consecutive body slots (else 0)
     uint32_t* body_shared;        // NB: 1 if a manifold owned by a body of ANOTHER tile touches the body (see k_solve_tiles)
     uint4* s_dep;                 // rank of this manifold among the contacts of its ref body, that body's contact count,
@@ -870,6 +876,10 @@ R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
     const float4 g0 = d.m_g0[p], g1 = d.m_g1[p];
     const ContactConst c = prestep_manifold(mk2(g0.x, g0.y), st1, st2, pr1.x, pr2.x, pr1.y, pr2.y, pr1.z, pr2.z);
     d.s_hdr[at] = make_uint4(h.x, h.y, np | (st1 ? 0x100u : 0u) | (st2 ? 0x200u : 0u), p);
+    if (d.world_hdr) {
+        const uint32_t base = d.world_base[f1 >> FLAG_WORLD_SHIFT];   // both bodies are in the same world
+        d.world_hdr[at] = make_uint2((h.x - base) | ((h.y - base) << 16), np | (st1 ? 0x100u : 0u) | (st2 ? 0x200u : 0u));
+    }
     if (d.tile_bodies && !st1 && !st2 && h.x / d.tile_bodies != h.y / d.tile_bodies)
         d.body_shared[h.x > h.y ? h.x : h.y] = 1u;  // the owner is the lower slot: the other body is foreign to its tile
     // Colours on one body are pairwise distinct, so the body's sweep sequence is its colour set in ascending order:
@@ -880,10 +890,10 @@ R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
         uint32_t rk[2] = {0, 0}, dg[2] = {0, 0};
         if (!st1) body_color_rank(d, from_flow, h.x, color, &rk[0], &dg[0]);
         if (!st2) body_color_rank(d, from_flow, h.y, color, &rk[1], &dg[1]);
-        d.s_dep[at] = make_uint4(rk[0], dg[0], rk[1], dg[1]);
+        if (!d.world_hdr) d.s_dep[at] = make_uint4(rk[0], dg[0], rk[1], dg[1]);
     }
     d.s_nf[at] = make_float4(c.normal.x, c.normal.y, c.friction, 0.0f);
-    d.s_inv[at] = make_float4(c.inv_m1, c.inv_m2, c.inv_i1, c.inv_i2);
+    if (!d.world_hdr) d.s_inv[at] = make_float4(c.inv_m1, c.inv_m2, c.inv_i1, c.inv_i2);   // the per-world solver derives them per body
     if (np > 0) {
         const float4 r = d.m_r0[p];
         ContactPointConst pc;
@@ -923,7 +933,13 @@ R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
 // instead of after the header has arrived (one memory round trip per manifold instead of two).
 template <bool DATAFLOW, bool DENSE = false>
 R2D_HD void solve_contact_thread(const Dev& d, uint32_t m, float sub_dt, uint32_t it = 0) {
-    const uint4 h = d.s_hdr[m];
+    uint4 h;
+    if (DENSE && !DATAFLOW && d.world_hdr) {
+        const uint2 q = d.world_hdr[m];
+        h = make_uint4(d.world_slot0 + (q.x & 0xFFFFu), d.world_slot0 + (q.x >> 16), q.y, 0u);
+    } else {
+        h = d.s_hdr[m];
+    }
     const bool empty = !DENSE && (h.z & S_EMPTY) != 0;
     if (!DATAFLOW && empty) return;
     const int np = empty ? 0 : (int)(h.z & 0xFFu);
@@ -934,14 +950,23 @@ R2D_HD void solve_contact_thread(const Dev& d, uint32_t m, float sub_dt, uint32_
     uint32_t e1 = 0, e2 = 0;
     float4 m1 = make_float4(0, 0, 0, 0), m2 = m1;
     if (!empty) {
-        const float4 nf = d.s_nf[m], inv = d.s_inv[m];
+        const float4 nf = d.s_nf[m];
         c.normal = mk2(nf.x, nf.y);
         c.tangent = rot90cw(c.normal);
         c.friction = nf.z;
-        c.inv_m1 = inv.x;
-        c.inv_m2 = inv.y;
-        c.inv_i1 = inv.z;
-        c.inv_i2 = inv.w;
+        if (d.inv_body) {  // the same values prestep_manifold stored in s_inv: static ? 0 : 1 / mass, 1 / inertia
+            const float2 i1 = d.inv_body[h.x], i2 = d.inv_body[h.y];
+            c.inv_m1 = i1.x;
+            c.inv_m2 = i2.x;
+            c.inv_i1 = i1.y;
+            c.inv_i2 = i2.y;
+        } else {
+            const float4 inv = d.s_inv[m];
+            c.inv_m1 = inv.x;
+            c.inv_m2 = inv.y;
+            c.inv_i1 = inv.z;
+            c.inv_i2 = inv.w;
+        }
         {  // point 0 is loaded unconditionally (almost every manifold has it): no dependent load level after the header
             const float4 r = d.s_r0[m], pm = d.s_pm0[m];
             const float2 a = d.s_acc0[m];

@@ -108,6 +108,7 @@ struct CudaBatch : BatchBase {
     bool seq_world_coloring = true;   // R2D_WORLD_COLORING=rounds: Jones-Plassmann rounds per world instead of sort + sequential greedy
     bool fine_grid = true;            // R2D_BROADPHASE=buckets: every body through the coarse buckets (the original pipeline)
     bool fine_now = false, ll_now = false;
+    bool world_hdr_now = false;       // this step is solved by k_solve_worlds: the partition writes compact headers into s_dep
     // pairs / manifolds
     DBuf<uint2> pairs;
     DBuf<uint4> m_hdr, s_hdr;
@@ -526,6 +527,8 @@ struct CudaBatch : BatchBase {
         d.adj_prio = adj_prio.p;
         d.flow_sleep_unit = flow_sleep_unit;
         d.tile_bodies = tile_bodies_now;
+        d.inv_body = nullptr;
+        d.world_hdr = world_hdr_now ? (uint2*)s_dep.p : nullptr; d.world_slot0 = 0;
         d.body_shared = (uint32_t*)(zeroed.p + off_body_shared);
         d.own_words = (d.n_bodies + 31u) / 32u;
         d.own_bits = (uint32_t*)(zeroed.p + off_own_bits);
@@ -633,6 +636,7 @@ struct CudaBatch : BatchBase {
         const bool use_world_solver = persistent_solver && world_solver && image.j_hdr.empty() &&
                                       max_world_bodies <= WORLD_MAX_BODIES &&
                                       worlds.size() >= (size_t)n_sms / 2;  // enough worlds to fill the GPU with one CTA each
+        world_hdr_now = use_world_solver && max_world_bodies <= 65536u;
         const uint32_t tile_b = (nb + (uint32_t)n_sms - 1) / (uint32_t)n_sms;
         const bool use_tile_solver = persistent_solver && tile_solver && !tile_declined && !use_world_solver && image.j_hdr.empty() &&
                                      tile_b <= TILE_MAX_BODIES && nb >= (uint32_t)n_sms * 8;
