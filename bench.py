@@ -247,7 +247,7 @@ def run_ours(args, rank, world, local_rank):
     dt = scenes.DT
     for _ in range(preroll):            # scene formation (the pile), not part of warm-up or timing
         solver.process(dt, S, I)
-    solver.reorder()                    # device memory order follows the formed pile (also redone every 256 calls)
+    solver.reorder()                    # device memory order follows the formed pile (also redone every 1,024 calls)
     for _ in range(args.warmup):
         solver.process(dt, S, I)
 
