@@ -615,8 +615,10 @@ struct CudaBatch : BatchBase {
             (st = pose.reserve(nb)) || (st = view.reserve(4 * (size_t)nb)) || (st = ncells.reserve(nb)) || (st = bkt.reserve(nb)) ||  (st = bucket_cnt.reserve(2 * (size_t)T + 1, true, stream)) ||
             (st = bucket_start.reserve(2 * (size_t)T + 2)) || (st = fcell.reserve(nb)) || (st = fine_cand.reserve(2 * (size_t)nb)) || (st = pair_cnt.reserve((size_t)nb + 3)) || (st = ent_off.reserve((size_t)T + 2)) || (st = work.reserve(2 * (size_t)T + 2)))
             return st;
-        if (cap_entries == 0 && (st = reserve_entries((size_t)nb * 3 + 4096))) return st;
-        if (cap_pairs == 0 && (st = reserve_pairs((size_t)nb * 6 + 4096))) return st;
+        // R2D_TEST_SMALL_BUFFERS=1 (tests): start with buffers that are too small, so that the grow-and-redo path runs
+        const bool tiny = getenv("R2D_TEST_SMALL_BUFFERS") && atoi(getenv("R2D_TEST_SMALL_BUFFERS")) != 0;
+        if (cap_entries == 0 && (st = reserve_entries(tiny ? 64 : (size_t)nb * 3 + 4096))) return st;
+        if (cap_pairs == 0 && (st = reserve_pairs(tiny ? 64 : (size_t)nb * 6 + 4096))) return st;
 
         // broadphase flavour: the fine grid whenever the upload found a usable fine cell; the bucket pair kernels then
         // only run for large-large pairs, i.e. when a dynamic large body exists.  Their pairs come first in the list, so

@@ -358,6 +358,19 @@ def test_gpu_write_forces_and_bulk_read():
     assert_bodies_equal(s.read_bodies(), o.read_bodies(), "write_forces")
 
 
+def test_gpu_buffers_grow_and_the_step_is_redone(monkeypatch):
+    """R2D_TEST_SMALL_BUFFERS=1: the grid-entry and pair buffers start far too small; process() notices the overflow at its
+    one synchronisation point, grows them and redoes the step (the broadphase does not modify body state and every later
+    kernel does nothing on an overflowed attempt) — results must be unaffected, fine grid and bucket pipeline alike."""
+    monkeypatch.setenv("R2D_TEST_SMALL_BUFFERS", "1")
+    run_parity(lambda: Solver(2.0, 4), scenes.build_box1k, 60, check_every=20, what="box1k small buffers")
+    def build(s):
+        return scenes.build_mixed(s, 40, 12, n_large=6)
+    run_parity(lambda: Solver(2.0, 4), build, 200, check_every=40, what="mixed small buffers")
+    monkeypatch.setenv("R2D_BROADPHASE", "buckets")
+    run_parity(lambda: Solver(2.0, 4), scenes.build_box1k, 40, check_every=20, what="box1k small buffers, buckets")
+
+
 def test_gpu_process_read_equals_process_then_read():
     """r2d_process_read / r2d_batch_process_read (export enqueued behind the step, one synchronisation) == process() followed
     by read_bodies(), with pinned and with pageable destinations, through the tile solver and through its fallback."""
