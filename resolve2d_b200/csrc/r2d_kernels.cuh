@@ -743,6 +743,7 @@ __global__ void __launch_bounds__(TPB, 4) k_color(Dev d) {
                 const int r = flow_try(d, tid + (uint32_t)k * nth, fa[k], fb[k], fm[k] & 3u, (fm[k] >> 2) & 0xFFFFu, &c, &lag);
                 if (r == 1) {
                     atomicAdd(&s_hist[c], 1u);
+                    owner_bit_set(d, fa[k], fb[k], fm[k] & 3u, c);
                     fm[k] = 0u;
                     n_pending -= 1u;
                     progress = true;
@@ -789,6 +790,7 @@ __global__ void __launch_bounds__(TPB, 4) k_color(Dev d) {
         // abandoned: forget the partial result and colour by rounds (maxprio / used are still zero)
         for (uint32_t p = tid; p < n; p += nth)
             if (d.m_color[p] < MAX_COLORS) d.m_color[p] = COLOR_PENDING;
+        for (size_t x = tid; x < (size_t)d.own_words * FLOW_COLORS; x += nth) d.own_bits[x] = 0u;   // owner bits of the partial result
         if (blockIdx.x == 0)
             for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x) d.color_count[c] = 0u;
         for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x) s_hist[c] = 0u;
@@ -826,6 +828,7 @@ __global__ void __launch_bounds__(TPB, 4) k_color(Dev d) {
             uint32_t c;
             if (color_round_core(d, tid + (uint32_t)k * nth, rh[k], rp[k], round, &c) == 1) {
                 atomicAdd(&s_hist[c], 1u);
+                owner_bit_set(d, rh[k].x, rh[k].y, rh[k].w, c);
                 pend[k] = false;
             } else {
                 left = 1;
@@ -833,10 +836,12 @@ __global__ void __launch_bounds__(TPB, 4) k_color(Dev d) {
         }
         for (uint32_t p = tid + COLOR_REG_SLOTS * nth; p < n; p += nth) {
             const int r = color_round_thread(d, p, round);
-            if (r == 2)
+            if (r == 2) {
                 left = 1;
-            else if (r == 1)
+            } else if (r == 1) {
                 atomicAdd(&s_hist[d.m_color[p]], 1u);
+                owner_bit_thread(d, p);
+            }
         }
         if (__syncthreads_or(left) && threadIdx.x == 0) atomicAdd(&d.round_left[round], 1u);
         grid.sync();
@@ -916,6 +921,7 @@ __global__ void __launch_bounds__(WORLD_TPB) k_color_worlds(Dev d) {
                 uint32_t c;
                 if (color_round_core(ds, p0 + threadIdx.x + (uint32_t)k * blockDim.x, rh[k], rp[k], round, &c) == 1) {
                     atomicAdd(&s_hist[c], 1u);
+                    owner_bit_set(d, rh[k].x, rh[k].y, rh[k].w, c);
                     pend[k] = false;
                 } else {
                     left = 1;
@@ -923,10 +929,12 @@ __global__ void __launch_bounds__(WORLD_TPB) k_color_worlds(Dev d) {
             }
             for (uint32_t p = p0 + threadIdx.x + WORLD_REG_SLOTS * blockDim.x; p < p1; p += blockDim.x) {
                 const int r = color_round_thread(ds, p, round);
-                if (r == 2)
+                if (r == 2) {
                     left = 1;
-                else if (r == 1)
+                } else if (r == 1) {
                     atomicAdd(&s_hist[d.m_color[p]], 1u);
+                    owner_bit_thread(d, p);
+                }
             }
             if (!__syncthreads_or(left)) break;
         }
@@ -1065,8 +1073,9 @@ __global__ void __launch_bounds__(WORLD_TPB) k_color_worlds_seq(Dev d, uint32_t 
             }
             __syncthreads();
             for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
-                const uint32_t i = (uint32_t)s_order[k];
+                const uint32_t i = (uint32_t)s_order[k], pr = s_pair[i];
                 d.m_color[p0 + i] = s_col[i];
+                owner_bit_set(d, b0 + (pr & 0xFFFu), b0 + ((pr >> 12) & 0xFFFu), (pr >> 24) & 3u, s_col[i]);
             }
             if (export_used)   // the dataflow sweep derives rank / degree from the per-body masks (body_color_rank)
                 for (uint32_t i = threadIdx.x; i < nb * COLOR_WORDS; i += blockDim.x) d.used[(size_t)b0 * COLOR_WORDS + i] = s_used_dyn[i];
@@ -1083,10 +1092,12 @@ __global__ void __launch_bounds__(WORLD_TPB) k_color_worlds_seq(Dev d, uint32_t 
                 int left = 0;
                 for (uint32_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
                     const int r = color_round_thread(d, p, round);
-                    if (r == 2)
+                    if (r == 2) {
                         left = 1;
-                    else if (r == 1)
+                    } else if (r == 1) {
                         atomicAdd(&s_hist[d.m_color[p]], 1u);
+                        owner_bit_thread(d, p);
+                    }
                 }
                 if (!__syncthreads_or(left)) break;
             }

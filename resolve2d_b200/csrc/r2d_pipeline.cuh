@@ -842,6 +842,11 @@ R2D_HD uint32_t manifold_owner(const uint4& h) {
     if (dyn1 && dyn2) return h.x < h.y ? h.x : h.y;
     return dyn1 ? h.x : h.y;
 }
+// the same for a manifold whose colour has just been decided (the colouring kernels set the bit on the spot: one launch less)
+R2D_HD void owner_bit_set(const Dev& d, uint32_t ref, uint32_t inc, uint32_t dyn, uint32_t color) {
+    const uint32_t o = manifold_owner(make_uint4(ref, inc, 0u, dyn));
+    atomic_or_u32(&d.own_bits[(size_t)color * d.own_words + (o >> 5)], 1u << (o & 31u));
+}
 R2D_HD void owner_bit_thread(const Dev& d, uint32_t p) {
     const uint32_t c = d.m_color[p];
     if (c >= MAX_COLORS) return;

@@ -694,7 +694,7 @@ struct CudaBatch : BatchBase {
                 launches += 1;
             }
             // owner bitmaps -> popcounts -> scan = position of every manifold in the colour-sorted, spatially ordered records
-            R2D_LAUNCH(R2D_KCLASS_COLORING, k_owner_bits, grid_for(cap_pairs), TPB, d);
+            // (the owner bitmaps are set by the colouring kernels themselves, at the moment a manifold gets its colour)
             R2D_LAUNCH(R2D_KCLASS_COLORING, k_owner_count, grid_for((own_w + 1) * 64), TPB, d);
             if ((st = scan(d.own_pos, d.own_pos, &d.counters->n_own_scan, (uint32_t)((own_w + 1) * MAX_COLORS), nullptr, R2D_KCLASS_COLORING, 2))) return st;
             R2D_LAUNCH(R2D_KCLASS_COLORING, k_partition_prestep, grid_for(cap_pairs), TPB, d);
