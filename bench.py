@@ -304,7 +304,7 @@ def run_ours(args, rank, world, local_rank):
     if prof.get("solve_joints", (0, 0))[1] == 0:
         abytes["solve_contacts"] += abytes["solve_joints"]
     kernel_names = {"broadphase": "k_grid_cells / k_scan_chained / k_fine_pairs (+ k_list_buckets / k_sort_buckets / k_bucket_count / k_bucket_write when dynamic large bodies exist)",
-                    "narrowphase": "k_narrow", "coloring": "k_color(+k_owner_bits/k_owner_count/k_scan_chained/k_partition_prestep)",
+                    "narrowphase": "k_narrow", "coloring": "k_color (sets the owner bitmaps) + k_scan_owners + k_partition_prestep",
                     "solve_contacts": "k_solve_tiles (single world without joints: tile-local momentum in shared memory) or "
                                       "k_solve_persistent; the substep loop: integrators + dataflow contact sweeps (+ joints)",
                     "integrate": "k_integrate_forces / k_integrate_positions", "solve_joints": "k_solve_joints"}

@@ -12,7 +12,7 @@ idx = {c: hdr.index(c) for c in cols if c in hdr}
 ki = hdr.index("Kernel Name")
 print(" | ".join(["Kernel Name"] + [f"{c}[{units[idx[c]]}]" for c in idx]))
 CLASS = [("k_grid_cells|k_scan_chained|k_list_buckets|k_sort_buckets|k_bucket_|k_fine_pairs", "broadphase"), ("k_narrow", "narrowphase"),
-         ("k_color|k_owner|k_partition", "coloring"), ("k_solve|k_integrate", "solve_contacts")]
+         ("k_color|k_owner|k_partition|k_scan_owners", "coloring"), ("k_solve|k_integrate", "solve_contacts")]
 def to_bytes(v, u):
     v = float(v.replace(",", ""))
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
@@ -24,9 +24,6 @@ for r in data:
     print(" | ".join([name] + [r[idx[c]] for c in idx]))
     b = sum(to_bytes(r[idx[c]], units[idx[c]]) for c in ("dram__bytes_read.sum", "dram__bytes_write.sum") if c in idx)
     cls = next((c for pat, c in CLASS if re.search(pat, name)), None)
-    if name.startswith("k_scan_chained"):  # 1st and 2nd scan of a step belong to the broadphase, the 3rd to the colouring
-        scan_seen += 1
-        cls = "coloring" if scan_seen % 3 == 0 else "broadphase"
     if cls: traffic[cls] = traffic.get(cls, 0.0) + b
 if len(sys.argv) > 3:
     path = sys.argv[3]

@@ -184,13 +184,14 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_down(const uint32_t* in, uint
 // so a CTA only ever waits for tiles that started before it; every tile publishes (flag, value) as ONE 64-bit word
 // (flag 1 = aggregate of the tile, 2 = inclusive prefix), which needs no fence.  `state` (n_tiles + 1 words, the last
 // one is the ticket) must be zero on entry.  in == out is allowed.
-__global__ void __launch_bounds__(SCAN_TPB) k_scan_chained(const uint32_t* in, uint32_t* out, const uint32_t* n_ptr, uint32_t n_max,
-                                                           unsigned long long* state, uint32_t state_tiles, uint32_t* total_out) {
+template <class Load>
+__device__ __forceinline__ void scan_chained_body(Load load, uint32_t* out, uint32_t n, unsigned long long* state, uint32_t state_tiles,
+                                                  uint32_t* total_out, uint32_t* first_cta) {
     __shared__ uint32_t s_tile, s_prefix;
-    const uint32_t n = scan_count(n_ptr, n_max);
     if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd(&state[state_tiles], 1ull);
     __syncthreads();
     const uint32_t tile = s_tile;
+    if (first_cta) *first_cta = tile == 0u ? 1u : 0u;
     const uint32_t n_tiles = n ? (n + SCAN_TILE - 1) / SCAN_TILE : 1u;
     if (tile >= n_tiles) return;
     const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_IPT;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_chained(const uint32_t* in, u
     uint32_t sum = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_IPT; ++k) {
-        v[k] = (base + k < n) ? in[base + k] : 0u;
+        v[k] = (base + k < n) ? load(base + k) : 0u;
         sum += v[k];
     }
     uint32_t aggregate;
@@ -245,6 +246,37 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_chained(const uint32_t* in, u
     for (int k = 0; k < SCAN_IPT; ++k) {
         if (base + k < n) out[base + k] = run;
         run += v[k];
+    }
+}
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_chained(const uint32_t* in, uint32_t* out, const uint32_t* n_ptr, uint32_t n_max,
+                                                           unsigned long long* state, uint32_t state_tiles, uint32_t* total_out) {
+    scan_chained_body([in](uint32_t i) { return in[i]; }, out, scan_count(n_ptr, n_max), state, state_tiles, total_out, nullptr);
+}
+// The scan that places the manifolds (see manifold_owner): its input — the popcount of every owner-bitmap word, plus one
+// entry per colour that pads the colour's segment to a whole warp — is computed on the fly (no k_owner_count launch), and
+// so is the number of colours (no k_color_finish launch after the per-world colouring): every CTA derives it from the
+// colour populations, the CTA with ticket 0 publishes it for the kernels that follow.
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_owners(Dev d, unsigned long long* state, uint32_t state_tiles) {
+    __shared__ uint32_t s_nc;
+    if (threadIdx.x == 0) s_nc = 0u;
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x)
+        if (d.color_count[c]) atomicMax(&s_nc, c + 1u);
+    __syncthreads();
+    const uint32_t nc = s_nc, stride = d.own_words + 1u;
+    const uint32_t n = overflowed(d) ? 0u : nc * stride;
+    uint32_t first = 0;
+    scan_chained_body(
+        [&d, stride](uint32_t k) {
+            const uint32_t c = k / stride, w = k % stride;
+            if (w < d.own_words) return (uint32_t)__popc(d.own_bits[(size_t)c * d.own_words + w]);
+            const uint32_t cnt = d.color_count[c];
+            return (COLOR_ALIGN - (cnt % COLOR_ALIGN)) % COLOR_ALIGN;
+        },
+        d.own_pos, n, state, state_tiles, nullptr, &first);
+    if (first && threadIdx.x == 0) {
+        d.counters->n_colors = nc;
+        d.counters->n_own_scan = nc * stride;
     }
 }
 

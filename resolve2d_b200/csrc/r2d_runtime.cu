@@ -685,7 +685,6 @@ struct CudaBatch : BatchBase {
                 } else {
                     R2D_LAUNCH(R2D_KCLASS_COLORING, k_color_worlds, blocks, WORLD_TPB, d);
                 }
-                R2D_LAUNCH(R2D_KCLASS_COLORING, k_color_finish, 1, 32, d);
             } else {
                 prof_begin(R2D_KCLASS_COLORING);
                 void* args[] = {(void*)&d};
@@ -695,8 +694,12 @@ struct CudaBatch : BatchBase {
             }
             // owner bitmaps -> popcounts -> scan = position of every manifold in the colour-sorted, spatially ordered records
             // (the owner bitmaps are set by the colouring kernels themselves, at the moment a manifold gets its colour)
-            R2D_LAUNCH(R2D_KCLASS_COLORING, k_owner_count, grid_for((own_w + 1) * 64), TPB, d);
-            if ((st = scan(d.own_pos, d.own_pos, &d.counters->n_own_scan, (uint32_t)((own_w + 1) * MAX_COLORS), nullptr, R2D_KCLASS_COLORING, 2))) return st;
+            {   // popcounts of the owner bitmaps (and the number of colours) are computed inside the scan
+                const uint32_t n_max = (uint32_t)((own_w + 1) * MAX_COLORS);
+                const uint32_t tiles = (n_max + SCAN_TILE - 1) / SCAN_TILE + 1;
+                if (tiles + 1 > scan_state_cap) return R2D_ERR_CUDA;
+                R2D_LAUNCH(R2D_KCLASS_COLORING, k_scan_owners, tiles, SCAN_TPB, d, scan_state(2), (uint32_t)(scan_state_cap - 1));
+            }
             R2D_LAUNCH(R2D_KCLASS_COLORING, k_partition_prestep, grid_for(cap_pairs), TPB, d);
             // ---- substeps: one persistent cooperative kernel (colour ranges are read on the device) ----
             if ((st = join_forces())) return st;  // forces written for this step have arrived (first reader of `frc`)
