@@ -1563,7 +1563,7 @@ __global__ void __launch_bounds__(TILE_TPB) k_solve_tiles(Dev d, float sub_dt, u
                                 lag += e2 - f2u(m2.w);
                             }
                         }
-                        if (lag == 0u) {
+                        if (lag == 0u || d.wait_mode == 2u) {   // wait_mode 2: DIAGNOSTIC ONLY (wrong results), the dependency-free cost
                             __threadfence_block();  // the version was written after the momentum it announces
                             if (loc1) m1 = ld_volatile_shared_f4(&t_mom[h.x - b0]);
                             if (loc2) m2 = ld_volatile_shared_f4(&t_mom[h.y - b0]);
