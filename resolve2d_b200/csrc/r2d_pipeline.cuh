@@ -660,19 +660,22 @@ R2D_HD void adj_append(const Dev& d, uint32_t body, unsigned long long prio) {
 // K6: one candidate pair -> raw manifold slot.  Returns the number of contact points, or -1 if SAT finds a gap.
 R2D_HD int narrow_pair_thread(const Dev& d, uint32_t p) {
     const uint2 pr = d.pairs[p];
-    const BodyView va = load_view(d, pr.x), vb = load_view(d, pr.y);
-    const bool a_lo = va.id < vb.id;  // performNarrowSAT orders the two passes by id (collision.zig:304-307)
-    const Manifold m = a_lo ? narrowphase(va, vb) : narrowphase(vb, va);
+    // performNarrowSAT orders the two passes by id (collision.zig:304-307): the slots are put in id order BEFORE the views
+    // are loaded, so that there is ONE call of narrowphase() — `a_lo ? narrowphase(va, vb) : narrowphase(vb, va)` inlines
+    // it twice and a warp runs both copies with half of its lanes each (ncu: 15 of 32 lanes on an all-disc scene).
+    const bool x_lo = body_id(d, pr.x) < body_id(d, pr.y);
+    const uint32_t lo_slot = x_lo ? pr.x : pr.y, hi_slot = x_lo ? pr.y : pr.x;
+    const BodyView vlo = load_view(d, lo_slot), vhi = load_view(d, hi_slot);
+    const Manifold m = narrowphase(vlo, vhi);
     if (!m.collides) {
         d.m_color[p] = COLOR_NONE;
         return -1;
     }
-    const uint32_t lo_slot = a_lo ? pr.x : pr.y, hi_slot = a_lo ? pr.y : pr.x;
     const uint32_t ref = m.ref_is_lo ? lo_slot : hi_slot, inc = m.ref_is_lo ? hi_slot : lo_slot;
-    const uint32_t f_ref = (m.ref_is_lo == a_lo) ? va.flags : vb.flags, f_inc = (m.ref_is_lo == a_lo) ? vb.flags : va.flags;
+    const uint32_t f_ref = m.ref_is_lo ? vlo.flags : vhi.flags, f_inc = m.ref_is_lo ? vhi.flags : vlo.flags;
     const uint32_t dyn = ((f_ref & FLAG_STATIC) ? 0u : 1u) | ((f_inc & FLAG_STATIC) ? 0u : 2u);
     d.m_hdr[p] = make_uint4(ref, inc, (uint32_t)m.n_points | ((uint32_t)m.normal_id << 8), dyn);
-    const unsigned long long prio = contact_priority(a_lo ? va.id : vb.id, a_lo ? vb.id : va.id);  // (lower id, higher id)
+    const unsigned long long prio = contact_priority(vlo.id, vhi.id);  // (lower id, higher id)
     d.m_prio[p] = prio;
     if (d.flow) {
         if (dyn & 1u) adj_append(d, ref, prio);
