@@ -185,6 +185,11 @@ pub const Solver = struct {
     pub fn process(self: *Self, dt: f32, sub_steps: usize, collision_iters: usize) Error!void {
         try check(c.r2d_process(self.handle, dt, @intCast(sub_steps), @intCast(collision_iters)));
     }
+    /// process() followed by a bulk read of every body (iteration order) in one call and one host synchronisation; any
+    /// slice may be null.  Replaces "solver.process(...); for (solver.bodies.values()) |b| ..." of the demos' frame loops.
+    pub fn processRead(self: *Self, dt: f32, sub_steps: usize, collision_iters: usize, ids: ?[]u32, pos_xy: ?[]f32, angle: ?[]f32, momentum_xy: ?[]f32, ang_momentum: ?[]f32, aabb_xywh: ?[]f32) Error!void {
+        try check(c.r2d_process_read(self.handle, dt, @intCast(sub_steps), @intCast(collision_iters), if (ids) |s| s.ptr else null, if (pos_xy) |s| s.ptr else null, if (angle) |s| s.ptr else null, if (momentum_xy) |s| s.ptr else null, if (ang_momentum) |s| s.ptr else null, if (aabb_xywh) |s| s.ptr else null, self.numBodies()));
+    }
     pub fn bodyHandle(self: *Self, id: Id) EntityFactory.BodyHandle {
         return .{ .id = id, .solver = self };
     }
