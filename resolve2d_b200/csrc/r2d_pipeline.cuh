@@ -224,6 +224,21 @@ R2D_HD void atomic_max_u64(unsigned long long* p, unsigned long long v) {
 #endif
 }
 
+// index of the lowest ZERO bit (the word must have one)
+R2D_HD uint32_t first_zero64(unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffsll((long long)~v) - 1u;
+#else
+    return (uint32_t)__builtin_ctzll(~v);
+#endif
+}
+R2D_HD uint32_t first_zero32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffs((int)~v) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(~v);
+#endif
+}
 R2D_HD uint32_t popc64(unsigned long long v) {
 #if defined(__CUDA_ARCH__)
     return (uint32_t)__popcll(v);
@@ -716,9 +731,7 @@ R2D_HD int color_round_core(const Dev& d, uint32_t p, const uint4& h, uint64_t p
         if (dyn1) u |= ld_shared_u64(&d.used[(size_t)h.x * COLOR_WORDS + w], sm);
         if (dyn2) u |= ld_shared_u64(&d.used[(size_t)h.y * COLOR_WORDS + w], sm);
         if (~u) {
-            uint32_t b = 0;
-            while ((u >> b) & 1ull) ++b;
-            color = w * 64 + b;
+            color = w * 64 + first_zero64(u);
             break;
         }
     }
@@ -790,9 +803,7 @@ R2D_HD int flow_try(const Dev& d, uint32_t p, uint32_t ref, uint32_t inc, uint32
     uint32_t color = FLOW_COLORS;
     for (uint32_t w = 0; w < 3; ++w)
         if (~u[w]) {
-            uint32_t b = 0;
-            while ((u[w] >> b) & 1u) ++b;
-            color = w * 32u + b;
+            color = w * 32u + first_zero32(u[w]);
             break;
         }
     if (color >= FLOW_COLORS) {
@@ -892,13 +903,13 @@ R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
         d.body_shared[h.x > h.y ? h.x : h.y] = 1u;  // the owner is the lower slot: the other body is foreign to its tile
     // Colours on one body are pairwise distinct, so the body's sweep sequence is its colour set in ascending order:
     // rank = colours below mine, degree = colours used.
-    {
+    if (!d.world_hdr) {   // (the CTA-per-world solver separates colours with barriers: no ranks needed, s_dep holds its headers)
         const uint32_t color = d.m_color[p];
         const bool from_flow = d.counters->flow_used != 0u;
         uint32_t rk[2] = {0, 0}, dg[2] = {0, 0};
         if (!st1) body_color_rank(d, from_flow, h.x, color, &rk[0], &dg[0]);
         if (!st2) body_color_rank(d, from_flow, h.y, color, &rk[1], &dg[1]);
-        if (!d.world_hdr) d.s_dep[at] = make_uint4(rk[0], dg[0], rk[1], dg[1]);
+        d.s_dep[at] = make_uint4(rk[0], dg[0], rk[1], dg[1]);
     }
     d.s_nf[at] = make_float4(c.normal.x, c.normal.y, c.friction, 0.0f);
     if (!d.world_hdr) d.s_inv[at] = make_float4(c.inv_m1, c.inv_m2, c.inv_i1, c.inv_i2);   // the per-world solver derives them per body
