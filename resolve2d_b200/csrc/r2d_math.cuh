@@ -259,6 +259,66 @@ R2D_HD float cos_ref(float x) {  // cos.zig cosf
     }
 }
 
+// sin_ref(x) and cos_ref(x) together.  In every argument range the two functions evaluate __sindf and __cosdf on the SAME
+// reduced argument up to its sign (x -+ k pi/2; IEEE subtraction is antisymmetric, __cosdf is even and __sindf odd bit for
+// bit: only z = x*x and sign-symmetric sums enter), so ONE polynomial of each kind serves both — half the arithmetic, and a
+// warp whose lanes fall in different ranges runs two polynomial bodies instead of the sixteen inlined copies of the
+// separate functions.  Checked against sin_ref / cos_ref on all 2^32 float bit patterns (tests/test_trig_exhaustive.py).
+R2D_HD void sincos_ref(float x, float* s_out, float* c_out) {
+    const double pio2 = 0x1.921fb54442d18p+0, pi = 0x1.921fb54442d18p+1, pio2_3 = 0x1.2d97c7f3321d2p+2, pi2 = 0x1.921fb54442d18p+2;
+    uint32_t ix = f2u(x);
+    const bool sign = (ix >> 31) != 0;
+    ix &= 0x7fffffffu;
+    const double xd = (double)x;
+    if (ix >= 0x4dc90fdbu) {   // inf / NaN, and the unsupported huge range
+        *s_out = *c_out = fsub(x, x) + u2f(0x7fc00000u);
+        return;
+    }
+    double a;       // the common argument
+    int form;       // 0: s = S, c = C   1: s = C, c = S   2: s = -C, c = S   3: s = S, c = -C   4: s = C, c = -S   5: s = -S, c = -C   6: s = -C, c = -S... (see below)
+    if (ix <= 0x3f490fdau) {
+        if (ix < 0x39800000u) {
+            *s_out = x;
+            *c_out = 1.0f;
+            return;
+        }
+        a = xd; form = 0;                                    // sin = S(x),            cos = C(x)
+    } else if (ix <= 0x407b53d1u) {
+        if (ix <= 0x4016cbe3u) {
+            if (sign) { a = dadd(xd, pio2); form = 2; }      // sin = -C(x + pi/2),     cos = S(x + pi/2)
+            else      { a = dsub(pio2, xd); form = 1; }      // sin = C(x - pi/2) = C(a), cos = S(pi/2 - x) = S(a)
+        } else {
+            a = sign ? -dadd(xd, pi) : -dsub(xd, pi); form = 3;   // sin = S(-(x -+ pi)) = S(a), cos = -C(x -+ pi) = -C(a)
+        }
+    } else if (ix <= 0x40e231d5u) {
+        if (ix <= 0x40afeddfu) {
+            if (sign) { a = dsub(-xd, pio2_3); form = 1; }   // sin = C(x + 3pi/2) = C(a), cos = S(-x - 3pi/2) = S(a)
+            else      { a = dsub(xd, pio2_3); form = 2; }    // sin = -C(x - 3pi/2),    cos = S(x - 3pi/2)
+        } else {
+            a = sign ? dadd(xd, pi2) : dsub(xd, pi2); form = 0;
+        }
+    } else {
+        double y;
+        const int n = rem_pio2f(x, &y);
+        a = y;
+        switch (n & 3) {
+            case 0: form = 0; break;                         // sin = S(y),  cos = C(y)
+            case 1: form = 4; break;                         // sin = C(y),  cos = S(-y) = -S(y)
+            case 2: form = 5; break;                         // sin = S(-y) = -S(y), cos = -C(y)
+            default: form = 2; break;                        // sin = -C(y), cos = S(y)
+        }
+    }
+    const float S = k_sindf(a), C = k_cosdf(a);
+    switch (form) {
+        case 0: *s_out = S; *c_out = C; break;
+        case 1: *s_out = C; *c_out = S; break;
+        case 2: *s_out = -C; *c_out = S; break;
+        case 3: *s_out = S; *c_out = -C; break;
+        case 4: *s_out = C; *c_out = -S; break;
+        default: *s_out = -S; *c_out = -C; break;
+    }
+}
+
 // SpatialHash.hash (SpatialHash.zig:78-81): u64(xi*92837111 ^ yi*689287499) % table_size  (`*` binds tighter than `^`)
 R2D_HD uint64_t cell_hash(int64_t xi, int64_t yi, uint64_t table_size) {
     const uint64_t h = ((uint64_t)xi * 92837111ull) ^ ((uint64_t)yi * 689287499ull);  // two's-complement wrap == i64 product

@@ -411,7 +411,9 @@ R2D_HD CellRange count_body_thread(const Dev& d, uint32_t i, bool count_inline) 
     const uint32_t flags = body_flags(d, i);
     // the rotation only enters through a rectangle's vertices and normals (store_view); a disc's pose carries no angle
     const bool rect = (flags & FLAG_RECT) != 0;
-    const float4 pose = make_float4(p.x, p.y, rect ? cos_ref(p.z) : 1.0f, rect ? sin_ref(p.z) : 0.0f);
+    float sn = 0.0f, cs = 1.0f;
+    if (rect) sincos_ref(p.z, &sn, &cs);
+    const float4 pose = make_float4(p.x, p.y, cs, sn);
     d.pose[i] = pose;
     store_view(d, i, pose);
     CellRange r = cell_range(d, i);
@@ -1187,7 +1189,9 @@ R2D_HD void integrate_forces_thread(const Dev& d, uint32_t i, float sub_dt, bool
         const float4 p = d.pos[i];
         float hw, hh;
         if (flags & FLAG_RECT) {
-            aabb_half_extents(flags, s.x, s.y, cos_ref(p.z), sin_ref(p.z), hw, hh);
+            float sn, cs;
+            sincos_ref(p.z, &sn, &cs);
+            aabb_half_extents(flags, s.x, s.y, cs, sn, hw, hh);
         } else {
             hw = s.x;
             hh = s.x;
@@ -1263,7 +1267,9 @@ R2D_HD void integrate_batch(const Dev& d, uint32_t i0, uint32_t stride, float su
         if (refresh_aabb) {                 // lib.zig:210
             float hw, hh;
             if (flags & FLAG_RECT) {
-                aabb_half_extents(flags, sh[k].x, sh[k].y, cos_ref(p.z), sin_ref(p.z), hw, hh);
+                float sn, cs;
+                sincos_ref(p.z, &sn, &cs);
+                aabb_half_extents(flags, sh[k].x, sh[k].y, cs, sn, hw, hh);
             } else {
                 hw = sh[k].x;
                 hh = sh[k].x;

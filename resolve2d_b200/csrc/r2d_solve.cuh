@@ -182,8 +182,9 @@ R2D_HD void solve_distance(JointBody& b1, JointBody& b2, float target, float bet
 R2D_HD void solve_offset_distance(JointBody& b1, JointBody& b2, v2 r1, v2 r2, float target, float beta,
                                   float power_min, float power_max) {
     const float epsilon = CONSTRAINT_GRADIENT_DIVISION_LIMIT;
-    const float c1 = cos_ref(b1.angle), s1 = sin_ref(b1.angle);
-    const float c2 = cos_ref(b2.angle), s2 = sin_ref(b2.angle);
+    float c1, s1, c2, s2;
+    sincos_ref(b1.angle, &s1, &c1);
+    sincos_ref(b2.angle, &s2, &c2);
     const v2 a1 = add2(rotate_cs(r1, c1, s1), b1.pos);  // localToWorld
     const v2 a2 = add2(rotate_cs(r2, c2, s2), b2.pos);
     const v2 normal = normalize2(sub2(a2, a1));
