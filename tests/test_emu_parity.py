@@ -135,3 +135,15 @@ def test_emu_process_read_equals_process_then_read():
     ref = b.read_bodies()
     for k in ("id", "pos", "angle", "momentum", "aabb"):
         assert np.array_equal(out[k].view(np.uint32), ref[k].view(np.uint32)), k
+
+
+def test_emu_process_read_rejects_a_wrong_body_count():
+    import ctypes as C
+    s = EmuSolver(2.0, 4)
+    scenes.setup_0_3_many_boxes(s)
+    n = s.num_bodies()
+    buf = np.empty((n, 2), np.float32)
+    st = s._fn("process_read")(s._h, scenes.DT, 4, 4, None, C.c_void_p(buf.ctypes.data), None, None, None, None, n - 1)
+    assert st != 0                                   # R2D_ERR_INVALID_ARGUMENT: n must equal the number of bodies
+    st = s._fn("process_read")(s._h, scenes.DT, 4, 4, None, C.c_void_p(buf.ctypes.data), None, None, None, None, n)
+    assert st == 0
