@@ -354,8 +354,8 @@ R2D_HD Manifold narrowphase(const BodyView& lo, const BodyView& hi) {
     ret.ref_is_first = 1;
     ret.axis_dir = ret.axis_closest = mk2(0.0f, 0.0f);
     m.normal = ret.normal;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {  // (lo, hi) then (hi, lo): one copy of the axis loop
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {  // (lo, hi) then (hi, lo): unrolled, so that select_view folds away
         const bool first = pass == 0;
         if (!overlap_sat(ret, select_view(first, lo, hi), select_view(first, hi, lo), first ? 1 : 0)) return m;
     }
