@@ -147,3 +147,23 @@ def test_emu_process_read_rejects_a_wrong_body_count():
     assert st != 0                                   # R2D_ERR_INVALID_ARGUMENT: n must equal the number of bodies
     st = s._fn("process_read")(s._h, scenes.DT, 4, 4, None, C.c_void_p(buf.ctypes.data), None, None, None, None, n)
     assert st == 0
+
+
+def test_emu_nan_or_infinite_pose_is_harmless():
+    """A body whose pose becomes NaN / infinite (the reference has no guard either: it simply never passes an AABB test
+    again) must not disturb anybody else, with the fine grid and with the bucket pipeline: every other body still matches
+    the oracle bit for bit, and nothing reads out of bounds or hangs."""
+    for bad in (float("nan"), float("inf"), -float("inf")):
+        cand, orc = EmuSolver(2.0, 4), OracleSolver(2.0, 4, order=ORDER_COLORED)
+        for s in (cand, orc):
+            scenes.build_box1k(s)
+            s.process(scenes.DT, 4, 4)
+            s.body_handle(int(s.read_bodies()["id"][10])).set_pos(bad, 3.0)
+        for _ in range(40):
+            cand.process(scenes.DT, 4, 4)
+            orc.process(scenes.DT, 4, 4)
+        a, b = cand.read_bodies(), orc.read_bodies()
+        keep = np.arange(len(a["id"])) != 10
+        for k in ("pos", "angle", "momentum", "ang_momentum"):
+            assert np.array_equal(a[k][keep].view(np.uint32), b[k][keep].view(np.uint32)), (bad, k)
+        assert not np.isfinite(a["pos"][10, 0])

@@ -344,6 +344,26 @@ def test_gpu_empty_and_tiny_worlds():
     assert h2.id == 1                               # the id counter survives clear() (Q16)
 
 
+def test_gpu_nan_or_infinite_pose_is_harmless():
+    """A body whose pose becomes NaN / infinite never passes an AABB test again (as in the reference, which has no guard);
+    it must not disturb anybody else — every other body still matches the oracle bit for bit — and nothing may read out of
+    bounds or hang (fine grid: its home cell is clamped; buckets: its cell index saturates)."""
+    for bad in (float("nan"), float("inf"), -float("inf")):
+        cand, orc = Solver(2.0, 4), OracleSolver(2.0, 4, order=ORDER_COLORED)
+        for s in (cand, orc):
+            scenes.build_box1k(s)
+            s.process(scenes.DT, 4, 4)
+            s.body_handle(int(s.read_bodies()["id"][10])).set_pos(bad, 3.0)
+        for _ in range(40):
+            cand.process(scenes.DT, 4, 4)
+            orc.process(scenes.DT, 4, 4)
+        a, b = cand.read_bodies(), orc.read_bodies()
+        keep = np.arange(len(a["id"])) != 10
+        for k in ("pos", "angle", "momentum", "ang_momentum"):
+            assert np.array_equal(a[k][keep].view(np.uint32), b[k][keep].view(np.uint32)), (bad, k)
+        assert not np.isfinite(a["pos"][10, 0])
+
+
 def test_gpu_ragged_batch_with_empty_and_single_body_worlds():
     """120 worlds of very different sizes in one batch — empty worlds, a single free body, a floor only, small and larger
     boxes — through the CTA-per-world kernels (colouring by sort, world solver): every non-empty world must match the
