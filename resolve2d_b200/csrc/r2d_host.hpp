@@ -242,7 +242,21 @@ inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image&
                 if (fy > 65535.0f) fy = 65535.0f;
                 keyed[k] = {morton16((uint32_t)fx, (uint32_t)fy), (uint32_t)k};
             }
-            std::stable_sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+            // stable LSD radix sort on the 32-bit Morton key (two 16-bit passes): the re-sort runs every reorder interval on
+            // the host, std::stable_sort was most of its cost at 100 k bodies
+            if (n > 2048) {
+                std::vector<std::pair<uint64_t, uint32_t>> tmp(n);
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int shift = 16 * pass;
+                    std::vector<uint32_t> cnt(65537, 0u);
+                    for (size_t k = 0; k < n; ++k) cnt[((keyed[k].first >> shift) & 0xFFFFu) + 1] += 1;
+                    for (size_t b = 0; b < 65536; ++b) cnt[b + 1] += cnt[b];
+                    for (size_t k = 0; k < n; ++k) tmp[cnt[(keyed[k].first >> shift) & 0xFFFFu]++] = keyed[k];
+                    keyed.swap(tmp);
+                }
+            } else {
+                std::stable_sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+            }
             for (size_t k = 0; k < n; ++k) {
                 im.host_of_dev[base + k] = base + keyed[k].second;
                 im.dev_of_host[base + keyed[k].second] = base + (uint32_t)k;
@@ -264,13 +278,14 @@ inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image&
     for (size_t w = 0; w < nw; ++w) {
         const World& W = *worlds[w];
         const uint32_t base = im.world_base[w];
-        for (size_t s = 0; s < W.bodies.size(); ++s) {
-            const bool large = body_is_large(W.bodies[s], im);
+        for (size_t k = 0; k < W.bodies.size(); ++k) {   // in DEVICE order: six sequential streams, one gather per body
+            const Body& bd = W.bodies[im.host_of_dev[base + k] - base];
+            const bool large = body_is_large(bd, im);
             if (large) {
                 im.n_large += 1;
-                if (!W.bodies[s].is_static) im.n_large_dynamic += 1;
+                if (!bd.is_static) im.n_large_dynamic += 1;
             }
-            body_to_image(W.bodies[s], (uint32_t)w, im, im.dev_of_host[base + s], large);
+            body_to_image(bd, (uint32_t)w, im, base + k, large);
         }
         for (const auto& pr : W.excluded) {
             const int s1 = W.find(pr.first), s2 = W.find(pr.second);
