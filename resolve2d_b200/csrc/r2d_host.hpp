@@ -437,7 +437,7 @@ struct BatchBase {
     const Readback* readback = nullptr;
     bool readback_done = false;
     // process() calls between spatial re-sorts of the device order (0 = never).  The re-sort goes through the host (download,
-    // sort, upload: 8 ms for 100 k bodies = 20 steps), and a settled pile loses only ~3 % over 650 steps without one
+    // sort, upload: 5.6 ms for 100 k bodies = 14 steps), and a settled pile loses only ~3 % over 650 steps without one
     // (profiles/reorder_cost.py), so it is rare by default; r2d_reorder() forces one.
     uint32_t reorder_interval = 1024;
     uint32_t steps_since_upload = 0;
