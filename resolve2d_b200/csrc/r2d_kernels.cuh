@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(TPB) k_grid_cells(Dev d) {
     }
 }
 
-// ---- K3: device-wide exclusive scan of u32 (reduce / spine / down-sweep) --------------------------------------------------
+// ---- K3: device-wide exclusive scan of u32 ----------------------------------------------------------------------------------
 constexpr int SCAN_TPB = 256;
 constexpr int SCAN_IPT = 8;
 constexpr int SCAN_TILE = SCAN_TPB * SCAN_IPT;
@@ -124,62 +124,6 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
     __syncthreads();
     return r;
 }
-__global__ void __launch_bounds__(SCAN_TPB) k_scan_reduce(const uint32_t* __restrict__ in, uint32_t* __restrict__ tile_sums,
-                                                          const uint32_t* n_ptr, uint32_t n_max) {
-    const uint32_t n = scan_count(n_ptr, n_max);
-    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
-    uint32_t s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_IPT; ++k)
-        if (base + k < n) s += in[base + k];
-    uint32_t total;
-    block_exclusive_scan(s, &total);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
-// one CTA: exclusive scan of the tile sums, writes the grand total to out[n] and (optionally) to *total_out
-__global__ void __launch_bounds__(SCAN_TPB) k_scan_spine(uint32_t* tile_sums, const uint32_t* n_ptr, uint32_t n_max,
-                                                         uint32_t* out, uint32_t* total_out) {
-    const uint32_t n = scan_count(n_ptr, n_max);
-    const uint32_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    __shared__ uint32_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n_tiles; base += SCAN_TPB) {
-        const uint32_t t = base + threadIdx.x;
-        const uint32_t v = t < n_tiles ? tile_sums[t] : 0u;
-        uint32_t total;
-        const uint32_t ex = block_exclusive_scan(v, &total);
-        const uint32_t carry = carry_s;
-        if (t < n_tiles) tile_sums[t] = carry + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        out[n] = carry_s;
-        if (total_out) *total_out = carry_s;
-    }
-}
-__global__ void __launch_bounds__(SCAN_TPB) k_scan_down(const uint32_t* in, uint32_t* out, const uint32_t* __restrict__ tile_sums,
-                                                        const uint32_t* n_ptr, uint32_t n_max) {
-    const uint32_t n = scan_count(n_ptr, n_max);
-    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
-    if (blockIdx.x * SCAN_TILE >= n) return;
-    uint32_t v[SCAN_IPT];
-    uint32_t s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_IPT; ++k) {
-        v[k] = (base + k < n) ? in[base + k] : 0u;
-        s += v[k];
-    }
-    uint32_t run = block_exclusive_scan(s, nullptr) + tile_sums[blockIdx.x];
-#pragma unroll
-    for (int k = 0; k < SCAN_IPT; ++k) {
-        if (base + k < n) out[base + k] = run;
-        run += v[k];
-    }
-}
-
 // Single-pass chained scan (decoupled look-back): one launch instead of three.  Tile ids come from an atomic ticket,
 // so a CTA only ever waits for tiles that started before it; every tile publishes (flag, value) as ONE 64-bit word
 // (flag 1 = aggregate of the tile, 2 = inclusive prefix), which needs no fence.  `state` (n_tiles + 1 words, the last
@@ -791,7 +735,7 @@ __global__ void __launch_bounds__(TPB, 4) k_color(Dev d) {
                 continue;
             }
             const uint32_t warp_lag = __reduce_min_sync(0xffffffffu, min_lag);
-            if (warp_lag > 1u) backoff_ns((warp_lag < 8u ? warp_lag - 1u : 7u) * d.flow_sleep_unit);
+            if (warp_lag > 1u) backoff_ns((warp_lag < 8u ? warp_lag - 1u : 7u) * FLOW_SLEEP_UNIT);
             if ((++idle & 63u) == 0u) {
                 if (*((volatile uint32_t*)&d.counters->flow_fail)) break;
                 if (idle > (1u << 20)) {  // a stall would be a bug; report it instead of hanging the GPU
@@ -975,7 +919,10 @@ __global__ void __launch_bounds__(WORLD_TPB) k_color_worlds(Dev d) {
         __syncthreads();
     }
     for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x)
-        if (s_hist[c]) atomicAdd(&d.color_count[c], s_hist[c]);
+        if (s_hist[c]) {
+            atomicAdd(&d.color_count[c], s_hist[c]);
+            if (d.world_fused) atomicMax(&d.counters->n_colors, c + 1u);   // (else k_scan_owners derives it)
+        }
     if (threadIdx.x == 0) atomicMax(&d.counters->n_rounds, max_round);
 }
 // ---- K8 for batches of small worlds, sorted form ------------------------------------------------------------------------------
@@ -1139,31 +1086,12 @@ __global__ void __launch_bounds__(WORLD_TPB) k_color_worlds_seq(Dev d, uint32_t 
     }
     __syncthreads();
     for (uint32_t c = threadIdx.x; c < MAX_COLORS; c += blockDim.x)
-        if (s_hist[c]) atomicAdd(&d.color_count[c], s_hist[c]);
+        if (s_hist[c]) {
+            atomicAdd(&d.color_count[c], s_hist[c]);
+            if (d.world_fused) atomicMax(&d.counters->n_colors, c + 1u);   // (else k_scan_owners derives it)
+        }
     if (threadIdx.x == 0 && max_round) atomicMax(&d.counters->n_rounds, max_round);
 }
-// closes the per-world colouring: number of colours and the length of the owner-position scan
-__global__ void k_color_finish(Dev d) {
-    if (threadIdx.x == 0) {
-        uint32_t nc = 0;
-        for (uint32_t c = 0; c < MAX_COLORS; ++c)
-            if (d.color_count[c]) nc = c + 1u;
-        d.counters->n_colors = nc;
-        d.counters->n_own_scan = nc * (d.own_words + 1u);
-    }
-}
-
-// ---- K9a: owner bitmaps and their popcounts (the scan of which places every manifold, see manifold_owner) ----------------------
-__global__ void __launch_bounds__(TPB) k_owner_bits(Dev d) {
-    if (overflowed(d)) return;
-    const uint32_t n = live_pairs(d);
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) owner_bit_thread(d, p);
-}
-__global__ void __launch_bounds__(TPB) k_owner_count(Dev d) {
-    const uint32_t n = d.counters->n_own_scan;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) owner_count_thread(d, k);
-}
-
 // ---- K9: group the manifolds by colour and evaluate the pre-step (collision.zig:102-133) ---------------------------------------
 __global__ void __launch_bounds__(TPB) k_partition_prestep(Dev d) {
     if (overflowed(d)) return;
@@ -1210,14 +1138,6 @@ __global__ void __launch_bounds__(SOLVE_TPB) k_solve_joints(Dev d, uint32_t begi
 // of the colour-sorted array, i.e. it walks its manifolds in ascending colour, which the dataflow order requires.
 // Colour ranges and counts are read from device memory, so the host never has to learn them before launching.
 // An abandoned attempt (buffer overflow, colouring error) leaves the body state untouched.
-__device__ __forceinline__ void stamp(const Dev& d, uint32_t slot) {
-    if (blockIdx.x == 0 && threadIdx.x == 0 && slot < 10) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        d.counters->stamp[slot] = t;
-        d.counters->n_stamps = slot + 1;
-    }
-}
 // Shared-memory cache of the solver records: thread t owns manifolds t, t + nth, ... for the whole kernel, so the first
 // SOLVE_SMEM_SLOTS of them are copied once into shared memory (record k of thread x at index k * PSOLVE_TPB + x of each array)
 // and every sweep reads its constants — and keeps its accumulated impulses — there; only the two body words of a
@@ -1235,7 +1155,6 @@ __global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float su
     if (overflowed(d) || d.counters->err != 0u) return;  // uniform across the grid
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const uint32_t n_manifolds = d.color_start[d.counters->n_colors];
-    stamp(d, 0);
     // ---- stage my records ----
     Dev ds = d;  // same code path, record arrays redirected to shared memory
     {
@@ -1273,9 +1192,7 @@ __global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float su
     for (uint32_t s = 0; s < S; ++s) {
         if (s == 0)
             for (uint32_t i = tid; i < d.n_bodies; i += 4u * nth) integrate_batch<4>(d, i, nth, sub_dt, false, true, S == 1);
-        if (s == 0) stamp(d, 1);
         grid.sync();
-        if (s == 0) stamp(d, 2);
         for (uint32_t it = 0; it < I; ++it) {
             for (uint32_t jc = 0; jc < n_joint_colors; ++jc) {
                 const uint32_t b = joint_color_start[jc], e = joint_color_start[jc + 1];
@@ -1289,72 +1206,17 @@ __global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float su
                 else
                     solve_contact_thread<true>(d, m, sub_dt, it);
             }
-            if (s == 0) stamp(d, 3 + it);     // block 0 finished its part of sweep `it`
             if (n_joint_colors) grid.sync();  // joints of the next iteration read what the contacts wrote
         }
         if (!n_joint_colors) grid.sync();
-        if (s == 0) stamp(d, 8);
         // end of substep s fused with the start of substep s + 1: both are per-body, same thread, no barrier needed
         for (uint32_t i = tid; i < d.n_bodies; i += 4u * nth) integrate_batch<4>(d, i, nth, sub_dt, true, s + 1 < S, s + 2 == S);
-        if (s == 0) stamp(d, 9);
     }
-    stamp(d, 10);
 }
-
-// ---- K13: worlds that fit in shared memory — one CTA per world, no inter-CTA synchronisation at all --------------------------------
-// A batch of small independent worlds (cfg5: 4,096 x 256 bodies) needs no grid barrier and no dataflow: world w's
-// manifolds of colour c are the contiguous range [slot(c, base_w), slot(c, base_{w+1})) of the colour-sorted records
-// (owner order is world-major), its momentum words live in shared memory for the whole substep loop, and colours are
-// separated by __syncthreads().  The per-body update sequence is the colour order, as everywhere else: bit-identical.
-constexpr uint32_t WORLD_MAX_BODIES = 512;    // 8 KB of momentum words
 
 __device__ __forceinline__ uint32_t owner_rank(const Dev& d, uint32_t c, uint32_t slot) {  // owners of colour c below `slot`
     const uint32_t word = d.own_bits[(size_t)c * d.own_words + (slot >> 5)];
     return d.own_pos[(size_t)c * (d.own_words + 1u) + (slot >> 5)] + (uint32_t)__popc(word & ((1u << (slot & 31u)) - 1u));
-}
-
-__global__ void __launch_bounds__(WORLD_TPB) k_solve_worlds(Dev d, float sub_dt, uint32_t S, uint32_t I) {
-    __shared__ float4 s_mom[WORLD_MAX_BODIES];
-    __shared__ float2 s_invb[WORLD_MAX_BODIES];
-    __shared__ uint32_t s_begin[MAX_COLORS], s_end[MAX_COLORS];
-    if (overflowed(d) || d.counters->err != 0u) return;
-    const uint32_t nc = d.counters->n_colors;
-    for (uint32_t w = blockIdx.x; w < d.n_worlds; w += gridDim.x) {
-        const uint32_t b0 = d.world_base[w], b1 = d.world_base[w + 1], nb = b1 - b0;
-        for (uint32_t c = threadIdx.x; c < nc; c += blockDim.x) {
-            s_begin[c] = owner_rank(d, c, b0);
-            // the last world's range ends where the colour's padding begins
-            s_end[c] = (b1 < d.n_bodies) ? owner_rank(d, c, b1) : d.own_pos[(size_t)c * (d.own_words + 1u) + d.own_words];
-        }
-        Dev ds = d;
-        ds.mom = s_mom - b0;  // ds.mom[global slot] addresses the shared copy of this world's momentum words
-        ds.inv_body = s_invb - b0;
-        ds.world_slot0 = b0;
-        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
-            const float4 pr = d.prop[b0 + i];
-            const bool st = (body_flags(d, b0 + i) & FLAG_STATIC) != 0;
-            s_invb[i] = make_float2(st ? 0.0f : fdiv(1.0f, pr.x), st ? 0.0f : fdiv(1.0f, pr.y));   // prestep_manifold, per body
-        }
-        for (uint32_t s = 0; s < S; ++s) {
-            for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
-                if (s > 0) integrate_positions_thread(d, b0 + i, sub_dt);
-                integrate_forces_thread(d, b0 + i, sub_dt, s + 1 == S);
-                s_mom[i] = d.mom[b0 + i];
-            }
-            __syncthreads();
-            for (uint32_t it = 0; it < I; ++it)
-                for (uint32_t c = 0; c < nc; ++c) {
-                    for (uint32_t m = s_begin[c] + threadIdx.x; m < s_end[c]; m += blockDim.x) solve_contact_thread<false, true>(ds, m, sub_dt);
-                    __syncthreads();
-                }
-            for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
-                const float4 m = s_mom[i];
-                if (!(body_flags(d, b0 + i) & FLAG_STATIC)) d.mom[b0 + i] = m;
-                if (s + 1 == S) integrate_positions_thread(d, b0 + i, sub_dt);
-            }
-            __syncthreads();
-        }
-    }
 }
 
 // ---- K14: one world, one spatial TILE of bodies per SM — the momentum words of a tile live in shared memory ---------------------
@@ -1447,7 +1309,6 @@ __global__ void __launch_bounds__(TILE_TPB) k_solve_tiles(Dev d, float sub_dt, u
     const uint32_t n_tasks = s_n_tasks;
     grid.sync();
     if (__ldcg(&d.counters->tile_fallback) != 0u) return;  // nothing has been modified: the host runs k_solve_persistent
-    stamp(d, 0);
     // ---- stage the cached records; remember which body words are tile-local ----
     for (uint32_t k = warp; k < n_tasks && k < cache_tasks; k += n_warps) {
         if (lane >= t_count[k]) continue;
@@ -1475,10 +1336,8 @@ __global__ void __launch_bounds__(TILE_TPB) k_solve_tiles(Dev d, float sub_dt, u
             t_mom[i] = d.mom[b0 + i];
             t_ver[i] = 0u;
         }
-        if (s == 0) stamp(d, 1);
         __syncthreads();
         grid.sync();
-        if (s == 0) stamp(d, 2);
         for (uint32_t it = 0; it < I; ++it) {
             for (uint32_t k = warp; k < n_tasks; k += n_warps) {
                 const bool cached = k < cache_tasks;
@@ -1563,7 +1422,7 @@ __global__ void __launch_bounds__(TILE_TPB) k_solve_tiles(Dev d, float sub_dt, u
                                 lag += e2 - f2u(m2.w);
                             }
                         }
-                        if (lag == 0u || d.wait_mode == 2u) {   // wait_mode 2: DIAGNOSTIC ONLY (wrong results), the dependency-free cost
+                        if (lag == 0u) {
                             __threadfence_block();  // the version was written after the momentum it announces
                             if (loc1) m1 = ld_volatile_shared_f4(&t_mom[h.x - b0]);
                             if (loc2) m2 = ld_volatile_shared_f4(&t_mom[h.y - b0]);
@@ -1591,11 +1450,9 @@ __global__ void __launch_bounds__(TILE_TPB) k_solve_tiles(Dev d, float sub_dt, u
                     }
                 }
             }
-            if (s == 0) stamp(d, 3 + it);
         }
         __syncthreads();
         grid.sync();
-        if (s == 0) stamp(d, 8);
         // end of substep s fused with the start of substep s + 1 (per body, same thread)
         for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
             const uint32_t b = b0 + i;
@@ -1603,7 +1460,6 @@ __global__ void __launch_bounds__(TILE_TPB) k_solve_tiles(Dev d, float sub_dt, u
             integrate_positions_thread(d, b, sub_dt);
             if (s + 1 < S) integrate_forces_thread(d, b, sub_dt, s + 2 == S);
         }
-        if (s == 0) stamp(d, 9);
     }
     // accumulated impulses of the cached records are not needed after the call (collision.zig:102-133 re-creates them)
 }
@@ -1637,3 +1493,5 @@ __global__ void __launch_bounds__(TPB) k_import_forces(Dev d, const uint32_t* __
 }
 
 }  // namespace r2d
+
+#include "r2d_world.cuh"

@@ -43,6 +43,11 @@ constexpr uint32_t MAX_COLOR_ROUNDS = 4000;        // < 2^12 (round tag field of
 constexpr uint32_t BIG_BODY_CELLS = 64;            // bodies covering more cells are walked by a whole CTA
 constexpr int64_t MAX_BODY_CELLS = 1 << 22;        // beyond this the pose is garbage (NaN/inf): R2D_ERR_GRID_RANGE
 
+// wait policy of the dataflow kernels (never affects results): lag <= WAIT_SPIN_LAG polls again at once, otherwise the
+// warp sleeps lag * WAIT_SLEEP_UNIT ns (at most WAIT_SLEEP_MAX); the dataflow colouring sleeps FLOW_SLEEP_UNIT ns per
+// manifold still ahead.  Values from the round-1 sweeps (profiles/tune_solver.py).
+constexpr uint32_t WAIT_SPIN_LAG = 1u, WAIT_SLEEP_UNIT = 200u, WAIT_SLEEP_MAX = 4000u, FLOW_SLEEP_UNIT = 150u;
+
 constexpr uint32_t ERR_COLOR_OVERFLOW = 1u;
 constexpr uint32_t ERR_GRID_RANGE = 2u;
 constexpr uint32_t ERR_ROUNDS = 4u;
@@ -63,12 +68,13 @@ struct Counters {
     uint32_t n_work;         // buckets holding 2..SMALL_BUCKET entries (a warp each in the pair kernels)
     uint32_t n_mid;          // SMALL_BUCKET+1..HEAVY_BUCKET entries (a warp or a CTA each, see medium_by_cta)
     uint32_t n_heavy;        // buckets holding more (a CTA each)
-    uint32_t n_stamps;
+    uint32_t pad0;
     uint32_t flow_abort;     // set by the narrowphase: a body has more than ADJ_CAP manifolds, colour by rounds
     uint32_t flow_fail;      // set inside the dataflow colouring: more than FLOW_COLORS colours needed (or a stall)
     uint32_t flow_used;      // the colours of this step come from the dataflow colouring (masks in cstate, not in used)
     uint32_t tile_fallback;  // k_solve_tiles declined (a tile has too many bodies / tasks): the host runs k_solve_persistent
-    unsigned long long stamp[10];   // %globaltimer at phase boundaries of the persistent solver (block 0; diagnostics)
+    uint32_t max_world_m;    // k_world_solve: most manifolds / most two-point manifolds found in one world of the batch (the
+    uint32_t max_world_k2;   // host sizes the shared-memory record cache of the next call from them)
 };
 
 // Everything the kernels need, passed by value.
@@ -154,12 +160,8 @@ struct Dev {
     float4* s_pm1;
     float2* s_acc0;               // point 0: accumulated_pn, accumulated_pt
     float2* s_acc1;
-    uint2* world_hdr;             // non-null (batches solved per world): compact header {ref | inc << 16 (world-local slots),
-                                  // n_points | static bits} written next to s_hdr; the per-world solver reads these 8 bytes
-                                  // instead of the 16 of s_hdr (lives in the s_dep buffer, which that solver does not use)
-    uint32_t world_slot0;         // first slot of the world a CTA-per-world kernel is working on (base of world_hdr's slots)
-    const float2* inv_body;       // non-null: per-body (1 / mass, 1 / inertia), 0 for static bodies, indexed like `mom` — the
-                                  // CTA-per-world solver keeps it in shared memory and skips the s_inv fetch (16 of 88 bytes)
+    uint32_t world_fused;         // 1: k_world_solve follows (batches of small worlds): it places and pre-steps the manifolds of
+                                  // a world itself, so the colouring sets no owner bits and no partition kernel runs
     uint32_t tile_bodies;         // B > 0: k_solve_tiles will run with tiles of B consecutive body slots (else 0)
     uint32_t* body_shared;        // NB: 1 if a manifold owned by a body of ANOTHER tile touches the body (see k_solve_tiles)
     uint4* s_dep;                 // rank of this manifold among the contacts of its ref body, that body's contact count,
@@ -170,14 +172,7 @@ struct Dev {
     const float4* j_par;          // power_max, power_min, beta, target (distance | omega)
     const float4* j_vec;          // r1.x, r1.y, r2.x, r2.y  |  target.x, target.y, -, -
     float sub_dt;                 // dt / sub_steps of the current process() call
-    uint32_t flow_sleep_unit;     // dataflow colouring wait policy: ns of back-off per manifold still ahead
-    // ---- dataflow sweep tuning (wait policy only; never affects results) ------------------------------------------------
     uint32_t color_smem;          // 1: maxprio / used point into shared memory (per-world colouring kernel)
-    uint32_t wait_mode;           // 0: the warp updates when all its lanes are ready; 1: ready lanes update as they come
-    uint32_t wait_probe;          // 1: lane 0 probes alone until its bodies are ready, then the whole warp loads
-    uint32_t wait_spin_lag;       // lag <= this: poll again immediately
-    uint32_t wait_sleep_unit;     // otherwise sleep lag * unit ns ...
-    uint32_t wait_sleep_max;      // ... capped at this many ns
 };
 
 R2D_HD uint32_t body_flags(const Dev& d, uint32_t i) { return f2u(d.shape[i].z); }
@@ -268,14 +263,6 @@ R2D_HD void st_body_word(float4* p, float4 v) {
                  : "memory");
 #else
     *p = v;
-#endif
-}
-// DIAGNOSTIC flavour: .cg load / default store of the same 16 bytes (weak accesses)
-R2D_HD float4 ld_body_word_cg(const float4* p) {
-#if defined(__CUDA_ARCH__)
-    return __ldcg(p);
-#else
-    return *p;
 #endif
 }
 R2D_HD void backoff_ns(uint32_t ns) {
@@ -860,12 +847,13 @@ R2D_HD uint32_t manifold_owner(const uint4& h) {
 }
 // the same for a manifold whose colour has just been decided (the colouring kernels set the bit on the spot: one launch less)
 R2D_HD void owner_bit_set(const Dev& d, uint32_t ref, uint32_t inc, uint32_t dyn, uint32_t color) {
+    if (d.world_fused) return;
     const uint32_t o = manifold_owner(make_uint4(ref, inc, 0u, dyn));
     atomic_or_u32(&d.own_bits[(size_t)color * d.own_words + (o >> 5)], 1u << (o & 31u));
 }
 R2D_HD void owner_bit_thread(const Dev& d, uint32_t p) {
     const uint32_t c = d.m_color[p];
-    if (c >= MAX_COLORS) return;
+    if (c >= MAX_COLORS || d.world_fused) return;
     const uint32_t o = manifold_owner(d.m_hdr[p]);
     atomic_or_u32(&d.own_bits[(size_t)c * d.own_words + (o >> 5)], 1u << (o & 31u));
 }
@@ -897,15 +885,11 @@ R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
     const float4 g0 = d.m_g0[p], g1 = d.m_g1[p];
     const ContactConst c = prestep_manifold(mk2(g0.x, g0.y), st1, st2, pr1.x, pr2.x, pr1.y, pr2.y, pr1.z, pr2.z);
     d.s_hdr[at] = make_uint4(h.x, h.y, np | (st1 ? 0x100u : 0u) | (st2 ? 0x200u : 0u), p);
-    if (d.world_hdr) {
-        const uint32_t base = d.world_base[f1 >> FLAG_WORLD_SHIFT];   // both bodies are in the same world
-        d.world_hdr[at] = make_uint2((h.x - base) | ((h.y - base) << 16), np | (st1 ? 0x100u : 0u) | (st2 ? 0x200u : 0u));
-    }
     if (d.tile_bodies && !st1 && !st2 && h.x / d.tile_bodies != h.y / d.tile_bodies)
         d.body_shared[h.x > h.y ? h.x : h.y] = 1u;  // the owner is the lower slot: the other body is foreign to its tile
     // Colours on one body are pairwise distinct, so the body's sweep sequence is its colour set in ascending order:
     // rank = colours below mine, degree = colours used.
-    if (!d.world_hdr) {   // (the CTA-per-world solver separates colours with barriers: no ranks needed, s_dep holds its headers)
+    {
         const uint32_t color = d.m_color[p];
         const bool from_flow = d.counters->flow_used != 0u;
         uint32_t rk[2] = {0, 0}, dg[2] = {0, 0};
@@ -914,7 +898,7 @@ R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
         d.s_dep[at] = make_uint4(rk[0], dg[0], rk[1], dg[1]);
     }
     d.s_nf[at] = make_float4(c.normal.x, c.normal.y, c.friction, 0.0f);
-    if (!d.world_hdr) d.s_inv[at] = make_float4(c.inv_m1, c.inv_m2, c.inv_i1, c.inv_i2);   // the per-world solver derives them per body
+    d.s_inv[at] = make_float4(c.inv_m1, c.inv_m2, c.inv_i1, c.inv_i2);
     if (np > 0) {
         const float4 r = d.m_r0[p];
         ContactPointConst pc;
@@ -950,18 +934,10 @@ R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
 //   bit-identical — but a manifold only waits for its own two bodies.  All waiting threads are resident (cooperative
 //   launch) and walk their manifolds in (iteration, colour) order, so the globally lowest pending manifold can always
 //   run: no deadlock.  A stall would be a bug; it is reported through ERR_STALL instead of hanging the GPU.
-// DENSE = true: the caller guarantees that slot m is a real record (no padding), so every array is fetched at once
-// instead of after the header has arrived (one memory round trip per manifold instead of two).
-template <bool DATAFLOW, bool DENSE = false>
+template <bool DATAFLOW>
 R2D_HD void solve_contact_thread(const Dev& d, uint32_t m, float sub_dt, uint32_t it = 0) {
-    uint4 h;
-    if (DENSE && !DATAFLOW && d.world_hdr) {
-        const uint2 q = d.world_hdr[m];
-        h = make_uint4(d.world_slot0 + (q.x & 0xFFFFu), d.world_slot0 + (q.x >> 16), q.y, 0u);
-    } else {
-        h = d.s_hdr[m];
-    }
-    const bool empty = !DENSE && (h.z & S_EMPTY) != 0;
+    const uint4 h = d.s_hdr[m];
+    const bool empty = (h.z & S_EMPTY) != 0;
     if (!DATAFLOW && empty) return;
     const int np = empty ? 0 : (int)(h.z & 0xFFu);
     const bool st1 = empty || (h.z & 0x100u) != 0, st2 = empty || (h.z & 0x200u) != 0;
@@ -975,19 +951,11 @@ R2D_HD void solve_contact_thread(const Dev& d, uint32_t m, float sub_dt, uint32_
         c.normal = mk2(nf.x, nf.y);
         c.tangent = rot90cw(c.normal);
         c.friction = nf.z;
-        if (d.inv_body) {  // the same values prestep_manifold stored in s_inv: static ? 0 : 1 / mass, 1 / inertia
-            const float2 i1 = d.inv_body[h.x], i2 = d.inv_body[h.y];
-            c.inv_m1 = i1.x;
-            c.inv_m2 = i2.x;
-            c.inv_i1 = i1.y;
-            c.inv_i2 = i2.y;
-        } else {
-            const float4 inv = d.s_inv[m];
-            c.inv_m1 = inv.x;
-            c.inv_m2 = inv.y;
-            c.inv_i1 = inv.z;
-            c.inv_i2 = inv.w;
-        }
+        const float4 inv = d.s_inv[m];
+        c.inv_m1 = inv.x;
+        c.inv_m2 = inv.y;
+        c.inv_i1 = inv.z;
+        c.inv_i2 = inv.w;
         {  // point 0 is loaded unconditionally (almost every manifold has it): no dependent load level after the header
             const float4 r = d.s_r0[m], pm = d.s_pm0[m];
             const float2 a = d.s_acc0[m];
@@ -1020,19 +988,19 @@ R2D_HD void solve_contact_thread(const Dev& d, uint32_t m, float sub_dt, uint32_
     }
     if (DATAFLOW) {
         // The 32 manifolds of a warp have one colour (segments are padded to whole warps), hence no dependencies among
-        // themselves: the warp polls until ALL its lanes are ready and then updates them in one converged pass.
-        uint32_t spins = 0;
+        // themselves.
 #if defined(__CUDA_ARCH__)
+        uint32_t spins = 0;
         // Stage 1: only lane 0 probes (one 16-byte load per warp instead of 64) until ITS body is ready; the other
         // lanes have the same colour and become ready at about the same time.
-        for (; d.wait_mode < 2u && d.wait_probe != 0u;) {
+        for (;;) {
             uint32_t lag0 = 0u;
             if ((threadIdx.x & 31u) == 0u && !st1) lag0 = e1 - f2u(ld_body_word(&d.mom[h.x]).w);
             lag0 = __shfl_sync(0xffffffffu, lag0, 0);
             if (lag0 == 0u) break;
-            if (lag0 > d.wait_spin_lag) {
-                const uint32_t ns = lag0 * d.wait_sleep_unit;
-                backoff_ns(ns < d.wait_sleep_max ? ns : d.wait_sleep_max);
+            if (lag0 > WAIT_SPIN_LAG) {
+                const uint32_t ns = lag0 * WAIT_SLEEP_UNIT;
+                backoff_ns(ns < WAIT_SLEEP_MAX ? ns : WAIT_SLEEP_MAX);
             }
             if ((++spins & 0xFFu) == 0u) {
                 if (spins > (1u << 20)) atomicOr(&d.counters->err, ERR_STALL);
@@ -1040,81 +1008,45 @@ R2D_HD void solve_contact_thread(const Dev& d, uint32_t m, float sub_dt, uint32_
                 if (__any_sync(0xffffffffu, flag != 0u)) return;
             }
         }
-#endif
-#if defined(__CUDA_ARCH__)
-        if (d.wait_mode == 2u) {  // DIAGNOSTIC ONLY (wrong results): no waiting at all, measures the dependency-free cost
-            if (!st1) m1 = ld_body_word(&d.mom[h.x]);
-            if (!st2) m2 = ld_body_word(&d.mom[h.y]);
-        } else if (d.wait_mode == 3u) {  // DIAGNOSTIC ONLY: same, with weak .cg loads and default stores
-            if (!st1) m1 = ld_body_word_cg(&d.mom[h.x]);
-            if (!st2) m2 = ld_body_word_cg(&d.mom[h.y]);
-            BodyVel b1 = {mk2(m1.x, m1.y), m1.z}, b2 = {mk2(m2.x, m2.y), m2.z};
-            solve_contact(c, np, pts, acc, st1, st2, b1, b2);
-            d.s_acc0[m] = make_float2(acc[0].x, acc[0].y);
-            if (np > 1) d.s_acc1[m] = make_float2(acc[1].x, acc[1].y);
-            if (!st1) d.mom[h.x] = make_float4(b1.mom.x, b1.mom.y, b1.ang, u2f(e1 + 1u));
-            if (!st2) d.mom[h.y] = make_float4(b2.mom.x, b2.mom.y, b2.ang, u2f(e2 + 1u));
-            return;
-        } else
-        if (d.wait_mode == 1u) {
-            // Ready lanes update as they come (a few converged sub-groups per warp instead of waiting for the slowest lane).
-            bool pending = !empty;
-            while (__any_sync(0xffffffffu, pending)) {
-                uint32_t lag = 0xffffffffu;
-                if (pending) {
-                    if (!st1) m1 = ld_body_word(&d.mom[h.x]);
-                    if (!st2) m2 = ld_body_word(&d.mom[h.y]);
-                    lag = (st1 ? 0u : e1 - f2u(m1.w)) + (st2 ? 0u : e2 - f2u(m2.w));
-                }
-                if (pending && lag == 0u) {
-                    BodyVel b1 = {mk2(m1.x, m1.y), m1.z}, b2 = {mk2(m2.x, m2.y), m2.z};
-                    solve_contact(c, np, pts, acc, st1, st2, b1, b2);
-                    d.s_acc0[m] = make_float2(acc[0].x, acc[0].y);
-                    if (np > 1) d.s_acc1[m] = make_float2(acc[1].x, acc[1].y);
-                    if (!st1) st_body_word(&d.mom[h.x], make_float4(b1.mom.x, b1.mom.y, b1.ang, u2f(e1 + 1u)));
-                    if (!st2) st_body_word(&d.mom[h.y], make_float4(b2.mom.x, b2.mom.y, b2.ang, u2f(e2 + 1u)));
-                    pending = false;
-                }
-                const uint32_t best = __reduce_min_sync(0xffffffffu, pending ? lag : 0xffffffffu);
-                if (best != 0xffffffffu && best > d.wait_spin_lag) {
-                    const uint32_t ns = best * d.wait_sleep_unit;
-                    backoff_ns(ns < d.wait_sleep_max ? ns : d.wait_sleep_max);
-                }
-                if ((++spins & 0xFFu) == 0u) {
-                    if (spins > (1u << 20)) atomicOr(&d.counters->err, ERR_STALL);
-                    const uint32_t flag = *((volatile uint32_t*)&d.counters->err) & ERR_STALL;
-                    if (__any_sync(0xffffffffu, flag != 0u)) return;
-                }
+        // Stage 2: ready lanes update as they come (a few converged sub-groups per warp instead of waiting for the slowest lane).
+        bool pending = !empty;
+        while (__any_sync(0xffffffffu, pending)) {
+            uint32_t lag = 0xffffffffu;
+            if (pending) {
+                if (!st1) m1 = ld_body_word(&d.mom[h.x]);
+                if (!st2) m2 = ld_body_word(&d.mom[h.y]);
+                lag = (st1 ? 0u : e1 - f2u(m1.w)) + (st2 ? 0u : e2 - f2u(m2.w));
             }
-            return;
-        }
-#endif
-        for (; d.wait_mode != 2u;) {
-            if (!st1) m1 = ld_body_word(&d.mom[h.x]);
-            if (!st2) m2 = ld_body_word(&d.mom[h.y]);
-            const uint32_t lag = (st1 ? 0u : e1 - f2u(m1.w)) + (st2 ? 0u : e2 - f2u(m2.w));
-#if defined(__CUDA_ARCH__)
-            const uint32_t worst = __reduce_max_sync(0xffffffffu, lag);
-            if (worst == 0u) break;
-            // `worst` updates still have to land before the slowest lane may run: sleep in proportion
-            if (worst > d.wait_spin_lag) {
-                const uint32_t ns = worst * d.wait_sleep_unit;
-                backoff_ns(ns < d.wait_sleep_max ? ns : d.wait_sleep_max);
+            if (pending && lag == 0u) {
+                BodyVel b1 = {mk2(m1.x, m1.y), m1.z}, b2 = {mk2(m2.x, m2.y), m2.z};
+                solve_contact(c, np, pts, acc, st1, st2, b1, b2);
+                d.s_acc0[m] = make_float2(acc[0].x, acc[0].y);
+                if (np > 1) d.s_acc1[m] = make_float2(acc[1].x, acc[1].y);
+                if (!st1) st_body_word(&d.mom[h.x], make_float4(b1.mom.x, b1.mom.y, b1.ang, u2f(e1 + 1u)));
+                if (!st2) st_body_word(&d.mom[h.y], make_float4(b2.mom.x, b2.mom.y, b2.ang, u2f(e2 + 1u)));
+                pending = false;
+            }
+            const uint32_t best = __reduce_min_sync(0xffffffffu, pending ? lag : 0xffffffffu);
+            if (best != 0xffffffffu && best > WAIT_SPIN_LAG) {
+                const uint32_t ns = best * WAIT_SLEEP_UNIT;
+                backoff_ns(ns < WAIT_SLEEP_MAX ? ns : WAIT_SLEEP_MAX);
             }
             if ((++spins & 0xFFu) == 0u) {
                 if (spins > (1u << 20)) atomicOr(&d.counters->err, ERR_STALL);
                 const uint32_t flag = *((volatile uint32_t*)&d.counters->err) & ERR_STALL;
-                if (__any_sync(0xffffffffu, flag != 0u)) return;  // warp-uniform exit
+                if (__any_sync(0xffffffffu, flag != 0u)) return;
             }
-#else
-            (void)spins;
-            if (lag != 0u) {  // serial emulation: the order must already be right
-                atomic_or_u32(&d.counters->err, ERR_STALL);
-                return;
-            }
-            break;
-#endif
         }
+        return;
+#else
+        if (!st1) m1 = ld_body_word(&d.mom[h.x]);
+        if (!st2) m2 = ld_body_word(&d.mom[h.y]);
+        const uint32_t lag = (st1 ? 0u : e1 - f2u(m1.w)) + (st2 ? 0u : e2 - f2u(m2.w));
+        if (lag != 0u) {  // serial emulation: the order must already be right
+            atomic_or_u32(&d.counters->err, ERR_STALL);
+            return;
+        }
+#endif
     }
     if (empty) return;
     BodyVel b1 = {mk2(m1.x, m1.y), m1.z}, b2 = {mk2(m2.x, m2.y), m2.z};
@@ -1179,38 +1111,50 @@ R2D_HD void solve_joint_thread(const Dev& d, uint32_t j, float sub_dt) {
 }
 
 // ---- integrators ------------------------------------------------------------------------------------------------------
+// Pure arithmetic of the three per-body steps (shared by every integrator flavour, so that they cannot drift apart).
+// AABB refresh (lib.zig:210; Disc.zig:63-66, Rectangle.zig:71-86)
+R2D_HD float4 refreshed_aabb(const float4& p, uint32_t flags, float shape_a, float shape_b) {
+    float hw, hh;
+    if (flags & FLAG_RECT) {
+        float sn, cs;
+        sincos_ref(p.z, &sn, &cs);
+        aabb_half_extents(flags, shape_a, shape_b, cs, sn, hw, hh);
+    } else {
+        hw = shape_a;
+        hh = shape_a;
+    }
+    return make_float4(p.x, p.y, hw, hh);
+}
+// gravity (DownwardsGravity.zig:35-39: force.addmult(g_vec = (0, -g), mass) per generator) + momentum integration
+// (lib.zig:211-215).  `m.w` (the version word of the dataflow sweep) restarts at 0: contact updates are counted per substep.
+R2D_HD void momentum_update(const Dev& d, uint32_t world, float4& m, float4 f, float mass, float sub_dt) {
+    for (uint32_t g = d.grav_off[world]; g < d.grav_off[world + 1]; ++g) {
+        f.x = fadd(f.x, fmul(0.0f, mass));
+        f.y = fadd(f.y, fmul(-d.grav[g], mass));
+    }
+    m.x = fadd(m.x, fmul(f.x, sub_dt));
+    m.y = fadd(m.y, fmul(f.y, sub_dt));
+    m.z = fadd(m.z, fmul(f.z, sub_dt));
+    m.w = u2f(0u);
+}
+// position integration (lib.zig:238-249)
+R2D_HD void position_update(float4& p, const float4& m, float mass, float inertia, float sub_dt) {
+    const float k = fdiv(sub_dt, mass);
+    p.x = fadd(p.x, fmul(m.x, k));
+    p.y = fadd(p.y, fmul(m.y, k));
+    p.z = fadd(p.z, fdiv(fmul(m.z, sub_dt), inertia));
+}
+
 // K1: gravity (DownwardsGravity.zig:35-39) + AABB refresh (lib.zig:210) + momentum integration (lib.zig:211-215).
 // The reference refreshes the AABB in every substep; only the last refresh is observable (the next process() and the
 // accessors read it), so it is evaluated when `refresh_aabb` is set.
 R2D_HD void integrate_forces_thread(const Dev& d, uint32_t i, float sub_dt, bool refresh_aabb) {
     const float4 s = d.shape[i];
     const uint32_t flags = f2u(s.z);
-    if (refresh_aabb) {
-        const float4 p = d.pos[i];
-        float hw, hh;
-        if (flags & FLAG_RECT) {
-            float sn, cs;
-            sincos_ref(p.z, &sn, &cs);
-            aabb_half_extents(flags, s.x, s.y, cs, sn, hw, hh);
-        } else {
-            hw = s.x;
-            hh = s.x;
-        }
-        d.aabb[i] = make_float4(p.x, p.y, hw, hh);
-    }
+    if (refresh_aabb) d.aabb[i] = refreshed_aabb(d.pos[i], flags, s.x, s.y);
     if (flags & FLAG_STATIC) return;
-    float4 f = d.frc[i];
-    const float mass = d.prop[i].x;
-    const uint32_t w = flags >> FLAG_WORLD_SHIFT;
-    for (uint32_t g = d.grav_off[w]; g < d.grav_off[w + 1]; ++g) {  // force.addmult(g_vec = (0, -g), mass)
-        f.x = fadd(f.x, fmul(0.0f, mass));
-        f.y = fadd(f.y, fmul(-d.grav[g], mass));
-    }
     float4 m = d.mom[i];
-    m.x = fadd(m.x, fmul(f.x, sub_dt));
-    m.y = fadd(m.y, fmul(f.y, sub_dt));
-    m.z = fadd(m.z, fmul(f.z, sub_dt));
-    m.w = u2f(0u);  // version: contact updates are counted per substep (dataflow sweep)
+    momentum_update(d, flags >> FLAG_WORLD_SHIFT, m, d.frc[i], d.prop[i].x, sub_dt);
     d.mom[i] = m;
     // force.xy is next read after the end-of-substep reset (positions kernel), so the gravity sum need not be stored
 }
@@ -1220,10 +1164,7 @@ R2D_HD void integrate_positions_thread(const Dev& d, uint32_t i, float sub_dt) {
     if (flags & FLAG_STATIC) return;
     const float4 m = d.mom[i], pr = d.prop[i];
     float4 p = d.pos[i];
-    const float k = fdiv(sub_dt, pr.x);
-    p.x = fadd(p.x, fmul(m.x, k));
-    p.y = fadd(p.y, fmul(m.y, k));
-    p.z = fadd(p.z, fdiv(fmul(m.z, sub_dt), pr.y));
+    position_update(p, m, pr.x, pr.y, sub_dt);
     d.pos[i] = p;
     d.frc[i] = make_float4(0.0f, 0.0f, 0.0f, d.frc[i].w);
 }
@@ -1255,38 +1196,15 @@ R2D_HD void integrate_batch(const Dev& d, uint32_t i0, uint32_t stride, float su
         const bool is_static = (flags & FLAG_STATIC) != 0;
         float4 p = po[k], m = mo[k], f = fr[k];
         if (do_positions && !is_static) {   // lib.zig:238-249
-            const float q = fdiv(sub_dt, pr[k].x);
-            p.x = fadd(p.x, fmul(m.x, q));
-            p.y = fadd(p.y, fmul(m.y, q));
-            p.z = fadd(p.z, fdiv(fmul(m.z, sub_dt), pr[k].y));
+            position_update(p, m, pr[k].x, pr[k].y, sub_dt);
             d.pos[i] = p;
             f = make_float4(0.0f, 0.0f, 0.0f, f.w);
             d.frc[i] = f;
         }
         if (!do_forces) continue;
-        if (refresh_aabb) {                 // lib.zig:210
-            float hw, hh;
-            if (flags & FLAG_RECT) {
-                float sn, cs;
-                sincos_ref(p.z, &sn, &cs);
-                aabb_half_extents(flags, sh[k].x, sh[k].y, cs, sn, hw, hh);
-            } else {
-                hw = sh[k].x;
-                hh = sh[k].x;
-            }
-            d.aabb[i] = make_float4(p.x, p.y, hw, hh);
-        }
+        if (refresh_aabb) d.aabb[i] = refreshed_aabb(p, flags, sh[k].x, sh[k].y);   // lib.zig:210
         if (is_static) continue;
-        const float mass = pr[k].x;
-        const uint32_t w = flags >> FLAG_WORLD_SHIFT;
-        for (uint32_t g = d.grav_off[w]; g < d.grav_off[w + 1]; ++g) {
-            f.x = fadd(f.x, fmul(0.0f, mass));
-            f.y = fadd(f.y, fmul(-d.grav[g], mass));
-        }
-        m.x = fadd(m.x, fmul(f.x, sub_dt));
-        m.y = fadd(m.y, fmul(f.y, sub_dt));
-        m.z = fadd(m.z, fmul(f.z, sub_dt));
-        m.w = u2f(0u);
+        momentum_update(d, flags >> FLAG_WORLD_SHIFT, m, f, pr[k].x, sub_dt);
         d.mom[i] = m;
     }
 }

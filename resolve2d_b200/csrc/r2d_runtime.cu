@@ -85,10 +85,11 @@ struct CudaBatch : BatchBase {
     bool zero_copy = true;            // R2D_ZERO_COPY=0: bulk reads always go through the staging buffer
     DBuf<unsigned char> staging_f;
     int color_blocks = 0, solve_blocks = 0, pair_blocks = 0;
-    uint32_t wait_mode = 1, wait_probe = 1, wait_spin_lag = 1, wait_sleep_unit = 200, wait_sleep_max = 4000;
-    int solve_blocks_per_sm = 1;
     uint32_t solve_smem_slots = SOLVE_SMEM_SLOTS;
-    int world_solve_tpb = WORLD_TPB;
+    bool test_small_buffers = false;  // R2D_TEST_SMALL_BUFFERS=1 (tests): start with buffers that are too small
+    bool world_cache_forced = false;
+    uint32_t world_rec_cap = 0, world_pt1_cap = 0;   // shared-memory record cache of k_world_solve (per world), see world_cache()
+    uint32_t seen_world_m = 0, seen_world_k2 = 0;    // largest world of the previous call
     bool persistent_solver = true;
     bool world_solver = true;       // CTA-per-world shared-memory solver when every world is small and there are no joints
     uint32_t max_world_bodies = 0;   // false: one launch per colour (kept for A/B measurements)
@@ -108,7 +109,7 @@ struct CudaBatch : BatchBase {
     bool seq_world_coloring = true;   // R2D_WORLD_COLORING=rounds: Jones-Plassmann rounds per world instead of sort + sequential greedy
     bool fine_grid = true;            // R2D_BROADPHASE=buckets: every body through the coarse buckets (the original pipeline)
     bool fine_now = false, ll_now = false;
-    bool world_hdr_now = false;       // this step is solved by k_solve_worlds: the partition writes compact headers into s_dep
+    bool world_fused_now = false;     // this step is solved by k_world_solve (which also places and pre-steps the manifolds)
     // pairs / manifolds
     DBuf<uint2> pairs;
     DBuf<uint4> m_hdr, s_hdr;
@@ -128,7 +129,6 @@ struct CudaBatch : BatchBase {
     bool tile_declined = false;
     DBuf<unsigned long long> adj_prio;
     bool flow_coloring = true, flow_now = false;   // dataflow colouring of single worlds (R2D_FLOW_COLORING=0: rounds only)
-    uint32_t flow_sleep_unit = 150;
     unsigned long long* scan_state(int which) { return (unsigned long long*)(zeroed.p + off_scan) + (size_t)which * scan_state_cap; }
     DBuf<uint32_t> own_pos;
     // staging for the boundary copies
@@ -181,38 +181,33 @@ struct CudaBatch : BatchBase {
         R2D_CUDA(cudaHostAlloc((void**)&pinned, sizeof(PinnedStep), cudaHostAllocDefault));
         int per_sm = 0;
         R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_color, TPB, 0));
-        if (per_sm < 1) per_sm = 1;
-        {
-            int want = 4;
-            if (const char* e = getenv("R2D_COLOR_BLOCKS_PER_SM")) want = atoi(e);
-            if (per_sm > want) per_sm = want;
-        }
-        color_blocks = per_sm * n_sms;
+        color_blocks = std::max(1, std::min(per_sm, 4)) * n_sms;
         R2D_CUDA(cudaFuncSetAttribute(k_solve_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_BYTES));
-        R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent, PSOLVE_TPB, SOLVE_SMEM_BYTES));
-        if (per_sm < 1) per_sm = 1;
-        if (const char* e = getenv("R2D_SOLVE_BLOCKS_PER_SM")) solve_blocks_per_sm = atoi(e);
-        if (const char* e = getenv("R2D_SOLVE_SMEM_SLOTS")) solve_smem_slots = std::min<uint32_t>((uint32_t)atoi(e), SOLVE_SMEM_SLOTS);
-        if (const char* e = getenv("R2D_WAIT_MODE")) wait_mode = (uint32_t)atoi(e);
-        if (const char* e = getenv("R2D_WAIT_PROBE")) wait_probe = (uint32_t)atoi(e);
-        if (const char* e = getenv("R2D_WAIT_SPIN_LAG")) wait_spin_lag = (uint32_t)atoi(e);
-        if (const char* e = getenv("R2D_WAIT_SLEEP_UNIT")) wait_sleep_unit = (uint32_t)atoi(e);
-        if (const char* e = getenv("R2D_WAIT_SLEEP_MAX")) wait_sleep_max = (uint32_t)atoi(e);
-        if (per_sm > solve_blocks_per_sm) per_sm = solve_blocks_per_sm;
-        solve_blocks = per_sm * n_sms;
+        solve_blocks = n_sms;   // one CTA per SM (the record cache takes the whole shared memory)
         R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bucket_count, TPB, 0));
         pair_blocks = (per_sm < 1 ? 1 : per_sm) * n_sms;  // resident CTAs: a CTA per heavy bucket, a warp per light one, grid-stride
-        if (const char* e = getenv("R2D_SOLVER")) persistent_solver = std::string(e) != "launches";
-        if (const char* e = getenv("R2D_WORLD_SOLVER")) world_solver = atoi(e) != 0;
-        if (const char* e = getenv("R2D_WORLD_SOLVE_TPB")) world_solve_tpb = std::max(32, std::min((int)WORLD_TPB, atoi(e) / 32 * 32));
-        if (const char* e = getenv("R2D_FLOW_COLORING")) flow_coloring = atoi(e) != 0;
-        if (const char* e = getenv("R2D_TILE_SOLVER")) tile_solver = atoi(e) != 0;
-        if (const char* e = getenv("R2D_TILE_MAX_TASKS")) tile_max_tasks = std::min<uint32_t>((uint32_t)atoi(e), TILE_MAX_TASKS);  // tests
         R2D_CUDA(cudaFuncSetAttribute(k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES));
-        if (const char* e = getenv("R2D_FLOW_SLEEP_UNIT")) flow_sleep_unit = (uint32_t)atoi(e);
-        if (const char* e = getenv("R2D_ZERO_COPY")) zero_copy = atoi(e) != 0;
-        if (const char* e = getenv("R2D_BROADPHASE")) fine_grid = std::string(e) != "buckets";
-        if (const char* e = getenv("R2D_WORLD_COLORING")) seq_world_coloring = std::string(e) != "rounds";
+        R2D_CUDA(cudaFuncSetAttribute(k_world_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
+        // Flavour switches for A/B measurements and tests.  Every one of them selects between paths that produce
+        // bit-identical results; they are read here once, never inside process().
+        auto env_is = [](const char* name, const char* value) {
+            const char* e = getenv(name);
+            return e && std::string(e) == value;
+        };
+        if (env_is("R2D_SOLVER", "launches")) persistent_solver = false;     // one launch per colour
+        if (env_is("R2D_WORLD_SOLVER", "0")) world_solver = false;           // batches through the single-world kernels
+        if (env_is("R2D_FLOW_COLORING", "0")) flow_coloring = false;         // Jones-Plassmann rounds only
+        if (env_is("R2D_TILE_SOLVER", "0")) tile_solver = false;             // k_solve_persistent instead of k_solve_tiles
+        if (const char* e = getenv("R2D_TILE_MAX_TASKS")) tile_max_tasks = std::min<uint32_t>((uint32_t)atoi(e), TILE_MAX_TASKS);
+        if (env_is("R2D_ZERO_COPY", "0")) zero_copy = false;                 // bulk reads through the staging buffer
+        if (env_is("R2D_BROADPHASE", "buckets")) fine_grid = false;          // every body through the hashed 4 m buckets
+        if (env_is("R2D_WORLD_COLORING", "rounds")) seq_world_coloring = false;
+        if (env_is("R2D_TEST_SMALL_BUFFERS", "1")) test_small_buffers = true;
+        if (const char* e = getenv("R2D_WORLD_CACHE")) {                     // tests: records per world kept in shared memory
+            world_rec_cap = (uint32_t)atoi(e);
+            world_pt1_cap = world_rec_cap / 2;
+            world_cache_forced = true;
+        }
         return R2D_OK;
     }
 
@@ -525,10 +520,8 @@ struct CudaBatch : BatchBase {
         d.adj_cnt = (uint32_t*)(zeroed.p + off_adj_cnt);
         d.cstate = (uint4*)(zeroed.p + off_cstate);
         d.adj_prio = adj_prio.p;
-        d.flow_sleep_unit = flow_sleep_unit;
         d.tile_bodies = tile_bodies_now;
-        d.inv_body = nullptr;
-        d.world_hdr = world_hdr_now ? (uint2*)s_dep.p : nullptr; d.world_slot0 = 0;
+        d.world_fused = world_fused_now ? 1u : 0u;
         d.body_shared = (uint32_t*)(zeroed.p + off_body_shared);
         d.own_words = (d.n_bodies + 31u) / 32u;
         d.own_bits = (uint32_t*)(zeroed.p + off_own_bits);
@@ -538,7 +531,7 @@ struct CudaBatch : BatchBase {
         d.s_dep = s_dep.p;
         d.n_joints = (uint32_t)image.j_hdr.size();
         d.j_hdr = j_hdr.p; d.j_par = j_par.p; d.j_vec = j_vec.p;
-        d.color_smem = 0; d.wait_mode = wait_mode; d.wait_probe = wait_probe; d.wait_spin_lag = wait_spin_lag; d.wait_sleep_unit = wait_sleep_unit; d.wait_sleep_max = wait_sleep_max;
+        d.color_smem = 0;
     }
 
     int reserve_entries(size_t n) {
@@ -564,6 +557,31 @@ struct CudaBatch : BatchBase {
             cap_pairs = std::min(cap_pairs, c);
         cap_pairs -= pad;
         return R2D_OK;
+    }
+
+    // Shared-memory budget of k_world_solve: room for the largest world of the previous call plus 1/8 (a world that still
+    // does not fit keeps its records in its slice of the global arrays, so this is a performance choice only), rounded
+    // so that a whole number of CTAs fills an SM.
+    static constexpr size_t WORLD_SMEM_MAX = 227 * 1024 - 4096;   // (the kernel also has a few KB of static shared memory)
+    size_t world_cache(uint32_t& nb_cap, uint32_t& R, uint32_t& R2) {
+        nb_cap = (max_world_bodies + 3u) & ~3u;
+        if (world_cache_forced) {
+            R = world_rec_cap;
+            R2 = world_pt1_cap;
+        } else if (seen_world_m == 0) {   // first call: a guess (about two manifolds per body in a settled box)
+            R = 2 * nb_cap;
+            R2 = nb_cap;
+        } else {
+            R = seen_world_m + seen_world_m / 8 + 8;
+            R2 = seen_world_k2 + seen_world_k2 / 8 + 8;
+        }
+        R = (R + 3u) & ~3u;
+        R2 = (R2 + 3u) & ~3u;
+        while (world_smem_bytes(nb_cap, R, R2) > WORLD_SMEM_MAX && (R > 0 || R2 > 0)) {
+            R = R / 2 & ~3u;
+            R2 = R2 / 2 & ~3u;
+        }
+        return world_smem_bytes(nb_cap, R, R2);
     }
 
     int launch_persistent(float sub_dt, uint32_t S, uint32_t I) {
@@ -615,8 +633,7 @@ struct CudaBatch : BatchBase {
             (st = pose.reserve(nb)) || (st = view.reserve(4 * (size_t)nb)) || (st = ncells.reserve(nb)) || (st = bkt.reserve(nb)) ||  (st = bucket_cnt.reserve(2 * (size_t)T + 1, true, stream)) ||
             (st = bucket_start.reserve(2 * (size_t)T + 2)) || (st = fcell.reserve(nb)) || (st = fine_cand.reserve(2 * (size_t)nb)) || (st = pair_cnt.reserve((size_t)nb + 3)) || (st = ent_off.reserve((size_t)T + 2)) || (st = work.reserve(2 * (size_t)T + 2)))
             return st;
-        // R2D_TEST_SMALL_BUFFERS=1 (tests): start with buffers that are too small, so that the grow-and-redo path runs
-        const bool tiny = getenv("R2D_TEST_SMALL_BUFFERS") && atoi(getenv("R2D_TEST_SMALL_BUFFERS")) != 0;
+        const bool tiny = test_small_buffers;   // (tests) so that the grow-and-redo path runs
         if (cap_entries == 0 && (st = reserve_entries(tiny ? 64 : (size_t)nb * 3 + 4096))) return st;
         if (cap_pairs == 0 && (st = reserve_pairs(tiny ? 64 : (size_t)nb * 6 + 4096))) return st;
 
@@ -638,7 +655,7 @@ struct CudaBatch : BatchBase {
         const bool use_world_solver = persistent_solver && world_solver && image.j_hdr.empty() &&
                                       max_world_bodies <= WORLD_MAX_BODIES &&
                                       worlds.size() >= (size_t)n_sms / 2;  // enough worlds to fill the GPU with one CTA each
-        world_hdr_now = use_world_solver && max_world_bodies <= 65536u;
+        world_fused_now = use_world_solver;
         const uint32_t tile_b = (nb + (uint32_t)n_sms - 1) / (uint32_t)n_sms;
         const bool use_tile_solver = persistent_solver && tile_solver && !tile_declined && !use_world_solver && image.j_hdr.empty() &&
                                      tile_b <= TILE_MAX_BODIES && nb >= (uint32_t)n_sms * 8;
@@ -677,7 +694,7 @@ struct CudaBatch : BatchBase {
                 const uint32_t blocks = (uint32_t)std::min<size_t>(worlds.size(), (size_t)n_sms * 8);
                 if (seq_world_coloring) {
                     const uint32_t smem_bodies = max_world_bodies;
-                    const uint32_t export_used = use_world_solver ? 0u : 1u;
+                    const uint32_t export_used = use_world_solver ? 0u : 1u;   // colour masks for the dataflow sweep
                     prof_begin(R2D_KCLASS_COLORING);
                     k_color_worlds_seq<<<blocks, WORLD_TPB, (size_t)smem_bodies * COLOR_WORDS * 8, stream>>>(d, smem_bodies, export_used);
                     prof_end();
@@ -693,19 +710,25 @@ struct CudaBatch : BatchBase {
                 launches += 1;
             }
             // owner bitmaps -> popcounts -> scan = position of every manifold in the colour-sorted, spatially ordered records
-            // (the owner bitmaps are set by the colouring kernels themselves, at the moment a manifold gets its colour)
-            {   // popcounts of the owner bitmaps (and the number of colours) are computed inside the scan
+            // (the owner bitmaps are set by the colouring kernels themselves, at the moment a manifold gets its colour);
+            // k_world_solve places and pre-steps the manifolds of its world itself
+            if (!use_world_solver) {   // popcounts of the owner bitmaps (and the number of colours) are computed inside the scan
                 const uint32_t n_max = (uint32_t)((own_w + 1) * MAX_COLORS);
                 const uint32_t tiles = (n_max + SCAN_TILE - 1) / SCAN_TILE + 1;
                 if (tiles + 1 > scan_state_cap) return R2D_ERR_CUDA;
                 R2D_LAUNCH(R2D_KCLASS_COLORING, k_scan_owners, tiles, SCAN_TPB, d, scan_state(2), (uint32_t)(scan_state_cap - 1));
+                R2D_LAUNCH(R2D_KCLASS_COLORING, k_partition_prestep, grid_for(cap_pairs), TPB, d);
             }
-            R2D_LAUNCH(R2D_KCLASS_COLORING, k_partition_prestep, grid_for(cap_pairs), TPB, d);
             // ---- substeps: one persistent cooperative kernel (colour ranges are read on the device) ----
             if ((st = join_forces())) return st;  // forces written for this step have arrived (first reader of `frc`)
             if (use_world_solver) {
+                uint32_t nb_cap = 0, R = 0, R2 = 0;
+                const size_t smem = world_cache(nb_cap, R, R2);
                 const uint32_t blocks = (uint32_t)std::min<size_t>(worlds.size(), (size_t)n_sms * 16);
-                R2D_LAUNCH(R2D_KCLASS_SOLVE_CONTACTS, k_solve_worlds, blocks, world_solve_tpb, d, sub_dt, S, I);
+                prof_begin(R2D_KCLASS_SOLVE_CONTACTS);
+                k_world_solve<<<blocks, WORLD_SOLVE_TPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, R2);
+                prof_end();
+                launches += 1;
             } else if (use_tile_solver) {
                 prof_begin(R2D_KCLASS_SOLVE_CONTACTS);
                 uint32_t S_ = S, I_ = I, cache = TILE_CACHE_TASKS, max_tasks = tile_max_tasks;
@@ -759,6 +782,8 @@ struct CudaBatch : BatchBase {
         }
         const Counters c = pinned->counters;
         last_pairs = c.n_pairs;
+        seen_world_m = c.max_world_m;
+        seen_world_k2 = c.max_world_k2;
         stats.n_buckets = T;
         stats.n_entries = c.n_entries;
         stats.n_pairs = c.n_pairs;
@@ -766,12 +791,6 @@ struct CudaBatch : BatchBase {
         stats.n_points = c.n_points;
         stats.n_colors = c.n_colors;
         stats.n_color_rounds = c.n_rounds;
-        if (getenv("R2D_STAMPS")) {
-            fprintf(stderr, "[r2d stamps ns]");
-            for (uint32_t k = 1; k < c.n_stamps && k < 10; ++k)
-                fprintf(stderr, " %u:%lld", k, c.stamp[k] ? (long long)(c.stamp[k] - c.stamp[0]) : -1LL);
-            fprintf(stderr, "\n");
-        }
         if (c.err & ERR_GRID_RANGE) {
             g_cuda_error = "a body AABB covers an unreasonable number of grid cells (NaN/inf pose?)";
             return R2D_ERR_GRID_RANGE;
