@@ -34,7 +34,7 @@ __device__ __forceinline__ uint32_t live_pairs(const Dev& d) {
 }
 // an over-capacity attempt is abandoned (the host grows the buffers and redoes the broadphase)
 __device__ __forceinline__ bool overflowed(const Dev& d) {
-    return d.counters->n_entries > d.cap_entries || d.counters->n_pairs > d.cap_pairs;
+    return d.counters->n_entries > d.cap_entries || d.counters->n_pairs > d.cap_pairs || d.counters->broad_fallback != 0u;
 }
 
 // ---- K2 / K4: per-body cell walk; FILL = false counts (SpatialHash.zig:46-49), true fills (:62-68) -------------------------

@@ -73,8 +73,8 @@ struct Counters {
     uint32_t flow_fail;      // set inside the dataflow colouring: more than FLOW_COLORS colours needed (or a stall)
     uint32_t flow_used;      // the colours of this step come from the dataflow colouring (masks in cstate, not in used)
     uint32_t tile_fallback;  // k_solve_tiles declined (a tile has too many bodies / tasks): the host runs k_solve_persistent
-    uint32_t max_world_m;    // k_world_solve: most manifolds / most two-point manifolds found in one world of the batch (the
-    uint32_t max_world_k2;   // host sizes the shared-memory record cache of the next call from them)
+    uint32_t max_world_m;    // k_world_solve: most slots (contact points) found in one world of the batch (the host sizes the
+    uint32_t broad_fallback; // shared-memory cache of the next call from it) | k_world_broad: a world's grid does not fit
 };
 
 // Everything the kernels need, passed by value.

@@ -88,8 +88,8 @@ struct CudaBatch : BatchBase {
     uint32_t solve_smem_slots = SOLVE_SMEM_SLOTS;
     bool test_small_buffers = false;  // R2D_TEST_SMALL_BUFFERS=1 (tests): start with buffers that are too small
     bool world_cache_forced = false;
-    uint32_t world_rec_cap = 0, world_pt1_cap = 0;   // shared-memory record cache of k_world_solve (per world), see world_cache()
-    uint32_t seen_world_m = 0, seen_world_k2 = 0;    // largest world of the previous call
+    uint32_t world_rec_cap = 0;       // R2D_WORLD_CACHE: slots per world kept in shared memory by k_world_solve, see world_cache()
+    uint32_t seen_world_m = 0;        // slots of the largest world of the previous call
     bool persistent_solver = true;
     bool world_solver = true;       // CTA-per-world shared-memory solver when every world is small and there are no joints
     uint32_t max_world_bodies = 0;   // false: one launch per colour (kept for A/B measurements)
@@ -109,6 +109,10 @@ struct CudaBatch : BatchBase {
     bool seq_world_coloring = true;   // R2D_WORLD_COLORING=rounds: Jones-Plassmann rounds per world instead of sort + sequential greedy
     bool fine_grid = true;            // R2D_BROADPHASE=buckets: every body through the coarse buckets (the original pipeline)
     bool fine_now = false, ll_now = false;
+    bool world_broad = true;          // k_world_broad for batches of small worlds (R2D_WORLD_BROAD=0: device-wide grid kernels)
+    bool world_broad_declined = false;  // a world's grid did not fit shared memory: device-wide kernels until the next upload
+    uint32_t max_world_large_cells = 0; // grid entries of the large bodies of the widest world (bound from the upload)
+    DBuf<unsigned long long> world_state;
     bool world_fused_now = false;     // this step is solved by k_world_solve (which also places and pre-steps the manifolds)
     // pairs / manifolds
     DBuf<uint2> pairs;
@@ -187,7 +191,8 @@ struct CudaBatch : BatchBase {
         R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bucket_count, TPB, 0));
         pair_blocks = (per_sm < 1 ? 1 : per_sm) * n_sms;  // resident CTAs: a CTA per heavy bucket, a warp per light one, grid-stride
         R2D_CUDA(cudaFuncSetAttribute(k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES));
-        R2D_CUDA(cudaFuncSetAttribute(k_world_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
+        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
+        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
         // Flavour switches for A/B measurements and tests.  Every one of them selects between paths that produce
         // bit-identical results; they are read here once, never inside process().
         auto env_is = [](const char* name, const char* value) {
@@ -202,10 +207,11 @@ struct CudaBatch : BatchBase {
         if (env_is("R2D_ZERO_COPY", "0")) zero_copy = false;                 // bulk reads through the staging buffer
         if (env_is("R2D_BROADPHASE", "buckets")) fine_grid = false;          // every body through the hashed 4 m buckets
         if (env_is("R2D_WORLD_COLORING", "rounds")) seq_world_coloring = false;
+        if (env_is("R2D_WORLD_BROAD", "0")) world_broad = false;
+        R2D_CUDA(cudaFuncSetAttribute(k_world_broad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
         if (env_is("R2D_TEST_SMALL_BUFFERS", "1")) test_small_buffers = true;
         if (const char* e = getenv("R2D_WORLD_CACHE")) {                     // tests: records per world kept in shared memory
             world_rec_cap = (uint32_t)atoi(e);
-            world_pt1_cap = world_rec_cap / 2;
             world_cache_forced = true;
         }
         return R2D_OK;
@@ -292,6 +298,7 @@ struct CudaBatch : BatchBase {
         R2D_CUDA(cudaStreamSynchronize(stream));  // the image vectors are pageable and may change after we return
         last_pairs = 0;
         tile_declined = false;
+        world_broad_declined = false;
         max_world_bodies = 0;
         for (size_t w = 0; w + 1 < image.world_base.size(); ++w)
             max_world_bodies = std::max(max_world_bodies, image.world_base[w + 1] - image.world_base[w]);
@@ -559,29 +566,21 @@ struct CudaBatch : BatchBase {
         return R2D_OK;
     }
 
-    // Shared-memory budget of k_world_solve: room for the largest world of the previous call plus 1/8 (a world that still
-    // does not fit keeps its records in its slice of the global arrays, so this is a performance choice only), rounded
-    // so that a whole number of CTAs fills an SM.
-    static constexpr size_t WORLD_SMEM_MAX = 227 * 1024 - 4096;   // (the kernel also has a few KB of static shared memory)
-    size_t world_cache(uint32_t& nb_cap, uint32_t& R, uint32_t& R2) {
+    // Shared-memory budget of k_world_solve: room for the slots (one per contact point) of the largest world of the
+    // previous call plus 1/32.  A world that still does not fit keeps its slots in its slice of the global record
+    // arrays, so this is a performance choice only.
+    static constexpr size_t WORLD_SMEM_MAX = 227 * 1024 - 4096;   // (the kernel also has 3 KB of static shared memory)
+    size_t world_cache(uint32_t& nb_cap, uint32_t& R) {
         nb_cap = (max_world_bodies + 3u) & ~3u;
-        if (world_cache_forced) {
+        if (world_cache_forced)
             R = world_rec_cap;
-            R2 = world_pt1_cap;
-        } else if (seen_world_m == 0) {   // first call: a guess (about two manifolds per body in a settled box)
-            R = 2 * nb_cap;
-            R2 = nb_cap;
-        } else {
-            R = seen_world_m + seen_world_m / 8 + 8;
-            R2 = seen_world_k2 + seen_world_k2 / 8 + 8;
-        }
+        else if (seen_world_m == 0)   // first call: a guess (about two contact points per body in a settled box)
+            R = 2 * nb_cap + 32;
+        else
+            R = seen_world_m + seen_world_m / 32 + 4;
         R = (R + 3u) & ~3u;
-        R2 = (R2 + 3u) & ~3u;
-        while (world_smem_bytes(nb_cap, R, R2) > WORLD_SMEM_MAX && (R > 0 || R2 > 0)) {
-            R = R / 2 & ~3u;
-            R2 = R2 / 2 & ~3u;
-        }
-        return world_smem_bytes(nb_cap, R, R2);
+        while (world_smem_bytes(nb_cap, R) > WORLD_SMEM_MAX && R > 0) R = R / 2 & ~3u;
+        return world_smem_bytes(nb_cap, R);
     }
 
     int launch_persistent(float sub_dt, uint32_t S, uint32_t I) {
@@ -614,7 +613,7 @@ struct CudaBatch : BatchBase {
         {   // layout of the zeroed arena for this body count
             auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
             const size_t max_scan = std::max<size_t>(2 * (size_t)T + 1, (own_w + 1) * MAX_COLORS + 2);
-            scan_state_cap = (max_scan + SCAN_TILE - 1) / SCAN_TILE + 4;
+            scan_state_cap = std::max((max_scan + SCAN_TILE - 1) / SCAN_TILE + 4, worlds.size() + 4);   // (k_world_broad: one word per world)
             size_t o = 0;
             off_counters = o; o = align(o + sizeof(Counters));
             off_color_misc = o; o = align(o + (MAX_COLORS * 3 + 1 + MAX_COLOR_ROUNDS) * 4);
@@ -660,26 +659,43 @@ struct CudaBatch : BatchBase {
         const bool use_tile_solver = persistent_solver && tile_solver && !tile_declined && !use_world_solver && image.j_hdr.empty() &&
                                      tile_b <= TILE_MAX_BODIES && nb >= (uint32_t)n_sms * 8;
         tile_bodies_now = use_tile_solver ? tile_b : 0u;
+        // broadphase of a batch of small worlds: per-world CTAs with the grid in shared memory, when the fine grid applies
+        // (no dynamic large bodies) and the tables of the largest world fit
+        const uint32_t wb_nb_cap = (max_world_bodies + 3u) & ~3u, wb_tw_cap = grid_mult() * max_world_bodies;
+        const uint32_t wb_ent_cap = wb_nb_cap + 512u;
+        const size_t wb_smem = world_broad_smem_bytes(wb_nb_cap, wb_tw_cap, wb_ent_cap);
+        bool use_world_broad = world_broad && !world_broad_declined && many_small_worlds && fine_now && !ll_now &&
+                               max_world_bodies <= WORLD_MAX_BODIES && wb_smem <= 100 * 1024 &&
+                               worlds.size() + 2 <= scan_state_cap;
         for (int attempt = 0;; ++attempt) {
             fill_dev();
             R2D_CUDA(cudaMemsetAsync(zeroed.p, 0, zeroed_bytes, stream));  // counters, colour tables, scan states, masks
             // ---- broadphase ----
-            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_grid_cells<false>, grid_for(nb), TPB, d);
-            if ((st = scan(d.bucket_cnt, d.bucket_start, nullptr, fine_now ? 2 * T : T, &d.counters->n_entries, R2D_KCLASS_BROADPHASE, 0))) return st;
-            R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_grid_cells<true>, grid_for(nb), TPB, d);
-            if (!fine_now || ll_now) {
-                R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_list_buckets, grid_for(T), TPB, d);
-                R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_sort_buckets, pair_blocks, TPB, d);
-                // pairs per BUCKET (one warp each) -> scan over the T buckets -> write at the scanned offsets
-                R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_bucket_count, pair_blocks, TPB, d);
-                if ((st = scan(d.ent_off, d.ent_off, nullptr, T, &d.counters->n_pairs, R2D_KCLASS_BROADPHASE, 1))) return st;
-                R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_bucket_write, pair_blocks, TPB, d);
-            }
-            if (fine_now) {
-                // pairs per small BODY (8 lanes each) -> scan over the bodies -> write at the scanned offsets
-                R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_fine_pairs<false>, grid_for(nb), TPB, d);
-                if ((st = scan(d.pair_cnt, d.pair_cnt, nullptr, nb + 1, &d.counters->n_pairs, R2D_KCLASS_BROADPHASE, 3))) return st;
-                R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_fine_pairs<true>, grid_for(nb), TPB, d);
+            if (use_world_broad) {   // one CTA per world, the world's grid in shared memory (r2d_world.cuh)
+                const uint32_t blocks = (uint32_t)std::min<size_t>(worlds.size(), (size_t)n_sms * 16);
+                prof_begin(R2D_KCLASS_BROADPHASE);
+                k_world_broad<<<blocks, WORLD_BROAD_TPB, wb_smem, stream>>>(d, wb_nb_cap, wb_tw_cap, wb_ent_cap, scan_state(0),
+                                                                             (uint32_t*)(scan_state(0) + scan_state_cap - 1));
+                prof_end();
+                launches += 1;
+            } else {
+                R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_grid_cells<false>, grid_for(nb), TPB, d);
+                if ((st = scan(d.bucket_cnt, d.bucket_start, nullptr, fine_now ? 2 * T : T, &d.counters->n_entries, R2D_KCLASS_BROADPHASE, 0))) return st;
+                R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_grid_cells<true>, grid_for(nb), TPB, d);
+                if (!fine_now || ll_now) {
+                    R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_list_buckets, grid_for(T), TPB, d);
+                    R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_sort_buckets, pair_blocks, TPB, d);
+                    // pairs per BUCKET (one warp each) -> scan over the T buckets -> write at the scanned offsets
+                    R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_bucket_count, pair_blocks, TPB, d);
+                    if ((st = scan(d.ent_off, d.ent_off, nullptr, T, &d.counters->n_pairs, R2D_KCLASS_BROADPHASE, 1))) return st;
+                    R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_bucket_write, pair_blocks, TPB, d);
+                }
+                if (fine_now) {
+                    // pairs per small BODY (8 lanes each) -> scan over the bodies -> write at the scanned offsets
+                    R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_fine_pairs<false>, grid_for(nb), TPB, d);
+                    if ((st = scan(d.pair_cnt, d.pair_cnt, nullptr, nb + 1, &d.counters->n_pairs, R2D_KCLASS_BROADPHASE, 3))) return st;
+                    R2D_LAUNCH(R2D_KCLASS_BROADPHASE, k_fine_pairs<true>, grid_for(nb), TPB, d);
+                }
             }
             // ---- narrowphase ----
             // larger re-deal tiles sort the shape classes better; small pair counts keep one pair per thread (more CTAs)
@@ -722,11 +738,14 @@ struct CudaBatch : BatchBase {
             // ---- substeps: one persistent cooperative kernel (colour ranges are read on the device) ----
             if ((st = join_forces())) return st;  // forces written for this step have arrived (first reader of `frc`)
             if (use_world_solver) {
-                uint32_t nb_cap = 0, R = 0, R2 = 0;
-                const size_t smem = world_cache(nb_cap, R, R2);
+                uint32_t nb_cap = 0, R = 0;
+                const size_t smem = world_cache(nb_cap, R);
                 const uint32_t blocks = (uint32_t)std::min<size_t>(worlds.size(), (size_t)n_sms * 16);
                 prof_begin(R2D_KCLASS_SOLVE_CONTACTS);
-                k_world_solve<<<blocks, WORLD_SOLVE_TPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, R2);
+                if (max_world_bodies <= 2u * WORLD_SOLVE_TPB)
+                    k_world_solve<2><<<blocks, WORLD_SOLVE_TPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R);
+                else
+                    k_world_solve<4><<<blocks, WORLD_SOLVE_TPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R);
                 prof_end();
                 launches += 1;
             } else if (use_tile_solver) {
@@ -756,6 +775,12 @@ struct CudaBatch : BatchBase {
             R2D_CUDA(cudaStreamSynchronize(stream));
             R2D_CUDA(cudaGetLastError());
             const Counters& c = pinned->counters;
+            if (c.broad_fallback && use_world_broad) {   // a world's grid did not fit shared memory: nothing was modified
+                if (attempt >= 4) return R2D_ERR_CUDA;
+                world_broad_declined = true;
+                use_world_broad = false;
+                continue;
+            }
             if (c.n_entries > cap_entries || c.n_pairs > cap_pairs) {
                 if (attempt >= 4) {
                     g_cuda_error = "broadphase buffers failed to converge";
@@ -783,7 +808,6 @@ struct CudaBatch : BatchBase {
         const Counters c = pinned->counters;
         last_pairs = c.n_pairs;
         seen_world_m = c.max_world_m;
-        seen_world_k2 = c.max_world_k2;
         stats.n_buckets = T;
         stats.n_entries = c.n_entries;
         stats.n_pairs = c.n_pairs;

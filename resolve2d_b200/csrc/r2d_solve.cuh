@@ -82,6 +82,46 @@ struct BodyVel {
     float ang;
 };
 
+// One contact point of calculateImpulses (collision.zig:146-206, the body of its point loop) up to — not including — the
+// accumulation into the bodies' scratch impulses: returns false when the point is skipped (:154-158 depth >= 0, which
+// also zeroes its accumulated impulses; :176 impulse below MIN_MANIFOLD_IMPULSE, Q6), else true with `dp` = the impulse
+// (applied negatively to body 1, positively to body 2) and `acc` updated.  Both points of a manifold see the same,
+// pre-loop body velocities (Q8).
+R2D_HD bool contact_point_impulse(const ContactConst& c, const ContactPointConst& p, v2& acc, v2 vlinear_1, float omega1,
+                                  v2 vlinear_2, float omega2, v2& dp) {
+    if (p.depth >= 0.0f) {  // :154-158
+        acc = mk2(0.0f, 0.0f);
+        return false;
+    }
+    const v2 r1 = p.r1, r2 = p.r2;
+    const v2 vrot_1 = mk2(fmul(-r1.y, omega1), fmul(r1.x, omega1));
+    const v2 v1 = add2(vlinear_1, vrot_1);
+    const v2 vrot_2 = mk2(fmul(-r2.y, omega2), fmul(r2.x, omega2));
+    const v2 v2_ = add2(vlinear_2, vrot_2);
+    const v2 dv = sub2(v1, v2_);
+
+    float num = fadd(dot2(dv, c.normal), p.bias);  // :172-173, bias evaluated once per call (contact_bias)
+    const float pn = fmul(num, p.mass_n);
+    if (pn < MIN_MANIFOLD_IMPULSE) return false;  // :176 (Q6)
+
+    num = dot2(dv, c.tangent);
+    const float pt = fmul(num, p.mass_t);
+
+    const float new_acc_pn = fmax_z(0.0f, fadd(acc.x, pn));
+    const float applied_pn = fsub(new_acc_pn, acc.x);
+    acc.x = new_acc_pn;
+
+    const float max_pt = fmul(c.friction, fabs_z(acc.x));
+    const float new_acc_pt = clamp_z(fadd(acc.y, pt), -max_pt, max_pt);
+    const float applied_pt = fsub(new_acc_pt, acc.y);
+    acc.y = new_acc_pt;
+
+    const v2 pn_vec = scale2(c.normal, applied_pn);
+    const v2 pt_vec = scale2(c.tangent, applied_pt);
+    dp = add2(pn_vec, pt_vec);
+    return true;
+}
+
 // calculateImpulses (collision.zig:135-218).  acc[k] = {accumulated_pn, accumulated_pt} persists for the whole
 // process() call (Q7).  Both points see the pre-loop velocities and are applied once at the end (Q8).
 R2D_HD void solve_contact(const ContactConst& c, int n_points, const ContactPointConst* pts, v2* acc, bool static1,
@@ -97,45 +137,15 @@ R2D_HD void solve_contact(const ContactConst& c, int n_points, const ContactPoin
 #pragma unroll
     for (int k = 0; k < 2; ++k) {  // fully unrolled: pts[] / acc[] stay in registers (no local-memory arrays)
         if (k >= n_points) break;
-        const ContactPointConst& p = pts[k];
-        if (p.depth >= 0.0f) {  // :154-158
-            acc[k] = mk2(0.0f, 0.0f);
-            continue;
-        }
-        const v2 r1 = p.r1, r2 = p.r2;
-        const v2 vrot_1 = mk2(fmul(-r1.y, omega1), fmul(r1.x, omega1));
-        const v2 v1 = add2(vlinear_1, vrot_1);
-        const v2 vrot_2 = mk2(fmul(-r2.y, omega2), fmul(r2.x, omega2));
-        const v2 v2_ = add2(vlinear_2, vrot_2);
-        const v2 dv = sub2(v1, v2_);
-
-        float num = fadd(dot2(dv, c.normal), p.bias);  // :172-173, bias evaluated once per call (contact_bias)
-        const float pn = fmul(num, p.mass_n);
-        if (pn < MIN_MANIFOLD_IMPULSE) continue;  // :176 (Q6)
-
-        num = dot2(dv, c.tangent);
-        const float pt = fmul(num, p.mass_t);
-
-        const float new_acc_pn = fmax_z(0.0f, fadd(acc[k].x, pn));
-        const float applied_pn = fsub(new_acc_pn, acc[k].x);
-        acc[k].x = new_acc_pn;
-
-        const float max_pt = fmul(c.friction, fabs_z(acc[k].x));
-        const float new_acc_pt = clamp_z(fadd(acc[k].y, pt), -max_pt, max_pt);
-        const float applied_pt = fsub(new_acc_pt, acc[k].y);
-        acc[k].y = new_acc_pt;
-
-        const v2 pn_vec = scale2(c.normal, applied_pn);
-        const v2 pt_vec = scale2(c.tangent, applied_pt);
-        const v2 dp = add2(pn_vec, pt_vec);
-
+        v2 dp;
+        if (!contact_point_impulse(c, pts[k], acc[k], vlinear_1, omega1, vlinear_2, omega2, dp)) continue;
         if (!static1) {
             lin1 = sub2(lin1, dp);
-            rot1 = fsub(rot1, cross2(r1, dp));
+            rot1 = fsub(rot1, cross2(pts[k].r1, dp));
         }
         if (!static2) {
             lin2 = add2(lin2, dp);
-            rot2 = fadd(rot2, cross2(r2, dp));
+            rot2 = fadd(rot2, cross2(pts[k].r2, dp));
         }
     }
     b1.mom = add2(b1.mom, lin1);   // :208-212

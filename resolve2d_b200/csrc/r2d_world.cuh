@@ -1,22 +1,29 @@
 // r2d_world.cuh — batches of small independent worlds (BASELINE config 5: 4,096 worlds x 256 bodies): ONE CTA runs the
-// whole substep loop of lib.zig:199-250 for ONE world out of shared memory.
+// whole substep loop of lib.zig:199-250 for ONE world out of shared memory and registers.
 //
-//   stage   bodies of the world (pose, momentum, force, 1/mass, 1/inertia, mu)            global -> shared, once
+//   stage   bodies of the world: momentum, 1/mass, 1/inertia -> shared; pose, force, mass, inertia -> registers of the
+//           thread that integrates the body                                                global -> on-chip, once
 //           the world's manifolds (its candidate pairs are a contiguous slice of the pair list): counting sort by colour
 //           in shared memory, preStep (collision.zig:102-133) and the Baumgarte bias evaluated on the way (inputs are
-//           constant during a call, Q5)                                                   global -> shared, once
-//   S x {   positions of the previous substep + gravity + momentum (lib.zig:200-216,238-249)    shared only
+//           constant during a call, Q5); ONE SLOT PER CONTACT POINT                         global -> shared, once
+//   S x {   positions of the previous substep + gravity + momentum (lib.zig:200-216,238-249)    registers / shared
 //           I x colours x { calculateImpulses (collision.zig:135-218), __syncthreads() }        shared only   }
-//   export  pos / momentum / force / AABB                                                 shared -> global, once
+//   export  pos / momentum / force / AABB                                                 on-chip -> global, once
 //
 // No record, accumulated impulse or momentum word goes through L2 between the staging and the export, there is no
 // inter-CTA synchronisation, and no separate partition / pre-step kernel (k_scan_owners, k_partition_prestep and the
 // owner bitmaps are not used on this path).  Manifolds of one colour share no non-static body, so their order inside a
 // colour is irrelevant: every body sees its contacts in ascending colour, as everywhere else — bit-identical results.
 //
-// A world whose manifolds do not fit the shared-memory cache (sized by the host from the largest world of the previous
-// call) runs the same code with its records in ITS OWN slice [p0, p0 + M) of the global record arrays (M <= P: the slice
-// of its candidate pairs), so capacity never limits correctness.
+// One lane per contact POINT: the two points of a manifold see the same pre-loop velocities (Q8) and are independent
+// until their impulses are summed, so they sit on two adjacent lanes; the second lane hands its impulse to the first
+// (5 shuffles), which applies "point 0, then point 1" in the reference's order.  Every lane of every warp then runs the
+// same ~130-instruction one-point chain — a sweep phase is bound by the latency of its longest chain, and with one
+// THREAD per manifold nearly every warp held a two-point manifold and ran both points back to back.
+//
+// A world whose slots do not fit the shared-memory cache (sized by the host from the largest world of the previous
+// call) runs the same code with its records in ITS OWN slice of the global record arrays (slot s -> array set s & 1,
+// index p0 + s / 2: at most two slots per candidate pair), so capacity never limits correctness.
 #pragma once
 #include "r2d_pipeline.cuh"
 
@@ -24,80 +31,48 @@ namespace r2d {
 
 constexpr uint32_t WORLD_MAX_BODIES = 512;
 constexpr int WORLD_SOLVE_TPB = 128;
-// record header: x = ref | inc << 16 (world-local body slots); y = flags | slot of point 1 << 8
-constexpr uint32_t WS_NP_MASK = 3u, WS_ST1 = 4u, WS_ST2 = 8u, WS_D0 = 16u, WS_D1 = 32u;
-constexpr uint32_t WORLD_REC_BYTES = 8 + 3 * 16;     // hdr, nfb, r0, ma0
-constexpr uint32_t WORLD_PT1_BYTES = 2 * 16 + 4;     // r1, ma1, b1
+// slot header: ref | inc << 10 (world-local body slots) | flags << 20
+constexpr uint32_t WS_ST1 = 1u << 20, WS_ST2 = 1u << 21;
+constexpr uint32_t WS_SKIP = 1u << 22;    // depth >= 0: the point is skipped and its accumulated impulses are zeroed (:154-158)
+constexpr uint32_t WS_NOPT = 1u << 23;    // a manifold without points (or a padding lane): contributes `momentum += 0` only
+constexpr uint32_t WS_B = 1u << 24;       // second point of a manifold: the lane only feeds the lane before it
+constexpr uint32_t WS_A = 1u << 25;       // first point of a two-point manifold
+constexpr uint32_t WORLD_SLOT_BYTES = 4 + 3 * 16;    // hdr, nfb, r, ma
+constexpr uint32_t WORLD_BODY_BYTES = 16 + 4 + 1;    // momentum word, 1 / inertia, static flag
 
-struct WorldRecs {
-    uint2* hdr;      // see above
-    float4* nfb;     // normal.x, normal.y, friction, bias of point 0
-    float4* r0;      // point 0: r1.x, r1.y, r2.x, r2.y
-    float4* ma0;     // point 0: mass_n, mass_t, accumulated_pn, accumulated_pt
-    float4* r1;      // point 1 (two-point manifolds only, own pool)
-    float4* ma1;
-    float* b1;       // bias of point 1
+__host__ __device__ inline size_t world_smem_bytes(uint32_t nb_cap, uint32_t R) {
+    return (size_t)nb_cap * 24 + (size_t)R * WORLD_SLOT_BYTES + 16;   // (nb_cap is a multiple of 4: the byte flags round up to 4 per body)
+}
+
+// where the slots of a world live
+template <bool SMEM>
+struct WorldSlots;
+template <>
+struct WorldSlots<true> {
+    uint32_t* hdr_;
+    float4 *nfb_, *r_, *ma_;
+    __device__ __forceinline__ uint32_t& hdr(uint32_t s) const { return hdr_[s]; }
+    __device__ __forceinline__ float4& nfb(uint32_t s) const { return nfb_[s]; }   // normal.x, normal.y, friction, bias
+    __device__ __forceinline__ float4& r(uint32_t s) const { return r_[s]; }       // r1.x, r1.y, r2.x, r2.y
+    __device__ __forceinline__ float4& ma(uint32_t s) const { return ma_[s]; }     // mass_n, mass_t, accumulated_pn, accumulated_pt
+};
+template <>
+struct WorldSlots<false> {   // even slots in one set of global arrays, odd slots in another, both at the world's pair slice
+    uint32_t* hdr_[2];
+    float4 *nfb_[2], *r_[2], *ma_[2];
+    __device__ __forceinline__ uint32_t& hdr(uint32_t s) const { return hdr_[s & 1u][s >> 1]; }
+    __device__ __forceinline__ float4& nfb(uint32_t s) const { return nfb_[s & 1u][s >> 1]; }
+    __device__ __forceinline__ float4& r(uint32_t s) const { return r_[s & 1u][s >> 1]; }
+    __device__ __forceinline__ float4& ma(uint32_t s) const { return ma_[s & 1u][s >> 1]; }
 };
 
-__host__ __device__ inline size_t world_smem_bytes(uint32_t nb_cap, uint32_t R, uint32_t R2) {
-    return (size_t)nb_cap * (3 * 16 + 8 + 8) + (size_t)R * WORLD_REC_BYTES + (size_t)R2 * WORLD_PT1_BYTES + 16;
-}
-
-// one manifold of the current colour (collision.zig:135-218); `rc` is shared or global memory
-__device__ __forceinline__ void world_sweep_record(const WorldRecs& rc, uint32_t l, float4* s_mom, const float2* s_inv) {
-    const uint2 h = rc.hdr[l];
-    const uint32_t i1 = h.x & 0xFFFFu, i2 = h.x >> 16;
-    const float4 nfb = rc.nfb[l], r = rc.r0[l], ma = rc.ma0[l];
-    const float4 m1 = s_mom[i1], m2 = s_mom[i2];
-    const float2 v1 = s_inv[i1], v2_ = s_inv[i2];
-    const int np = (int)(h.y & WS_NP_MASK);
-    const bool st1 = (h.y & WS_ST1) != 0, st2 = (h.y & WS_ST2) != 0;
-    ContactConst c;
-    c.normal = mk2(nfb.x, nfb.y);
-    c.tangent = rot90cw(c.normal);
-    c.friction = nfb.z;
-    c.inv_m1 = v1.x;
-    c.inv_i1 = v1.y;
-    c.inv_m2 = v2_.x;
-    c.inv_i2 = v2_.y;
-    ContactPointConst pts[2];
-    v2 acc[2];
-    pts[0].r1 = mk2(r.x, r.y);
-    pts[0].r2 = mk2(r.z, r.w);
-    pts[0].mass_n = ma.x;
-    pts[0].mass_t = ma.y;
-    pts[0].depth = (h.y & WS_D0) ? 0.0f : -1.0f;   // only the sign test of collision.zig:154 looks at it (the bias is precomputed)
-    pts[0].bias = nfb.w;
-    acc[0] = mk2(ma.z, ma.w);
-    const uint32_t q = h.y >> 8;
-    float4 mb = make_float4(0, 0, 0, 0);
-    if (np > 1) {
-        const float4 rb = rc.r1[q];
-        mb = rc.ma1[q];
-        pts[1].r1 = mk2(rb.x, rb.y);
-        pts[1].r2 = mk2(rb.z, rb.w);
-        pts[1].mass_n = mb.x;
-        pts[1].mass_t = mb.y;
-        pts[1].depth = (h.y & WS_D1) ? 0.0f : -1.0f;
-        pts[1].bias = rc.b1[q];
-        acc[1] = mk2(mb.z, mb.w);
-    }
-    BodyVel b1 = {mk2(m1.x, m1.y), m1.z}, b2 = {mk2(m2.x, m2.y), m2.z};
-    solve_contact(c, np, pts, acc, st1, st2, b1, b2);
-    if (np > 0) *reinterpret_cast<float2*>(&rc.ma0[l].z) = make_float2(acc[0].x, acc[0].y);
-    if (np > 1) *reinterpret_cast<float2*>(&rc.ma1[q].z) = make_float2(acc[1].x, acc[1].y);
-    // static bodies receive a zero impulse in the reference (`momentum += 0`); not writing them is the same value
-    if (!st1) s_mom[i1] = make_float4(b1.mom.x, b1.mom.y, b1.ang, 0.0f);
-    if (!st2) s_mom[i2] = make_float4(b2.mom.x, b2.mom.y, b2.ang, 0.0f);
-}
-
-// Everything after the colour counts are known, for one world whose records live in `rc` (shared memory, or the world's
-// slice of the global record arrays).  Inlined once per storage so that the shared-memory copy uses LDS / STS.
-__device__ __forceinline__ void world_run(const Dev& d, const WorldRecs& rc, uint32_t w, uint32_t b0, uint32_t nb, uint32_t p0,
-                                          uint32_t p1, uint32_t nc, float sub_dt, uint32_t S, uint32_t I, float4* s_mom,
-                                          float4* s_pos, float4* s_frc, float2* s_inv, const uint2* s_fm, uint32_t* s_cnt,
-                                          const uint32_t* s_beg, uint32_t* s_n2p) {
-    const uint32_t tid = threadIdx.x, nth = blockDim.x;
+// Everything after the colour counts are known, for one world.  BPT = bodies a thread integrates (registers).
+template <bool SMEM, int BPT>
+__device__ __forceinline__ void world_run(const Dev& d, const WorldSlots<SMEM>& rc, uint32_t w, uint32_t b0, uint32_t nb,
+                                          uint32_t p0, uint32_t p1, uint32_t nc, float sub_dt, uint32_t S, uint32_t I,
+                                          float4* s_mom, float* s_ii, const unsigned char* s_st, const uint32_t* s_cnt,
+                                          uint32_t* s_cur, const uint32_t* s_beg, float4 (&rp)[BPT], float4 (&rf)[BPT]) {
+    const uint32_t tid = threadIdx.x, nth = blockDim.x, lane = tid & 31u;
     // ---- place + preStep (collision.zig:102-133; once per call, Q5) ----
     for (uint32_t p = p0 + tid; p < p1; p += nth) {
         const uint32_t col = d.m_color[p];
@@ -106,152 +81,233 @@ __device__ __forceinline__ void world_run(const Dev& d, const WorldRecs& rc, uin
         const float4 g0 = d.m_g0[p], g1 = d.m_g1[p], ra = d.m_r0[p];
         const uint32_t np = h.z & 0xFFu;
         const uint32_t i1 = h.x - b0, i2 = h.y - b0;
-        const uint2 fm1 = s_fm[i1], fm2 = s_fm[i2];
-        const float2 v1 = s_inv[i1], v2_ = s_inv[i2];
+        const float mu1 = d.prop[h.x].z, mu2 = d.prop[h.y].z;
         ContactConst c;
         c.normal = mk2(g0.x, g0.y);
-        c.tangent = rot90cw(c.normal);                      // :113
-        c.friction = fsqrt(fmul(u2f(fm1.y), u2f(fm2.y)));   // :114
-        c.inv_m1 = v1.x;
-        c.inv_i1 = v1.y;
-        c.inv_m2 = v2_.x;
-        c.inv_i2 = v2_.y;
-        const uint32_t l = s_beg[col] + atomicAdd(&s_cnt[col], 1u);
-        uint32_t flags = np | ((fm1.x & FLAG_STATIC) ? WS_ST1 : 0u) | ((fm2.x & FLAG_STATIC) ? WS_ST2 : 0u);
+        c.tangent = rot90cw(c.normal);          // :113
+        c.friction = fsqrt(fmul(mu1, mu2));     // :114
+        c.inv_m1 = s_mom[i1].w;                 // static ? 0 : 1 / mass  (prestep_manifold, evaluated per body)
+        c.inv_i1 = s_ii[i1];
+        c.inv_m2 = s_mom[i2].w;
+        c.inv_i2 = s_ii[i2];
+        const uint32_t lb = s_beg[col], n2 = s_cnt[col] >> 16;
+        const uint32_t base = i1 | (i2 << 10) | (s_st[i1] ? WS_ST1 : 0u) | (s_st[i2] ? WS_ST2 : 0u);
         ContactPointConst pc;
         pc.r1 = mk2(ra.x, ra.y);
         pc.r2 = mk2(ra.z, ra.w);
         pc.depth = g1.x;
         pc.mass_n = pc.mass_t = 0.0f;
         if (np > 0) prestep_point(c, pc);
-        if (g1.x >= 0.0f) flags |= WS_D0;
-        rc.nfb[l] = make_float4(c.normal.x, c.normal.y, c.friction, np > 0 ? contact_bias(g1.x, sub_dt) : 0.0f);
-        rc.r0[l] = ra;
-        rc.ma0[l] = make_float4(pc.mass_n, pc.mass_t, 0.0f, 0.0f);
-        if (np > 1) {
-            const uint32_t slot = atomicAdd(s_n2p, 1u);
+        const float bias0 = np > 0 ? contact_bias(g1.x, sub_dt) : 0.0f;
+        const uint32_t f0 = np == 0 ? WS_NOPT : (g1.x >= 0.0f ? WS_SKIP : 0u);
+        if (np <= 1) {
+            const uint32_t s = lb + 2u * n2 + (atomicAdd(&s_cur[col], 0x10000u) >> 16);
+            rc.hdr(s) = base | f0;
+            rc.nfb(s) = make_float4(c.normal.x, c.normal.y, c.friction, bias0);
+            rc.r(s) = ra;
+            rc.ma(s) = make_float4(pc.mass_n, pc.mass_t, 0.0f, 0.0f);
+        } else {
+            const uint32_t s = lb + (atomicAdd(&s_cur[col], 2u) & 0xFFFFu);
+            rc.hdr(s) = base | f0 | WS_A;
+            rc.nfb(s) = make_float4(c.normal.x, c.normal.y, c.friction, bias0);
+            rc.r(s) = ra;
+            rc.ma(s) = make_float4(pc.mass_n, pc.mass_t, 0.0f, 0.0f);
             const float4 rb = d.m_r1[p];
             pc.r1 = mk2(rb.x, rb.y);
             pc.r2 = mk2(rb.z, rb.w);
             pc.depth = g1.y;
             prestep_point(c, pc);
-            if (g1.y >= 0.0f) flags |= WS_D1;
-            rc.r1[slot] = rb;
-            rc.ma1[slot] = make_float4(pc.mass_n, pc.mass_t, 0.0f, 0.0f);
-            rc.b1[slot] = contact_bias(g1.y, sub_dt);
-            flags |= slot << 8;
+            rc.hdr(s + 1u) = base | (g1.y >= 0.0f ? WS_SKIP : 0u) | WS_B;
+            rc.nfb(s + 1u) = make_float4(c.normal.x, c.normal.y, c.friction, contact_bias(g1.y, sub_dt));
+            rc.r(s + 1u) = rb;
+            rc.ma(s + 1u) = make_float4(pc.mass_n, pc.mass_t, 0.0f, 0.0f);
         }
-        rc.hdr[l] = make_uint2(i1 | (i2 << 16), flags);
     }
     // ---- substeps ----
     const uint32_t g_lo = d.grav_off[w], g_hi = d.grav_off[w + 1];
     for (uint32_t s = 0; s < S; ++s) {
-        for (uint32_t i = tid; i < nb; i += nth) {
-            const uint2 fm = s_fm[i];
-            const bool st = (fm.x & FLAG_STATIC) != 0;
-            float4 p = s_pos[i], m = s_mom[i], f = s_frc[i];
+#pragma unroll
+        for (int k = 0; k < BPT; ++k) {
+            const uint32_t i = tid + (uint32_t)k * WORLD_SOLVE_TPB;
+            if (i >= nb) continue;
+            const bool st = s_st[i] != 0;
+            float4 m = s_mom[i];
+            const float inv_m = m.w;
             if (s > 0 && !st) {   // end of substep s - 1 (lib.zig:238-249)
-                position_update(p, m, p.w, f.w, sub_dt);
-                f = make_float4(0.0f, 0.0f, 0.0f, f.w);
-                s_pos[i] = p;
-                s_frc[i] = f;
+                position_update(rp[k], m, rp[k].w, rf[k].w, sub_dt);
+                rf[k] = make_float4(0.0f, 0.0f, 0.0f, rf[k].w);
             }
             if (s + 1 == S) {     // only the last AABB refresh is observable (Q3)
                 const float4 sh = d.shape[b0 + i];
-                d.aabb[b0 + i] = refreshed_aabb(p, fm.x, sh.x, sh.y);
+                d.aabb[b0 + i] = refreshed_aabb(rp[k], f2u(sh.z), sh.x, sh.y);
             }
             if (st) continue;
-            float mw = p.w;
+            float4 f = rf[k];
+            const float mass = rp[k].w;
             for (uint32_t g = g_lo; g < g_hi; ++g) {   // momentum_update with the world's gravity list
-                f.x = fadd(f.x, fmul(0.0f, mw));
-                f.y = fadd(f.y, fmul(-d.grav[g], mw));
+                f.x = fadd(f.x, fmul(0.0f, mass));
+                f.y = fadd(f.y, fmul(-d.grav[g], mass));
             }
             m.x = fadd(m.x, fmul(f.x, sub_dt));
             m.y = fadd(m.y, fmul(f.y, sub_dt));
             m.z = fadd(m.z, fmul(f.z, sub_dt));
+            m.w = inv_m;
             s_mom[i] = m;
         }
         __syncthreads();
         for (uint32_t it = 0; it < I; ++it)
             for (uint32_t c = 0; c < nc; ++c) {
-                const uint32_t lb = s_beg[c], le = s_beg[c + 1];
-                if (lb == le) continue;   // uniform
-                for (uint32_t l = lb + tid; l < le; l += nth) world_sweep_record(rc, l, s_mom, s_inv);
+                const uint32_t cnt = s_cnt[c];
+                if (cnt == 0u) continue;   // uniform
+                const uint32_t lb = s_beg[c], le = lb + (cnt & 0xFFFFu) + 2u * (cnt >> 16);
+                // whole warps (the two lanes of a manifold are in one warp: lb is even); idle lanes only shuffle
+                for (uint32_t sb = lb + (tid & ~31u); sb < le; sb += nth) {
+                    const uint32_t sl = sb + lane;
+                    const bool live = sl < le;
+                    const uint32_t h = live ? rc.hdr(sl) : (WS_NOPT | WS_ST1 | WS_ST2 | WS_B);
+                    const uint32_t i1 = h & 0x3FFu, i2 = (h >> 10) & 0x3FFu;
+                    const bool st1 = (h & WS_ST1) != 0, st2 = (h & WS_ST2) != 0;
+                    bool applied = false;
+                    v2 dp = mk2(0.0f, 0.0f);
+                    float c1 = 0.0f, c2 = 0.0f;
+                    float4 m1 = make_float4(0, 0, 0, 0), m2 = m1;
+                    if (live) {
+                        m1 = s_mom[i1];
+                        m2 = s_mom[i2];
+                        if (!(h & WS_NOPT)) {
+                            const float4 nfb = rc.nfb(sl), r = rc.r(sl), ma = rc.ma(sl);
+                            ContactConst cc;
+                            cc.normal = mk2(nfb.x, nfb.y);
+                            cc.tangent = rot90cw(cc.normal);
+                            cc.friction = nfb.z;
+                            ContactPointConst pt;
+                            pt.r1 = mk2(r.x, r.y);
+                            pt.r2 = mk2(r.z, r.w);
+                            pt.mass_n = ma.x;
+                            pt.mass_t = ma.y;
+                            pt.depth = (h & WS_SKIP) ? 0.0f : -1.0f;   // only the sign test of :154 looks at it (the bias is precomputed)
+                            pt.bias = nfb.w;
+                            v2 acc = mk2(ma.z, ma.w);
+                            // calculateImpulses :139-145: pre-loop velocities of the two bodies
+                            const v2 vl1 = scale2(mk2(m1.x, m1.y), m1.w), vl2 = scale2(mk2(m2.x, m2.y), m2.w);
+                            const float om1 = fmul(m1.z, s_ii[i1]), om2 = fmul(m2.z, s_ii[i2]);
+                            applied = contact_point_impulse(cc, pt, acc, vl1, om1, vl2, om2, dp);
+                            *reinterpret_cast<float2*>(&rc.ma(sl).z) = make_float2(acc.x, acc.y);
+                            if (applied) {
+                                c1 = cross2(pt.r1, dp);
+                                c2 = cross2(pt.r2, dp);
+                            }
+                        }
+                    }
+                    // the second point's impulse goes to the lane of the first
+                    const float bx = __shfl_down_sync(0xffffffffu, dp.x, 1), by = __shfl_down_sync(0xffffffffu, dp.y, 1);
+                    const float bc1 = __shfl_down_sync(0xffffffffu, c1, 1), bc2 = __shfl_down_sync(0xffffffffu, c2, 1);
+                    const bool b_applied = __shfl_down_sync(0xffffffffu, applied ? 1 : 0, 1) != 0 && (h & WS_A) != 0;
+                    if (live && !(h & WS_B)) {
+                        v2 lin1 = mk2(0.0f, 0.0f), lin2 = mk2(0.0f, 0.0f);
+                        float rot1 = 0.0f, rot2 = 0.0f;
+                        if (applied) {      // :197-206, point 0
+                            if (!st1) {
+                                lin1 = sub2(lin1, dp);
+                                rot1 = fsub(rot1, c1);
+                            }
+                            if (!st2) {
+                                lin2 = add2(lin2, dp);
+                                rot2 = fadd(rot2, c2);
+                            }
+                        }
+                        if (b_applied) {    // point 1
+                            const v2 dq = mk2(bx, by);
+                            if (!st1) {
+                                lin1 = sub2(lin1, dq);
+                                rot1 = fsub(rot1, bc1);
+                            }
+                            if (!st2) {
+                                lin2 = add2(lin2, dq);
+                                rot2 = fadd(rot2, bc2);
+                            }
+                        }
+                        // :208-212; static bodies receive a zero impulse in the reference (`momentum += 0`): not written
+                        if (!st1) s_mom[i1] = make_float4(fadd(m1.x, lin1.x), fadd(m1.y, lin1.y), fadd(m1.z, rot1), m1.w);
+                        if (!st2) s_mom[i2] = make_float4(fadd(m2.x, lin2.x), fadd(m2.y, lin2.y), fadd(m2.z, rot2), m2.w);
+                    }
+                }
                 __syncthreads();
             }
     }
     // ---- export ----
-    for (uint32_t i = tid; i < nb; i += nth) {
-        const uint2 fm = s_fm[i];
-        if (fm.x & FLAG_STATIC) continue;
-        float4 p = s_pos[i];
-        const float4 m = s_mom[i], f = s_frc[i];
-        if (S > 0) {
-            position_update(p, m, p.w, f.w, sub_dt);
-            d.pos[b0 + i] = make_float4(p.x, p.y, p.z, 0.0f);
+    if (S > 0) {
+#pragma unroll
+        for (int k = 0; k < BPT; ++k) {
+            const uint32_t i = tid + (uint32_t)k * WORLD_SOLVE_TPB;
+            if (i >= nb || s_st[i]) continue;
+            const float4 m = s_mom[i];
+            position_update(rp[k], m, rp[k].w, rf[k].w, sub_dt);
+            d.pos[b0 + i] = make_float4(rp[k].x, rp[k].y, rp[k].z, 0.0f);
             d.frc[b0 + i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             d.mom[b0 + i] = make_float4(m.x, m.y, m.z, 0.0f);
         }
     }
 }
 
-__global__ void __launch_bounds__(WORLD_SOLVE_TPB) k_world_solve(Dev d, float sub_dt, uint32_t S, uint32_t I, uint32_t nb_cap,
-                                                                 uint32_t R, uint32_t R2) {
+template <int BPT>
+__global__ void __launch_bounds__(WORLD_SOLVE_TPB, BPT == 2 ? 6 : 4) k_world_solve(Dev d, float sub_dt, uint32_t S, uint32_t I,
+                                                                                  uint32_t nb_cap, uint32_t R) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint32_t s_cnt[MAX_COLORS], s_beg[MAX_COLORS + 1];
-    __shared__ uint32_t s_n2, s_nc, s_fits;
+    __shared__ uint32_t s_cnt[MAX_COLORS];      // per colour: one-point manifolds | two-point manifolds << 16
+    __shared__ uint32_t s_cur[MAX_COLORS];      // fill cursors: pairs from the front of the colour's slots, singles behind them
+    __shared__ uint32_t s_beg[MAX_COLORS + 1];  // first slot of the colour (even)
+    __shared__ uint32_t s_nc, s_fits;
     if (overflowed(d) || d.counters->err != 0u) return;   // an abandoned attempt leaves the body state untouched
     // ---- shared memory layout ----
     unsigned char* q = smem_raw;
-    float4* s_mom = (float4*)q;   q += (size_t)nb_cap * 16;   // momentum.x, momentum.y, ang_momentum, -
-    float4* s_pos = (float4*)q;   q += (size_t)nb_cap * 16;   // x, y, angle, mass
-    float4* s_frc = (float4*)q;   q += (size_t)nb_cap * 16;   // force.x, force.y, torque, inertia
-    WorldRecs sm;
-    sm.nfb = (float4*)q;          q += (size_t)R * 16;
-    sm.r0 = (float4*)q;           q += (size_t)R * 16;
-    sm.ma0 = (float4*)q;          q += (size_t)R * 16;
-    sm.r1 = (float4*)q;           q += (size_t)R2 * 16;
-    sm.ma1 = (float4*)q;          q += (size_t)R2 * 16;
-    float2* s_inv = (float2*)q;   q += (size_t)nb_cap * 8;    // 1 / mass, 1 / inertia (0 for static bodies)
-    uint2* s_fm = (uint2*)q;      q += (size_t)nb_cap * 8;    // flags, bits(mu)
-    sm.hdr = (uint2*)q;           q += (size_t)R * 8;
-    sm.b1 = (float*)q;
+    float4* s_mom = (float4*)q;   q += (size_t)nb_cap * 16;   // momentum.x, momentum.y, ang_momentum, 1 / mass (0: static)
+    WorldSlots<true> sm;
+    sm.nfb_ = (float4*)q;         q += (size_t)R * 16;
+    sm.r_ = (float4*)q;           q += (size_t)R * 16;
+    sm.ma_ = (float4*)q;          q += (size_t)R * 16;
+    sm.hdr_ = (uint32_t*)q;       q += (size_t)R * 4;
+    float* s_ii = (float*)q;      q += (size_t)nb_cap * 4;    // 1 / inertia (0: static)
+    unsigned char* s_st = q;                                  // 1: static
     const uint32_t tid = threadIdx.x, nth = blockDim.x;
     for (uint32_t w = blockIdx.x; w < d.n_worlds; w += gridDim.x) {
         const uint32_t b0 = d.world_base[w], b1 = d.world_base[w + 1], nb = b1 - b0;
         // the world's candidate pairs: body-major list with the fine grid, bucket-major without
         const uint32_t p0 = d.fine_on ? d.pair_cnt[b0 + 1] : d.ent_off[d.table_mult * b0];
         const uint32_t p1 = d.fine_on ? d.pair_cnt[b1 + 1] : d.ent_off[d.table_mult * b1];
-        for (uint32_t c = tid; c < MAX_COLORS; c += nth) s_cnt[c] = 0u;
-        if (tid == 0) s_n2 = 0u;
+        for (uint32_t c = tid; c < MAX_COLORS; c += nth) s_cnt[c] = s_cur[c] = 0u;
         // ---- stage the bodies ----
-        for (uint32_t i = tid; i < nb; i += nth) {
+        float4 rp[BPT], rf[BPT];   // pose + mass, force + inertia of the bodies this thread integrates
+#pragma unroll
+        for (int k = 0; k < BPT; ++k) {
+            const uint32_t i = tid + (uint32_t)k * WORLD_SOLVE_TPB;
+            rp[k] = rf[k] = make_float4(0, 0, 0, 0);
+            if (i >= nb) continue;
             const float4 p = d.pos[b0 + i], m = d.mom[b0 + i], f = d.frc[b0 + i], pr = d.prop[b0 + i];
-            const uint32_t flags = body_flags(d, b0 + i);
-            const bool st = (flags & FLAG_STATIC) != 0;
-            s_pos[i] = make_float4(p.x, p.y, p.z, pr.x);
-            s_mom[i] = make_float4(m.x, m.y, m.z, 0.0f);
-            s_frc[i] = make_float4(f.x, f.y, f.z, pr.y);
-            s_inv[i] = make_float2(st ? 0.0f : fdiv(1.0f, pr.x), st ? 0.0f : fdiv(1.0f, pr.y));   // prestep_manifold, per body
-            s_fm[i] = make_uint2(flags, f2u(pr.z));
+            const bool st = (body_flags(d, b0 + i) & FLAG_STATIC) != 0;
+            rp[k] = make_float4(p.x, p.y, p.z, pr.x);
+            rf[k] = make_float4(f.x, f.y, f.z, pr.y);
+            s_mom[i] = make_float4(m.x, m.y, m.z, st ? 0.0f : fdiv(1.0f, pr.x));   // prestep_manifold :104-111, per body
+            s_ii[i] = st ? 0.0f : fdiv(1.0f, pr.y);
+            s_st[i] = st ? 1 : 0;
         }
         __syncthreads();
         // ---- counting sort of the world's manifolds by colour ----
         for (uint32_t p = p0 + tid; p < p1; p += nth) {
             const uint32_t c = d.m_color[p];
             if (c >= MAX_COLORS) continue;
-            atomicAdd(&s_cnt[c], 1u);
-            if ((d.m_hdr[p].z & 0xFFu) > 1u) atomicAdd(&s_n2, 1u);
+            atomicAdd(&s_cnt[c], (d.m_hdr[p].z & 0xFFu) > 1u ? 0x10000u : 1u);
         }
         __syncthreads();
-        if (tid < 32u) {   // exclusive scan of the colour populations by one warp (8 per lane)
+        if (tid < 32u) {   // slots per colour (1 per one-point, 2 per two-point manifold), exclusive scan by one warp (8 per lane)
             constexpr uint32_t PER = MAX_COLORS / 32;
             uint32_t v[PER], sum = 0, last = 0;
 #pragma unroll
             for (uint32_t k = 0; k < PER; ++k) {
-                v[k] = s_cnt[tid * PER + k];
+                const uint32_t cnt = s_cnt[tid * PER + k];
+                v[k] = ((cnt & 0xFFFFu) + 2u * (cnt >> 16) + 1u) & ~1u;   // even: the next colour starts on an even slot
                 sum += v[k];
-                if (v[k]) last = tid * PER + k + 1u;
+                if (cnt) last = tid * PER + k + 1u;
             }
             uint32_t inc = sum;
 #pragma unroll
@@ -264,35 +320,268 @@ __global__ void __launch_bounds__(WORLD_SOLVE_TPB) k_world_solve(Dev d, float su
             for (uint32_t k = 0; k < PER; ++k) {
                 s_beg[tid * PER + k] = run;
                 run += v[k];
-                s_cnt[tid * PER + k] = 0u;   // becomes the fill cursor
             }
             last = __reduce_max_sync(0xffffffffu, last);
             if (tid == 31u) {
                 s_beg[MAX_COLORS] = run;
                 s_nc = last;
-                const uint32_t n2 = s_n2;
-                s_fits = (run <= R && n2 <= R2) ? 1u : 0u;
-                s_n2 = 0u;                    // becomes the allocation cursor of the point-1 pool
+                s_fits = run <= R ? 1u : 0u;
                 atomicMax(&d.counters->max_world_m, run);
-                atomicMax(&d.counters->max_world_k2, n2);
             }
         }
         __syncthreads();
         const uint32_t nc = s_nc;
         if (s_fits) {
-            world_run(d, sm, w, b0, nb, p0, p1, nc, sub_dt, S, I, s_mom, s_pos, s_frc, s_inv, s_fm, s_cnt, s_beg, &s_n2);
+            world_run<true, BPT>(d, sm, w, b0, nb, p0, p1, nc, sub_dt, S, I, s_mom, s_ii, s_st, s_cnt, s_cur, s_beg, rp, rf);
         } else {   // the world's own slice of the global record arrays (see the header comment)
-            WorldRecs rg;
-            rg.hdr = (uint2*)d.s_dep + p0;
-            rg.nfb = d.s_nf + p0;
-            rg.r0 = d.s_r0 + p0;
-            rg.ma0 = d.s_pm0 + p0;
-            rg.r1 = d.s_r1 + p0;
-            rg.ma1 = d.s_pm1 + p0;
-            rg.b1 = (float*)d.s_acc1 + p0;
-            world_run(d, rg, w, b0, nb, p0, p1, nc, sub_dt, S, I, s_mom, s_pos, s_frc, s_inv, s_fm, s_cnt, s_beg, &s_n2);
+            WorldSlots<false> rg;
+            rg.hdr_[0] = (uint32_t*)d.s_acc0 + p0;  rg.hdr_[1] = (uint32_t*)d.s_acc1 + p0;
+            rg.nfb_[0] = d.s_nf + p0;               rg.nfb_[1] = d.s_inv + p0;
+            rg.r_[0] = d.s_r0 + p0;                 rg.r_[1] = d.s_r1 + p0;
+            rg.ma_[0] = d.s_pm0 + p0;               rg.ma_[1] = d.s_pm1 + p0;
+            world_run<false, BPT>(d, rg, w, b0, nb, p0, p1, nc, sub_dt, S, I, s_mom, s_ii, s_st, s_cnt, s_cur, s_beg, rp, rf);
         }
         __syncthreads();   // the next world of this CTA reuses the shared arrays
+    }
+}
+
+
+// =====================================================================================================================
+// Broadphase of a batch of small worlds: ONE CTA builds the grid of ONE world in shared memory and emits its candidate
+// pairs — the same per-body functions as the device-wide kernels (count_body_thread, fill_fine, fill_cell,
+// fine_body_pairs: SpatialHash.zig:19-137 + the filters of lib.zig:273-282), with the bucket tables, the grid entries,
+// the stored AABBs and the remembered bucket lists of the world redirected to shared memory.  Count -> scan -> fill ->
+// pair count -> scan -> pair write are separated by __syncthreads() instead of six kernel boundaries, no bucket counter
+// or entry goes through L2, and nothing has to be zeroed in global memory.  The only inter-CTA step is the position of
+// the world's pairs in the (world-major) pair list: a decoupled look-back over the per-world pair counts; worlds are
+// handed out by an atomic ticket, so a CTA only ever waits for worlds that started before it.
+// A world whose grid does not fit (entries of large bodies) raises `broad_fallback`: the attempt is abandoned (the
+// broadphase does not modify body state) and the host redoes the step with the device-wide kernels.
+// =====================================================================================================================
+constexpr int WORLD_BROAD_TPB = 128;
+constexpr uint32_t WORLD_BROAD_BIG = 16;   // large bodies of a world walked by the whole CTA
+
+__host__ __device__ inline size_t world_broad_smem_bytes(uint32_t nb_cap, uint32_t tw_cap, uint32_t ent_cap) {
+    return (size_t)nb_cap * (16 + 16 + 16 + 32 + 4) + (size_t)(2 * tw_cap + 1) * 8 + (size_t)ent_cap * 24 + 64;
+}
+
+__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {   // blockDim <= 1024
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = (blockDim.x + 31u) >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+    }
+    __syncthreads();   // s_warp may still be read by the previous call
+    if (lane == 31u) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, sum = 0;
+    for (uint32_t k = 0; k < nw; ++k) {
+        const uint32_t x = s_warp[k];
+        if (k < warp) base += x;
+        sum += x;
+    }
+    *total = sum;
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(WORLD_BROAD_TPB) k_world_broad(Dev d, uint32_t nb_cap, uint32_t tw_cap, uint32_t ent_cap,
+                                                                 unsigned long long* state, uint32_t* ticket) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_warp[32], s_big[WORLD_BROAD_BIG];
+    __shared__ uint32_t s_world, s_nbig, s_base;
+    unsigned char* q = smem_raw;
+    float4* s_aabb = (float4*)q;     q += (size_t)nb_cap * 16;
+    uint4* s_bkt = (uint4*)q;        q += (size_t)nb_cap * 16;
+    int4* s_fcell = (int4*)q;        q += (size_t)nb_cap * 16;
+    uint4* s_cand = (uint4*)q;       q += (size_t)nb_cap * 32;
+    float4* s_eaabb = (float4*)q;    q += (size_t)ent_cap * 16;
+    uint32_t* s_ebody = (uint32_t*)q; q += (size_t)ent_cap * 4;
+    uint32_t* s_ekey = (uint32_t*)q; q += (size_t)ent_cap * 4;
+    uint32_t* s_cnt = (uint32_t*)q;  q += (size_t)(2 * tw_cap + 1) * 4;
+    uint32_t* s_start = (uint32_t*)q; q += (size_t)(2 * tw_cap + 1) * 4;
+    uint32_t* s_pcnt = (uint32_t*)q;   // nb_cap + 2
+    const uint32_t tid = threadIdx.x, nth = blockDim.x;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_world = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t w = s_world;
+        if (w >= d.n_worlds) return;
+        const uint32_t b0 = d.world_base[w], b1 = d.world_base[w + 1], nb = b1 - b0;
+        const uint32_t tw = d.table_mult * nb;   // coarse buckets of the world; as many fine ones behind them
+        // the per-body functions index with global slots / global bucket ids: shift the shared arrays accordingly
+        Dev ds = d;
+        ds.n_buckets = tw;                       // fine_bucket(): fine table right behind the world's coarse table
+        ds.bucket_cnt = s_cnt - (size_t)d.table_mult * b0;
+        ds.bucket_start = s_start - (size_t)d.table_mult * b0;
+        ds.aabb = s_aabb - b0;
+        ds.bkt = s_bkt - b0;
+        ds.fcell = s_fcell - b0;
+        ds.fine_cand = s_cand - 2 * (size_t)b0;
+        ds.ent_body = s_ebody;
+        ds.ent_key = s_ekey;
+        ds.ent_aabb = s_eaabb;
+        ds.cap_entries = ent_cap;
+        ds.pair_cnt = s_pcnt - b0;
+        for (uint32_t k = tid; k < 2u * tw + 1u; k += nth) s_cnt[k] = 0u;
+        for (uint32_t i = tid; i < nb; i += nth) s_aabb[i] = d.aabb[b0 + i];
+        if (tid == 0) s_nbig = 0u;
+        __syncthreads();
+        // ---- count (SpatialHash.zig:46-49) ----
+        for (uint32_t i = tid; i < nb; i += nth) {
+            const CellRange r = count_body_thread(ds, b0 + i, false);   // small bodies count their home cell themselves
+            if (r.count == 0u) continue;
+            const uint32_t slot = r.count > 32u ? atomicAdd(&s_nbig, 1u) : WORLD_BROAD_BIG;
+            if (slot < WORLD_BROAD_BIG) {
+                s_big[slot] = i;
+            } else {
+                for (uint32_t k = 0; k < r.count; ++k) atomicAdd(&ds.bucket_cnt[cell_bucket(r, k)], 1u);
+            }
+        }
+        __syncthreads();
+        const uint32_t nbig = s_nbig < WORLD_BROAD_BIG ? s_nbig : WORLD_BROAD_BIG;
+        for (uint32_t x = 0; x < nbig; ++x) {
+            const CellRange r = cell_range(ds, b0 + s_big[x]);
+            for (uint32_t k = tid; k < r.count; k += nth) atomicAdd(&ds.bucket_cnt[cell_bucket(r, k)], 1u);
+        }
+        __syncthreads();
+        // ---- scan of the 2 tw bucket counts (:52-57) ----
+        uint32_t n_entries = 0;
+        {
+            uint32_t carry = 0;
+            for (uint32_t base = 0; base < 2u * tw; base += nth) {
+                const uint32_t k = base + tid;
+                const uint32_t v = k < 2u * tw ? s_cnt[k] : 0u;
+                uint32_t total;
+                const uint32_t ex = cta_exclusive_scan(v, s_warp, &total);
+                if (k < 2u * tw) s_start[k] = carry + ex;
+                carry += total;
+            }
+            if (tid == 0) s_start[2u * tw] = carry;
+            n_entries = carry;
+        }
+        __syncthreads();
+        if (n_entries > ent_cap) {   // uniform: the grid of this world does not fit — the whole attempt is abandoned
+            if (tid == 0) atomicOr(&d.counters->broad_fallback, 1u);
+            n_entries = 0;
+        }
+        const bool dead = n_entries == 0u && nb != 0u && s_start[2u * tw] != 0u;
+        // ---- fill (:62-68) ----
+        if (!dead) {
+            for (uint32_t i = tid; i < nb; i += nth) {
+                if (body_is_small(ds, body_flags(d, b0 + i))) {
+                    fill_fine(ds, b0 + i);
+                } else {
+                    bool big = false;
+                    for (uint32_t x = 0; x < nbig; ++x) big = big || s_big[x] == i;
+                    if (big) continue;
+                    const CellRange r = cell_range(ds, b0 + i);
+                    for (uint32_t k = 0; k < r.count; ++k) fill_cell(ds, b0 + i, cell_bucket(r, k));
+                }
+            }
+            for (uint32_t x = 0; x < nbig; ++x) {
+                const CellRange r = cell_range(ds, b0 + s_big[x]);
+                for (uint32_t k = tid; k < r.count; k += nth) fill_cell(ds, b0 + s_big[x], cell_bucket(r, k));
+            }
+        }
+        __syncthreads();
+        // ---- pairs of every small body: count, park the first 8 partners ----
+        for (uint32_t i = tid; i < nb; i += nth) {
+            uint32_t got[8];
+            const uint32_t a = b0 + i;
+            const bool live = !dead && body_is_small(ds, body_flags(d, a));
+            const uint32_t n = live ? fine_body_pairs(ds, a, got, nullptr) : 0u;
+            s_pcnt[i + 1] = n;
+            if (n > 0u) s_cand[2 * i] = make_uint4(got[0], n > 1u ? got[1] : 0u, n > 2u ? got[2] : 0u, n > 3u ? got[3] : 0u);
+            if (n > 4u) s_cand[2 * i + 1] = make_uint4(got[4], n > 5u ? got[5] : 0u, n > 6u ? got[6] : 0u, n > 7u ? got[7] : 0u);
+        }
+        __syncthreads();
+        // ---- scan of the pair counts inside the world; position of the world in the pair list by look-back ----
+        uint32_t n_pairs_w = 0;
+        {
+            uint32_t carry = 0;
+            for (uint32_t base = 0; base < nb; base += nth) {
+                const uint32_t i = base + tid;
+                const uint32_t v = i < nb ? s_pcnt[i + 1] : 0u;
+                uint32_t total;
+                const uint32_t ex = cta_exclusive_scan(v, s_warp, &total);
+                if (i < nb) s_pcnt[i + 1] = carry + ex;    // first pair of body i, relative to the world
+                carry += total;
+            }
+            n_pairs_w = carry;
+        }
+        if (tid < 32u) {
+            const uint32_t lane = tid;
+            uint32_t prefix = 0;
+            if (w == 0) {
+                if (lane == 0) atomicExch(&state[0], (2ull << 32) | n_pairs_w);
+            } else {
+                if (lane == 0) atomicExch(&state[w], (1ull << 32) | n_pairs_w);
+                int first = (int)w - 1;
+                for (;;) {
+                    const int t = first - (int)lane;
+                    unsigned long long x = 3ull << 32;   // beyond world 0: neutral, counts as "ready"
+                    if (t >= 0) {
+                        do {
+                            x = *((volatile unsigned long long*)&state[t]);
+                        } while ((x >> 32) == 0ull);
+                    }
+                    const uint32_t is_prefix = __ballot_sync(0xffffffffu, (x >> 32) == 2ull);
+                    const uint32_t upto = is_prefix ? (uint32_t)__ffs((int)is_prefix) - 1u : 31u;
+                    uint32_t v = (t >= 0 && lane <= upto) ? (uint32_t)x : 0u;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    prefix += v;
+                    if (is_prefix || first < 32) break;
+                    first -= 32;
+                }
+                if (lane == 0) atomicExch(&state[w], (2ull << 32) | (unsigned long long)(uint32_t)(prefix + n_pairs_w));
+            }
+            if (lane == 0) {
+                s_base = prefix;
+                atomicAdd(&d.counters->n_entries, s_start[2u * tw]);
+                if (w == 0) d.pair_cnt[0] = 0u;
+                if (w + 1 == d.n_worlds) {
+                    d.pair_cnt[d.n_bodies + 1] = prefix + n_pairs_w;
+                    d.counters->n_pairs = prefix + n_pairs_w;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t pbase = s_base;
+        // ---- write (sorted by partner slot: the list must not depend on the order the fill's atomics landed in) ----
+        for (uint32_t i = tid; i < nb; i += nth) {
+            const uint32_t a = b0 + i;
+            const uint32_t off = s_pcnt[i + 1], n = (i + 1 < nb ? s_pcnt[i + 2] : n_pairs_w) - off;
+            const uint32_t at = pbase + off;
+            d.pair_cnt[a + 1] = at;
+            if (n == 0u || at + n > d.cap_pairs) continue;
+            uint2* out = d.pairs + at;
+            if (n <= 8u) {
+                uint32_t got[8];
+                const uint4 q0 = s_cand[2 * i], q1 = n > 4u ? s_cand[2 * i + 1] : make_uint4(0u, 0u, 0u, 0u);
+                got[0] = q0.x; got[1] = q0.y; got[2] = q0.z; got[3] = q0.w;
+                got[4] = q1.x; got[5] = q1.y; got[6] = q1.z; got[7] = q1.w;
+#pragma unroll
+                for (int x = 1; x < 8; ++x) {
+#pragma unroll
+                    for (int y = x; y > 0; --y)
+                        if ((uint32_t)x < n && got[y - 1] > got[y]) {
+                            const uint32_t t = got[y - 1];
+                            got[y - 1] = got[y];
+                            got[y] = t;
+                        }
+                }
+#pragma unroll
+                for (int x = 0; x < 8; ++x)
+                    if ((uint32_t)x < n) out[x] = make_uint2(a, got[x]);
+            } else {
+                fine_body_pairs(ds, a, nullptr, out);
+                sort_item_pairs(out, n);
+            }
+        }
     }
 }
 

@@ -184,9 +184,16 @@ def test_gpu_batch_matches_standalone_worlds():
         at += n
 
 
-def test_gpu_large_batch_uses_world_solver_and_matches_oracle():
-    """>= 74 worlds switches the substep loop to the CTA-per-world shared-memory kernel; sampled worlds must still match
-    the oracle bit for bit (the other batch test, with 24 worlds, goes through the persistent dataflow kernel)."""
+@pytest.mark.parametrize("cache", [None, "0", "300", "device-wide broadphase"])
+def test_gpu_large_batch_uses_world_solver_and_matches_oracle(monkeypatch, cache):
+    """>= 74 worlds switches the substep loop to the CTA-per-world kernel (k_world_solve: one lane per contact point, the
+    world's slots in shared memory); sampled worlds must still match the oracle bit for bit (the other batch test, with 24
+    worlds, goes through the persistent dataflow kernel).  R2D_WORLD_CACHE=0 keeps every world's slots in its slice of the
+    global record arrays, 300 only those of the worlds that have outgrown 300 slots — same bits every way."""
+    if cache == "device-wide broadphase":     # default: k_world_broad, the grid of a world in shared memory
+        monkeypatch.setenv("R2D_WORLD_BROAD", "0")
+    elif cache is not None:
+        monkeypatch.setenv("R2D_WORLD_CACHE", cache)
     n_worlds, steps = 96, 60
     batch = Batch(n_worlds, 2.0, 4)
     sample = (0, 1, 37, 95)
