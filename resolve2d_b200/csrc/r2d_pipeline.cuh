@@ -562,7 +562,7 @@ R2D_HD uint32_t entry_pairs_thread(const Dev& d, uint32_t e, uint2* out) {
 }
 
 // K5 with the fine grid: the pairs emitted by small body a — its small partners from the home cell and the four forward
-// neighbours in the fine table, then its large partners from its own coarse buckets.  The first 8 accepted partners are
+// neighbours in the fine table, then its large partners from its own coarse buckets.  The first PARK accepted partners are
 // returned in `got` (if non-null); all of them are written to `out` as (a, partner) if non-null.  Returns how many.
 R2D_HD bool bucket_lists_share(const uint4& x, const uint4& y) {
     const uint32_t a[4] = {x.x, x.y, x.z, x.w}, b[4] = {y.x, y.y, y.z, y.w};
@@ -573,6 +573,7 @@ R2D_HD bool bucket_lists_share(const uint4& x, const uint4& y) {
         for (int j = 0; j < 4; ++j) share = share || (a[i] != 0xFFFFFFFFu && a[i] == b[j]);
     return share;
 }
+template <uint32_t PARK = 8>
 R2D_HD uint32_t fine_body_pairs(const Dev& d, uint32_t a, uint32_t* got, uint2* out) {
     const uint32_t fa = body_flags(d, a);
     const float4 aa = d.aabb[a];
@@ -612,7 +613,7 @@ R2D_HD uint32_t fine_body_pairs(const Dev& d, uint32_t a, uint32_t* got, uint2* 
             if (!aabb_intersects(aa.x, aa.y, aa.z, aa.w, ab.x, ab.y, ab.z, ab.w)) continue;         // :282
             if (!bucket_lists_share(ba, d.bkt[b])) continue;   // the reference only sees b through a shared hashed bucket
             if (pair_excluded(d, a, b)) continue;                                                   // :275-276
-            if (got && n < 8u) got[n] = b;
+            if (got && n < PARK) got[n] = b;
             if (out) out[n] = make_uint2(a, b);
             ++n;
         }
@@ -632,7 +633,7 @@ R2D_HD uint32_t fine_body_pairs(const Dev& d, uint32_t a, uint32_t* got, uint2* 
             const float4 ab = d.aabb[b];
             if (!aabb_intersects(aa.x, aa.y, aa.z, aa.w, ab.x, ab.y, ab.z, ab.w)) continue;
             if (pair_excluded(d, a, b)) continue;
-            if (got && n < 8u) got[n] = b;
+            if (got && n < PARK) got[n] = b;
             if (out) out[n] = make_uint2(a, b);
             ++n;
         }

@@ -662,7 +662,7 @@ struct CudaBatch : BatchBase {
         // broadphase of a batch of small worlds: per-world CTAs with the grid in shared memory, when the fine grid applies
         // (no dynamic large bodies) and the tables of the largest world fit
         const uint32_t wb_nb_cap = (max_world_bodies + 3u) & ~3u, wb_tw_cap = grid_mult() * max_world_bodies;
-        const uint32_t wb_ent_cap = wb_nb_cap + 512u;
+        const uint32_t wb_ent_cap = wb_nb_cap + 256u;   // one entry per small body + the cells of the large ones
         const size_t wb_smem = world_broad_smem_bytes(wb_nb_cap, wb_tw_cap, wb_ent_cap);
         bool use_world_broad = world_broad && !world_broad_declined && many_small_worlds && fine_now && !ll_now &&
                                max_world_bodies <= WORLD_MAX_BODIES && wb_smem <= 100 * 1024 &&

@@ -358,11 +358,12 @@ __global__ void __launch_bounds__(WORLD_SOLVE_TPB, BPT == 2 ? 6 : 4) k_world_sol
 // A world whose grid does not fit (entries of large bodies) raises `broad_fallback`: the attempt is abandoned (the
 // broadphase does not modify body state) and the host redoes the step with the device-wide kernels.
 // =====================================================================================================================
-constexpr int WORLD_BROAD_TPB = 128;
-constexpr uint32_t WORLD_BROAD_BIG = 16;   // large bodies of a world walked by the whole CTA
+constexpr int WORLD_BROAD_TPB = 256;
+constexpr uint32_t WORLD_BROAD_BIG = 32;   // large bodies of a world (floor, walls, bars), walked by the whole CTA
+constexpr uint32_t WORLD_PARK = 16;        // partners a small body parks between the count and the write pass
 
 __host__ __device__ inline size_t world_broad_smem_bytes(uint32_t nb_cap, uint32_t tw_cap, uint32_t ent_cap) {
-    return (size_t)nb_cap * (16 + 16 + 16 + 32 + 4) + (size_t)(2 * tw_cap + 1) * 8 + (size_t)ent_cap * 24 + 64;
+    return (size_t)nb_cap * (16 + 16 + 16 + 4 * WORLD_PARK + 4) + (size_t)(2 * tw_cap + 1) * 8 + (size_t)ent_cap * 24 + 64;
 }
 
 __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {   // blockDim <= 1024
@@ -395,13 +396,13 @@ __global__ void __launch_bounds__(WORLD_BROAD_TPB) k_world_broad(Dev d, uint32_t
     float4* s_aabb = (float4*)q;     q += (size_t)nb_cap * 16;
     uint4* s_bkt = (uint4*)q;        q += (size_t)nb_cap * 16;
     int4* s_fcell = (int4*)q;        q += (size_t)nb_cap * 16;
-    uint4* s_cand = (uint4*)q;       q += (size_t)nb_cap * 32;
+    uint32_t* s_cand = (uint32_t*)q; q += (size_t)nb_cap * 4 * WORLD_PARK;
     float4* s_eaabb = (float4*)q;    q += (size_t)ent_cap * 16;
     uint32_t* s_ebody = (uint32_t*)q; q += (size_t)ent_cap * 4;
     uint32_t* s_ekey = (uint32_t*)q; q += (size_t)ent_cap * 4;
     uint32_t* s_cnt = (uint32_t*)q;  q += (size_t)(2 * tw_cap + 1) * 4;
     uint32_t* s_start = (uint32_t*)q; q += (size_t)(2 * tw_cap + 1) * 4;
-    uint32_t* s_pcnt = (uint32_t*)q;   // nb_cap + 2
+    uint32_t* s_pcnt = (uint32_t*)q;   // nb_cap + 1
     const uint32_t tid = threadIdx.x, nth = blockDim.x;
     for (;;) {
         __syncthreads();
@@ -419,21 +420,20 @@ __global__ void __launch_bounds__(WORLD_BROAD_TPB) k_world_broad(Dev d, uint32_t
         ds.aabb = s_aabb - b0;
         ds.bkt = s_bkt - b0;
         ds.fcell = s_fcell - b0;
-        ds.fine_cand = s_cand - 2 * (size_t)b0;
         ds.ent_body = s_ebody;
         ds.ent_key = s_ekey;
         ds.ent_aabb = s_eaabb;
         ds.cap_entries = ent_cap;
-        ds.pair_cnt = s_pcnt - b0;
-        for (uint32_t k = tid; k < 2u * tw + 1u; k += nth) s_cnt[k] = 0u;
         for (uint32_t i = tid; i < nb; i += nth) s_aabb[i] = d.aabb[b0 + i];
+        for (uint32_t k = tid; k < 2u * tw + 1u; k += nth) s_cnt[k] = 0u;
         if (tid == 0) s_nbig = 0u;
         __syncthreads();
         // ---- count (SpatialHash.zig:46-49) ----
         for (uint32_t i = tid; i < nb; i += nth) {
             const CellRange r = count_body_thread(ds, b0 + i, false);   // small bodies count their home cell themselves
             if (r.count == 0u) continue;
-            const uint32_t slot = r.count > 32u ? atomicAdd(&s_nbig, 1u) : WORLD_BROAD_BIG;
+            // a large body: all of them are walked by the whole CTA (a thread walking 20 cells alone keeps 255 waiting)
+            const uint32_t slot = atomicAdd(&s_nbig, 1u);
             if (slot < WORLD_BROAD_BIG) {
                 s_big[slot] = i;
             } else {
@@ -463,11 +463,8 @@ __global__ void __launch_bounds__(WORLD_BROAD_TPB) k_world_broad(Dev d, uint32_t
             n_entries = carry;
         }
         __syncthreads();
-        if (n_entries > ent_cap) {   // uniform: the grid of this world does not fit — the whole attempt is abandoned
-            if (tid == 0) atomicOr(&d.counters->broad_fallback, 1u);
-            n_entries = 0;
-        }
-        const bool dead = n_entries == 0u && nb != 0u && s_start[2u * tw] != 0u;
+        const bool dead = n_entries > ent_cap;   // uniform: the grid of this world does not fit — the whole attempt is abandoned
+        if (dead && tid == 0) atomicOr(&d.counters->broad_fallback, 1u);
         // ---- fill (:62-68) ----
         if (!dead) {
             for (uint32_t i = tid; i < nb; i += nth) {
@@ -485,17 +482,38 @@ __global__ void __launch_bounds__(WORLD_BROAD_TPB) k_world_broad(Dev d, uint32_t
                 const CellRange r = cell_range(ds, b0 + s_big[x]);
                 for (uint32_t k = tid; k < r.count; k += nth) fill_cell(ds, b0 + s_big[x], cell_bucket(r, k));
             }
+            __syncthreads();
+            // The fill's atomics decide the order inside a bucket; sorting every bucket by slot (they hold 0-3 entries)
+            // makes the order in which a body meets its partners — and with it the pair list — a pure function of the state.
+            for (uint32_t k = tid; k < 2u * tw; k += nth) {
+                const uint32_t bs = s_start[k], be = s_start[k + 1];
+                for (uint32_t x = bs + 1u; x < be; ++x) {
+                    const uint32_t vb = s_ebody[x], vk = s_ekey[x];
+                    const float4 va = s_eaabb[x];
+                    uint32_t y = x;
+                    while (y > bs && (s_ebody[y - 1] & ~ENT_STATIC) > (vb & ~ENT_STATIC)) {
+                        s_ebody[y] = s_ebody[y - 1];
+                        s_ekey[y] = s_ekey[y - 1];
+                        s_eaabb[y] = s_eaabb[y - 1];
+                        --y;
+                    }
+                    s_ebody[y] = vb;
+                    s_ekey[y] = vk;
+                    s_eaabb[y] = va;
+                }
+            }
         }
         __syncthreads();
-        // ---- pairs of every small body: count, park the first 8 partners ----
+        // ---- pairs of every small body: count, park the first WORLD_PARK partners ----
         for (uint32_t i = tid; i < nb; i += nth) {
-            uint32_t got[8];
+            uint32_t got[WORLD_PARK];
             const uint32_t a = b0 + i;
             const bool live = !dead && body_is_small(ds, body_flags(d, a));
-            const uint32_t n = live ? fine_body_pairs(ds, a, got, nullptr) : 0u;
-            s_pcnt[i + 1] = n;
-            if (n > 0u) s_cand[2 * i] = make_uint4(got[0], n > 1u ? got[1] : 0u, n > 2u ? got[2] : 0u, n > 3u ? got[3] : 0u);
-            if (n > 4u) s_cand[2 * i + 1] = make_uint4(got[4], n > 5u ? got[5] : 0u, n > 6u ? got[6] : 0u, n > 7u ? got[7] : 0u);
+            const uint32_t n = live ? fine_body_pairs<WORLD_PARK>(ds, a, got, nullptr) : 0u;
+            s_pcnt[i] = n;
+#pragma unroll
+            for (uint32_t x = 0; x < WORLD_PARK; x += 4)
+                if (n > x) *reinterpret_cast<uint4*>(&s_cand[i * WORLD_PARK + x]) = make_uint4(got[x], got[x + 1], got[x + 2], got[x + 3]);
         }
         __syncthreads();
         // ---- scan of the pair counts inside the world; position of the world in the pair list by look-back ----
@@ -504,10 +522,10 @@ __global__ void __launch_bounds__(WORLD_BROAD_TPB) k_world_broad(Dev d, uint32_t
             uint32_t carry = 0;
             for (uint32_t base = 0; base < nb; base += nth) {
                 const uint32_t i = base + tid;
-                const uint32_t v = i < nb ? s_pcnt[i + 1] : 0u;
+                const uint32_t v = i < nb ? s_pcnt[i] : 0u;
                 uint32_t total;
                 const uint32_t ex = cta_exclusive_scan(v, s_warp, &total);
-                if (i < nb) s_pcnt[i + 1] = carry + ex;    // first pair of body i, relative to the world
+                if (i < nb) s_cnt[i] = carry + ex;    // first pair of body i, relative to the world (the bucket counts are done with)
                 carry += total;
             }
             n_pairs_w = carry;
@@ -524,9 +542,11 @@ __global__ void __launch_bounds__(WORLD_BROAD_TPB) k_world_broad(Dev d, uint32_t
                     const int t = first - (int)lane;
                     unsigned long long x = 3ull << 32;   // beyond world 0: neutral, counts as "ready"
                     if (t >= 0) {
-                        do {
+                        for (;;) {
                             x = *((volatile unsigned long long*)&state[t]);
-                        } while ((x >> 32) == 0ull);
+                            if ((x >> 32) != 0ull) break;
+                            __nanosleep(200);
+                        }
                     }
                     const uint32_t is_prefix = __ballot_sync(0xffffffffu, (x >> 32) == 2ull);
                     const uint32_t upto = is_prefix ? (uint32_t)__ffs((int)is_prefix) - 1u : 31u;
@@ -541,7 +561,7 @@ __global__ void __launch_bounds__(WORLD_BROAD_TPB) k_world_broad(Dev d, uint32_t
             }
             if (lane == 0) {
                 s_base = prefix;
-                atomicAdd(&d.counters->n_entries, s_start[2u * tw]);
+                atomicAdd(&d.counters->n_entries, n_entries);
                 if (w == 0) d.pair_cnt[0] = 0u;
                 if (w + 1 == d.n_worlds) {
                     d.pair_cnt[d.n_bodies + 1] = prefix + n_pairs_w;
@@ -551,35 +571,17 @@ __global__ void __launch_bounds__(WORLD_BROAD_TPB) k_world_broad(Dev d, uint32_t
         }
         __syncthreads();
         const uint32_t pbase = s_base;
-        // ---- write (sorted by partner slot: the list must not depend on the order the fill's atomics landed in) ----
+        // ---- write, in the order the partners were met (deterministic: the buckets are sorted) ----
         for (uint32_t i = tid; i < nb; i += nth) {
             const uint32_t a = b0 + i;
-            const uint32_t off = s_pcnt[i + 1], n = (i + 1 < nb ? s_pcnt[i + 2] : n_pairs_w) - off;
-            const uint32_t at = pbase + off;
+            const uint32_t n = s_pcnt[i], at = pbase + s_cnt[i];
             d.pair_cnt[a + 1] = at;
             if (n == 0u || at + n > d.cap_pairs) continue;
             uint2* out = d.pairs + at;
-            if (n <= 8u) {
-                uint32_t got[8];
-                const uint4 q0 = s_cand[2 * i], q1 = n > 4u ? s_cand[2 * i + 1] : make_uint4(0u, 0u, 0u, 0u);
-                got[0] = q0.x; got[1] = q0.y; got[2] = q0.z; got[3] = q0.w;
-                got[4] = q1.x; got[5] = q1.y; got[6] = q1.z; got[7] = q1.w;
-#pragma unroll
-                for (int x = 1; x < 8; ++x) {
-#pragma unroll
-                    for (int y = x; y > 0; --y)
-                        if ((uint32_t)x < n && got[y - 1] > got[y]) {
-                            const uint32_t t = got[y - 1];
-                            got[y - 1] = got[y];
-                            got[y] = t;
-                        }
-                }
-#pragma unroll
-                for (int x = 0; x < 8; ++x)
-                    if ((uint32_t)x < n) out[x] = make_uint2(a, got[x]);
+            if (n <= WORLD_PARK) {
+                for (uint32_t x = 0; x < n; ++x) out[x] = make_uint2(a, s_cand[i * WORLD_PARK + x]);
             } else {
-                fine_body_pairs(ds, a, nullptr, out);
-                sort_item_pairs(out, n);
+                fine_body_pairs<WORLD_PARK>(ds, a, nullptr, out);
             }
         }
     }
