@@ -223,8 +223,9 @@ def build_box1k(solver, seed=CONFIG_SEED["box1k"]):
     fac.make_downwards_gravity(GRAVITY)
     rng = SplitMix64(seed)
     statics = np.concatenate([_static_rect((0, -1), 60, 2), _static_rect((-31, 30), 2, 60), _static_rect((31, 30), 2, 60)])
-    fac.make_bodies(np.concatenate([statics, descs_box(rng, 40, 25)]))
-    return {"sub_steps": 4, "iters": 4}
+    d = np.concatenate([statics, descs_box(rng, 40, 25)])
+    fac.make_bodies(d)
+    return {"sub_steps": 4, "iters": 4, "n_rect": int(np.count_nonzero(d["shape"] == SHAPE_RECT))}
 
 
 def build_pile(solver, nx=400, ny=250, seed=CONFIG_SEED["pile100k"]):
@@ -247,7 +248,7 @@ def build_pile(solver, nx=400, ny=250, seed=CONFIG_SEED["pile100k"]):
     d["shape"] = SHAPE_DISC
     d["a"] = f32(0.3) + r[:, 2] * f32(0.2)
     fac.make_bodies(np.concatenate([statics, d]))
-    return {"sub_steps": 4, "iters": 4}
+    return {"sub_steps": 4, "iters": 4, "n_rect": 3}
 
 
 def build_pile100k(solver):
@@ -293,13 +294,17 @@ def build_mixed(solver, nx=1250, ny=800, n_large=1000, seed=CONFIG_SEED["mixed1M
         big["b"] = f32(8.0) + rb[:, 1] * f32(8.0)
         big["angle"] = (rb[:, 2] * f32(2.0) - f32(1.0)) * f32(np.pi)
         parts.append(big)
-    fac.make_bodies(np.concatenate(parts))
-    return {"sub_steps": 4, "iters": 4}
+    allb = np.concatenate(parts)
+    fac.make_bodies(allb)
+    return {"sub_steps": 4, "iters": 4, "n_rect": int(np.count_nonzero(allb["shape"] == SHAPE_RECT))}
 
 
 def build_mixed1M(solver):
-    """cfg3.  5000 x 200 lattice (shallow for the same reason as pile100k) + 1000 large rectangles above it."""
-    return build_mixed(solver, 5000, 200, 1000)
+    """cfg3.  20000 x 50 lattice + 1000 large rectangles above it: as wide and shallow as pile100k (2000 x 50), so that a
+    pile HAS formed after the 200-call pre-roll (SURVEY 8d's 1250 x 800 lattice is 880 m tall and round 1's 5000 x 200 is
+    220 m: both are still in free fall when they are timed — profiles/r02_mixed1M_evolution.md); same body count, size
+    distributions, pitch and materials."""
+    return build_mixed(solver, 20000, 50, 1000)
 
 
 def build_hub(solver, n_discs=48):
@@ -358,7 +363,7 @@ def build_pyramid(solver, base=199, n_spinners=50, seed=CONFIG_SEED["pyramid20k"
         h = fac.make_rectangle_body(BodyOptions(pos=pos, density=DENSITY, mu=MU), RectangleOptions(10.5, 0.5))
         fac.make_fixed_position_joint(Parameters(), h, pos)
         fac.make_motor_joint(Parameters(beta=100, power_max=100, power_min=-100), h, f32(3.14))
-    return {"sub_steps": 4, "iters": 10}
+    return {"sub_steps": 4, "iters": 10, "n_rect": count + 1 + n_spinners}
 
 
 def build_pyramid20k(solver):

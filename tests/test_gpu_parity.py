@@ -519,21 +519,23 @@ def _full_size_handoff(build, settle_steps, check_steps, what):
 
 
 def test_gpu_full_size_pile100k():
-    gpu = _full_size_handoff(scenes.build_pile100k, 180, 2, "pile100k")
+    gpu = _full_size_handoff(scenes.build_pile100k, 180, 5, "pile100k")
     st = gpu.stats()
     assert st.n_bodies == 100003 and st.n_manifolds > 150000
 
 
 def test_gpu_full_size_pyramid20k():
-    gpu = _full_size_handoff(scenes.build_pyramid20k, 40, 2, "pyramid20k")
+    gpu = _full_size_handoff(scenes.build_pyramid20k, 40, 5, "pyramid20k")
     st = gpu.stats()
     assert st.n_bodies == 19951 and st.n_joints > 1500
 
 
 def test_gpu_full_size_mixed1M():
-    gpu = _full_size_handoff(scenes.build_mixed1M, 90, 1, "mixed1M")
+    """cfg3, settled (20000 x 50 lattice, 200 calls: the pile has formed and the large rectangles have landed on it): three
+    consecutive process() calls bit for bit against the oracle."""
+    gpu = _full_size_handoff(scenes.build_mixed1M, 200, 3, "mixed1M")
     st = gpu.stats()
-    assert st.n_bodies == 1001003 and st.n_manifolds > 100000
+    assert st.n_bodies == 1001003 and st.n_manifolds > 1500000
 
 
 def test_gpu_full_size_batch4096_sampled_worlds_and_determinism():
@@ -541,7 +543,7 @@ def test_gpu_full_size_batch4096_sampled_worlds_and_determinism():
     on thread timing anywhere: atomics only ever feed order-independent results)."""
     n_worlds, steps = 4096, 70
     a, b = Batch(n_worlds, 2.0, 4), Batch(n_worlds, 2.0, 4)
-    sample = (0, 1234, 4095)
+    sample = tuple(range(0, 4096, 132)) + (4095,)   # 33 worlds
     oracles = {}
     for w in range(n_worlds):
         d = scenes.descs_batch_world(w)
