@@ -227,7 +227,8 @@ def run_reference(args, rank, world):
         return
     t0 = time.time()
     cores = os.cpu_count() or 1
-    if world > 1 or args.workload == "batch4096x256":
+    n_gpus = max(world, args.gpus)
+    if n_gpus > 1 or args.workload == "batch4096x256":
         n_cpu_worlds = min(N_WORLDS, 16 * cores)
         cpu_steps = max(args.steps, 20)
         wsps, cores, sec = cpu_batch(n_cpu_worlds, cpu_steps, args.batch_preroll + args.warmup)
@@ -237,7 +238,7 @@ def run_reference(args, rank, world):
             "impl": "reference", "metric": "world-steps/s", "value": wsps, "unit": "world-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * N_WORLDS / wsps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": batch_config(world, N_WORLDS),
+            "config": batch_config(n_gpus, N_WORLDS),
             "cpu_baseline": {"value": wsps, "unit": "world-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": wsps, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0,
