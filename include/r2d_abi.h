@@ -219,6 +219,32 @@ int r2d_batch_read_bodies(r2d_batch* b, uint32_t* ids, float* pos_xy, float* ang
 int r2d_batch_write_forces(r2d_batch* b, const float* force_xy_torque, size_t n);
 int r2d_batch_get_stats(r2d_batch* b, r2d_step_stats* out);
 
+/* ---- batched worlds sharded over several GPUs of one box (BASELINE config 5) -------------------
+ * World w lives on shard floor(w * G / n_worlds) (contiguous blocks of worlds); shard k is an ordinary batch on
+ * devices[k] with its own stream, resident there for the whole run.  One persistent host thread per shard issues its
+ * work, so the shards step concurrently; there is NO collective and no peer traffic on the data path — worlds are
+ * independent Solvers (every structure hangs off one `Solver`, lib.zig:132-142).  The same device may be named twice
+ * (two shards on one GPU).  Bulk arrays are world-major over ALL worlds, i.e. the shards' arrays back to back. */
+typedef struct r2d_sharded r2d_sharded;
+int r2d_sharded_create(uint32_t n_worlds, const int* devices, uint32_t n_devices, float cell_width, uint32_t table_mult,
+                       r2d_sharded** out);
+int r2d_sharded_destroy(r2d_sharded* b);
+int r2d_sharded_num_worlds(r2d_sharded* b, uint32_t* out);
+int r2d_sharded_num_shards(r2d_sharded* b, uint32_t* out);
+int r2d_sharded_shard(r2d_sharded* b, uint32_t shard, r2d_batch** out, uint32_t* first_world, uint32_t* n_worlds); /* borrowed */
+int r2d_sharded_world(r2d_sharded* b, uint32_t world, r2d_solver** out);   /* borrowed handle (global world index) */
+int r2d_sharded_set_mode(r2d_sharded* b, int mode);
+int r2d_sharded_reorder(r2d_sharded* b);
+int r2d_sharded_process(r2d_sharded* b, float dt, uint32_t sub_steps, uint32_t collision_iters);
+int r2d_sharded_process_read(r2d_sharded* b, float dt, uint32_t sub_steps, uint32_t collision_iters, uint32_t* ids,
+                             float* pos_xy, float* angle, float* momentum_xy, float* ang_momentum, float* aabb_xywh, size_t n);
+int r2d_sharded_synchronize(r2d_sharded* b);
+int r2d_sharded_num_bodies(r2d_sharded* b, size_t* out);
+int r2d_sharded_read_bodies(r2d_sharded* b, uint32_t* ids, float* pos_xy, float* angle, float* momentum_xy,
+                            float* ang_momentum, float* aabb_xywh, size_t capacity);
+int r2d_sharded_write_forces(r2d_sharded* b, const float* force_xy_torque, size_t n);
+int r2d_sharded_get_stats(r2d_sharded* b, r2d_step_stats* out);   /* counters summed over the shards */
+
 /* ---- measurement hooks (bench.py's roofline leg) ----------------------------------------- */
 #define R2D_KCLASS_BROADPHASE 0   /* pose/count, scan, fill, bucket sort, pair count/write */
 #define R2D_KCLASS_NARROWPHASE 1

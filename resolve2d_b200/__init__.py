@@ -5,10 +5,11 @@ Python here is only the host-side mirror of the reference's `Solver`/`EntityFact
 """
 from ._abi import (MODE_FAST, MODE_PARITY, SHAPE_DISC, SHAPE_RECT, BodyState, R2DError, StepStats, body_desc_dtype,
                    load_library, manifold_dtype)
-from .solver import (Batch, BodyHandle, BodyOptions, DiscOptions, EntityFactory, Parameters, RectangleOptions, Solver)
+from .solver import (Batch, BodyHandle, BodyOptions, DiscOptions, EntityFactory, Parameters, RectangleOptions, ShardedBatch,
+                     Solver)
 
 __all__ = [
     "Batch", "BodyHandle", "BodyOptions", "BodyState", "DiscOptions", "EntityFactory", "MODE_FAST", "MODE_PARITY",
-    "Parameters", "R2DError", "RectangleOptions", "SHAPE_DISC", "SHAPE_RECT", "Solver", "StepStats",
+    "Parameters", "R2DError", "RectangleOptions", "SHAPE_DISC", "SHAPE_RECT", "ShardedBatch", "Solver", "StepStats",
     "body_desc_dtype", "load_library", "manifold_dtype",
 ]

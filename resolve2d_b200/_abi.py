@@ -170,6 +170,21 @@ SIGNATURES = {
     "r2d_batch_read_bodies": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _SZ]),
     "r2d_batch_write_forces": (C.c_int, [_P, _P, _SZ]),
     "r2d_batch_get_stats": (C.c_int, [_P, C.POINTER(StepStats)]),
+    "r2d_sharded_create": (C.c_int, [_U32, C.POINTER(C.c_int), _U32, _F, _U32, C.POINTER(_P)]),
+    "r2d_sharded_destroy": (C.c_int, [_P]),
+    "r2d_sharded_num_worlds": (C.c_int, [_P, _UP]),
+    "r2d_sharded_num_shards": (C.c_int, [_P, _UP]),
+    "r2d_sharded_shard": (C.c_int, [_P, _U32, C.POINTER(_P), _UP, _UP]),
+    "r2d_sharded_world": (C.c_int, [_P, _U32, C.POINTER(_P)]),
+    "r2d_sharded_set_mode": (C.c_int, [_P, C.c_int]),
+    "r2d_sharded_reorder": (C.c_int, [_P]),
+    "r2d_sharded_process": (C.c_int, [_P, _F, _U32, _U32]),
+    "r2d_sharded_process_read": (C.c_int, [_P, _F, _U32, _U32, _P, _P, _P, _P, _P, _P, _SZ]),
+    "r2d_sharded_synchronize": (C.c_int, [_P]),
+    "r2d_sharded_num_bodies": (C.c_int, [_P, C.POINTER(_SZ)]),
+    "r2d_sharded_read_bodies": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _SZ]),
+    "r2d_sharded_write_forces": (C.c_int, [_P, _P, _SZ]),
+    "r2d_sharded_get_stats": (C.c_int, [_P, C.POINTER(StepStats)]),
     "r2d_batch_profile_enable": (C.c_int, [_P, C.c_int]),
     "r2d_profile_enable": (C.c_int, [_P, C.c_int]),
     "r2d_batch_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),

@@ -8,11 +8,15 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -447,7 +451,9 @@ struct BatchBase {
         dev_fresh = false;
         return R2D_OK;
     }
+    bool poisoned = false;
     int process(float dt, uint32_t sub_steps, uint32_t iters, const Readback* rb = nullptr) {
+        if (poisoned) return R2D_ERR_BAD_STATE;
         if (dev_fresh && reorder_interval && steps_since_upload >= reorder_interval) {
             const int sr = reorder();
             if (sr != R2D_OK) return sr;
@@ -464,7 +470,16 @@ struct BatchBase {
         readback_done = false;
         const int st2 = backend_process(dt, sub_steps, iters);
         readback = nullptr;
-        if (st2 == R2D_OK || st2 == R2D_ERR_COLOR_OVERFLOW) host_fresh = false;
+        if (st2 == R2D_OK || st2 == R2D_ERR_COLOR_OVERFLOW) {
+            host_fresh = false;
+        } else if (st2 == R2D_ERR_CUDA) {
+            // a stall or a CUDA failure: the state of the step is undefined on the device (every other status is raised
+            // before a kernel has modified a body).  Re-upload from the host mirror if that is still the truth ...
+            if (host_fresh)
+                dev_fresh = false;
+            else
+                poisoned = true;   // ... else no good copy is left: process() reports R2D_ERR_BAD_STATE until r2d_clear()
+        }
         if (st2 == R2D_OK && rb && !readback_done && image.n_bodies)
             return backend_read_bodies(0, image.n_bodies, rb->ids, rb->pos_xy, rb->angle, rb->momentum_xy, rb->ang_momentum, rb->aabb_xywh);
         return st2;

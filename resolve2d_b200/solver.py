@@ -439,3 +439,106 @@ class Batch:
             self.destroy()
         except Exception:
             pass
+
+
+class ShardedBatch:
+    """BASELINE config 5 as a library object: `n_worlds` independent worlds sharded over the GPUs `devices` of one box
+    (world w -> shard floor(w * G / n_worlds)), one host thread + one stream per device inside the library,
+    state resident per device, no collective on the data path.  Bulk arrays are world-major over all worlds."""
+
+    _prefix = "r2d_"
+    _world_class = Solver
+
+    def __init__(self, n_worlds: int, devices: Sequence[int], spatialhash_cell_width: float = 2.0,
+                 spatialhash_table_size_mult: int = 4, *, _lib=None):
+        self._lib = _lib if _lib is not None else _abi.load_library()
+        h = C.c_void_p()
+        dev = (C.c_int * len(devices))(*devices)
+        self._check(self._fn("sharded_create")(n_worlds, dev, len(devices), spatialhash_cell_width,
+                                               spatialhash_table_size_mult, C.byref(h)), "sharded_create")
+        self._h = h
+        self.n_worlds = n_worlds
+        self.n_shards = len(devices)
+
+    def _fn(self, name):
+        return getattr(self._lib, self._prefix + name)
+
+    def _check(self, status, what):
+        if status != 0:
+            detail = ""
+            if self._prefix == "r2d_":
+                detail = (self._lib.r2d_last_error() or b"").decode("utf-8", "replace")
+            raise R2DError(status, what, detail)
+
+    def world(self, w: int) -> Solver:
+        h = C.c_void_p()
+        self._check(self._fn("sharded_world")(self._h, w, C.byref(h)), "sharded_world")
+        return self._world_class(_lib=self._lib, _handle=h, _owner=self)
+
+    def shard(self, k: int):
+        """(first world, number of worlds) of shard k."""
+        first, n = C.c_uint32(), C.c_uint32()
+        self._check(self._fn("sharded_shard")(self._h, k, None, C.byref(first), C.byref(n)), "sharded_shard")
+        return first.value, n.value
+
+    def set_mode(self, mode: int):
+        self._check(self._fn("sharded_set_mode")(self._h, mode), "sharded_set_mode")
+
+    def reorder(self):
+        self._check(self._fn("sharded_reorder")(self._h), "sharded_reorder")
+
+    def process(self, dt: float, sub_steps: int, collision_iters: int):
+        self._check(self._fn("sharded_process")(self._h, dt, sub_steps, collision_iters), "sharded_process")
+
+    def process_read(self, dt: float, sub_steps: int, collision_iters: int, out: dict) -> dict:
+        def p(k):
+            a = out.get(k)
+            return None if a is None else C.c_void_p(a.ctypes.data)
+        self._check(self._fn("sharded_process_read")(self._h, dt, sub_steps, collision_iters, p("id"), p("pos"), p("angle"),
+                                                     p("momentum"), p("ang_momentum"), p("aabb"), self.num_bodies()),
+                    "sharded_process_read")
+        return out
+
+    def synchronize(self):
+        self._check(self._fn("sharded_synchronize")(self._h), "sharded_synchronize")
+
+    def num_bodies(self) -> int:
+        n = C.c_size_t()
+        self._check(self._fn("sharded_num_bodies")(self._h, C.byref(n)), "sharded_num_bodies")
+        return n.value
+
+    def read_bodies(self, out: Optional[dict] = None) -> dict:
+        n = self.num_bodies()
+        if out is None:
+            out = {
+                "id": np.empty(n, np.uint32), "pos": np.empty((n, 2), np.float32), "angle": np.empty(n, np.float32),
+                "momentum": np.empty((n, 2), np.float32), "ang_momentum": np.empty(n, np.float32),
+                "aabb": np.empty((n, 4), np.float32),
+            }
+
+        def p(k):
+            a = out.get(k)
+            return None if a is None else C.c_void_p(a.ctypes.data)
+        self._check(self._fn("sharded_read_bodies")(self._h, p("id"), p("pos"), p("angle"), p("momentum"),
+                                                    p("ang_momentum"), p("aabb"), n), "sharded_read_bodies")
+        return out
+
+    def write_forces(self, force_xy_torque: np.ndarray):
+        a = np.ascontiguousarray(force_xy_torque, dtype=np.float32)
+        self._check(self._fn("sharded_write_forces")(self._h, C.c_void_p(a.ctypes.data), a.shape[0]), "sharded_write_forces")
+
+    def stats(self) -> StepStats:
+        st = StepStats()
+        self._check(self._fn("sharded_get_stats")(self._h, C.byref(st)), "sharded_get_stats")
+        return st
+
+    def destroy(self):
+        if getattr(self, "_h", None) is not None:
+            self._fn("sharded_destroy")(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass

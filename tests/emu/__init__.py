@@ -5,7 +5,7 @@ import os
 import subprocess
 
 from resolve2d_b200 import _abi
-from resolve2d_b200.solver import Batch, Solver
+from resolve2d_b200.solver import Batch, ShardedBatch, Solver
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libr2d_emu.so")
@@ -53,3 +53,13 @@ class EmuBatch:
             self._lib.emu_batch_destroy(self._h)
         except Exception:
             pass
+
+
+class EmuShardedBatch(ShardedBatch):
+    """r2d_sharded_* over the CPU emulator backend: the world -> shard map, the per-shard host threads and the world-major
+    slicing of the bulk arrays are the product's own code (r2d_capi.inc); only the kernels are emulated."""
+    _prefix = "emu_"
+    _world_class = EmuSolver
+
+    def __init__(self, n_worlds, n_shards, cell_width=2.0, table_mult=4):
+        super().__init__(n_worlds, [0] * n_shards, cell_width, table_mult, _lib=load())

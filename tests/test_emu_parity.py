@@ -7,7 +7,7 @@ import pytest
 from emu import EmuBatch, EmuSolver
 from oracle import ORDER_COLORED, OracleSolver
 from parity import assert_bodies_equal, run_parity
-from resolve2d_b200 import scenes
+from resolve2d_b200 import R2DError, scenes
 
 
 def test_emu_0_3_many_boxes():
@@ -167,3 +167,48 @@ def test_emu_nan_or_infinite_pose_is_harmless():
         for k in ("pos", "angle", "momentum", "ang_momentum"):
             assert np.array_equal(a[k][keep].view(np.uint32), b[k][keep].view(np.uint32)), (bad, k)
         assert not np.isfinite(a["pos"][10, 0])
+
+
+def test_sharded_batch_matches_one_oracle_per_world():
+    """r2d_sharded_* (SURVEY 8e): 7 worlds over 3 shards — world w on shard floor(w * 3 / 7), one host thread per shard —
+    step exactly like 7 standalone oracle Solvers; bulk arrays are world-major over all shards."""
+    from emu import EmuShardedBatch
+    n_worlds, n_shards = 7, 3
+    sb = EmuShardedBatch(n_worlds, n_shards)
+    assert [sb.shard(k) for k in range(n_shards)] == [(0, 3), (3, 2), (5, 2)]
+    for w in range(n_worlds):
+        assert w * n_shards // n_worlds == [k for k in range(n_shards) if sb.shard(k)[0] <= w < sum(sb.shard(k))][0]
+    oracles = []
+    for w in range(n_worlds):
+        scenes.build_batch_world(sb.world(w), w, nx=6 + w % 3, ny=3)
+        o = OracleSolver(2.0, 4, order=ORDER_COLORED)
+        scenes.build_batch_world(o, w, nx=6 + w % 3, ny=3)
+        oracles.append(o)
+    n = sb.num_bodies()
+    assert n == sum(o.num_bodies() for o in oracles)
+    rng = np.random.default_rng(3)
+    out = None
+    for step in range(25):
+        f = (rng.normal(size=(n, 3)) * 2).astype(np.float32)
+        sb.write_forces(f)
+        at = 0
+        for o in oracles:
+            k = o.num_bodies()
+            o.write_forces(f[at:at + k])
+            o.process(scenes.DT, 2, 3)
+            at += k
+        if step % 2:
+            sb.process(scenes.DT, 2, 3)
+            out = sb.read_bodies()
+        else:
+            out = sb.process_read(scenes.DT, 2, 3, sb.read_bodies())
+    at = 0
+    for w, o in enumerate(oracles):
+        ob = o.read_bodies()
+        k = len(ob["id"])
+        assert_bodies_equal({key: v[at:at + k] for key, v in out.items()}, ob, f"sharded world {w}")
+        assert_bodies_equal(sb.world(w).read_bodies(), ob, f"sharded world {w} via its handle")
+        at += k
+    assert sb.stats().n_bodies == n
+    with pytest.raises(R2DError):
+        EmuShardedBatch(2, 3)   # fewer worlds than shards

@@ -8,7 +8,7 @@ import pytest
 import hashing as H
 from oracle import ORDER_COLORED, ORDER_REFERENCE, OracleSolver
 from parity import assert_bodies_equal, assert_manifolds_equal, run_parity
-from resolve2d_b200 import MODE_FAST, Batch, R2DError, Solver, scenes
+from resolve2d_b200 import MODE_FAST, Batch, R2DError, ShardedBatch, Solver, scenes
 
 pytestmark = pytest.mark.gpu
 
@@ -213,6 +213,42 @@ def test_gpu_large_batch_uses_world_solver_and_matches_oracle(monkeypatch, cache
         assert np.array_equal(ws.read_pairs(), o.read_pairs()), w
         assert_manifolds_equal(ws.read_manifolds(), o.read_manifolds(), f"world {w}")
         assert_bodies_equal(ws.read_bodies(), o.read_bodies(), f"world {w}")
+
+
+def test_gpu_sharded_batch_equals_one_batch():
+    """r2d_sharded_* (world w -> shard floor(w * G / n_worlds), one host thread + stream per shard, no
+    collective): 200 worlds over 2 and over 3 shards — on two different GPUs when the box has them, else on one — stay
+    bit-identical to the same 200 worlds in one batch, through process(), process_read() and write_forces()."""
+    import ctypes as C
+    from resolve2d_b200 import _abi
+    n_dev = C.c_int()
+    _abi.load_library().r2d_device_count(C.byref(n_dev))
+    n_worlds = 200
+    one = Batch(n_worlds, 2.0, 4)
+    variants = [ShardedBatch(n_worlds, [0, 1 % n_dev.value]), ShardedBatch(n_worlds, [0, 1 % n_dev.value, 2 % n_dev.value])]
+    assert variants[1].shard(1) == (67, 67) and variants[1].shard(2) == (134, 66)
+    for w in range(n_worlds):
+        d = scenes.descs_batch_world(w, nx=12, ny=6)
+        for x in [one] + variants:
+            fac = x.world(w).entity_factory()
+            fac.make_downwards_gravity(scenes.GRAVITY)
+            fac.make_bodies(d)
+    n = one.num_bodies()
+    rng = np.random.default_rng(11)
+    for step in range(40):
+        f = (rng.normal(size=(n, 3)) * 3).astype(np.float32)
+        outs = []
+        for x in [one] + variants:
+            x.write_forces(f)
+            if step % 3 == 0:
+                outs.append(x.process_read(scenes.DT, 4, 4, x.read_bodies()))
+            else:
+                x.process(scenes.DT, 4, 4)
+                outs.append(x.read_bodies())
+        for k, o in enumerate(outs[1:]):
+            assert_bodies_equal(o, outs[0], f"sharded variant {k} step {step}")
+    assert variants[0].stats().n_manifolds == one.stats().n_manifolds > 5000
+    assert np.array_equal(variants[1].world(150).read_pairs(), one.world(150).read_pairs())
 
 
 def test_gpu_large_batch_with_joints_uses_per_world_colouring_and_dataflow_sweep():
