@@ -786,9 +786,13 @@ struct CudaBatch : BatchBase {
                     g_cuda_error = "broadphase buffers failed to converge";
                     return R2D_ERR_OUT_OF_MEMORY;
                 }
-                if (c.n_entries > cap_entries && (st = reserve_entries((size_t)c.n_entries + c.n_entries / 4))) return st;
-                // P is only meaningful once all entries fit; grow generously when it is known to be too small
-                if (c.n_pairs > cap_pairs && (st = reserve_pairs((size_t)c.n_pairs + c.n_pairs / 4))) return st;
+                // P is only meaningful once all entries fit (the pair kernels do nothing on an attempt whose grid overflowed,
+                // so n_pairs is then the scan of stale counts)
+                if (c.n_entries > cap_entries) {
+                    if ((st = reserve_entries((size_t)c.n_entries + c.n_entries / 4))) return st;
+                } else if ((st = reserve_pairs((size_t)c.n_pairs + c.n_pairs / 4))) {
+                    return st;
+                }
                 continue;
             }
             if (c.tile_fallback && use_tile_solver) {
