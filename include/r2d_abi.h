@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define R2D_ABI_VERSION 1
+#define R2D_ABI_VERSION 2
 
 /* ---- status codes ---------------------------------------------------------------------------- */
 #define R2D_OK 0
@@ -36,11 +36,17 @@ extern "C" {
 #define R2D_ERR_INVALID_ARGUMENT (-4)  /* NULL handle / out-of-range argument (reference: `unreachable`) */
 #define R2D_ERR_NO_DEVICE (-5)         /* no usable CUDA device: the product path has no CPU fallback */
 #define R2D_ERR_CUDA (-6)              /* CUDA runtime error; text via r2d_last_error() */
-#define R2D_ERR_COLOR_OVERFLOW (-7)    /* contact graph needs more than R2D_MAX_COLORS colours */
+#define R2D_ERR_COLOR_OVERFLOW (-7)    /* the graph colouring did not terminate (internal limit of 4,000 rounds) */
 #define R2D_ERR_BAD_STATE (-8)         /* e.g. r2d_process on a world that belongs to a multi-world batch */
 #define R2D_ERR_GRID_RANGE (-9)        /* a body AABB covers an unreasonable number of grid cells (NaN/inf pose) */
 
+/* HARD LIMIT of this boundary (the reference has none): the contacts of a body are swept in colour order and a body
+ * can hold R2D_MAX_COLORS colours, so a non-static body with more than 256 simultaneous manifolds keeps its 256
+ * highest-priority ones (contact_priority of the two ids); the others are reported by
+ * r2d_read_manifolds with colour R2D_COLOR_DROPPED, counted in r2d_step_stats.n_dropped and left out of that call's
+ * sweeps.  Everything else of the step — every other contact, joints, integration — proceeds normally. */
 #define R2D_MAX_COLORS 256
+#define R2D_COLOR_DROPPED 0xFFFFFFFDu
 
 /* ---- shapes and joint kinds (reference enums: RigidBody.zig:28-31, Constraint.zig:15-20) ------ */
 #define R2D_SHAPE_DISC 0
@@ -57,6 +63,12 @@ extern "C" {
  * FAST:   honours cell_width / table_mult given to r2d_create (the reference's stated intent, README roadmap). */
 #define R2D_MODE_PARITY 0
 #define R2D_MODE_FAST 1
+/* REFERENCE_ORDER (validation only, slow, single worlds): the PARITY broadphase and narrowphase, but the contacts are
+ *         swept SEQUENTIALLY in the reference's own order — manifolds in the order updateManifolds discovers them
+ *         (lib.zig:262-297 over the SpatialHash query order, replayed on the host), joints in list order — instead of the
+ *         graph-colour order.  Gauss-Seidel is order dependent, so this is the mode whose body state equals the
+ *         reference binary's bit for bit on every step (tests/golden/wasm_golden.json: 1,285 steps). */
+#define R2D_MODE_REFERENCE_ORDER 2
 
 typedef struct r2d_solver r2d_solver;
 typedef struct r2d_batch r2d_batch;
@@ -127,6 +139,7 @@ typedef struct r2d_step_stats {
     uint32_t n_joints;     /* C */
     uint32_t n_joint_colors;
     uint32_t n_launches;   /* kernels launched by the last process() */
+    uint32_t n_dropped;    /* manifolds left out of the sweeps: no colour free (see R2D_MAX_COLORS); 0 in any sane scene */
 } r2d_step_stats;
 
 /* ---- library ---------------------------------------------------------------------------------- */

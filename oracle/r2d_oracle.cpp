@@ -771,7 +771,7 @@ struct Solver {
     // instrumentation
     std::set<std::pair<uint32_t, uint32_t>> candidate_pairs;  // the set C of SURVEY A.2, logged at lib.zig:282
     size_t stat_entries = 0, stat_raw_candidates = 0;
-    uint32_t stat_colors = 0, stat_joint_colors = 0;
+    uint32_t stat_colors = 0, stat_joint_colors = 0, stat_dropped = 0;
     std::vector<size_t> manifold_order, joint_order;          // sweep order actually used by the last process()
 
     RigidBody* find(uint32_t id) {
@@ -880,6 +880,7 @@ struct Solver {
         for (size_t i = 0; i < constraints.size(); ++i) joint_order[i] = i;
         stat_colors = 0;
         stat_joint_colors = 0;
+        stat_dropped = 0;
         for (CollisionManifold& m : manifolds) m.color = 0;
         for (Constraint& c : constraints) c.color = 0;
         if (gs_order != ORDER_COLORED) return;
@@ -904,6 +905,14 @@ struct Solver {
                     }
                     if (!taken) break;
                 }
+                // The CUDA path has 256 colours (a hard limit of the boundary, include/r2d_abi.h R2D_MAX_COLORS): a manifold
+                // that finds none free — a body with more than 256 simultaneous contacts — is left out of this call's sweeps
+                // (it keeps its place in the manifold list, colour R2D_COLOR_DROPPED).
+                if (c >= 256) {
+                    m.color = 0xFFFFFFFDu;
+                    stat_dropped += 1;
+                    continue;
+                }
                 m.color = c;
                 for (size_t b : bs)
                     if (!bodies[b].is_static) used[b].push_back(c);
@@ -911,6 +920,7 @@ struct Solver {
             }
             std::stable_sort(manifold_order.begin(), manifold_order.end(),
                              [&](size_t a, size_t b) { return manifolds[a].color < manifolds[b].color; });
+            while (!manifold_order.empty() && manifolds[manifold_order.back()].color == 0xFFFFFFFDu) manifold_order.pop_back();
         }
         {
             std::unordered_map<uint32_t, std::vector<uint32_t>> used;
@@ -1147,7 +1157,7 @@ struct orc_body_state {  // == r2d_body_state
 };
 struct orc_step_stats {  // == r2d_step_stats
     uint32_t n_bodies, n_buckets, n_entries, n_pairs, n_manifolds, n_points, n_colors, n_color_rounds, n_joints,
-        n_joint_colors, n_launches;
+        n_joint_colors, n_launches, n_dropped;
 };
 
 int orc_create(float cell_width, uint32_t table_mult, int /*device*/, void** out) {
@@ -1441,6 +1451,7 @@ int orc_get_stats(void* h, orc_step_stats* out) {
     out->n_colors = s->stat_colors;
     out->n_joints = (uint32_t)s->constraints.size();
     out->n_joint_colors = s->stat_joint_colors;
+    out->n_dropped = s->stat_dropped;
     return 0;
 }
 uint64_t orc_raw_candidates(void* h) { return ((Solver*)h)->stat_raw_candidates; }

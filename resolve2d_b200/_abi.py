@@ -23,7 +23,7 @@ ERRORS = {
 
 SHAPE_DISC, SHAPE_RECT = 0, 1
 JOINT_DISTANCE, JOINT_OFFSET_DISTANCE, JOINT_FIXED_POSITION, JOINT_MOTOR = 0, 1, 2, 3
-MODE_PARITY, MODE_FAST = 0, 1
+MODE_PARITY, MODE_FAST, MODE_REFERENCE_ORDER = 0, 1, 2
 KCLASS_NAMES = ["broadphase", "narrowphase", "coloring", "integrate", "solve_contacts", "solve_joints"]
 
 
@@ -72,7 +72,7 @@ class Manifold(C.Structure):
 class StepStats(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in (
         "n_bodies", "n_buckets", "n_entries", "n_pairs", "n_manifolds", "n_points", "n_colors", "n_color_rounds",
-        "n_joints", "n_joint_colors", "n_launches")]
+        "n_joints", "n_joint_colors", "n_launches", "n_dropped")]
 
 
 # numpy dtype twins of the structures above (bulk creation / bulk readback)

@@ -352,6 +352,59 @@ inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image&
     return R2D_OK;
 }
 
+// R2D_MODE_REFERENCE_ORDER: the order in which the reference's updateManifolds (lib.zig:262-297) creates the manifolds of
+// one world, replayed on the host from the AABBs the broadphase saw: SpatialHash.init (SpatialHash.zig:19-71: count,
+// inclusive prefix, decrement-then-store fill, so a bucket lists its entries in REVERSE insertion order), then for every
+// body in iteration order its query (:108-137: cells row-major, y outer; bucket contents appended, duplicates kept).  A
+// pair becomes a manifold the first time the walk meets it.  `aabb[k]` = stored AABB (centre, half extents) of the k-th
+// body in ITERATION order; `manifold_of(lo, hi)` = the manifold's index for that unordered pair of iteration indices, or
+// -1.  Returns the manifold indices in creation order.
+template <class Lookup>
+inline std::vector<uint32_t> reference_manifold_order(const std::vector<float4>& aabb, float cell, uint32_t table_size,
+                                                      size_t n_manifolds, Lookup manifold_of) {
+    const size_t n = aabb.size();
+    std::vector<uint32_t> order;
+    order.reserve(n_manifolds);
+    if (n == 0 || table_size == 0) return order;
+    struct Range { int64_t x0, y0, x1, y1; };
+    std::vector<Range> rg(n);
+    for (size_t i = 0; i < n; ++i) {   // iterateAABBHashes :83-96 (getVertices: min = pos - half, max = pos + half)
+        const float4 a = aabb[i];
+        rg[i] = {cell_coord(fsub(a.x, a.z), cell), cell_coord(fsub(a.y, a.w), cell), cell_coord(fadd(a.x, a.z), cell),
+                 cell_coord(fadd(a.y, a.w), cell)};
+        if (rg[i].x1 - rg[i].x0 > MAX_BODY_CELLS || rg[i].y1 - rg[i].y0 > MAX_BODY_CELLS) rg[i] = {0, 0, -1, -1};   // NaN / inf pose
+    }
+    std::vector<uint32_t> table(table_size + 1, 0u);
+    for (size_t i = 0; i < n; ++i)
+        for (int64_t y = rg[i].y0; y <= rg[i].y1; ++y)
+            for (int64_t x = rg[i].x0; x <= rg[i].x1; ++x) table[cell_hash(x, y, table_size)] += 1;
+    uint32_t start = 0;
+    for (uint32_t h = 0; h < table_size; ++h) {
+        start += table[h];
+        table[h] = start;
+    }
+    table[table_size] = start;
+    std::vector<uint32_t> entries(start);
+    for (size_t i = 0; i < n; ++i)
+        for (int64_t y = rg[i].y0; y <= rg[i].y1; ++y)
+            for (int64_t x = rg[i].x0; x <= rg[i].x1; ++x) entries[--table[cell_hash(x, y, table_size)]] = (uint32_t)i;
+    std::vector<unsigned char> seen(n_manifolds, 0);
+    for (size_t i = 0; i < n; ++i)
+        for (int64_t y = rg[i].y0; y <= rg[i].y1; ++y)
+            for (int64_t x = rg[i].x0; x <= rg[i].x1; ++x) {
+                const uint64_t h = cell_hash(x, y, table_size);
+                for (uint32_t e = table[h]; e < table[h + 1]; ++e) {
+                    const uint32_t j = entries[e];
+                    if (j == i) continue;
+                    const long m = manifold_of(std::min<uint32_t>((uint32_t)i, j), std::max<uint32_t>((uint32_t)i, j));
+                    if (m < 0 || seen[m]) continue;
+                    seen[m] = 1;
+                    order.push_back((uint32_t)m);
+                }
+            }
+    return order;
+}
+
 struct RawManifold {   // one occupied pair slot of the last process(), slots are global
     uint32_t ref, inc, normal_id, n_points, color;
     float normal_x, normal_y;
@@ -387,8 +440,8 @@ struct BatchBase {
     virtual int backend_profile_enable(int on) = 0;
     virtual int backend_profile_read(double* ms, uint64_t* launches, int reset) = 0;
 
-    float grid_cell() const { return mode == R2D_MODE_PARITY ? 4.0f : cell_width; }      // lib.zig:254-255 (Q2)
-    uint32_t grid_mult() const { return mode == R2D_MODE_PARITY ? 2u : (table_mult ? table_mult : 1u); }
+    float grid_cell() const { return mode != R2D_MODE_FAST ? 4.0f : cell_width; }      // lib.zig:254-255 (Q2)
+    uint32_t grid_mult() const { return mode != R2D_MODE_FAST ? 2u : (table_mult ? table_mult : 1u); }
 
     int ensure_host() {
         if (!host_fresh) {

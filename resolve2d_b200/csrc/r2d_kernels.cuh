@@ -802,13 +802,15 @@ __global__ void __launch_bounds__(TPB, 4) k_color(Dev d) {
         for (int k = 0; k < COLOR_REG_SLOTS; ++k) {
             if (!pend[k]) continue;
             uint32_t c;
-            if (color_round_core(d, tid + (uint32_t)k * nth, rh[k], rp[k], round, &c) == 1) {
+            const int r = color_round_core(d, tid + (uint32_t)k * nth, rh[k], rp[k], round, &c);
+            if (r == 1) {
                 atomicAdd(&s_hist[c], 1u);
                 owner_bit_set(d, rh[k].x, rh[k].y, rh[k].w, c);
-                pend[k] = false;
-            } else {
-                left = 1;
             }
+            if (r == 2)
+                left = 1;
+            else
+                pend[k] = false;
         }
         for (uint32_t p = tid + COLOR_REG_SLOTS * nth; p < n; p += nth) {
             const int r = color_round_thread(d, p, round);
@@ -895,13 +897,15 @@ __global__ void __launch_bounds__(WORLD_TPB) k_color_worlds(Dev d) {
             for (int k = 0; k < WORLD_REG_SLOTS; ++k) {
                 if (!pend[k]) continue;
                 uint32_t c;
-                if (color_round_core(ds, p0 + threadIdx.x + (uint32_t)k * blockDim.x, rh[k], rp[k], round, &c) == 1) {
+                const int r = color_round_core(ds, p0 + threadIdx.x + (uint32_t)k * blockDim.x, rh[k], rp[k], round, &c);
+                if (r == 1) {
                     atomicAdd(&s_hist[c], 1u);
                     owner_bit_set(d, rh[k].x, rh[k].y, rh[k].w, c);
-                    pend[k] = false;
-                } else {
-                    left = 1;
                 }
+                if (r == 2)
+                    left = 1;
+                else
+                    pend[k] = false;
             }
             for (uint32_t p = p0 + threadIdx.x + WORLD_REG_SLOTS * blockDim.x; p < p1; p += blockDim.x) {
                 const int r = color_round_thread(ds, p, round);
@@ -938,7 +942,7 @@ __global__ void __launch_bounds__(WORLD_TPB) k_color_worlds_seq(Dev d, uint32_t 
     extern __shared__ unsigned long long s_used_dyn[];   // smem_bodies x COLOR_WORDS
     __shared__ unsigned long long s_key[SEQ_WORLD_PAIRS];
     __shared__ uint32_t s_pair[SEQ_WORLD_PAIRS];
-    __shared__ unsigned char s_col[SEQ_WORLD_PAIRS];
+    __shared__ unsigned short s_col[SEQ_WORLD_PAIRS];   // colour, or 0xFFFF: no colour free (COLOR_DROPPED)
     __shared__ uint32_t s_hist[MAX_COLORS];
     __shared__ uint32_t s_lanes[COLOR_WORLD_MAX_BODIES];   // per body: the lanes of the current chunk that touch it
     __shared__ unsigned short s_order[SEQ_WORLD_PAIRS];    // pair indices in descending priority
@@ -1035,15 +1039,16 @@ __global__ void __launch_bounds__(WORLD_TPB) k_color_worlds_seq(Dev d, uint32_t 
                                     break;
                                 }
                             }
-                            if (color >= MAX_COLORS) {
-                                atomicOr(&d.counters->err, ERR_COLOR_OVERFLOW);
-                                color = MAX_COLORS - 1;
+                            if (color >= MAX_COLORS) {   // a body with more than MAX_COLORS contacts: the manifold sits this call out
+                                atomicAdd(&d.counters->n_dropped, 1u);
+                                s_col[i] = 0xFFFFu;
+                            } else {
+                                const unsigned long long bit = 1ull << (color & 63u);
+                                if (dyn1) s_used_dyn[l1 * COLOR_WORDS + (color >> 6)] |= bit;
+                                if (dyn2) s_used_dyn[l2 * COLOR_WORDS + (color >> 6)] |= bit;
+                                s_col[i] = (unsigned short)color;
+                                atomicAdd(&s_hist[color], 1u);
                             }
-                            const unsigned long long bit = 1ull << (color & 63u);
-                            if (dyn1) s_used_dyn[l1 * COLOR_WORDS + (color >> 6)] |= bit;
-                            if (dyn2) s_used_dyn[l2 * COLOR_WORDS + (color >> 6)] |= bit;
-                            s_col[i] = (unsigned char)color;
-                            atomicAdd(&s_hist[color], 1u);
                             pending = false;
                         }
                         __syncwarp();
@@ -1053,6 +1058,10 @@ __global__ void __launch_bounds__(WORLD_TPB) k_color_worlds_seq(Dev d, uint32_t 
             __syncthreads();
             for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
                 const uint32_t i = (uint32_t)s_order[k], pr = s_pair[i];
+                if (s_col[i] == 0xFFFFu) {
+                    d.m_color[p0 + i] = COLOR_DROPPED;
+                    continue;
+                }
                 d.m_color[p0 + i] = s_col[i];
                 owner_bit_set(d, b0 + (pr & 0xFFFu), b0 + ((pr >> 12) & 0xFFFu), (pr >> 24) & 3u, s_col[i]);
             }
@@ -1462,6 +1471,30 @@ __global__ void __launch_bounds__(TILE_TPB) k_solve_tiles(Dev d, float sub_dt, u
         }
     }
     // accumulated impulses of the cached records are not needed after the call (collision.zig:102-133 re-creates them)
+}
+
+// ---- R2D_MODE_REFERENCE_ORDER (validation, slow): the substep loop of lib.zig:199-250 with the SEQUENTIAL Gauss-Seidel sweep
+// of the reference — joints in list order, then manifolds in the order updateManifolds created them (`order`: pair slots,
+// replayed on the host by reference_manifold_order) — by ONE thread of one CTA; the per-body phases use the whole CTA.
+__global__ void __launch_bounds__(TPB) k_solve_reference_order(Dev d, float sub_dt, uint32_t S, uint32_t I,
+                                                               const uint32_t* __restrict__ order, uint32_t n_order,
+                                                               const uint32_t* __restrict__ joint_list, uint32_t n_joints) {
+    if (overflowed(d) || d.counters->err != 0u) return;
+    // preStep (collision.zig:102-133) into the record slot of the manifold's own pair slot
+    for (uint32_t k = threadIdx.x; k < n_order; k += blockDim.x) gather_prestep_thread(d, order[k], order[k]);
+    __syncthreads();
+    for (uint32_t s = 0; s < S; ++s) {
+        for (uint32_t i = threadIdx.x; i < d.n_bodies; i += blockDim.x) integrate_forces_thread(d, i, sub_dt, s + 1 == S);
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (uint32_t it = 0; it < I; ++it) {   // lib.zig:226-236
+                for (uint32_t j = 0; j < n_joints; ++j) solve_joint_thread(d, joint_list[j], sub_dt);
+                for (uint32_t k = 0; k < n_order; ++k) solve_contact_thread<false>(d, order[k], sub_dt);
+            }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < d.n_bodies; i += blockDim.x) integrate_positions_thread(d, i, sub_dt);
+        __syncthreads();
+    }
 }
 
 // ---- boundary kernels: SoA export for bulk readback, force import ---------------------------------------------------------------

@@ -33,6 +33,8 @@ namespace r2d {
 
 constexpr uint32_t COLOR_NONE = 0xFFFFFFFFu;       // pair slot holds no manifold
 constexpr uint32_t COLOR_PENDING = 0xFFFFFFFEu;    // manifold not coloured yet
+constexpr uint32_t COLOR_DROPPED = 0xFFFFFFFDu;    // manifold found none of the MAX_COLORS colours free on one of its bodies (a
+                                                   // body with more than 256 simultaneous contacts): left out of this call's sweeps
 constexpr uint32_t MAX_COLORS = 256;
 constexpr uint32_t S_EMPTY = 0x400u;              // s_hdr.z: padding slot (colour segments are padded to whole warps)
 constexpr uint32_t COLOR_ALIGN = 32;
@@ -68,7 +70,7 @@ struct Counters {
     uint32_t n_work;         // buckets holding 2..SMALL_BUCKET entries (a warp each in the pair kernels)
     uint32_t n_mid;          // SMALL_BUCKET+1..HEAVY_BUCKET entries (a warp or a CTA each, see medium_by_cta)
     uint32_t n_heavy;        // buckets holding more (a CTA each)
-    uint32_t pad0;
+    uint32_t n_dropped;      // manifolds left without a colour (COLOR_DROPPED)
     uint32_t flow_abort;     // set by the narrowphase: a body has more than ADJ_CAP manifolds, colour by rounds
     uint32_t flow_fail;      // set inside the dataflow colouring: more than FLOW_COLORS colours needed (or a stall)
     uint32_t flow_used;      // the colours of this step come from the dataflow colouring (masks in cstate, not in used)
@@ -704,7 +706,7 @@ R2D_HD void color_post(const Dev& d, uint32_t ref, uint32_t inc, bool dyn1, bool
     if (dyn2) atomic_max_u64(&mp[inc], v);
 }
 // One colouring round for a pending manifold whose header / priority the caller holds (registers across rounds).
-// Returns 1 coloured now (colour in *out_color), 2 still pending (re-posted for round + 1).
+// Returns 1 coloured now (colour in *out_color), 2 still pending (re-posted for round + 1), 3 dropped (no colour free).
 R2D_HD int color_round_core(const Dev& d, uint32_t p, const uint4& h, uint64_t prio, uint32_t round, uint32_t* out_color) {
     const bool dyn1 = (h.w & 1u) != 0, dyn2 = (h.w & 2u) != 0;
     const unsigned long long mine = ((unsigned long long)round << PRIO_ROUND_SHIFT) | prio;
@@ -725,9 +727,10 @@ R2D_HD int color_round_core(const Dev& d, uint32_t p, const uint4& h, uint64_t p
             break;
         }
     }
-    if (color >= MAX_COLORS) {
-        atomic_or_u32(&d.counters->err, ERR_COLOR_OVERFLOW);
-        color = MAX_COLORS - 1;
+    if (color >= MAX_COLORS) {   // every colour is taken on one of its bodies: the manifold sits this call out (R2D_MAX_COLORS)
+        atomic_add_u32(&d.counters->n_dropped, 1u);
+        d.m_color[p] = COLOR_DROPPED;
+        return 3;
     }
     const unsigned long long bit = 1ull << (color & 63u);
     // unique winner per body and round: a plain read-modify-write cannot race

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "r2d_host.hpp"
@@ -112,7 +113,7 @@ struct CudaBatch : BatchBase {
     bool world_broad = true;          // k_world_broad for batches of small worlds (R2D_WORLD_BROAD=0: device-wide grid kernels)
     bool world_broad_declined = false;  // a world's grid did not fit shared memory: device-wide kernels until the next upload
     uint32_t max_world_large_cells = 0; // grid entries of the large bodies of the widest world (bound from the upload)
-    DBuf<unsigned long long> world_state;
+    DBuf<uint32_t> ref_order, ref_joints;   // R2D_MODE_REFERENCE_ORDER: manifold / joint sweep order of the reference
     bool world_fused_now = false;     // this step is solved by k_world_solve (which also places and pre-steps the manifolds)
     // pairs / manifolds
     DBuf<uint2> pairs;
@@ -705,6 +706,68 @@ struct CudaBatch : BatchBase {
                 R2D_LAUNCH(R2D_KCLASS_NARROWPHASE, k_narrow<2>, grid_for((cap_pairs + 1) / 2), TPB, d);
             else
                 R2D_LAUNCH(R2D_KCLASS_NARROWPHASE, k_narrow<1>, grid_for(cap_pairs), TPB, d);
+            if (mode == R2D_MODE_REFERENCE_ORDER) {   // validation: the reference's own sequential sweep order (see r2d_abi.h)
+                R2D_CUDA(cudaMemcpyAsync(&pinned->counters, d.counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+                R2D_CUDA(cudaStreamSynchronize(stream));
+                const Counters c0 = pinned->counters;
+                if (c0.n_entries > cap_entries || c0.n_pairs > cap_pairs) {
+                    if (attempt >= 4) return R2D_ERR_OUT_OF_MEMORY;
+                    if (c0.n_entries > cap_entries) {
+                        if ((st = reserve_entries((size_t)c0.n_entries + c0.n_entries / 4))) return st;
+                    } else if ((st = reserve_pairs((size_t)c0.n_pairs + c0.n_pairs / 4))) {
+                        return st;
+                    }
+                    continue;
+                }
+                if ((st = join_forces())) return st;
+                const uint32_t P = c0.n_pairs;
+                std::vector<uint2> hp(P);
+                std::vector<uint32_t> hc(P);
+                std::vector<float4> ha(nb), ha_iter(nb);
+                if (P) {
+                    R2D_CUDA(cudaMemcpyAsync(hp.data(), pairs.p, (size_t)P * 8, cudaMemcpyDeviceToHost, stream));
+                    R2D_CUDA(cudaMemcpyAsync(hc.data(), m_color.p, (size_t)P * 4, cudaMemcpyDeviceToHost, stream));
+                }
+                R2D_CUDA(cudaMemcpyAsync(ha.data(), aabb.p, (size_t)nb * 16, cudaMemcpyDeviceToHost, stream));
+                R2D_CUDA(cudaStreamSynchronize(stream));
+                for (uint32_t k = 0; k < nb; ++k) ha_iter[k] = ha[image.dev_of_host[k]];   // iteration order of the host registry
+                std::unordered_map<uint64_t, uint32_t> slot_of_pair;
+                for (uint32_t p = 0; p < P; ++p) {
+                    if (hc[p] == COLOR_NONE) continue;   // SAT found a gap: no manifold
+                    const uint32_t a = image.host_of_dev[hp[p].x], b = image.host_of_dev[hp[p].y];
+                    slot_of_pair[((uint64_t)std::min(a, b) << 32) | std::max(a, b)] = p;
+                }
+                std::vector<uint32_t> pair_slots;   // manifold index -> pair slot, filled through the lookup below
+                pair_slots.reserve(slot_of_pair.size());
+                std::unordered_map<uint64_t, long> index_of_pair;
+                for (auto& kv : slot_of_pair) {
+                    index_of_pair[kv.first] = (long)pair_slots.size();
+                    pair_slots.push_back(kv.second);
+                }
+                const std::vector<uint32_t> by_creation = host::reference_manifold_order(
+                    ha_iter, grid_cell(), T, pair_slots.size(), [&](uint32_t lo, uint32_t hi) -> long {
+                        auto it = index_of_pair.find(((uint64_t)lo << 32) | hi);
+                        return it == index_of_pair.end() ? -1L : it->second;
+                    });
+                if (by_creation.size() != pair_slots.size()) {
+                    g_cuda_error = "internal error: a manifold was not met by the replay of the reference's grid walk";
+                    return R2D_ERR_CUDA;
+                }
+                std::vector<uint32_t> order(by_creation.size());
+                for (size_t k = 0; k < order.size(); ++k) order[k] = pair_slots[by_creation[k]];
+                const size_t nj = image.j_hdr.size();
+                std::vector<uint32_t> joint_list(nj);   // list order: the device joints are sorted by colour
+                for (size_t k = 0; k < nj; ++k) joint_list[image.joint_local_index[k]] = (uint32_t)k;
+                if ((st = ref_order.reserve(order.size() + 1)) || (st = ref_joints.reserve(nj + 1))) return st;
+                if (!order.empty()) R2D_CUDA(cudaMemcpyAsync(ref_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, stream));
+                if (nj) R2D_CUDA(cudaMemcpyAsync(ref_joints.p, joint_list.data(), nj * 4, cudaMemcpyHostToDevice, stream));
+                R2D_LAUNCH(R2D_KCLASS_SOLVE_CONTACTS, k_solve_reference_order, 1, TPB, d, sub_dt, S, I, (const uint32_t*)ref_order.p,
+                           (uint32_t)order.size(), (const uint32_t*)ref_joints.p, (uint32_t)nj);
+                R2D_CUDA(cudaMemcpyAsync(&pinned->counters, d.counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+                R2D_CUDA(cudaStreamSynchronize(stream));   // (also keeps the host vectors alive until the copies are done)
+                R2D_CUDA(cudaGetLastError());
+                break;
+            }
             // ---- colouring + partition + pre-step ----
             if (color_per_world) {
                 const uint32_t blocks = (uint32_t)std::min<size_t>(worlds.size(), (size_t)n_sms * 8);
@@ -835,8 +898,9 @@ struct CudaBatch : BatchBase {
             g_cuda_error = "internal error: the dataflow contact sweep stalled (state of this step is undefined)";
             return R2D_ERR_CUDA;
         }
-        if (c.err & (ERR_COLOR_OVERFLOW | ERR_ROUNDS)) {
-            g_cuda_error = "contact graph needs more than R2D_MAX_COLORS colours";
+        stats.n_dropped = c.n_dropped;
+        if (c.err & ERR_ROUNDS) {
+            g_cuda_error = "the colouring did not finish within its round limit";
             return R2D_ERR_COLOR_OVERFLOW;
         }
         // ---- substeps, one launch per colour (A/B path: R2D_SOLVER=launches) ----

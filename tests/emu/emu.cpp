@@ -292,7 +292,6 @@ struct EmuBatch : BatchBase {
             rounds = round;
             if (left == 0) break;
         }
-        if (counters.err & ERR_COLOR_OVERFLOW) return R2D_ERR_COLOR_OVERFLOW;
         if (counters.err & ERR_GRID_RANGE) return R2D_ERR_GRID_RANGE;
         // ---- owner bitmaps -> positions (colour-sorted, owner-slot order) + pre-step ----
         counters.n_colors = n_colors;
@@ -342,6 +341,7 @@ struct EmuBatch : BatchBase {
         stats.n_points = K;
         stats.n_colors = n_colors;
         stats.n_color_rounds = rounds;
+        stats.n_dropped = counters.n_dropped;
         return R2D_OK;
     }
 };

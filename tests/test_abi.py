@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     assert set(declared) == set(_abi.SIGNATURES), set(declared) ^ set(_abi.SIGNATURES)
     _abi.bind(lib)
-    assert lib.r2d_abi_version() == 1
+    assert lib.r2d_abi_version() == 2
 
 
 def test_no_device_is_an_error_not_a_fallback():
@@ -43,7 +43,7 @@ def test_no_device_is_an_error_not_a_fallback():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_abi.BodyOpts) == 36 and ctypes.sizeof(_abi.BodyDesc) == 52
     assert ctypes.sizeof(_abi.JointParams) == 12 and ctypes.sizeof(_abi.BodyState) == 84
-    assert ctypes.sizeof(_abi.Manifold) == 84 and ctypes.sizeof(_abi.StepStats) == 44
+    assert ctypes.sizeof(_abi.Manifold) == 84 and ctypes.sizeof(_abi.StepStats) == 48
     assert _abi.body_desc_dtype().itemsize == 52 and _abi.manifold_dtype().itemsize == 84
 
 

@@ -212,3 +212,17 @@ def test_sharded_batch_matches_one_oracle_per_world():
     assert sb.stats().n_bodies == n
     with pytest.raises(R2DError):
         EmuShardedBatch(2, 3)   # fewer worlds than shards
+
+
+def test_emu_hub_body_beyond_256_colours_keeps_stepping():
+    """A plank resting on 300 discs has 300 manifolds on ONE non-static body; the boundary has 256 colours (R2D_MAX_COLORS,
+    a declared hard limit).  The 44 lowest-priority manifolds are reported with colour R2D_COLOR_DROPPED and left out of
+    the sweeps; the step itself — every other contact, integration — goes on, bit for bit like the oracle under the same
+    rule (round 1 returned ColorOverflow here and the world froze for good)."""
+    def build(s):
+        return scenes.build_hub(s, n_discs=300)
+    cand, orc = run_parity(lambda: EmuSolver(2.0, 4), build, 12, check_every=4, what="hub300")
+    st = cand.stats()
+    assert st.n_colors == 256 and st.n_dropped >= 40 and st.n_dropped == orc.stats().n_dropped
+    man = cand.read_manifolds()
+    assert np.count_nonzero(man["color"] == 0xFFFFFFFD) == st.n_dropped

@@ -8,7 +8,7 @@ import pytest
 import hashing as H
 from oracle import ORDER_COLORED, ORDER_REFERENCE, OracleSolver
 from parity import assert_bodies_equal, assert_manifolds_equal, run_parity
-from resolve2d_b200 import MODE_FAST, Batch, R2DError, ShardedBatch, Solver, scenes
+from resolve2d_b200 import MODE_FAST, MODE_REFERENCE_ORDER, Batch, R2DError, ShardedBatch, Solver, scenes
 
 pytestmark = pytest.mark.gpu
 
@@ -19,7 +19,7 @@ def test_library_reports_device():
     lib = _abi.load_library()
     n = C.c_int()
     assert lib.r2d_device_count(C.byref(n)) == 0 and n.value >= 1
-    assert lib.r2d_abi_version() == 1
+    assert lib.r2d_abi_version() == 2
 
 
 def test_gpu_0_3_many_boxes():
@@ -60,6 +60,53 @@ def test_gpu_golden_prefix_of_reference_binary():
                 assert st.n_entries <= g["E"]     # fine grid: small bodies list one home cell instead of their 4 m cells
 
 
+def _golden_runs():
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "wasm_golden.json")))
+    return {k: v for k, v in gold.items() if not k.startswith("_")}
+
+
+@pytest.mark.parametrize("name", sorted(_golden_runs()))
+def test_gpu_reference_order_mode_reproduces_the_reference_binary(name):
+    """R2D_MODE_REFERENCE_ORDER: the CUDA broadphase, narrowphase, integrators, joints and contact arithmetic with the
+    reference's own SEQUENTIAL sweep order (manifolds in creation order, joints in list order).  Compared DIRECTLY with the
+    outputs of the reference's shipped binary (tests/golden/wasm_golden.json, produced by executing resolve2d.wasm): state and
+    AABB hashes after EVERY process() call of all six runs — 1,285 steps, both example scenes, all four joint kinds,
+    exclusions, key-driven inputs, other (dt, sub_steps, iters), body removal — plus the raw body dumps, bit for bit.  No
+    oracle and no colouring spec in between."""
+    g = _golden_runs()[name]
+    s = Solver(2.0, 4)
+    s.set_mode(MODE_REFERENCE_ORDER)
+    (scenes.setup_0_1_car_platformer if g["scene"] == "0_1" else scenes.setup_0_3_many_boxes)(s)
+    dt = np.float32(1.0) / np.float32(g["dt_rate"])
+    removals = {}
+    for r in g["removals"]:
+        _, step, ids = r.split(":")
+        removals[int(step)] = [int(x) for x in ids.split(",")]
+    for rec in g["steps"]:
+        step = rec["step"]
+        if step > 0:
+            for rid in removals.get(step, []):
+                s.remove_rigid_body(rid)
+            if g["driven"]:
+                scenes.drive_0_1(s)
+            s.process(dt, g["sub_steps"], g["iters"])
+        b = s.read_bodies()
+        assert len(b["id"]) == rec["n"], f"{name} step {step}: body count"
+        assert f"{H.state_hash(b):016x}" == rec["state"], f"{name} step {step}: state hash"
+        assert f"{H.aabb_hash(b):016x}" == rec["aabb"], f"{name} step {step}: aabb hash"
+        if "bodies" in rec:
+            want = np.array(rec["bodies"], dtype=np.uint32)
+            got = np.empty_like(want)
+            got[:, 0] = b["id"]
+            got[:, 1:3] = b["pos"].view(np.uint32)
+            got[:, 3] = b["angle"].view(np.uint32)
+            got[:, 4:6] = b["momentum"].view(np.uint32)
+            got[:, 6] = b["ang_momentum"].view(np.uint32)
+            got[:, 7:11] = b["aabb"].view(np.uint32)
+            assert np.array_equal(got, want), f"{name} step {step}: raw body dump"
+
+
 def test_gpu_box1k():
     """cfg1: 1,000 mixed bodies falling into a box; 600 steps = fall, pile, settle."""
     cand, orc = run_parity(lambda: Solver(2.0, 4), scenes.build_box1k, 600, check_every=50, what="box1k")
@@ -74,6 +121,18 @@ def test_gpu_dataflow_colouring_and_its_fallback():
     cand, _ = run_parity(lambda: Solver(2.0, 4), scenes.build_hub, 90, check_every=10, what="hub")
     st = cand.stats()
     assert st.n_colors >= 40 and st.n_color_rounds > 0
+
+
+def test_gpu_hub_body_beyond_256_colours_keeps_stepping():
+    """300 manifolds on one non-static body (a plank on 300 discs) against the 256 colours of the boundary: the 44
+    lowest-priority manifolds are dropped from the sweeps (colour R2D_COLOR_DROPPED, stats.n_dropped), everything else
+    of the step proceeds — bit for bit like the oracle under the same rule."""
+    def build(s):
+        return scenes.build_hub(s, n_discs=300)
+    cand, orc = run_parity(lambda: Solver(2.0, 4), build, 40, check_every=10, what="hub300")
+    st = cand.stats()
+    assert st.n_colors == 256 and st.n_dropped >= 40 and st.n_dropped == orc.stats().n_dropped
+    assert np.count_nonzero(cand.read_manifolds()["color"] == 0xFFFFFFFD) == st.n_dropped
 
 
 def test_gpu_solver_flavours_agree(monkeypatch):
