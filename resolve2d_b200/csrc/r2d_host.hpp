@@ -135,6 +135,13 @@ struct Image {
     std::vector<float4> j_par, j_vec;
     std::vector<uint32_t> joint_color_start;   // n_joint_colors + 1
     std::vector<uint32_t> joint_world, joint_local_index, joint_color;  // per sorted joint
+    // joints inside the dataflow sweep (r2d_pipeline.cuh solve_joint_flow): per sorted joint {rank among the joints of its
+    // first body, that body's joint count, same for the second body}; per device slot the number of joints naming the body.
+    // `joints_flow_ok`: no two-body joint names a static body or the same body twice (those write a static body's momentum,
+    // Q10, which the contacts read without waiting: they keep the barrier sweep).
+    std::vector<uint4> j_dep;
+    std::vector<uint32_t> body_nj;
+    bool joints_flow_ok = false;
     uint32_t n_bodies = 0;
     // Fine broadphase grid (r2d_pipeline.cuh, "fine grid"): cell width chosen from the body sizes of this upload (0 = no
     // fine grid), the coarse cell it was chosen for, and how many bodies are too wide for it (FLAG_LARGE).
@@ -348,6 +355,22 @@ inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image&
             im.joint_color_start[g.color + 1] += 1;
         }
         for (size_t c = 0; c < n_colors; ++c) im.joint_color_start[c + 1] += im.joint_color_start[c];
+        im.body_nj.assign(nb, 0u);
+        im.j_dep.assign(nj, make_uint4(0u, 0u, 0u, 0u));
+        im.joints_flow_ok = nj > 0;
+        for (size_t k = 0; k < nj; ++k) {   // sweep order = sorted order: ranks are counted on the way
+            const GJ& g = gj[k];
+            const bool two = joint_has_two_bodies(g.j);
+            im.j_dep[k].x = im.body_nj[g.s1]++;
+            if (two) {
+                if (g.s2 == g.s1 || (f2u(im.shape[g.s1].z) & FLAG_STATIC) || (f2u(im.shape[g.s2].z) & FLAG_STATIC)) im.joints_flow_ok = false;
+                if (g.s2 != g.s1) im.j_dep[k].z = im.body_nj[g.s2]++;
+            }
+        }
+        for (size_t k = 0; k < nj; ++k) {
+            im.j_dep[k].y = im.body_nj[gj[k].s1];
+            im.j_dep[k].w = im.body_nj[gj[k].s2];
+        }
     }
     return R2D_OK;
 }

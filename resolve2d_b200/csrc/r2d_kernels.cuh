@@ -1164,6 +1164,7 @@ __global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float su
     if (overflowed(d) || d.counters->err != 0u) return;  // uniform across the grid
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const uint32_t n_manifolds = d.color_start[d.counters->n_colors];
+    const bool jflow = d.joints_flow != 0u && n_joint_colors != 0u;
     // ---- stage my records ----
     Dev ds = d;  // same code path, record arrays redirected to shared memory
     {
@@ -1203,10 +1204,17 @@ __global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float su
             for (uint32_t i = tid; i < d.n_bodies; i += 4u * nth) integrate_batch<4>(d, i, nth, sub_dt, false, true, S == 1);
         grid.sync();
         for (uint32_t it = 0; it < I; ++it) {
-            for (uint32_t jc = 0; jc < n_joint_colors; ++jc) {
-                const uint32_t b = joint_color_start[jc], e = joint_color_start[jc + 1];
-                for (uint32_t j = b + tid; j < e; j += nth) solve_joint_thread(d, j, sub_dt);
-                grid.sync();
+            if (jflow) {   // joints through the version words, like the contacts: no barrier between colours or iterations
+                for (uint32_t jb = tid & ~31u; jb < d.n_joints; jb += nth) {
+                    const uint32_t j = jb + (tid & 31u);
+                    solve_joint_flow(d, j, j < d.n_joints, sub_dt, it);
+                }
+            } else {
+                for (uint32_t jc = 0; jc < n_joint_colors; ++jc) {
+                    const uint32_t b = joint_color_start[jc], e = joint_color_start[jc + 1];
+                    for (uint32_t j = b + tid; j < e; j += nth) solve_joint_thread(d, j, sub_dt);
+                    grid.sync();
+                }
             }
             uint32_t k = 0;
             for (uint32_t m = tid; m < n_manifolds; m += nth, ++k) {
@@ -1215,9 +1223,9 @@ __global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float su
                 else
                     solve_contact_thread<true>(d, m, sub_dt, it);
             }
-            if (n_joint_colors) grid.sync();  // joints of the next iteration read what the contacts wrote
+            if (n_joint_colors && !jflow) grid.sync();  // joints of the next iteration read what the contacts wrote
         }
-        if (!n_joint_colors) grid.sync();
+        if (!n_joint_colors || jflow) grid.sync();
         // end of substep s fused with the start of substep s + 1: both are per-body, same thread, no barrier needed
         for (uint32_t i = tid; i < d.n_bodies; i += 4u * nth) integrate_batch<4>(d, i, nth, sub_dt, true, s + 1 < S, s + 2 == S);
     }

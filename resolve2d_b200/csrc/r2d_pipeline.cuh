@@ -173,6 +173,11 @@ struct Dev {
     const uint4* j_hdr;           // type, slot1, slot2, -
     const float4* j_par;          // power_max, power_min, beta, target (distance | omega)
     const float4* j_vec;          // r1.x, r1.y, r2.x, r2.y  |  target.x, target.y, -, -
+    // joints inside the dataflow sweep: the update sequence of a body in one iteration is [its joints in sweep order
+    // (colour, list index)] then [its contacts in colour order]; versions count both
+    uint32_t joints_flow;         // 1: k_solve_persistent sweeps the joints through the version words too (no grid barrier)
+    const uint32_t* body_nj;      // NB: joints naming the body (null / unused when joints_flow == 0)
+    const uint4* j_dep;           // per joint: rank among the joints of body 1, that body's joint count, same for body 2
     float sub_dt;                 // dt / sub_steps of the current process() call
     uint32_t color_smem;          // 1: maxprio / used point into shared memory (per-world colouring kernel)
 };
@@ -899,6 +904,10 @@ R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
         uint32_t rk[2] = {0, 0}, dg[2] = {0, 0};
         if (!st1) body_color_rank(d, from_flow, h.x, color, &rk[0], &dg[0]);
         if (!st2) body_color_rank(d, from_flow, h.y, color, &rk[1], &dg[1]);
+        if (d.joints_flow) {   // the joints of a body come first in every iteration
+            const uint32_t j1 = d.body_nj[h.x], j2 = d.body_nj[h.y];
+            rk[0] += j1; dg[0] += j1; rk[1] += j2; dg[1] += j2;
+        }
         d.s_dep[at] = make_uint4(rk[0], dg[0], rk[1], dg[1]);
     }
     d.s_nf[at] = make_float4(c.normal.x, c.normal.y, c.friction, 0.0f);
@@ -1113,6 +1122,78 @@ R2D_HD void solve_joint_thread(const Dev& d, uint32_t j, float sub_dt) {
         } break;
     }
 }
+
+// contacts of body b in this call (= colours used on it)
+R2D_HD uint32_t body_contact_degree(const Dev& d, uint32_t b) {
+    uint32_t rk, dg;
+    body_color_rank(d, d.counters->flow_used != 0u, b, 0u, &rk, &dg);
+    return dg;
+}
+#if defined(__CUDACC__)
+// K10 inside the dataflow sweep: joint j of iteration `it` waits until each of its (non-static) bodies has received
+// exactly the updates that precede it in that body's sequence — it * (joints + contacts of the body) + rank of the joint
+// among the body's joints — and publishes momentum and version + 1 in ONE 16-byte store, like a contact.  Called by whole
+// warps (`live` = this lane has a joint); ready lanes update as they come, every pass ends in a warp vote, so lanes of
+// different joint colours in one warp cannot starve each other.
+__device__ __forceinline__ void solve_joint_flow(const Dev& d, uint32_t j, bool live, float sub_dt, uint32_t it) {
+    uint4 h = make_uint4(0u, 0u, 0u, 0u);
+    float4 par = make_float4(0, 0, 0, 0), vec = par;
+    uint32_t e1 = 0, e2 = 0;
+    bool two = false, st1 = true, st2 = true;
+    JointBody b1{}, b2{};
+    if (live) {
+        h = d.j_hdr[j];
+        par = d.j_par[j];
+        vec = d.j_vec[j];
+        const uint4 dep = d.j_dep[j];
+        two = h.x == 0u || h.x == 1u;
+        b1 = load_joint_body(d, h.y);
+        st1 = b1.is_static;
+        e1 = it * (dep.y + body_contact_degree(d, h.y)) + dep.x;
+        if (two) {
+            b2 = load_joint_body(d, h.z);
+            st2 = b2.is_static;
+            e2 = it * (dep.w + body_contact_degree(d, h.z)) + dep.z;
+        }
+    }
+    bool pending = live;
+    uint32_t spins = 0;
+    while (__any_sync(0xffffffffu, pending)) {
+        if (pending) {
+            float4 m1 = make_float4(0, 0, 0, 0), m2 = m1;
+            uint32_t lag = 0u;
+            if (!st1) {
+                m1 = ld_body_word(&d.mom[h.y]);
+                lag += e1 - f2u(m1.w);
+            }
+            if (two && !st2) {
+                m2 = ld_body_word(&d.mom[h.z]);
+                lag += e2 - f2u(m2.w);
+            }
+            if (lag == 0u) {
+                if (!st1) { b1.mom = mk2(m1.x, m1.y); b1.ang = m1.z; }
+                if (two && !st2) { b2.mom = mk2(m2.x, m2.y); b2.ang = m2.z; }
+                const float power_max = par.x, power_min = par.y, beta = par.z, target = par.w;
+                switch (h.x) {
+                    case 0: solve_distance(b1, b2, target, beta, power_min, power_max); break;
+                    case 1: solve_offset_distance(b1, b2, mk2(vec.x, vec.y), mk2(vec.z, vec.w), target, beta, power_min, power_max); break;
+                    case 2: solve_fixed_position(b1, mk2(vec.x, vec.y), beta, power_min, power_max); break;
+                    default: solve_motor(b1, target, beta, power_min, power_max, sub_dt); break;
+                }
+                // (two-body joints with a static body are swept with grid barriers instead: they write its momentum, Q10)
+                if (!st1) st_body_word(&d.mom[h.y], make_float4(b1.mom.x, b1.mom.y, b1.ang, u2f(e1 + 1u)));
+                if (two && !st2) st_body_word(&d.mom[h.z], make_float4(b2.mom.x, b2.mom.y, b2.ang, u2f(e2 + 1u)));
+                pending = false;
+            }
+        }
+        if ((++spins & 0xFFu) == 0u) {
+            if (spins > (1u << 20)) atomicOr(&d.counters->err, ERR_STALL);
+            const uint32_t flag = *((volatile uint32_t*)&d.counters->err) & ERR_STALL;
+            if (__any_sync(0xffffffffu, flag != 0u)) return;
+        }
+    }
+}
+#endif
 
 // ---- integrators ------------------------------------------------------------------------------------------------------
 // Pure arithmetic of the three per-body steps (shared by every integrator flavour, so that they cannot drift apart).

@@ -99,7 +99,9 @@ struct CudaBatch : BatchBase {
     DBuf<uint32_t> ncells, world_base, grav_off, joint_color_start, dev_of_host;
     DBuf<float> grav;
     DBuf<uint64_t> excl;
-    DBuf<uint4> j_hdr, bkt;
+    DBuf<uint4> j_hdr, bkt, j_dep;
+    DBuf<uint32_t> body_nj;
+    bool joints_flow = true;          // R2D_JOINTS_FLOW=0: joints swept with a grid barrier per joint colour (A/B, tests)
     DBuf<float4> j_par, j_vec;
     // grid
     DBuf<uint32_t> bucket_cnt, bucket_start, ent_body, ent_key, ent_off, tile_sums, work, hit_bits;
@@ -209,6 +211,7 @@ struct CudaBatch : BatchBase {
         if (env_is("R2D_BROADPHASE", "buckets")) fine_grid = false;          // every body through the hashed 4 m buckets
         if (env_is("R2D_WORLD_COLORING", "rounds")) seq_world_coloring = false;
         if (env_is("R2D_WORLD_BROAD", "0")) world_broad = false;
+        if (env_is("R2D_JOINTS_FLOW", "0")) joints_flow = false;
         R2D_CUDA(cudaFuncSetAttribute(k_world_broad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
         if (env_is("R2D_TEST_SMALL_BUFFERS", "1")) test_small_buffers = true;
         if (const char* e = getenv("R2D_WORLD_CACHE")) {                     // tests: records per world kept in shared memory
@@ -294,6 +297,7 @@ struct CudaBatch : BatchBase {
             (st = up(shape, image.shape)) || (st = up(aabb, image.aabb)) || (st = up(world_base, image.world_base)) ||
             (st = up(grav_off, image.grav_off)) || (st = up(grav, image.grav)) || (st = up(excl, image.excl)) ||
             (st = up(j_hdr, image.j_hdr)) || (st = up(j_par, image.j_par)) || (st = up(j_vec, image.j_vec)) ||
+            (st = up(j_dep, image.j_dep)) || (st = up(body_nj, image.body_nj)) ||
             (st = up(joint_color_start, image.joint_color_start)) || (st = up(dev_of_host, image.dev_of_host)))
             return st;
         R2D_CUDA(cudaStreamSynchronize(stream));  // the image vectors are pageable and may change after we return
@@ -539,6 +543,8 @@ struct CudaBatch : BatchBase {
         d.s_dep = s_dep.p;
         d.n_joints = (uint32_t)image.j_hdr.size();
         d.j_hdr = j_hdr.p; d.j_par = j_par.p; d.j_vec = j_vec.p;
+        d.j_dep = j_dep.p; d.body_nj = body_nj.p;
+        d.joints_flow = (joints_flow && image.joints_flow_ok && mode != R2D_MODE_REFERENCE_ORDER) ? 1u : 0u;
         d.color_smem = 0;
     }
 

@@ -570,22 +570,46 @@ def test_gpu_process_read_equals_process_then_read():
     assert np.array_equal(out["angle"].view(np.uint32), ref["angle"].view(np.uint32))
 
 
-def test_gpu_ordering_effect_is_reported_not_asserted():
-    """Colour order vs the reference's insertion order: identical until real impacts, chaotic afterwards.
-    Only the impact-free prefix is asserted; the divergence is printed for the record."""
-    s, ref = Solver(2.0, 4), OracleSolver(2.0, 4, order=ORDER_REFERENCE)
-    for x in (s, ref):
-        scenes.setup_0_3_many_boxes(x)
+def _pile_metrics(s):
+    b, m = s.read_bodies(), s.read_manifolds()
+    dyn = b["pos"][3:, 1]                                   # (both scenes list their static bodies first)
+    pen = float(-m["depth"][m["n_points"] > 0][:, 0].min()) if len(m) else 0.0
+    return {"mean_y": float(b["pos"][:, 1].mean()), "min_y": float(dyn.min()), "max_penetration": pen, "manifolds": len(m),
+            "p2": float(np.sum(b["momentum"].astype(np.float64) ** 2))}
+
+
+@pytest.mark.parametrize("scene", ["0_3", "box1k"])
+def test_gpu_colour_order_vs_reference_order_bounded_divergence(scene):
+    """The graph-colour sweep order against the reference's list order (R2D_MODE_REFERENCE_ORDER, which reproduces the
+    reference binary bit for bit): identical until real impacts start, chaotic body by body afterwards (metres) — Gauss-
+    Seidel is order dependent — but the two runs must remain the same physics.  Asserted at steps 120 / 240 / 400: nothing
+    tunnels through the floor, the piles have the same height (mean y within 5 % + 0.15 m), the same number of contacts
+    (within 8 %), comparable residual motion and comparable worst penetration."""
+    setup = scenes.setup_0_3_many_boxes if scene == "0_3" else scenes.build_box1k
+    col, ref = Solver(2.0, 4), Solver(2.0, 4)
+    ref.set_mode(MODE_REFERENCE_ORDER)
+    for x in (col, ref):
+        setup(x)
     first = None
-    for step in range(1, 121):
-        s.process(scenes.DT, 4, 4)
+    for step in range(1, 401):
+        col.process(scenes.DT, 4, 4)
         ref.process(scenes.DT, 4, 4)
-        d = np.max(np.abs(s.read_bodies()["pos"] - ref.read_bodies()["pos"]))
-        if step <= 40:
-            assert d == 0.0, step
-        if first is None and d > 1e-3:
+        d = float(np.max(np.abs(col.read_bodies()["pos"] - ref.read_bodies()["pos"]))) if step <= 130 or step % 40 == 0 else None
+        if scene == "0_3" and step <= 40:
+            assert d == 0.0, step                           # no impact yet: the order cannot matter
+        if first is None and d is not None and d > 1e-3:
             first = step
-    print(f"ordering effect on 0_3: max |dpos| first exceeds 1e-3 at step {first}; at step 120 it is {d:.3g} m")
+        if step in (120, 240, 400):
+            a, b = _pile_metrics(col), _pile_metrics(ref)
+            print(f"{scene} step {step}: max |dpos| {d:.3g} m; colour order {a}; reference order {b}")
+            for m in (a, b):
+                assert m["min_y"] > 0.2, (step, m)                       # bodies rest ON the floor (top at y = 0)
+                assert m["max_penetration"] < 0.7, (step, m)
+            assert abs(a["mean_y"] - b["mean_y"]) <= 0.05 * max(a["mean_y"], b["mean_y"]) + 0.15, (step, a, b)
+            assert abs(a["manifolds"] - b["manifolds"]) <= 0.08 * b["manifolds"], (step, a, b)
+            assert max(a["p2"], b["p2"]) < 1000.0 or 1 / 3 < a["p2"] / b["p2"] < 3, (step, a, b)
+            assert abs(a["max_penetration"] - b["max_penetration"]) < 0.25, (step, a, b)
+    print(f"ordering effect on {scene}: max |dpos| first exceeds 1e-3 at step {first}")
 
 
 # ---------------------------------------------------------------------------------------------------------------------
