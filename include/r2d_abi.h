@@ -153,6 +153,21 @@ int r2d_destroy(r2d_solver* s);
 int r2d_clear(r2d_solver* s);                     /* keeps exclusions and the id counter, like lib.zig:181-187 (Q16) */
 int r2d_set_mode(r2d_solver* s, int mode);        /* R2D_MODE_*; default PARITY */
 int r2d_set_stream(r2d_solver* s, void* cuda_stream); /* run on the caller's cudaStream_t (default: own stream) */
+/* Options the reference lists on its roadmap but does not have (/root/reference/README.md:59-64).  They change results, so
+ * they are OFF by default (parity with the reference is defined without them); the CPU oracle implements the same rules
+ * and the CUDA path is bit-identical to it with the options on (tests/test_gpu_parity.py).
+ *   R2D_OPT_WARM_START   "Persist manifolds across frames by keying with stable body IDs": every contact remembers, keyed by
+ *                        (ref id, inc id), the impulses it had accumulated at the end of a call (per substep); a contact of
+ *                        the next call with the same key, reference face and point count adds them to its FIRST update as
+ *                        the initial guess of the iteration.  (ids < 2^24, worlds < 2^16.)
+ *   R2D_OPT_SLEEPING     "Sleeping/awakening": a non-static body whose linear and angular speed stayed below 0.2 m/s and
+ *                        0.2 rad/s for R2D_OPT_SLEEP_CALLS consecutive calls (default 30) and that has no user force or
+ *                        torque IS A STATIC BODY for the duration of a call; a body that moved faster than the thresholds
+ *                        in a call wakes every body it touched in that call (one hop per call). */
+#define R2D_OPT_WARM_START 1
+#define R2D_OPT_SLEEPING 2
+#define R2D_OPT_SLEEP_CALLS 3
+int r2d_set_option(r2d_solver* s, int option, uint32_t value);
 /* Device memory keeps the bodies in a spatial (Morton) order so that bodies in contact are neighbours in HBM; ids,
  * iteration order and results are unaffected.  The order is re-derived from the current positions every `steps`
  * process() calls (default 1024, 0 = only when the scene is edited) or on demand (through the host: ~6 ms per 100k bodies). */
@@ -219,6 +234,7 @@ int r2d_batch_world(r2d_batch* b, uint32_t world, r2d_solver** out);   /* borrow
 int r2d_batch_num_worlds(r2d_batch* b, uint32_t* out);
 int r2d_batch_set_mode(r2d_batch* b, int mode);
 int r2d_batch_set_stream(r2d_batch* b, void* cuda_stream);
+int r2d_batch_set_option(r2d_batch* b, int option, uint32_t value);   /* R2D_OPT_*, for every world of the batch */
 int r2d_batch_set_reorder_interval(r2d_batch* b, uint32_t steps);
 int r2d_batch_reorder(r2d_batch* b);
 int r2d_batch_process(r2d_batch* b, float dt, uint32_t sub_steps, uint32_t collision_iters);

@@ -45,6 +45,8 @@ def load():
         _abi.bind(lib, sigs, "r2d_", "orc_")
         lib.orc_set_gs_order.restype = C.c_int
         lib.orc_set_gs_order.argtypes = [C.c_void_p, C.c_int]
+        lib.orc_set_option.restype = C.c_int
+        lib.orc_set_option.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
         lib.orc_timed_steps.restype = C.c_double
         lib.orc_timed_steps.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32]
         lib.orc_load_state.restype = C.c_int
@@ -76,6 +78,9 @@ class OracleSolver(Solver):
 
     def set_gs_order(self, order: int):
         self._lib.orc_set_gs_order(self._h, order)
+
+    def set_option(self, option: int, value: int):
+        assert self._lib.orc_set_option(self._h, option, value) == 0
 
     def set_stream(self, cuda_stream):  # no device
         raise NotImplementedError

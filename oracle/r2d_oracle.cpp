@@ -564,6 +564,10 @@ struct CollisionManifold {  // :54-69
     float applied_rot_p_1 = 0, applied_rot_p_2 = 0;
     float friction = 0;
     uint32_t color = 0;  // oracle-side colouring for the `permuted` Gauss-Seidel order (not in the reference)
+    // R2D_OPT_WARM_START (README.md:60-61, not in the reference): the per-substep average of the impulses this contact had
+    // accumulated at the end of the previous call, added to the FIRST update of this call as the initial guess
+    bool warm_first = false;
+    float warm_pn[2] = {0, 0}, warm_pt[2] = {0, 0};
 
     void updateTGSDepth(std::vector<RigidBody>& B) {  // :73-100
         RigidBody& b1 = B[ref_body];
@@ -638,10 +642,12 @@ struct CollisionManifold {  // :54-69
             const Vector2 dv = sub2(v1, v2);
             const float bias = BAUMGARTE * zmax(0, (-point.depth) - BAUMGARTE_SLOP) / dt;
             float num = dot2(dv, normal) + bias;
-            const float pn = num * point.mass_n;
+            float pn = num * point.mass_n;
+            if (warm_first) pn = pn + warm_pn[k];
             if (pn < MIN_MANIFOLD_IMPULSE) continue;
             num = dot2(dv, tangent);
-            const float pt = num * point.mass_t;
+            float pt = num * point.mass_t;
+            if (warm_first) pt = pt + warm_pt[k];
             const float new_accumulated_pn = zmax(0, point.accumulated_pn + pn);
             const float applied_pn = new_accumulated_pn - point.accumulated_pn;
             point.accumulated_pn = new_accumulated_pn;
@@ -669,6 +675,7 @@ struct CollisionManifold {  // :54-69
         applied_rot_p_1 = 0;
         applied_linear_p2 = Vector2();
         applied_rot_p_2 = 0;
+        warm_first = false;
     }
 };
 
@@ -754,6 +761,7 @@ static uint64_t contactPriority(uint32_t id_a, uint32_t id_b) {
 }
 
 enum GsOrder { ORDER_REFERENCE = 0, ORDER_COLORED = 1 };
+static const float SLEEP_LIN2 = 0.04f, SLEEP_ANG2 = 0.04f;   // (0.2 m/s)^2, (0.2 rad/s)^2
 
 // ---- lib.zig: Solver ----------------------------------------------------------------------------------------------------
 struct Solver {
@@ -768,6 +776,12 @@ struct Solver {
     float spatialhash_cell_width;
     size_t spatialhash_table_size_mult;
     int gs_order = ORDER_REFERENCE;
+    // ---- roadmap options (README.md:59-64; not in the reference, off by default) ----
+    bool opt_warm_start = false, opt_sleeping = false;
+    uint32_t opt_sleep_calls = 30;
+    struct WarmEntry { uint32_t normal_id, n_points; float pn[2], pt[2]; };
+    std::unordered_map<uint64_t, WarmEntry> warm_store;   // key: ref id << 32 | inc id (stable ids, not pointers)
+    std::unordered_map<uint32_t, uint32_t> sleep_counter; // id -> consecutive calls below the speed thresholds
     // instrumentation
     std::set<std::pair<uint32_t, uint32_t>> candidate_pairs;  // the set C of SURVEY A.2, logged at lib.zig:282
     size_t stat_entries = 0, stat_raw_candidates = 0;
@@ -786,7 +800,33 @@ struct Solver {
         }
         const float f32_sub = (float)sub_steps;
         const float sub_dt = dt / f32_sub;
+        // sleeping: a body that has been slow for opt_sleep_calls calls in a row and is not being pushed IS A STATIC BODY
+        // for the duration of this call (broadphase filters, contacts, joints, integration)
+        std::vector<size_t> asleep;
+        if (opt_sleeping)
+            for (size_t i = 0; i < bodies.size(); ++i) {
+                RigidBody& b = bodies[i];
+                if (b.is_static) continue;
+                uint32_t& cnt = sleep_counter[b.id];
+                if (b.props.force.x != 0 || b.props.force.y != 0 || b.props.torque != 0) cnt = 0;   // user input wakes
+                if (cnt >= opt_sleep_calls) {
+                    b.is_static = true;
+                    asleep.push_back(i);
+                }
+            }
         updateManifolds();
+        if (opt_warm_start)
+            for (CollisionManifold& m : manifolds) {
+                auto it = warm_store.find(((uint64_t)bodies[m.ref_body].id << 32) | bodies[m.inc_body].id);
+                if (it == warm_store.end()) continue;
+                const uint32_t np = (m.points[0].present ? 1u : 0u) + (m.points[1].present ? 1u : 0u);
+                if (it->second.normal_id != (uint32_t)m.reference_normal_id || it->second.n_points != np) continue;
+                m.warm_first = true;
+                for (int k = 0; k < 2; ++k) {
+                    m.warm_pn[k] = it->second.pn[k];
+                    m.warm_pt[k] = it->second.pt[k];
+                }
+            }
         buildSweepOrder();
         for (size_t s = 0; s < sub_steps; ++s) {
             for (float g : force_generators)  // :200-205
@@ -815,6 +855,40 @@ struct Solver {
                 props.angle += props.ang_momentum * sub_dt / props.inertia;
                 props.force = Vector2();
                 props.torque = 0;
+            }
+        }
+        if (opt_warm_start) {   // remember what every contact ended the call with, per substep
+            warm_store.clear();
+            for (const CollisionManifold& m : manifolds) {
+                WarmEntry e{};
+                e.normal_id = (uint32_t)m.reference_normal_id;
+                e.n_points = (m.points[0].present ? 1u : 0u) + (m.points[1].present ? 1u : 0u);
+                for (int k = 0; k < 2; ++k)
+                    if (m.points[k].present) {
+                        e.pn[k] = m.points[k].p.accumulated_pn / f32_sub;
+                        e.pt[k] = m.points[k].p.accumulated_pt / f32_sub;
+                    }
+                warm_store[((uint64_t)bodies[m.ref_body].id << 32) | bodies[m.inc_body].id] = e;
+            }
+        }
+        if (opt_sleeping) {
+            for (size_t i : asleep) bodies[i].is_static = false;
+            std::vector<unsigned char> moving(bodies.size(), 0), was_asleep(bodies.size(), 0);
+            for (size_t i : asleep) was_asleep[i] = 1;
+            for (size_t i = 0; i < bodies.size(); ++i) {
+                RigidBody& b = bodies[i];
+                if (b.is_static || was_asleep[i]) continue;
+                const float vx = b.props.momentum.x / b.props.mass, vy = b.props.momentum.y / b.props.mass;
+                const float w = b.props.ang_momentum / b.props.inertia;
+                const bool slow = (vx * vx + vy * vy) < SLEEP_LIN2 && (w * w) < SLEEP_ANG2;
+                uint32_t& cnt = sleep_counter[b.id];
+                cnt = slow ? cnt + 1 : 0;
+                moving[i] = slow ? 0 : 1;
+            }
+            // one hop: a body that moved fast in this call wakes what it touches (the woken bodies do not wake others yet)
+            for (const CollisionManifold& m : manifolds) {
+                if (moving[m.ref_body] && !bodies[m.inc_body].is_static) sleep_counter[bodies[m.inc_body].id] = 0;
+                if (moving[m.inc_body] && !bodies[m.ref_body].is_static) sleep_counter[bodies[m.ref_body].id] = 0;
             }
         }
         return 0;
@@ -1178,6 +1252,15 @@ int orc_clear(void* h) {
 // mode 0: reference behaviour (cell 4.0, 2N buckets); 1: honour cell_width/table_mult ("fast" mode of the CUDA path)
 int orc_set_mode(void* h, int mode) {
     ((Solver*)h)->use_init_grid_params = (mode != 0);
+    return 0;
+}
+// roadmap options (r2d_set_option): 1 warm start, 2 sleeping, 3 calls below the thresholds before a body sleeps
+int orc_set_option(void* h, int option, uint32_t value) {
+    Solver* s = (Solver*)h;
+    if (option == 1) s->opt_warm_start = value != 0;
+    else if (option == 2) s->opt_sleeping = value != 0;
+    else if (option == 3) s->opt_sleep_calls = value;
+    else return -4;
     return 0;
 }
 // 0: reference insertion order; 1: the coloured order the CUDA path sweeps in

@@ -24,6 +24,7 @@ ERRORS = {
 SHAPE_DISC, SHAPE_RECT = 0, 1
 JOINT_DISTANCE, JOINT_OFFSET_DISTANCE, JOINT_FIXED_POSITION, JOINT_MOTOR = 0, 1, 2, 3
 MODE_PARITY, MODE_FAST, MODE_REFERENCE_ORDER = 0, 1, 2
+OPT_WARM_START, OPT_SLEEPING, OPT_SLEEP_CALLS = 1, 2, 3
 KCLASS_NAMES = ["broadphase", "narrowphase", "coloring", "integrate", "solve_contacts", "solve_joints"]
 
 
@@ -123,6 +124,8 @@ SIGNATURES = {
     "r2d_clear": (C.c_int, [_P]),
     "r2d_set_mode": (C.c_int, [_P, C.c_int]),
     "r2d_set_stream": (C.c_int, [_P, _P]),
+    "r2d_set_option": (C.c_int, [_P, C.c_int, _U32]),
+    "r2d_batch_set_option": (C.c_int, [_P, C.c_int, _U32]),
     "r2d_set_reorder_interval": (C.c_int, [_P, _U32]),
     "r2d_reorder": (C.c_int, [_P]),
     "r2d_make_disc": (C.c_int, [_P, C.POINTER(BodyOpts), _F, _UP]),

@@ -37,6 +37,7 @@ struct Body {
     float mass = 0, inertia = 0, mu = 0;
     float aabb_x = 0, aabb_y = 0, aabb_hw = 0, aabb_hh = 0;
     float a = 0, b = 0;  // disc: radius; rect: width, height
+    uint32_t sleep_counter = 0;  // R2D_OPT_SLEEPING: consecutive calls below the speed thresholds
 };
 
 struct Joint {
@@ -127,6 +128,7 @@ struct World {
 // All worlds of a batch flattened for the device (layout: r2d_pipeline.cuh `Dev`).
 struct Image {
     std::vector<float4> pos, mom, frc, prop, shape, aabb;
+    std::vector<uint32_t> sleep;   // per device slot: Body::sleep_counter
     std::vector<uint32_t> world_base, grav_off;
     std::vector<float> grav;
     std::vector<uint64_t> excl;
@@ -179,6 +181,7 @@ inline void body_to_image(const Body& b, uint32_t world, Image& im, size_t at, b
     im.prop[at] = mkf4(b.mass, b.inertia, b.mu, 0.0f);
     im.shape[at] = mkf4(b.a, b.b, u2f(flags), u2f(b.id));
     im.aabb[at] = mkf4(b.aabb_x, b.aabb_y, b.aabb_hw, b.aabb_hh);
+    im.sleep[at] = b.sleep_counter;
 }
 
 // Returns R2D_OK or R2D_ERR_INVALID_BODY_ID (a joint names a body that no longer exists — the reference fails inside
@@ -280,6 +283,7 @@ inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image&
     im.prop.resize(nb);
     im.shape.resize(nb);
     im.aabb.resize(nb);
+    im.sleep.resize(nb);
     im.excl.clear();
     struct GJ {
         Joint j;
@@ -442,6 +446,9 @@ struct BatchBase {
     float cell_width = 2.0f;
     uint32_t table_mult = 4;
     int mode = R2D_MODE_PARITY;
+    // roadmap options (README.md:59-64), off by default: see include/r2d_abi.h R2D_OPT_*
+    bool opt_warm_start = false, opt_sleeping = false;
+    uint32_t opt_sleep_calls = 30;
     bool host_fresh = true;   // host mirror holds the truth
     bool dev_fresh = false;   // device arrays hold the truth (and the image layout is current)
     Image image;              // layout of the last upload (world_base etc.)

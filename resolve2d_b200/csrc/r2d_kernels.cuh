@@ -1180,6 +1180,8 @@ __global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float su
         ds.s_pm1 = (float4*)q;   q += n * 16;
         ds.s_acc0 = (float2*)q;  q += n * 8;
         ds.s_acc1 = (float2*)q;
+    }
+    auto stage = [&]() {
         for (uint32_t k = 0; k < smem_slots; ++k) {
             const uint32_t m = tid + k * nth, l = k * PSOLVE_TPB + threadIdx.x;
             if (m >= n_manifolds) break;
@@ -1198,7 +1200,11 @@ __global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float su
                 ds.s_acc1[l] = d.s_acc1[m];
             }
         }
-    }
+    };
+    // warm starting: the first sweep of the call reads its records (and their warm terms) from global memory; the cache is
+    // filled after it, with the accumulated impulses that sweep left
+    const bool warm = d.warm_on != 0u;
+    if (!warm) stage();
     for (uint32_t s = 0; s < S; ++s) {
         if (s == 0)
             for (uint32_t i = tid; i < d.n_bodies; i += 4u * nth) integrate_batch<4>(d, i, nth, sub_dt, false, true, S == 1);
@@ -1216,18 +1222,103 @@ __global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float su
                     grid.sync();
                 }
             }
+            const bool first = warm && s == 0 && it == 0;
             uint32_t k = 0;
             for (uint32_t m = tid; m < n_manifolds; m += nth, ++k) {
-                if (k < smem_slots)
+                if (k < smem_slots && !first)
                     solve_contact_thread<true>(ds, k * PSOLVE_TPB + threadIdx.x, sub_dt, it);  // cached record
                 else
-                    solve_contact_thread<true>(d, m, sub_dt, it);
+                    solve_contact_thread<true>(d, m, sub_dt, it, first);
             }
+            if (first) stage();
             if (n_joint_colors && !jflow) grid.sync();  // joints of the next iteration read what the contacts wrote
         }
         if (!n_joint_colors || jflow) grid.sync();
         // end of substep s fused with the start of substep s + 1: both are per-body, same thread, no barrier needed
         for (uint32_t i = tid; i < d.n_bodies; i += 4u * nth) integrate_batch<4>(d, i, nth, sub_dt, true, s + 1 < S, s + 2 == S);
+    }
+    if (warm && S * I > 0u)   // k_warm_save reads what every contact accumulated: flush the cached ones
+        for (uint32_t k = 0; k < smem_slots; ++k) {
+            const uint32_t m = tid + k * nth, l = k * PSOLVE_TPB + threadIdx.x;
+            if (m >= n_manifolds) break;
+            const uint4 h = ds.s_hdr[l];
+            if (h.z & S_EMPTY) continue;
+            d.s_acc0[m] = ds.s_acc0[l];
+            if ((h.z & 0xFFu) > 1u) d.s_acc1[m] = ds.s_acc1[l];
+        }
+}
+
+// ---- roadmap options (README.md:59-64; off by default) ----------------------------------------------------------------------
+// warm starting: after the substep loop every contact leaves its accumulated impulses (per substep) in a hash table keyed
+// by the stable ids of its two bodies; the next call's pre-step looks them up (gather_prestep_thread)
+__global__ void __launch_bounds__(TPB) k_warm_save(Dev d, float inv_scale_div) {
+    if (overflowed(d) || d.counters->err != 0u) return;
+    const uint32_t n = d.color_start[d.counters->n_colors];
+    for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
+        const uint4 h = d.s_hdr[m];
+        if (h.z & S_EMPTY) continue;
+        const uint32_t np = h.z & 0xFFu;
+        const float2 a0 = np > 0u ? d.s_acc0[m] : make_float2(0.0f, 0.0f), a1 = np > 1u ? d.s_acc1[m] : make_float2(0.0f, 0.0f);
+        const float4 v = make_float4(fdiv(a0.x, inv_scale_div), fdiv(a0.y, inv_scale_div), fdiv(a1.x, inv_scale_div), fdiv(a1.y, inv_scale_div));
+        const unsigned long long key = warm_make_key(body_flags(d, h.x) >> FLAG_WORLD_SHIFT, body_id(d, h.x), body_id(d, h.y));
+        const uint32_t meta = d.m_hdr[h.w].z;   // n_points | normal_id << 8
+        uint32_t slot = warm_hash(key) & d.warm_mask;
+        for (uint32_t probe = 0; probe < WARM_PROBES; ++probe, slot = (slot + 1u) & d.warm_mask) {
+            const unsigned long long old = atomicCAS(&d.warm_key[slot], WARM_EMPTY, key);
+            if (old == WARM_EMPTY || old == key) {
+                d.warm_val[slot] = v;
+                d.warm_meta[slot] = meta;
+                break;
+            }
+        }
+    }
+}
+// sleeping, start of a call: a body that has been slow for `calls` calls in a row and is not being pushed IS A STATIC BODY for
+// the duration of this call — its static flag is set here and cleared by k_sleep_bodies
+__global__ void __launch_bounds__(TPB) k_sleep_begin(Dev d, uint32_t calls) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n_bodies; i += gridDim.x * blockDim.x) {
+        const float4 sh = d.shape[i];
+        const uint32_t flags = f2u(sh.z);
+        uint32_t state = 0u;
+        if (!(flags & FLAG_STATIC)) {
+            const float4 f = d.frc[i];
+            uint32_t cnt = d.sleep_cnt[i];
+            if (f.x != 0.0f || f.y != 0.0f || f.z != 0.0f) d.sleep_cnt[i] = cnt = 0u;   // user input wakes
+            if (cnt >= calls) {
+                state = 1u;
+                d.shape[i] = make_float4(sh.x, sh.y, u2f(flags | FLAG_STATIC), sh.w);
+            }
+        }
+        d.sleep_state[i] = state;
+    }
+}
+// end of a call: sleepers get their flag back; everybody else is measured against the speed thresholds
+__global__ void __launch_bounds__(TPB) k_sleep_bodies(Dev d) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n_bodies; i += gridDim.x * blockDim.x) {
+        const float4 sh = d.shape[i];
+        const uint32_t flags = f2u(sh.z);
+        if (d.sleep_state[i] & 1u) {
+            d.shape[i] = make_float4(sh.x, sh.y, u2f(flags & ~FLAG_STATIC), sh.w);
+            continue;
+        }
+        if (flags & FLAG_STATIC) continue;
+        const float4 m = d.mom[i], pr = d.prop[i];
+        const float vx = fdiv(m.x, pr.x), vy = fdiv(m.y, pr.x), w = fdiv(m.z, pr.y);
+        const bool slow = fadd(fmul(vx, vx), fmul(vy, vy)) < SLEEP_LIN2 && fmul(w, w) < SLEEP_ANG2;
+        d.sleep_cnt[i] = slow ? d.sleep_cnt[i] + 1u : 0u;
+        d.sleep_state[i] = slow ? 0u : 2u;
+    }
+}
+// one hop: a body that moved fast in this call wakes what it touches (the woken bodies do not wake others yet)
+__global__ void __launch_bounds__(TPB) k_sleep_wake(Dev d) {
+    if (overflowed(d)) return;
+    const uint32_t n = live_pairs(d);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        if (d.m_color[p] == COLOR_NONE) continue;
+        const uint4 h = d.m_hdr[p];
+        // (true statics have no counter; a sleeper's flag has been cleared by k_sleep_bodies already)
+        if ((d.sleep_state[h.x] & 2u) && !(body_flags(d, h.y) & FLAG_STATIC)) d.sleep_cnt[h.y] = 0u;
+        if ((d.sleep_state[h.y] & 2u) && !(body_flags(d, h.x) & FLAG_STATIC)) d.sleep_cnt[h.x] = 0u;
     }
 }
 

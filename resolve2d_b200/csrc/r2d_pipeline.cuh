@@ -37,6 +37,7 @@ constexpr uint32_t COLOR_DROPPED = 0xFFFFFFFDu;    // manifold found none of the
                                                    // body with more than 256 simultaneous contacts): left out of this call's sweeps
 constexpr uint32_t MAX_COLORS = 256;
 constexpr uint32_t S_EMPTY = 0x400u;              // s_hdr.z: padding slot (colour segments are padded to whole warps)
+constexpr uint32_t S_WARM = 0x800u;               // s_hdr.z: the record carries warm-start terms (s_warm0 / s_warm1)
 constexpr uint32_t COLOR_ALIGN = 32;
 constexpr uint32_t COLOR_WORDS = MAX_COLORS / 64;
 constexpr uint32_t ADJ_CAP = 32;                   // manifolds a non-static body can list for the dataflow colouring
@@ -168,6 +169,18 @@ struct Dev {
     uint32_t* body_shared;        // NB: 1 if a manifold owned by a body of ANOTHER tile touches the body (see k_solve_tiles)
     uint4* s_dep;                 // rank of this manifold among the contacts of its ref body, that body's contact count,
                                   // same for the inc body  (dataflow ordering of the sweep, see solve_contact_thread)
+    // ---- roadmap options (README.md:59-64; off by default) ----------------------------------------
+    // warm starting: open-addressing hash table of the previous call's contacts, keyed by stable ids
+    uint32_t warm_on;
+    uint32_t warm_mask;            // table size - 1 (a power of two)
+    unsigned long long* warm_key;  // world << 48 | ref id << 24 | inc id; WARM_EMPTY = free
+    uint32_t* warm_meta;           // n_points | normal_id << 8
+    float4* warm_val;              // accumulated (pn, pt) of point 0 and point 1 at the end of the call, per substep
+    float2* s_warm0;               // per record: warm terms of point 0 / point 1 (valid where S_WARM)
+    float2* s_warm1;
+    // sleeping: a slow body is a static body for the duration of a call
+    uint32_t* sleep_cnt;           // NB: consecutive calls below the speed thresholds
+    uint32_t* sleep_state;         // NB: bit 0 asleep in this call, bit 1 moved fast in this call
     // ---- joints, grouped by colour -----------------------------------------------------------------------------------
     uint32_t n_joints;
     const uint4* j_hdr;           // type, slot1, slot2, -
@@ -884,6 +897,34 @@ R2D_HD uint32_t manifold_slot(const Dev& d, uint32_t p) {
     return d.own_pos[(size_t)c * (d.own_words + 1u) + (o >> 5)] + popc64(word & ((1u << (o & 31u)) - 1u));
 }
 
+// ---- warm starting (R2D_OPT_WARM_START) ---------------------------------------------------------------------------------
+constexpr unsigned long long WARM_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint32_t WARM_MAX_ID = 1u << 24, WARM_MAX_WORLD = 1u << 16, WARM_PROBES = 128;
+constexpr float SLEEP_LIN2 = 0.04f, SLEEP_ANG2 = 0.04f;   // (0.2 m/s)^2, (0.2 rad/s)^2: the Baumgarte push-out alone keeps a resting pile at ~0.1 m/s
+R2D_HD unsigned long long warm_make_key(uint32_t world, uint32_t ref_id, uint32_t inc_id) {
+    return ((unsigned long long)world << 48) | ((unsigned long long)ref_id << 24) | (unsigned long long)inc_id;
+}
+R2D_HD uint32_t warm_hash(unsigned long long key) {
+    key ^= key >> 33;
+    key *= 0xff51afd7ed558ccdull;
+    key ^= key >> 33;
+    return (uint32_t)key;
+}
+// the previous call's entry of this contact, if it had the same reference face and point count
+R2D_HD bool warm_lookup(const Dev& d, unsigned long long key, uint32_t meta, float4* out) {
+    uint32_t h = warm_hash(key) & d.warm_mask;
+    for (uint32_t probe = 0; probe < WARM_PROBES; ++probe, h = (h + 1u) & d.warm_mask) {
+        const unsigned long long k = d.warm_key[h];
+        if (k == WARM_EMPTY) return false;
+        if (k == key) {
+            if (d.warm_meta[h] != meta) return false;
+            *out = d.warm_val[h];
+            return true;
+        }
+    }
+    return false;
+}
+
 // ---- colour partition + pre-step (collision.zig:102-133, evaluated once per process(): inputs are constant, Q5) -----------
 R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
     const uint4 h = d.m_hdr[p];
@@ -893,7 +934,17 @@ R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
     const float4 pr1 = d.prop[h.x], pr2 = d.prop[h.y];
     const float4 g0 = d.m_g0[p], g1 = d.m_g1[p];
     const ContactConst c = prestep_manifold(mk2(g0.x, g0.y), st1, st2, pr1.x, pr2.x, pr1.y, pr2.y, pr1.z, pr2.z);
-    d.s_hdr[at] = make_uint4(h.x, h.y, np | (st1 ? 0x100u : 0u) | (st2 ? 0x200u : 0u), p);
+    uint32_t warm_bit = 0u;
+    if (d.warm_on) {
+        float4 w;
+        const uint32_t world = f1 >> FLAG_WORLD_SHIFT;
+        if (warm_lookup(d, warm_make_key(world, body_id(d, h.x), body_id(d, h.y)), h.z, &w)) {
+            warm_bit = S_WARM;
+            d.s_warm0[at] = make_float2(w.x, w.y);
+            d.s_warm1[at] = make_float2(w.z, w.w);
+        }
+    }
+    d.s_hdr[at] = make_uint4(h.x, h.y, np | (st1 ? 0x100u : 0u) | (st2 ? 0x200u : 0u) | warm_bit, p);
     if (d.tile_bodies && !st1 && !st2 && h.x / d.tile_bodies != h.y / d.tile_bodies)
         d.body_shared[h.x > h.y ? h.x : h.y] = 1u;  // the owner is the lower slot: the other body is foreign to its tile
     // Colours on one body are pairwise distinct, so the body's sweep sequence is its colour set in ascending order:
@@ -948,7 +999,7 @@ R2D_HD void gather_prestep_thread(const Dev& d, uint32_t p, uint32_t at) {
 //   launch) and walk their manifolds in (iteration, colour) order, so the globally lowest pending manifold can always
 //   run: no deadlock.  A stall would be a bug; it is reported through ERR_STALL instead of hanging the GPU.
 template <bool DATAFLOW>
-R2D_HD void solve_contact_thread(const Dev& d, uint32_t m, float sub_dt, uint32_t it = 0) {
+R2D_HD void solve_contact_thread(const Dev& d, uint32_t m, float sub_dt, uint32_t it = 0, bool first = false) {
     const uint4 h = d.s_hdr[m];
     const bool empty = (h.z & S_EMPTY) != 0;
     if (!DATAFLOW && empty) return;
@@ -957,6 +1008,13 @@ R2D_HD void solve_contact_thread(const Dev& d, uint32_t m, float sub_dt, uint32_
     ContactConst c;
     ContactPointConst pts[2];
     v2 acc[2];
+    v2 warm[2] = {mk2(0.0f, 0.0f), mk2(0.0f, 0.0f)};
+    const bool use_warm = first && !empty && (h.z & S_WARM) != 0;   // first update of the call (R2D_OPT_WARM_START)
+    if (use_warm) {
+        const float2 w0 = d.s_warm0[m], w1 = d.s_warm1[m];
+        warm[0] = mk2(w0.x, w0.y);
+        warm[1] = mk2(w1.x, w1.y);
+    }
     uint32_t e1 = 0, e2 = 0;
     float4 m1 = make_float4(0, 0, 0, 0), m2 = m1;
     if (!empty) {
@@ -1032,7 +1090,7 @@ R2D_HD void solve_contact_thread(const Dev& d, uint32_t m, float sub_dt, uint32_
             }
             if (pending && lag == 0u) {
                 BodyVel b1 = {mk2(m1.x, m1.y), m1.z}, b2 = {mk2(m2.x, m2.y), m2.z};
-                solve_contact(c, np, pts, acc, st1, st2, b1, b2);
+                solve_contact(c, np, pts, acc, st1, st2, b1, b2, use_warm, warm);
                 d.s_acc0[m] = make_float2(acc[0].x, acc[0].y);
                 if (np > 1) d.s_acc1[m] = make_float2(acc[1].x, acc[1].y);
                 if (!st1) st_body_word(&d.mom[h.x], make_float4(b1.mom.x, b1.mom.y, b1.ang, u2f(e1 + 1u)));
@@ -1063,7 +1121,7 @@ R2D_HD void solve_contact_thread(const Dev& d, uint32_t m, float sub_dt, uint32_
     }
     if (empty) return;
     BodyVel b1 = {mk2(m1.x, m1.y), m1.z}, b2 = {mk2(m2.x, m2.y), m2.z};
-    solve_contact(c, np, pts, acc, st1, st2, b1, b2);
+    solve_contact(c, np, pts, acc, st1, st2, b1, b2, use_warm, warm);
     if (np > 0) d.s_acc0[m] = make_float2(acc[0].x, acc[0].y);
     if (np > 1) d.s_acc1[m] = make_float2(acc[1].x, acc[1].y);
     // static bodies receive a zero impulse in the reference (`momentum += 0`); not writing them is the same value

@@ -115,6 +115,16 @@ struct CudaBatch : BatchBase {
     bool world_broad = true;          // k_world_broad for batches of small worlds (R2D_WORLD_BROAD=0: device-wide grid kernels)
     bool world_broad_declined = false;  // a world's grid did not fit shared memory: device-wide kernels until the next upload
     uint32_t max_world_large_cells = 0; // grid entries of the large bodies of the widest world (bound from the upload)
+    // roadmap options: warm-start table (keyed by stable ids, survives re-uploads), sleep counters
+    // (two tables: the pre-step of a call reads the previous call's, k_warm_save fills the other one; they swap when the call
+    // has succeeded, so an abandoned attempt loses nothing)
+    DBuf<unsigned long long> warm_key[2];
+    DBuf<uint32_t> warm_meta[2], sleep_cnt, sleep_state;
+    DBuf<float4> warm_val[2];
+    DBuf<float2> s_warm0, s_warm1;
+    uint32_t warm_slots = 0;
+    int warm_cur = 0;
+    bool warm_saving = false;   // fill_dev points the table at the one being written
     DBuf<uint32_t> ref_order, ref_joints;   // R2D_MODE_REFERENCE_ORDER: manifold / joint sweep order of the reference
     bool world_fused_now = false;     // this step is solved by k_world_solve (which also places and pre-steps the manifolds)
     // pairs / manifolds
@@ -297,7 +307,7 @@ struct CudaBatch : BatchBase {
             (st = up(shape, image.shape)) || (st = up(aabb, image.aabb)) || (st = up(world_base, image.world_base)) ||
             (st = up(grav_off, image.grav_off)) || (st = up(grav, image.grav)) || (st = up(excl, image.excl)) ||
             (st = up(j_hdr, image.j_hdr)) || (st = up(j_par, image.j_par)) || (st = up(j_vec, image.j_vec)) ||
-            (st = up(j_dep, image.j_dep)) || (st = up(body_nj, image.body_nj)) ||
+            (st = up(j_dep, image.j_dep)) || (st = up(body_nj, image.body_nj)) || (st = up(sleep_cnt, image.sleep)) ||
             (st = up(joint_color_start, image.joint_color_start)) || (st = up(dev_of_host, image.dev_of_host)))
             return st;
         R2D_CUDA(cudaStreamSynchronize(stream));  // the image vectors are pageable and may change after we return
@@ -314,7 +324,9 @@ struct CudaBatch : BatchBase {
         const size_t nb = image.n_bodies;
         if (nb == 0) return R2D_OK;
         std::vector<float4> hp(nb), hm(nb), hf(nb), ha(nb);
+        std::vector<uint32_t> hs(opt_sleeping ? nb : 0);
         R2D_TRY(join_forces());
+        if (opt_sleeping) R2D_CUDA(cudaMemcpyAsync(hs.data(), sleep_cnt.p, nb * 4, cudaMemcpyDeviceToHost, stream));
         R2D_CUDA(cudaMemcpyAsync(hp.data(), pos.p, nb * 16, cudaMemcpyDeviceToHost, stream));
         R2D_CUDA(cudaMemcpyAsync(hm.data(), mom.p, nb * 16, cudaMemcpyDeviceToHost, stream));
         R2D_CUDA(cudaMemcpyAsync(hf.data(), frc.p, nb * 16, cudaMemcpyDeviceToHost, stream));
@@ -330,6 +342,7 @@ struct CudaBatch : BatchBase {
                 b.mom_x = m.x; b.mom_y = m.y; b.ang_mom = m.z;
                 b.force_x = f.x; b.force_y = f.y; b.torque = f.z;
                 b.aabb_x = a.x; b.aabb_y = a.y; b.aabb_hw = a.z; b.aabb_hh = a.w;
+                if (opt_sleeping) b.sleep_counter = hs[ds];
             }
         }
         return R2D_OK;
@@ -534,6 +547,14 @@ struct CudaBatch : BatchBase {
         d.adj_prio = adj_prio.p;
         d.tile_bodies = tile_bodies_now;
         d.world_fused = world_fused_now ? 1u : 0u;
+        d.warm_on = opt_warm_start ? 1u : 0u;
+        d.warm_mask = warm_slots ? warm_slots - 1u : 0u;
+        {
+            const int t = warm_saving ? 1 - warm_cur : warm_cur;
+            d.warm_key = warm_key[t].p; d.warm_meta = warm_meta[t].p; d.warm_val = warm_val[t].p;
+        }
+        d.s_warm0 = s_warm0.p; d.s_warm1 = s_warm1.p;
+        d.sleep_cnt = sleep_cnt.p; d.sleep_state = sleep_state.p;
         d.body_shared = (uint32_t*)(zeroed.p + off_body_shared);
         d.own_words = (d.n_bodies + 31u) / 32u;
         d.own_bits = (uint32_t*)(zeroed.p + off_own_bits);
@@ -563,7 +584,7 @@ struct CudaBatch : BatchBase {
             (st = m_r0.reserve(n)) || (st = m_r1.reserve(n)) || (st = m_color.reserve(n)) || (st = m_prio.reserve(n)) || (st = s_hdr.reserve(n)) ||
             (st = s_nf.reserve(n)) || (st = s_inv.reserve(n)) || (st = s_r0.reserve(n)) || (st = s_r1.reserve(n)) ||
             (st = s_pm0.reserve(n)) || (st = s_pm1.reserve(n)) || (st = s_acc0.reserve(n)) || (st = s_acc1.reserve(n)) ||
-            (st = s_dep.reserve(n)))
+            (st = s_dep.reserve(n)) || (opt_warm_start && ((st = s_warm0.reserve(n)) || (st = s_warm1.reserve(n)))))
             return st;
         cap_pairs = pairs.cap;
         for (size_t c : {m_prio.cap, m_hdr.cap, m_g0.cap, m_g1.cap, m_r0.cap, m_r1.cap, m_color.cap, s_hdr.cap, s_nf.cap, s_inv.cap,
@@ -658,12 +679,33 @@ struct CudaBatch : BatchBase {
         if (flow_now && (st = adj_prio.reserve((size_t)nb * ADJ_CAP))) return st;
         // solver flavour: CTA-per-world for batches of small worlds; one spatial tile of bodies per SM for a single world
         // without joints that fits (k_solve_tiles may still decline on the device); else the persistent dataflow sweep
-        const bool use_world_solver = persistent_solver && world_solver && image.j_hdr.empty() &&
+        if ((opt_warm_start || opt_sleeping) && (mode == R2D_MODE_REFERENCE_ORDER || !persistent_solver)) {
+            g_cuda_error = "R2D_OPT_WARM_START / R2D_OPT_SLEEPING need the default solver (not REFERENCE_ORDER, not R2D_SOLVER=launches)";
+            return R2D_ERR_BAD_STATE;
+        }
+        if (opt_warm_start) {   // table of the previous call's contacts (16 slots per body: load factor < 0.2 in a dense pile)
+            if (worlds.size() >= WARM_MAX_WORLD) return R2D_ERR_INVALID_ARGUMENT;
+            for (auto& w : worlds)
+                if (w->current_body_id >= WARM_MAX_ID) return R2D_ERR_INVALID_ARGUMENT;
+            uint32_t want = 1024;
+            while (want < 16u * nb && want < (1u << 30)) want <<= 1;
+            if (want > warm_slots) {   // (a grown table starts empty: one call without warm terms)
+                for (int t = 0; t < 2; ++t) {
+                    if ((st = warm_key[t].reserve(want)) || (st = warm_meta[t].reserve(want)) || (st = warm_val[t].reserve(want))) return st;
+                    R2D_CUDA(cudaMemsetAsync(warm_key[t].p, 0xFF, (size_t)want * 8, stream));
+                }
+                warm_slots = want;
+            }
+            if (s_warm0.cap < s_hdr.cap && ((st = s_warm0.reserve(s_hdr.cap)) || (st = s_warm1.reserve(s_hdr.cap)))) return st;
+        }
+        if (opt_sleeping && (st = sleep_state.reserve(nb))) return st;
+        const bool use_world_solver = persistent_solver && world_solver && image.j_hdr.empty() && !opt_warm_start &&
                                       max_world_bodies <= WORLD_MAX_BODIES &&
                                       worlds.size() >= (size_t)n_sms / 2;  // enough worlds to fill the GPU with one CTA each
         world_fused_now = use_world_solver;
         const uint32_t tile_b = (nb + (uint32_t)n_sms - 1) / (uint32_t)n_sms;
         const bool use_tile_solver = persistent_solver && tile_solver && !tile_declined && !use_world_solver && image.j_hdr.empty() &&
+                                     !opt_warm_start && !opt_sleeping &&
                                      tile_b <= TILE_MAX_BODIES && nb >= (uint32_t)n_sms * 8;
         tile_bodies_now = use_tile_solver ? tile_b : 0u;
         // broadphase of a batch of small worlds: per-world CTAs with the grid in shared memory, when the fine grid applies
@@ -674,6 +716,11 @@ struct CudaBatch : BatchBase {
         bool use_world_broad = world_broad && !world_broad_declined && many_small_worlds && fine_now && !ll_now &&
                                max_world_bodies <= WORLD_MAX_BODIES && wb_smem <= 100 * 1024 &&
                                worlds.size() + 2 <= scan_state_cap;
+        if (opt_sleeping) {   // once per call, not per attempt: it edits the static flags
+            fill_dev();
+            if ((st = join_forces())) return st;   // user forces wake
+            R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_sleep_begin, grid_for(nb), TPB, d, opt_sleep_calls);
+        }
         for (int attempt = 0;; ++attempt) {
             fill_dev();
             R2D_CUDA(cudaMemsetAsync(zeroed.p, 0, zeroed_bytes, stream));  // counters, colour tables, scan states, masks
@@ -828,6 +875,14 @@ struct CudaBatch : BatchBase {
             } else if (persistent_solver) {
                 if ((st = launch_persistent(sub_dt, S, I))) return st;
             }
+            if (opt_warm_start) {   // (an abandoned attempt stores nothing — the kernel checks — and the tables do not swap)
+                warm_saving = true;
+                fill_dev();
+                R2D_CUDA(cudaMemsetAsync(d.warm_key, 0xFF, (size_t)warm_slots * 8, stream));
+                R2D_LAUNCH(R2D_KCLASS_COLORING, k_warm_save, grid_for(cap_pairs), TPB, d, (float)S);
+                warm_saving = false;
+                fill_dev();
+            }
             // r2d_process_read: the export of the new state rides behind the solver, inside the same synchronisation
             if (readback && persistent_solver) {
                 const uint32_t keep = launches;
@@ -877,6 +932,12 @@ struct CudaBatch : BatchBase {
                 R2D_CUDA(cudaGetLastError());
             }
             break;
+        }
+        if (opt_sleeping) {   // sleepers get their flag back, speeds are measured, movers wake what they touched
+            fill_dev();
+            R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_sleep_bodies, grid_for(nb), TPB, d);
+            R2D_LAUNCH(R2D_KCLASS_INTEGRATE, k_sleep_wake, grid_for(cap_pairs), TPB, d);
+            R2D_CUDA(cudaStreamSynchronize(stream));
         }
         const Counters c = pinned->counters;
         last_pairs = c.n_pairs;
@@ -928,6 +989,7 @@ struct CudaBatch : BatchBase {
         }
         R2D_CUDA(cudaGetLastError());
         stats.n_launches = launches;
+        if (opt_warm_start) warm_cur ^= 1;   // the table this call filled is the next call's input
         return R2D_OK;
     }
 };

@@ -87,8 +87,10 @@ struct BodyVel {
 // also zeroes its accumulated impulses; :176 impulse below MIN_MANIFOLD_IMPULSE, Q6), else true with `dp` = the impulse
 // (applied negatively to body 1, positively to body 2) and `acc` updated.  Both points of a manifold see the same,
 // pre-loop body velocities (Q8).
+// `warm` (R2D_OPT_WARM_START, not in the reference): the previous call's per-substep impulse of this contact, added to the
+// FIRST update of the call as the initial guess; `use_warm` is false everywhere else (and the additions are not executed).
 R2D_HD bool contact_point_impulse(const ContactConst& c, const ContactPointConst& p, v2& acc, v2 vlinear_1, float omega1,
-                                  v2 vlinear_2, float omega2, v2& dp) {
+                                  v2 vlinear_2, float omega2, v2& dp, bool use_warm = false, v2 warm = v2{0.0f, 0.0f}) {
     if (p.depth >= 0.0f) {  // :154-158
         acc = mk2(0.0f, 0.0f);
         return false;
@@ -101,11 +103,13 @@ R2D_HD bool contact_point_impulse(const ContactConst& c, const ContactPointConst
     const v2 dv = sub2(v1, v2_);
 
     float num = fadd(dot2(dv, c.normal), p.bias);  // :172-173, bias evaluated once per call (contact_bias)
-    const float pn = fmul(num, p.mass_n);
+    float pn = fmul(num, p.mass_n);
+    if (use_warm) pn = fadd(pn, warm.x);
     if (pn < MIN_MANIFOLD_IMPULSE) return false;  // :176 (Q6)
 
     num = dot2(dv, c.tangent);
-    const float pt = fmul(num, p.mass_t);
+    float pt = fmul(num, p.mass_t);
+    if (use_warm) pt = fadd(pt, warm.y);
 
     const float new_acc_pn = fmax_z(0.0f, fadd(acc.x, pn));
     const float applied_pn = fsub(new_acc_pn, acc.x);
@@ -125,7 +129,7 @@ R2D_HD bool contact_point_impulse(const ContactConst& c, const ContactPointConst
 // calculateImpulses (collision.zig:135-218).  acc[k] = {accumulated_pn, accumulated_pt} persists for the whole
 // process() call (Q7).  Both points see the pre-loop velocities and are applied once at the end (Q8).
 R2D_HD void solve_contact(const ContactConst& c, int n_points, const ContactPointConst* pts, v2* acc, bool static1,
-                          bool static2, BodyVel& b1, BodyVel& b2) {
+                          bool static2, BodyVel& b1, BodyVel& b2, bool use_warm = false, const v2* warm = nullptr) {
     const v2 vlinear_1 = scale2(b1.mom, c.inv_m1);
     const float omega1 = fmul(b1.ang, c.inv_i1);
     const v2 vlinear_2 = scale2(b2.mom, c.inv_m2);
@@ -138,7 +142,9 @@ R2D_HD void solve_contact(const ContactConst& c, int n_points, const ContactPoin
     for (int k = 0; k < 2; ++k) {  // fully unrolled: pts[] / acc[] stay in registers (no local-memory arrays)
         if (k >= n_points) break;
         v2 dp;
-        if (!contact_point_impulse(c, pts[k], acc[k], vlinear_1, omega1, vlinear_2, omega2, dp)) continue;
+        if (!contact_point_impulse(c, pts[k], acc[k], vlinear_1, omega1, vlinear_2, omega2, dp, use_warm,
+                                   use_warm ? warm[k] : v2{0.0f, 0.0f}))
+            continue;
         if (!static1) {
             lin1 = sub2(lin1, dp);
             rot1 = fsub(rot1, cross2(pts[k].r1, dp));

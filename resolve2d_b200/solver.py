@@ -228,6 +228,10 @@ class Solver:
     def set_mode(self, mode: int):
         self._check(self._fn("set_mode")(self._h, mode), "set_mode")
 
+    def set_option(self, option: int, value: int):
+        """R2D_OPT_* (warm starting, sleeping: the reference's roadmap items, off by default)."""
+        self._check(self._fn("set_option")(self._h, option, value), "set_option")
+
     def set_stream(self, cuda_stream: int):
         self._check(self._fn("set_stream")(self._h, C.c_void_p(cuda_stream)), "set_stream")
 
@@ -363,6 +367,9 @@ class Batch:
 
     def set_mode(self, mode: int):
         _abi.check(self._lib, self._lib.r2d_batch_set_mode(self._h, mode), "batch_set_mode")
+
+    def set_option(self, option: int, value: int):
+        _abi.check(self._lib, self._lib.r2d_batch_set_option(self._h, option, value), "batch_set_option")
 
     def set_stream(self, cuda_stream: int):
         _abi.check(self._lib, self._lib.r2d_batch_set_stream(self._h, C.c_void_p(cuda_stream)), "batch_set_stream")

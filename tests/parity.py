@@ -50,11 +50,15 @@ def assert_manifolds_equal(got: np.ndarray, want: np.ndarray, what="", colors=Tr
 
 
 def run_parity(make_candidate, build_scene, steps, check_every=1, pre_step=None, what="", sub_steps=None, iters=None,
-               dt=None):
-    """Steps candidate and oracle (coloured Gauss-Seidel order) side by side; everything must be bit-identical."""
+               dt=None, options=()):
+    """Steps candidate and oracle (coloured Gauss-Seidel order) side by side; everything must be bit-identical.
+    `options`: (R2D_OPT_*, value) pairs set on both."""
     from resolve2d_b200 import scenes
     cand = make_candidate()
     orc = OracleSolver(2.0, 4, order=ORDER_COLORED)
+    for opt, val in options:
+        cand.set_option(opt, val)
+        orc.set_option(opt, val)
     cfg = build_scene(cand) or {}
     build_scene(orc)
     S = sub_steps if sub_steps is not None else cfg.get("sub_steps", 4)

@@ -8,7 +8,8 @@ import pytest
 import hashing as H
 from oracle import ORDER_COLORED, ORDER_REFERENCE, OracleSolver
 from parity import assert_bodies_equal, assert_manifolds_equal, run_parity
-from resolve2d_b200 import MODE_FAST, MODE_REFERENCE_ORDER, Batch, R2DError, ShardedBatch, Solver, scenes
+from resolve2d_b200 import (MODE_FAST, MODE_REFERENCE_ORDER, OPT_SLEEP_CALLS, OPT_SLEEPING, OPT_WARM_START, Batch, R2DError,
+                            ShardedBatch, Solver, scenes)
 
 pytestmark = pytest.mark.gpu
 
@@ -133,6 +134,82 @@ def test_gpu_hub_body_beyond_256_colours_keeps_stepping():
     st = cand.stats()
     assert st.n_colors == 256 and st.n_dropped >= 40 and st.n_dropped == orc.stats().n_dropped
     assert np.count_nonzero(cand.read_manifolds()["color"] == 0xFFFFFFFD) == st.n_dropped
+
+
+# ---- the reference's roadmap items (README.md:59-64), behind options, off by default ------------------------------------------
+def test_gpu_warm_starting_matches_the_oracle_and_helps():
+    """R2D_OPT_WARM_START: contacts persist across calls keyed by stable ids — the CUDA path (hash table on the device, warm
+    terms looked up in the pre-step, first sweep of the call) against the oracle's std::unordered_map, bit for bit, on a
+    settling box (contacts appear, flip reference faces, vanish), a pyramid with all four joint kinds, and with a body
+    removed mid-run.  And it does what it is for: with ONE iteration per substep the warm-started pile sinks less."""
+    opts = ((OPT_WARM_START, 1),)
+    run_parity(lambda: Solver(2.0, 4), scenes.build_box1k, 160, check_every=20, what="box1k warm", options=opts)
+    def build(s):
+        return scenes.build_pyramid(s, base=24, n_spinners=3)
+    run_parity(lambda: Solver(2.0, 4), build, 60, check_every=20, what="pyramid24 warm", options=opts)
+    removed = []
+    def remove(s):
+        if len(removed) < 2 and s.num_bodies() == 1003 - len(removed) // 2 and s.stats().n_manifolds > 1500:
+            s.remove_rigid_body(500)
+            removed.append(1)
+    cand, _ = run_parity(lambda: Solver(2.0, 4), scenes.build_box1k, 130, check_every=10, pre_step=remove, what="box1k warm, removal",
+                         options=opts)
+    assert cand.num_bodies() == 1002
+    pen = {}
+    for warm in (0, 1):
+        s = Solver(2.0, 4)
+        s.set_option(OPT_WARM_START, warm)
+        scenes.build_box1k(s)
+        for _ in range(400):
+            s.process(scenes.DT, 4, 1)
+        m = s.read_manifolds()
+        pen[warm] = float(np.mean(-m["depth"][m["n_points"] > 0][:, 0]))
+    print(f"mean penetration after 400 calls at 1 iteration: cold {pen[0]:.4f} m, warm {pen[1]:.4f} m")
+    assert pen[1] < pen[0]
+
+
+def test_gpu_sleeping_matches_the_oracle():
+    """R2D_OPT_SLEEPING: bodies that stayed slow for 10 calls are static for the duration of a call, a fast body wakes what it
+    touched (one hop per call), user forces wake — CUDA path vs the oracle bit for bit through falling, settling, sleeping
+    and a kick that wakes part of the pile; then the same in a batch of worlds (k_world_broad / k_world_solve)."""
+    opts = ((OPT_SLEEPING, 1), (OPT_SLEEP_CALLS, 10))
+    kicked = []
+    def kick(s):
+        if s.stats().n_manifolds > 1900 and len(kicked) < 40:   # 20 calls of a sideways push on one body of the settled pile
+            s.body_handle(400).set_force(4000.0, 1500.0)
+            kicked.append(1)
+    cand, orc = run_parity(lambda: Solver(2.0, 4), scenes.build_box1k, 420, check_every=30, pre_step=kick, what="box1k sleeping",
+                           options=opts)
+    assert kicked
+    # a settled pile sleeps: the two resting bodies of a sleeping pair are both static for the call, so their pair is gone
+    cold = Solver(2.0, 4)
+    scenes.build_box1k(cold)
+    for _ in range(420):
+        cold.process(scenes.DT, 4, 4)
+    for _ in range(800):
+        cand.process(scenes.DT, 4, 4)
+        cold.process(scenes.DT, 4, 4)
+    print(f"candidate pairs after 1220 calls: {cand.stats().n_pairs} with sleeping, {cold.stats().n_pairs} without")
+    assert cand.stats().n_pairs < 0.8 * cold.stats().n_pairs
+    batch = Batch(96, 2.0, 4)
+    batch.set_option(OPT_SLEEPING, 1)
+    batch.set_option(OPT_SLEEP_CALLS, 10)
+    oracles = {}
+    for w in range(96):
+        scenes.build_batch_world(batch.world(w), w, nx=10, ny=5)
+        if w in (0, 50, 95):
+            o = OracleSolver(2.0, 4, order=ORDER_COLORED)
+            o.set_option(OPT_SLEEPING, 1)
+            o.set_option(OPT_SLEEP_CALLS, 10)
+            scenes.build_batch_world(o, w, nx=10, ny=5)
+            oracles[w] = o
+    for _ in range(200):
+        batch.process(scenes.DT, 4, 4)
+        for o in oracles.values():
+            o.process(scenes.DT, 4, 4)
+    for w, o in oracles.items():
+        assert np.array_equal(batch.world(w).read_pairs(), o.read_pairs()), w
+        assert_bodies_equal(batch.world(w).read_bodies(), o.read_bodies(), f"sleeping world {w}")
 
 
 def test_gpu_solver_flavours_agree(monkeypatch):
