@@ -128,8 +128,9 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
 // so a CTA only ever waits for tiles that started before it; every tile publishes (flag, value) as ONE 64-bit word
 // (flag 1 = aggregate of the tile, 2 = inclusive prefix), which needs no fence.  `state` (n_tiles + 1 words, the last
 // one is the ticket) must be zero on entry.  in == out is allowed.
+// Returns false when the ticket drawn is beyond the last tile (nothing done).
 template <class Load>
-__device__ __forceinline__ void scan_chained_body(Load load, uint32_t* out, uint32_t n, unsigned long long* state, uint32_t state_tiles,
+__device__ __forceinline__ bool scan_chained_body(Load load, uint32_t* out, uint32_t n, unsigned long long* state, uint32_t state_tiles,
                                                   uint32_t* total_out, uint32_t* first_cta) {
     __shared__ uint32_t s_tile, s_prefix;
     if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd(&state[state_tiles], 1ull);
@@ -137,7 +138,7 @@ __device__ __forceinline__ void scan_chained_body(Load load, uint32_t* out, uint
     const uint32_t tile = s_tile;
     if (first_cta) *first_cta = tile == 0u ? 1u : 0u;
     const uint32_t n_tiles = n ? (n + SCAN_TILE - 1) / SCAN_TILE : 1u;
-    if (tile >= n_tiles) return;
+    if (tile >= n_tiles) return false;
     const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_IPT;
     uint32_t v[SCAN_IPT];
     uint32_t sum = 0;
@@ -191,6 +192,7 @@ __device__ __forceinline__ void scan_chained_body(Load load, uint32_t* out, uint
         if (base + k < n) out[base + k] = run;
         run += v[k];
     }
+    return true;
 }
 __global__ void __launch_bounds__(SCAN_TPB) k_scan_chained(const uint32_t* in, uint32_t* out, const uint32_t* n_ptr, uint32_t n_max,
                                                            unsigned long long* state, uint32_t state_tiles, uint32_t* total_out) {

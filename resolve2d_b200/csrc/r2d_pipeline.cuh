@@ -97,6 +97,7 @@ struct Dev {
     // ---- worlds ----------------------------------------------------------------------------------------------------
     uint32_t n_worlds;
     const uint32_t* world_base;   // n_worlds + 1
+    const uint64_t* world_magic;  // n_worlds: hash_magic(table_mult * bodies of the world) (cell_hash_magic)
     const uint32_t* grav_off;     // n_worlds + 1
     const float* grav;            // g values, world-major
     float cell;                   // grid cell size
@@ -309,6 +310,7 @@ struct CellRange {
     int64_t min_xi, min_yi, max_xi, max_yi;
     uint32_t bucket_base;   // first bucket of the body's world
     uint32_t table_size;    // buckets of the body's world (T_w = table_mult * N_w)
+    uint64_t magic;         // hash_magic(table_size)
     uint32_t nx;            // cells per row
     uint32_t count;         // total cells (0 if out of range)
 };
@@ -326,6 +328,7 @@ R2D_HD CellRange cell_range(const Dev& d, uint32_t i) {
     const uint32_t b0 = d.world_base[w], b1 = d.world_base[w + 1];
     r.bucket_base = d.table_mult * b0;
     r.table_size = d.table_mult * (b1 - b0);
+    r.magic = d.world_magic[w];
     const int64_t nx = r.max_xi - r.min_xi + 1, ny = r.max_yi - r.min_yi + 1;
     if (nx <= 0 || ny <= 0 || nx > MAX_BODY_CELLS || ny > MAX_BODY_CELLS || nx * ny > MAX_BODY_CELLS) {
         r.nx = 0;
@@ -342,7 +345,7 @@ R2D_HD CellRange cell_range(const Dev& d, uint32_t i) {
 R2D_HD uint32_t cell_bucket(const CellRange& r, uint32_t k) {
     const int64_t yi = r.min_yi + (int64_t)(k / r.nx);
     const int64_t xi = r.min_xi + (int64_t)(k % r.nx);
-    return r.bucket_base + (uint32_t)cell_hash(xi, yi, (uint64_t)r.table_size);
+    return r.bucket_base + (uint32_t)cell_hash_magic(xi, yi, (uint64_t)r.table_size, r.magic);
 }
 
 // The world vertices and edge normals of a rectangle are evaluated once per body and process() call (K2) and

@@ -125,6 +125,8 @@ struct CudaBatch : BatchBase {
     uint32_t warm_slots = 0;
     int warm_cur = 0;
     bool warm_saving = false;   // fill_dev points the table at the one being written
+    DBuf<uint64_t> world_magic;
+    uint32_t magic_for_mult = 0;
     DBuf<uint32_t> ref_order, ref_joints;   // R2D_MODE_REFERENCE_ORDER: manifold / joint sweep order of the reference
     bool world_fused_now = false;     // this step is solved by k_world_solve (which also places and pre-steps the manifolds)
     // pairs / manifolds
@@ -311,6 +313,7 @@ struct CudaBatch : BatchBase {
             (st = up(joint_color_start, image.joint_color_start)) || (st = up(dev_of_host, image.dev_of_host)))
             return st;
         R2D_CUDA(cudaStreamSynchronize(stream));  // the image vectors are pageable and may change after we return
+        magic_for_mult = 0;   // (the bucket count of a world depends on the mode's table multiplier: refreshed in process())
         last_pairs = 0;
         tile_declined = false;
         world_broad_declined = false;
@@ -519,7 +522,7 @@ struct CudaBatch : BatchBase {
         d.pos = pos.p; d.mom = mom.p; d.frc = frc.p; d.prop = prop.p; d.shape = shape.p; d.aabb = aabb.p;
         d.pose = pose.p; d.view = view.p; d.ncells = ncells.p; d.bkt = bkt.p;
         d.n_worlds = (uint32_t)worlds.size();
-        d.world_base = world_base.p; d.grav_off = grav_off.p; d.grav = grav.p;
+        d.world_base = world_base.p; d.grav_off = grav_off.p; d.grav = grav.p; d.world_magic = world_magic.p;
         d.cell = grid_cell(); d.table_mult = grid_mult();
         d.n_buckets = d.table_mult * d.n_bodies;
         d.bucket_cnt = bucket_cnt.p; d.bucket_start = bucket_start.p;
@@ -633,6 +636,15 @@ struct CudaBatch : BatchBase {
         stats.n_joints = (uint32_t)image.j_hdr.size();
         stats.n_joint_colors = (uint32_t)image.joint_color_start.size() - 1;
         if (nb == 0) return R2D_OK;
+        if (magic_for_mult != grid_mult()) {   // per world: the reciprocal that replaces the 64-bit modulo of the cell hash
+            std::vector<uint64_t> mg(worlds.size());
+            for (size_t w = 0; w < worlds.size(); ++w)
+                mg[w] = hash_magic((uint64_t)grid_mult() * (image.world_base[w + 1] - image.world_base[w]));
+            R2D_TRY(world_magic.reserve(mg.size()));
+            R2D_CUDA(cudaMemcpyAsync(world_magic.p, mg.data(), mg.size() * 8, cudaMemcpyHostToDevice, stream));
+            R2D_CUDA(cudaStreamSynchronize(stream));
+            magic_for_mult = grid_mult();
+        }
         const float sub_dt = dt / (float)S;  // lib.zig:190-191 (host f32 division, IEEE)
         d.sub_dt = sub_dt;
         const uint32_t T = grid_mult() * nb;

@@ -33,6 +33,7 @@ struct EmuBatch : BatchBase {
     std::vector<uint32_t> adj_cnt;
     std::vector<uint4> cstate;
     std::vector<uint32_t> color_count, color_start, color_cursor, round_left, own_bits, own_pos;
+    std::vector<uint64_t> world_magic;
     Counters counters{};
     uint32_t n_pairs_last = 0;
 
@@ -149,6 +150,10 @@ struct EmuBatch : BatchBase {
         d.pose = pose.data(); d.view = view.data(); d.ncells = ncells.data(); d.bkt = bkt.data();
         d.n_worlds = (uint32_t)worlds.size();
         d.world_base = image.world_base.data(); d.grav_off = image.grav_off.data(); d.grav = image.grav.data();
+        world_magic.resize(worlds.size());
+        for (size_t w = 0; w < worlds.size(); ++w)
+            world_magic[w] = hash_magic((uint64_t)grid_mult() * (image.world_base[w + 1] - image.world_base[w]));
+        d.world_magic = world_magic.data();
         d.cell = grid_cell(); d.table_mult = grid_mult();
         d.n_buckets = d.table_mult * nb;
         d.excl = image.excl.data(); d.n_excl = (uint32_t)image.excl.size();

@@ -88,3 +88,26 @@ def test_cell_hash(oracle_lib):
     for xi, yi, t in [(0, 0, 1046), (3, -2, 1046), (-7, 11, 222), (-1, -1, 2_000_000), (123456, -98765, 200006)]:
         want = ((xi * 92837111) ^ (yi * 689287499)) % (1 << 64) % t
         assert h(t, xi, yi) == want
+
+
+def test_magic_modulo_equals_the_64_bit_modulo():
+    """cell_hash_magic (mulhi by floor((2^64 - 1) / T) + two corrections) == u64(xi * 92837111 ^ yi * 689287499) % T, the
+    reference's hash (SpatialHash.zig:78-81): checked against Python's big integers on random and extreme operands."""
+    import random
+    rng = random.Random(5)
+    M64 = (1 << 64) - 1
+    cases = [(0, 0), (-1, -1), (2 ** 40, -2 ** 40), (-2 ** 62, 2 ** 62), (123456789, -987654321)]
+    cases += [(rng.randrange(-2 ** 62, 2 ** 62), rng.randrange(-2 ** 62, 2 ** 62)) for _ in range(3000)]
+    cases += [(rng.randrange(-5000, 5000), rng.randrange(-5000, 5000)) for _ in range(3000)]
+    for T in (1, 2, 3, 512, 2006, 200006, 2002006, 2 ** 31 - 1, 2 ** 32 - 1, 4000000007 % 2 ** 32):
+        magic = M64 // T
+        for xi, yi in cases:
+            h = ((xi * 92837111) & M64) ^ ((yi * 689287499) & M64)
+            q = (h * magic) >> 64
+            r = h - q * T
+            assert 0 <= r < 3 * T
+            if r >= T:
+                r -= T
+            if r >= T:
+                r -= T
+            assert r == h % T, (T, xi, yi)
