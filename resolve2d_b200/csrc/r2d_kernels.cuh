@@ -1350,7 +1350,17 @@ constexpr size_t TILE_FIXED_SMEM = (size_t)TILE_MAX_BODIES * 20 + (size_t)TILE_M
 constexpr size_t TILE_SMEM_BYTES = 232448 - 1024;  // all of it (the static part of the kernel is tiny)
 constexpr uint32_t TILE_CACHE_TASKS = (uint32_t)((TILE_SMEM_BYTES - TILE_FIXED_SMEM) / (32 * 144));
 
-__device__ __forceinline__ uint32_t ld_volatile_shared_u32(const uint32_t* p) { return *((const volatile uint32_t*)p); }
+// Hand-off of a tile-local body between two warps of the CTA: the version word is read with acquire and written with
+// release semantics at block scope (ld.acquire.cta / st.release.cta), the momentum word it announces with ordinary
+// (volatile: never cached in registers) accesses that those two order — the release/acquire pattern of the PTX memory model.
+__device__ __forceinline__ uint32_t ld_acquire_shared_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_shared_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
 __device__ __forceinline__ float4 ld_volatile_shared_f4(const float4* p) {
     float4 v;
     asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -1518,7 +1528,7 @@ __global__ void __launch_bounds__(TILE_TPB) k_solve_tiles(Dev d, float sub_dt, u
                         uint32_t lag = 0u;
                         if (!st1) {
                             if (loc1) {
-                                lag += e1 - ld_volatile_shared_u32(&t_ver[h.x - b0]);
+                                lag += e1 - ld_acquire_shared_u32(&t_ver[h.x - b0]);
                             } else {
                                 m1 = ld_body_word(&d.mom[h.x]);
                                 lag += e1 - f2u(m1.w);
@@ -1526,14 +1536,14 @@ __global__ void __launch_bounds__(TILE_TPB) k_solve_tiles(Dev d, float sub_dt, u
                         }
                         if (!st2) {
                             if (loc2) {
-                                lag += e2 - ld_volatile_shared_u32(&t_ver[h.y - b0]);
+                                lag += e2 - ld_acquire_shared_u32(&t_ver[h.y - b0]);
                             } else {
                                 m2 = ld_body_word(&d.mom[h.y]);
                                 lag += e2 - f2u(m2.w);
                             }
                         }
                         if (lag == 0u) {
-                            __threadfence_block();  // the version was written after the momentum it announces
+                            // (the acquire loads of the versions above order these reads after the momentum stores they announce)
                             if (loc1) m1 = ld_volatile_shared_f4(&t_mom[h.x - b0]);
                             if (loc2) m2 = ld_volatile_shared_f4(&t_mom[h.y - b0]);
                             BodyVel v1 = {mk2(m1.x, m1.y), m1.z}, v2_ = {mk2(m2.x, m2.y), m2.z};
@@ -1545,9 +1555,8 @@ __global__ void __launch_bounds__(TILE_TPB) k_solve_tiles(Dev d, float sub_dt, u
                             if (!st1 && !loc1) st_body_word(&d.mom[h.x], make_float4(v1.mom.x, v1.mom.y, v1.ang, u2f(e1 + 1u)));
                             if (!st2 && !loc2) st_body_word(&d.mom[h.y], make_float4(v2_.mom.x, v2_.mom.y, v2_.ang, u2f(e2 + 1u)));
                             if (loc1 || loc2) {
-                                __threadfence_block();
-                                if (loc1) *((volatile uint32_t*)&t_ver[h.x - b0]) = e1 + 1u;
-                                if (loc2) *((volatile uint32_t*)&t_ver[h.y - b0]) = e2 + 1u;
+                                if (loc1) st_release_shared_u32(&t_ver[h.x - b0], e1 + 1u);
+                                if (loc2) st_release_shared_u32(&t_ver[h.y - b0], e2 + 1u);
                             }
                             pending = false;
                         }
