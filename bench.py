@@ -304,11 +304,15 @@ class Gpu:
     def max(self, x, collective=True):
         return self.reduce(x, self.dist.ReduceOp.MAX, collective)
 
+    profile_range = False   # --profile-range: cudaProfilerStart/Stop around the timed steps of the main leg only
+
     def timed_steps(self, stepper, k, collective=True):
         """k process() calls, L2 flushed before each, per-step CUDA events on the launching stream; returns seconds."""
         torch = self.torch
         evs = []
         self.barrier(collective)
+        if self.profile_range:
+            torch.cuda.cudart().cudaProfilerStart()
         for _ in range(k):
             self.flush_buf.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -317,6 +321,9 @@ class Gpu:
             b.record(self.stream)
             evs.append((a, b))
         self.barrier(collective)
+        if self.profile_range:
+            torch.cuda.cudart().cudaProfilerStop()
+            self.profile_range = False
         return sum(a.elapsed_time(b) for a, b in evs) * 1e-3
 
     def pinned(self, shape):
@@ -496,15 +503,12 @@ def compact(leg):
 def run_ours(args, rank, world, local_rank):
     gpu = Gpu(local_rank, world)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    if args.profile_range:
-        gpu.torch.cuda.cudart().cudaProfilerStart()
+    gpu.profile_range = args.profile_range
 
     if world == 1 and args.workload != "batch4096x256":
         # ---- N = 1: pile100k headline + batched + the other configs ----
         main = world_leg(gpu, args.workload, args, cpu=not args.no_cpu)
         clocks = sampler.stop() if sampler else None
-        if args.profile_range:
-            gpu.torch.cuda.cudart().cudaProfilerStop()
         batched = None
         if args.batch_worlds > 0:
             batched = batch_leg(gpu, args.batch_worlds, 0, args, collective=False)
@@ -540,8 +544,6 @@ def run_ours(args, rank, world, local_rank):
     lo, hi = rank * total // world, (rank + 1) * total // world
     main = batch_leg(gpu, hi - lo, lo, args, collective=True, total_worlds=total, steps=args.steps)
     clocks = sampler.stop() if sampler else None
-    if args.profile_range:
-        gpu.torch.cuda.cudart().cudaProfilerStop()
     extras = {}
     if world > 1 and not args.no_extras:
         weak = batch_leg(gpu, total, rank * total, args, collective=True, e2e=False, total_worlds=total * world)

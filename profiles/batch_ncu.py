@@ -11,6 +11,6 @@ for _ in range(3): b.process(scenes.DT, 4, 4)
 b.synchronize()
 rt = ctypes.CDLL("libcudart.so.12")
 rt.cudaProfilerStart()
-for _ in range(2): b.process(scenes.DT, 4, 4)
+for _ in range(1): b.process(scenes.DT, 4, 4)
 b.synchronize()
 rt.cudaProfilerStop()

@@ -1,6 +1,6 @@
 """Small workloads for compute-sanitizer (memcheck / racecheck / initcheck): every kernel of the pipeline runs, on a
 single world with joints and exclusions, a mixed world with multi-cell bodies, and a batch large enough for the
-CTA-per-world solver."""
+CTA-per-world kernels (k_world_broad, k_world_solve)."""
 import sys
 sys.path.insert(0, '.')
 from resolve2d_b200 import Batch, Solver, scenes
@@ -29,4 +29,17 @@ f = torch.zeros((n, 3), dtype=torch.float32).pin_memory().numpy()
 out = {"pos": torch.empty((n, 2), dtype=torch.float32).pin_memory().numpy(), "angle": None, "momentum": None, "ang_momentum": None, "id": None, "aabb": None}
 for _ in range(3):
     m.write_forces(f); m.process(scenes.DT, 4, 4); m.read_bodies(out)
+# roadmap options: warm-start table (k_warm_save, lookup in the pre-step), sleeping kernels; reference-order validation mode
+from resolve2d_b200 import MODE_REFERENCE_ORDER, OPT_SLEEP_CALLS, OPT_SLEEPING, OPT_WARM_START, ShardedBatch
+o = Solver(2.0, 4); o.set_option(OPT_WARM_START, 1); o.set_option(OPT_SLEEPING, 1); o.set_option(OPT_SLEEP_CALLS, 5)
+scenes.build_box1k(o)
+for _ in range(100): o.process(scenes.DT, 4, 4)
+r = Solver(2.0, 4); r.set_mode(MODE_REFERENCE_ORDER); scenes.setup_0_1_car_platformer(r)
+for _ in range(30): r.process(scenes.DT, 4, 4)
+h = Solver(2.0, 4); scenes.build_hub(h, n_discs=300)          # colours exhausted on one body: dropped manifolds
+for _ in range(10): h.process(scenes.DT, 4, 4)
+sb = ShardedBatch(90, [0, 0])                                   # two shards on one device, one host thread each
+for w in range(90): scenes.build_batch_world(sb.world(w), w, nx=8, ny=4)
+for _ in range(30): sb.process(scenes.DT, 4, 4)
+sb.read_bodies()
 print("sanitize probe done", s.stats().n_manifolds, m.stats().n_manifolds, b.stats().n_manifolds)

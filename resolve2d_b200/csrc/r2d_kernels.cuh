@@ -38,6 +38,11 @@ __device__ __forceinline__ bool overflowed(const Dev& d) {
 }
 
 // ---- K2 / K4: per-body cell walk; FILL = false counts (SpatialHash.zig:46-49), true fills (:62-68) -------------------------
+// Bodies that cover more than BIG_BODY_CELLS cells (the floor of a 100k-body pile: 1,100 cells) are not walked by the thread
+// that holds them.  The count pass lets its whole CTA walk them and appends them to a device-wide list; the fill pass
+// spreads the cells of every listed body over the WHOLE grid (one CTA walking 1,100 cells with a dependent atomic and
+// three stores each was the tail of the fill kernel: 19.7 of its 20 us).
+constexpr uint32_t BIG_GLOBAL_LIST = 1024;   // bodies the device-wide list holds (more: walked by their CTA, as in the count pass)
 template <bool FILL>
 __global__ void __launch_bounds__(TPB) k_grid_cells(Dev d) {
     __shared__ uint32_t big_list[BIG_LIST];
@@ -55,7 +60,16 @@ __global__ void __launch_bounds__(TPB) k_grid_cells(Dev d) {
             r = cell_range(d, i);
         }
         bool inline_walk = r.count <= BIG_BODY_CELLS;
-        if (!inline_walk) {  // e.g. the floor: hundreds of cells — deferred to the end, walked by the whole CTA
+        if (!inline_walk) {  // e.g. the floor: hundreds of cells
+            if (FILL) {      // on the device-wide list (complete: written by the count kernel)? then the whole grid walks it below
+                bool listed = false;
+                const uint32_t n_global = min(d.counters->n_big, BIG_GLOBAL_LIST);
+                for (uint32_t q = 0; q < n_global; ++q) listed = listed || d.big_bodies[q] == i;
+                if (listed) continue;
+            } else {
+                const uint32_t g = atomicAdd(&d.counters->n_big, 1u);
+                if (g < BIG_GLOBAL_LIST) d.big_bodies[g] = i;
+            }
             const uint32_t slot = atomicAdd(&n_big, 1u);
             if (slot < BIG_LIST)
                 big_list[slot] = i;
@@ -83,6 +97,15 @@ __global__ void __launch_bounds__(TPB) k_grid_cells(Dev d) {
                 fill_cell(d, bi, b);
             else
                 atomicAdd(&d.bucket_cnt[b], 1u);
+        }
+    }
+    if (FILL) {
+        const uint32_t n_global = min(d.counters->n_big, BIG_GLOBAL_LIST);
+        for (uint32_t q = 0; q < n_global; ++q) {
+            const uint32_t bi = d.big_bodies[q];
+            const CellRange r = cell_range(d, bi);
+            for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < r.count; k += gridDim.x * blockDim.x)
+                fill_cell(d, bi, cell_bucket(r, k));
         }
     }
 }

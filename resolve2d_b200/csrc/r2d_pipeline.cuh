@@ -77,6 +77,8 @@ struct Counters {
     uint32_t flow_used;      // the colours of this step come from the dataflow colouring (masks in cstate, not in used)
     uint32_t tile_fallback;  // k_solve_tiles declined (a tile has too many bodies / tasks): the host runs k_solve_persistent
     uint32_t max_world_m;    // k_world_solve: most slots (contact points) found in one world of the batch (the host sizes the
+    uint32_t n_big;          // bodies covering more than BIG_BODY_CELLS cells, listed by the count kernel (big_bodies)
+    uint32_t pad2;
     uint32_t broad_fallback; // shared-memory cache of the next call from it) | k_world_broad: a world's grid does not fit
 };
 
@@ -112,6 +114,7 @@ struct Dev {
     uint32_t* ent_off;            // T + 1: pairs emitted per BUCKET, then its exclusive scan ([T] = P)
     uint32_t* work;               // 2T: ids of the small buckets from the front of [0, T), of the heavy ones from its back
                                   // (work[T - 1 - k]), of the medium ones in [T, 2T); order irrelevant
+    uint32_t* big_bodies;         // BIG_GLOBAL_LIST: bodies whose cells the fill kernel spreads over the whole grid
     uint32_t* hit_bits;           // 4 * cap_entries: 32-test ballots of the count pass, bucket b's words at 4 * bucket_start[b]
     const uint64_t* excl;         // sorted (lo_slot << 32 | hi_slot)
     uint32_t n_excl;

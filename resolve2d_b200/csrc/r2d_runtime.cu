@@ -126,6 +126,7 @@ struct CudaBatch : BatchBase {
     int warm_cur = 0;
     bool warm_saving = false;   // fill_dev points the table at the one being written
     DBuf<uint64_t> world_magic;
+    DBuf<uint32_t> big_bodies;
     uint32_t magic_for_mult = 0;
     DBuf<uint32_t> ref_order, ref_joints;   // R2D_MODE_REFERENCE_ORDER: manifold / joint sweep order of the reference
     bool world_fused_now = false;     // this step is solved by k_world_solve (which also places and pre-steps the manifolds)
@@ -522,7 +523,7 @@ struct CudaBatch : BatchBase {
         d.pos = pos.p; d.mom = mom.p; d.frc = frc.p; d.prop = prop.p; d.shape = shape.p; d.aabb = aabb.p;
         d.pose = pose.p; d.view = view.p; d.ncells = ncells.p; d.bkt = bkt.p;
         d.n_worlds = (uint32_t)worlds.size();
-        d.world_base = world_base.p; d.grav_off = grav_off.p; d.grav = grav.p; d.world_magic = world_magic.p;
+        d.world_base = world_base.p; d.grav_off = grav_off.p; d.grav = grav.p; d.world_magic = world_magic.p; d.big_bodies = big_bodies.p;
         d.cell = grid_cell(); d.table_mult = grid_mult();
         d.n_buckets = d.table_mult * d.n_bodies;
         d.bucket_cnt = bucket_cnt.p; d.bucket_start = bucket_start.p;
@@ -636,6 +637,7 @@ struct CudaBatch : BatchBase {
         stats.n_joints = (uint32_t)image.j_hdr.size();
         stats.n_joint_colors = (uint32_t)image.joint_color_start.size() - 1;
         if (nb == 0) return R2D_OK;
+        R2D_TRY(big_bodies.reserve(BIG_GLOBAL_LIST));
         if (magic_for_mult != grid_mult()) {   // per world: the reciprocal that replaces the 64-bit modulo of the cell hash
             std::vector<uint64_t> mg(worlds.size());
             for (size_t w = 0; w < worlds.size(); ++w)
