@@ -11,8 +11,9 @@ cols = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 idx = {c: hdr.index(c) for c in cols if c in hdr}
 ki = hdr.index("Kernel Name")
 print(" | ".join(["Kernel Name"] + [f"{c}[{units[idx[c]]}]" for c in idx]))
-CLASS = [("k_grid_cells|k_scan_chained|k_list_buckets|k_sort_buckets|k_bucket_|k_fine_pairs", "broadphase"), ("k_narrow", "narrowphase"),
-         ("k_color|k_owner|k_partition|k_scan_owners", "coloring"), ("k_solve|k_integrate", "solve_contacts")]
+CLASS = [("k_grid_cells|k_scan_chained|k_list_buckets|k_sort_buckets|k_bucket_|k_fine_pairs|k_world_broad", "broadphase"),
+         ("k_narrow", "narrowphase"), ("k_color|k_owner|k_partition|k_scan_owners", "coloring"),
+         ("k_solve|k_integrate|k_world_solve", "solve_contacts")]
 def to_bytes(v, u):
     v = float(v.replace(",", ""))
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
