@@ -404,6 +404,9 @@ def measure(gpu: Gpu, obj, n_units, S, I, steps, warmup, n_rect, batch, traffic_
                                       "avg_launch_us": dk["avg_launch_us"]},
                        "limiter": LIMITER.get(dominant),
                        "note": BYTES_NOTE}
+    if traffic.get(dominant):   # the same fraction on MEASURED DRAM bytes (one ncu --set full capture of the workload)
+        out["roofline"]["dram"] = {"bytes": traffic[dominant], "gbs": traffic[dominant] / (dk["ms_per_step"] * 1e-3) / 1e9,
+                                   "frac": traffic[dominant] / (dk["ms_per_step"] * 1e-3) / 1e9 / peak}
     if dominant == "solve_contacts":
         out["roofline"]["if_every_sweep_streamed_from_hbm"] = {"bytes": streamed + abytes["integrate"],
                                                                "gbs": (streamed + abytes["integrate"]) / (dk["ms_per_step"] * 1e-3) / 1e9}

@@ -697,6 +697,7 @@ __global__ void __launch_bounds__(TPB, NARROW_CTAS) k_narrow(Dev d) {
 // posted for r in maxprio[r & 1] and posts those of the losers for r + 1 into the other array.  The result equals a
 // sequential greedy colouring in descending priority, so it is a pure function of the contact graph and the body ids.
 constexpr int COLOR_REG_SLOTS = 2;  // pending manifolds a thread keeps in registers across the rounds
+constexpr uint32_t COLOR_COMPACT_ROUND = 3;   // from this round on the streamed manifolds are kept in compacted lists
 constexpr int FLOW_SLOTS = 8;       // manifolds per thread the dataflow colouring can hold (registers)
 
 __global__ void __launch_bounds__(TPB, 4) k_color(Dev d) {
@@ -837,13 +838,41 @@ __global__ void __launch_bounds__(TPB, 4) k_color(Dev d) {
             else
                 pend[k] = false;
         }
-        for (uint32_t p = tid + COLOR_REG_SLOTS * nth; p < n; p += nth) {
-            const int r = color_round_thread(d, p, round);
-            if (r == 2) {
-                left = 1;
-            } else if (r == 1) {
-                atomicAdd(&s_hist[d.m_color[p]], 1u);
-                owner_bit_thread(d, p);
+        // Manifolds beyond the register slots (worlds with more than ~300k pairs) are streamed.  For the first
+        // COLOR_COMPACT_ROUND rounds every slot is visited; from then on only the survivors, kept in two lists that swap
+        // every round (a million-body pile is coloured within ~10 rounds except for the contacts of its few hub bodies,
+        // which take one round per contact: 47 rounds over 2.7 M slots cost 1.35 ms on mixed1M).
+        {
+            const uint32_t* list_in = d.pend_list + (size_t)(round & 1u) * d.cap_pairs;
+            uint32_t* list_out = d.pend_list + (size_t)((round + 1u) & 1u) * d.cap_pairs;
+            const bool compact = round >= COLOR_COMPACT_ROUND;
+            const bool from_list = round > COLOR_COMPACT_ROUND;
+            const uint32_t first = from_list ? tid : tid + COLOR_REG_SLOTS * nth;
+            const uint32_t count = from_list ? __ldcg(&d.pend_cnt[round]) : n;
+            // whole warps: the survivors of a warp are appended with one atomic
+            for (uint32_t x0 = first - (tid & 31u); x0 < count; x0 += nth) {
+                const uint32_t x = x0 + (tid & 31u);
+                uint32_t p = 0;
+                int r = 0;
+                if (x < count) {
+                    p = from_list ? __ldcg(&list_in[x]) : x;
+                    r = color_round_thread(d, p, round);
+                }
+                if (r == 2) {
+                    left = 1;
+                } else if (r == 1) {
+                    atomicAdd(&s_hist[d.m_color[p]], 1u);
+                    owner_bit_thread(d, p);
+                }
+                if (compact) {
+                    const uint32_t votes = __ballot_sync(0xffffffffu, r == 2);
+                    if (votes) {
+                        uint32_t base = 0;
+                        if ((tid & 31u) == 0u) base = atomicAdd(&d.pend_cnt[round + 1u], (uint32_t)__popc(votes));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (r == 2) list_out[base + (uint32_t)__popc(votes & ((1u << (tid & 31u)) - 1u))] = p;
+                    }
+                }
             }
         }
         if (__syncthreads_or(left) && threadIdx.x == 0) atomicAdd(&d.round_left[round], 1u);

@@ -146,6 +146,8 @@ struct Dev {
     uint32_t* color_start;        // MAX_COLORS + 1
     uint32_t* color_cursor;       // MAX_COLORS
     uint32_t* round_left;         // MAX_COLOR_ROUNDS
+    uint32_t* pend_cnt;           // MAX_COLOR_ROUNDS + 1: length of the pending list of each round (k_color, streamed manifolds)
+    uint32_t* pend_list;          // 2 x cap_pairs: pair slots still pending, two lists that swap every round
     // dataflow colouring (single worlds): the manifolds of a body, and one 16-byte word per body that is both the wait
     // target and the data — {96-bit colour mask, manifolds coloured so far}
     uint32_t flow;                // 1: k_narrow lists every manifold on its non-static bodies (adj_*), k_color may use them

@@ -125,6 +125,7 @@ struct CudaBatch : BatchBase {
     uint32_t warm_slots = 0;
     int warm_cur = 0;
     bool warm_saving = false;   // fill_dev points the table at the one being written
+    DBuf<uint32_t> pend_list;
     DBuf<uint64_t> world_magic;
     DBuf<uint32_t> big_bodies;
     uint32_t magic_for_mult = 0;
@@ -143,7 +144,7 @@ struct CudaBatch : BatchBase {
     DBuf<unsigned char> zeroed;
     size_t zeroed_bytes = 0, scan_state_cap = 0;
     size_t off_counters = 0, off_color_misc = 0, off_scan = 0, off_maxprio0 = 0, off_maxprio1 = 0, off_used = 0, off_own_bits = 0;
-    size_t off_adj_cnt = 0, off_cstate = 0, off_body_shared = 0;
+    size_t off_adj_cnt = 0, off_cstate = 0, off_body_shared = 0, off_pend_cnt = 0;
     bool tile_solver = true;          // k_solve_tiles for single worlds without joints that fit (R2D_TILE_SOLVER=0: never)
     uint32_t tile_bodies_now = 0, tile_max_tasks = TILE_MAX_TASKS;
     bool tile_declined = false;
@@ -560,6 +561,8 @@ struct CudaBatch : BatchBase {
         d.s_warm0 = s_warm0.p; d.s_warm1 = s_warm1.p;
         d.sleep_cnt = sleep_cnt.p; d.sleep_state = sleep_state.p;
         d.body_shared = (uint32_t*)(zeroed.p + off_body_shared);
+        d.pend_cnt = (uint32_t*)(zeroed.p + off_pend_cnt);
+        d.pend_list = pend_list.p;
         d.own_words = (d.n_bodies + 31u) / 32u;
         d.own_bits = (uint32_t*)(zeroed.p + off_own_bits);
         d.own_pos = own_pos.p;
@@ -588,7 +591,7 @@ struct CudaBatch : BatchBase {
             (st = m_r0.reserve(n)) || (st = m_r1.reserve(n)) || (st = m_color.reserve(n)) || (st = m_prio.reserve(n)) || (st = s_hdr.reserve(n)) ||
             (st = s_nf.reserve(n)) || (st = s_inv.reserve(n)) || (st = s_r0.reserve(n)) || (st = s_r1.reserve(n)) ||
             (st = s_pm0.reserve(n)) || (st = s_pm1.reserve(n)) || (st = s_acc0.reserve(n)) || (st = s_acc1.reserve(n)) ||
-            (st = s_dep.reserve(n)) || (opt_warm_start && ((st = s_warm0.reserve(n)) || (st = s_warm1.reserve(n)))))
+            (st = s_dep.reserve(n)) || (st = pend_list.reserve(2 * n)) || (opt_warm_start && ((st = s_warm0.reserve(n)) || (st = s_warm1.reserve(n)))))
             return st;
         cap_pairs = pairs.cap;
         for (size_t c : {m_prio.cap, m_hdr.cap, m_g0.cap, m_g1.cap, m_r0.cap, m_r1.cap, m_color.cap, s_hdr.cap, s_nf.cap, s_inv.cap,
@@ -667,6 +670,7 @@ struct CudaBatch : BatchBase {
             off_adj_cnt = o; o = align(o + (size_t)nb * 4);
             off_cstate = o; o = align(o + (size_t)nb * 16);
             off_body_shared = o; o = align(o + (size_t)nb * 4);
+            off_pend_cnt = o; o = align(o + (MAX_COLOR_ROUNDS + 2) * 4);
             zeroed_bytes = o;
             if ((st = zeroed.reserve(zeroed_bytes))) return st;
         }

@@ -59,6 +59,16 @@ const c = struct {
     pub extern "c" fn r2d_body_set_ang_momentum(s: ?*r2d_solver, id: u32, l: f32) c_int;
     pub extern "c" fn r2d_body_set_force(s: ?*r2d_solver, id: u32, x: f32, y: f32) c_int;
     pub extern "c" fn r2d_body_set_torque(s: ?*r2d_solver, id: u32, t: f32) c_int;
+    pub extern "c" fn r2d_set_mode(s: ?*r2d_solver, mode: c_int) c_int; // 0 parity, 1 fast, 2 reference order (validation)
+    pub extern "c" fn r2d_set_option(s: ?*r2d_solver, option: c_int, value: u32) c_int; // 1 warm start, 2 sleeping, 3 sleep calls
+    // a batch of worlds sharded over several GPUs (world w -> shard w * G / n_worlds), include/r2d_abi.h "r2d_sharded_*"
+    pub const r2d_sharded = opaque {};
+    pub extern "c" fn r2d_sharded_create(n_worlds: u32, devices: [*]const c_int, n_devices: u32, cell_width: f32, table_mult: u32, out: *?*r2d_sharded) c_int;
+    pub extern "c" fn r2d_sharded_destroy(b: ?*r2d_sharded) c_int;
+    pub extern "c" fn r2d_sharded_world(b: ?*r2d_sharded, world: u32, out: *?*r2d_solver) c_int;
+    pub extern "c" fn r2d_sharded_process(b: ?*r2d_sharded, dt: f32, sub_steps: u32, collision_iters: u32) c_int;
+    pub extern "c" fn r2d_sharded_process_read(b: ?*r2d_sharded, dt: f32, sub_steps: u32, collision_iters: u32, ids: ?[*]u32, pos_xy: ?[*]f32, angle: ?[*]f32, momentum_xy: ?[*]f32, ang_momentum: ?[*]f32, aabb_xywh: ?[*]f32, n: usize) c_int;
+    pub extern "c" fn r2d_sharded_write_forces(b: ?*r2d_sharded, force_xy_torque: [*]const f32, n: usize) c_int;
     pub extern "c" fn r2d_read_bodies(s: ?*r2d_solver, ids: ?[*]u32, pos_xy: ?[*]f32, angle: ?[*]f32, momentum_xy: ?[*]f32, ang_momentum: ?[*]f32, aabb_xywh: ?[*]f32, capacity: usize) c_int;
 };
 
@@ -189,6 +199,11 @@ pub const Solver = struct {
     /// slice may be null.  Replaces "solver.process(...); for (solver.bodies.values()) |b| ..." of the demos' frame loops.
     pub fn processRead(self: *Self, dt: f32, sub_steps: usize, collision_iters: usize, ids: ?[]u32, pos_xy: ?[]f32, angle: ?[]f32, momentum_xy: ?[]f32, ang_momentum: ?[]f32, aabb_xywh: ?[]f32) Error!void {
         try check(c.r2d_process_read(self.handle, dt, @intCast(sub_steps), @intCast(collision_iters), if (ids) |s| s.ptr else null, if (pos_xy) |s| s.ptr else null, if (angle) |s| s.ptr else null, if (momentum_xy) |s| s.ptr else null, if (ang_momentum) |s| s.ptr else null, if (aabb_xywh) |s| s.ptr else null, self.numBodies()));
+    }
+    /// Roadmap items of the reference (README.md:59-64), off by default: warm starting, sleeping.
+    pub const Option = enum(c_int) { warm_start = 1, sleeping = 2, sleep_calls = 3 };
+    pub fn setOption(self: *Self, option: Option, value: u32) Error!void {
+        try check(c.r2d_set_option(self.handle, @intFromEnum(option), value));
     }
     pub fn bodyHandle(self: *Self, id: Id) EntityFactory.BodyHandle {
         return .{ .id = id, .solver = self };
