@@ -539,6 +539,9 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks, "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "roofline": main["roofline"],
             "kernels": main["kernels"], "cpu_baseline": main.get("cpu_baseline"), "batched": batched, "configs": configs,
         }
+        if batched is not None:   # the N = 1 point of the multi-GPU series (the lines at N > 1 report this metric as `value`)
+            line["strong_scaling_series"] = {"metric": "world-steps/s", "workload": f"batch{args.batch_worlds}x256", "n_gpus": 1,
+                                             "value": batched["value"], "e2e_value": batched["e2e"]["value"]}
         emit(line)
         return
 
@@ -571,6 +574,9 @@ def run_ours(args, rank, world, local_rank):
             "kernels": main["kernels"], "cpu_baseline": None, "body_steps_per_s": main["body_steps_per_s"],
         }
         line.update(extras)
+        line["strong_scaling_series"] = {"metric": "world-steps/s", "workload": f"batch{total}x256", "n_gpus": world,
+                                         "value": main["value"], "e2e_value": main["e2e"]["value"],
+                                         "n1_value_same_box": extras.get("single_gpu_same_box", {}).get("value")}
         emit(line)
 
 

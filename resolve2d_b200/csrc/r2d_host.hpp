@@ -469,6 +469,9 @@ struct BatchBase {
     virtual int backend_set_stream(void* stream) = 0;
     virtual int backend_profile_enable(int on) = 0;
     virtual int backend_profile_read(double* ms, uint64_t* launches, int reset) = 0;
+    // does the periodic spatial re-sort pay for this batch?  (not for batches of small worlds: their kernels keep a whole
+    // world in shared memory, the order of its bodies in HBM is irrelevant, and the re-sort goes through the host)
+    virtual bool backend_reorder_pays() const { return true; }
 
     float grid_cell() const { return mode != R2D_MODE_FAST ? 4.0f : cell_width; }      // lib.zig:254-255 (Q2)
     uint32_t grid_mult() const { return mode != R2D_MODE_FAST ? 2u : (table_mult ? table_mult : 1u); }
@@ -537,7 +540,7 @@ struct BatchBase {
     bool poisoned = false;
     int process(float dt, uint32_t sub_steps, uint32_t iters, const Readback* rb = nullptr) {
         if (poisoned) return R2D_ERR_BAD_STATE;
-        if (dev_fresh && reorder_interval && steps_since_upload >= reorder_interval) {
+        if (dev_fresh && reorder_interval && steps_since_upload >= reorder_interval && backend_reorder_pays()) {
             const int sr = reorder();
             if (sr != R2D_OK) return sr;
         }

@@ -324,6 +324,10 @@ struct CudaBatch : BatchBase {
             max_world_bodies = std::max(max_world_bodies, image.world_base[w + 1] - image.world_base[w]);
         return R2D_OK;
     }
+    bool backend_reorder_pays() const override {
+        const bool small_worlds = world_solver && worlds.size() >= (size_t)n_sms / 2 && max_world_bodies <= WORLD_MAX_BODIES;
+        return !small_worlds;
+    }
     int backend_download() override {
         R2D_CUDA(cudaSetDevice(device));
         const size_t nb = image.n_bodies;
