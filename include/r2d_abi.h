@@ -163,7 +163,7 @@ int r2d_set_stream(r2d_solver* s, void* cuda_stream); /* run on the caller's cud
  *   R2D_OPT_SLEEPING     "Sleeping/awakening": a non-static body whose linear and angular speed stayed below 0.2 m/s and
  *                        0.2 rad/s for R2D_OPT_SLEEP_CALLS consecutive calls (default 30) and that has no user force or
  *                        torque IS A STATIC BODY for the duration of a call; a body that moved faster than the thresholds
- *                        in a call wakes every body it touched in that call (one hop per call). */
+ *                        in a call wakes every body it touched in that call (one hop per call).  A body named by a joint never sleeps. */
 #define R2D_OPT_WARM_START 1
 #define R2D_OPT_SLEEPING 2
 #define R2D_OPT_SLEEP_CALLS 3

@@ -803,17 +803,24 @@ struct Solver {
         // sleeping: a body that has been slow for opt_sleep_calls calls in a row and is not being pushed IS A STATIC BODY
         // for the duration of this call (broadphase filters, contacts, joints, integration)
         std::vector<size_t> asleep;
-        if (opt_sleeping)
+        if (opt_sleeping) {
+            std::set<uint32_t> jointed;   // a body named by a joint never sleeps (a distance joint between two static bodies
+            for (const Constraint& c : constraints) {   // divides by w1 + w2 = 0)
+                jointed.insert(c.id1);
+                if (c.type == DISTANCE || c.type == OFFSET_DISTANCE) jointed.insert(c.id2);
+            }
             for (size_t i = 0; i < bodies.size(); ++i) {
                 RigidBody& b = bodies[i];
                 if (b.is_static) continue;
                 uint32_t& cnt = sleep_counter[b.id];
                 if (b.props.force.x != 0 || b.props.force.y != 0 || b.props.torque != 0) cnt = 0;   // user input wakes
+                if (jointed.count(b.id)) cnt = 0;
                 if (cnt >= opt_sleep_calls) {
                     b.is_static = true;
                     asleep.push_back(i);
                 }
             }
+        }
         updateManifolds();
         if (opt_warm_start)
             for (CollisionManifold& m : manifolds) {

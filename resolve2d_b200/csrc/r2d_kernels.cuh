@@ -1338,6 +1338,8 @@ __global__ void __launch_bounds__(TPB) k_sleep_begin(Dev d, uint32_t calls) {
             const float4 f = d.frc[i];
             uint32_t cnt = d.sleep_cnt[i];
             if (f.x != 0.0f || f.y != 0.0f || f.z != 0.0f) d.sleep_cnt[i] = cnt = 0u;   // user input wakes
+            // a body named by a joint never sleeps (a distance joint between two static bodies divides by w1 + w2 = 0)
+            if (d.n_joints && d.body_nj[i] != 0u) d.sleep_cnt[i] = cnt = 0u;
             if (cnt >= calls) {
                 state = 1u;
                 d.shape[i] = make_float4(sh.x, sh.y, u2f(flags | FLAG_STATIC), sh.w);

@@ -576,7 +576,8 @@ struct CudaBatch : BatchBase {
         d.n_joints = (uint32_t)image.j_hdr.size();
         d.j_hdr = j_hdr.p; d.j_par = j_par.p; d.j_vec = j_vec.p;
         d.j_dep = j_dep.p; d.body_nj = body_nj.p;
-        d.joints_flow = (joints_flow && image.joints_flow_ok && mode != R2D_MODE_REFERENCE_ORDER) ? 1u : 0u;
+        // (a sleeper is a static body for the call, and two-body joints write a static body's momentum, Q10: barrier sweep)
+        d.joints_flow = (joints_flow && image.joints_flow_ok && mode != R2D_MODE_REFERENCE_ORDER && !opt_sleeping) ? 1u : 0u;
         d.color_smem = 0;
     }
 

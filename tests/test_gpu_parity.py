@@ -191,6 +191,11 @@ def test_gpu_sleeping_matches_the_oracle():
         cold.process(scenes.DT, 4, 4)
     print(f"candidate pairs after 1220 calls: {cand.stats().n_pairs} with sleeping, {cold.stats().n_pairs} without")
     assert cand.stats().n_pairs < 0.8 * cold.stats().n_pairs
+    # joints: a sleeper is a static body for the call, and two-body joints write momentum into static bodies too (Q10)
+    def build(s):
+        return scenes.build_pyramid(s, base=16, n_spinners=2)
+    run_parity(lambda: Solver(2.0, 4), build, 150, check_every=25, what="pyramid16 sleeping", options=opts)
+    run_parity(lambda: Solver(2.0, 4), scenes.setup_0_1_car_platformer, 200, check_every=25, what="0_1 sleeping", options=opts)
     batch = Batch(96, 2.0, 4)
     batch.set_option(OPT_SLEEPING, 1)
     batch.set_option(OPT_SLEEP_CALLS, 10)
@@ -464,6 +469,32 @@ def test_gpu_fast_mode_grid_parameters():
     assert np.array_equal(cand.read_pairs(), orc.read_pairs())
     assert np.array_equal(cand.read_pairs(), ref.read_pairs())
     assert_bodies_equal(cand.read_bodies(), orc.read_bodies(), "fast mode")
+
+
+def test_gpu_fast_mode_batch_of_small_worlds():
+    """R2D_MODE_FAST with the per-world kernels (k_world_broad builds the grid of a world in shared memory with the caller's
+    cell width and table multiplier): sampled worlds vs the oracle in the same mode."""
+    n_worlds = 90
+    batch = Batch(n_worlds, 3.0, 3)
+    batch.set_mode(MODE_FAST)
+    oracles = {}
+    for w in range(n_worlds):
+        scenes.build_batch_world(batch.world(w), w, nx=12, ny=6)
+        if w in (0, 44, 89):
+            o = OracleSolver(3.0, 3, order=ORDER_COLORED)
+            o.set_mode(MODE_FAST)
+            scenes.build_batch_world(o, w, nx=12, ny=6)
+            oracles[w] = o
+    for _ in range(80):
+        batch.process(scenes.DT, 4, 4)
+        for o in oracles.values():
+            o.process(scenes.DT, 4, 4)
+    assert batch.stats().n_launches == 4
+    for w, o in oracles.items():
+        ws = batch.world(w)
+        assert np.array_equal(ws.read_pairs(), o.read_pairs()), w
+        assert_manifolds_equal(ws.read_manifolds(), o.read_manifolds(), f"fast world {w}")
+        assert_bodies_equal(ws.read_bodies(), o.read_bodies(), f"fast world {w}")
 
 
 def test_gpu_fast_mode_small_cells_make_rectangles_large():
