@@ -158,18 +158,6 @@ struct Image {
     uint32_t dev_world(uint32_t dev) const { return f2u(shape[dev].z) >> FLAG_WORLD_SHIFT; }
 };
 
-inline uint32_t morton16(uint32_t x, uint32_t y) {
-    auto spread = [](uint32_t v) {
-        v &= 0xFFFFu;
-        v = (v | (v << 8)) & 0x00FF00FFu;
-        v = (v | (v << 4)) & 0x0F0F0F0Fu;
-        v = (v | (v << 2)) & 0x33333333u;
-        v = (v | (v << 1)) & 0x55555555u;
-        return v;
-    };
-    return spread(x) | (spread(y) << 1);
-}
-
 inline float4 mkf4(float x, float y, float z, float w) { return make_float4(x, y, z, w); }
 
 inline void body_to_image(const Body& b, uint32_t world, Image& im, size_t at, bool large) {
@@ -216,6 +204,7 @@ inline bool body_is_large(const Body& b, const Image& im) {
     return !(im.fine_cell > 0.0f && body_width_bound(b) + FINE_MARGIN <= im.fine_cell);
 }
 
+inline int build_slot_tables(const std::vector<std::unique_ptr<World>>& worlds, Image& im);
 inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image& im, float coarse_cell) {
     const size_t nw = worlds.size();
     choose_fine_cell(worlds, coarse_cell, im);
@@ -249,12 +238,7 @@ inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image&
             keyed.resize(n);
             for (size_t k = 0; k < n; ++k) {
                 const Body& b = W.bodies[k];
-                float fx = (b.pos_x - minx) * 0.5f, fy = (b.pos_y - miny) * 0.5f;  // 2 m quantum
-                if (!(fx >= 0.0f)) fx = 0.0f;
-                if (!(fy >= 0.0f)) fy = 0.0f;
-                if (fx > 65535.0f) fx = 65535.0f;
-                if (fy > 65535.0f) fy = 65535.0f;
-                keyed[k] = {morton16((uint32_t)fx, (uint32_t)fy), (uint32_t)k};
+                keyed[k] = {resort_key(b.pos_x, b.pos_y, minx, miny), (uint32_t)k};   // (shared with the device re-sort)
             }
             // stable LSD radix sort on the 32-bit Morton key (two 16-bit passes): the re-sort runs every reorder interval on
             // the host, std::stable_sort was most of its cost at 100 k bodies
@@ -284,12 +268,6 @@ inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image&
     im.shape.resize(nb);
     im.aabb.resize(nb);
     im.sleep.resize(nb);
-    im.excl.clear();
-    struct GJ {
-        Joint j;
-        uint32_t world, local, s1, s2, color;
-    };
-    std::vector<GJ> gj;
     for (size_t w = 0; w < nw; ++w) {
         const World& W = *worlds[w];
         const uint32_t base = im.world_base[w];
@@ -302,6 +280,26 @@ inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image&
             }
             body_to_image(bd, (uint32_t)w, im, base + k, large);
         }
+    }
+    return build_slot_tables(worlds, im);
+}
+
+// Everything in the image that names bodies by DEVICE slot and is not a per-body array: the exclusion list and the joints
+// (slots, colours, dataflow ranks).  Rebuilt alone after a device-side re-sort (BatchBase::reorder), which permutes the
+// body arrays on the device and hands back the new order.
+inline int build_slot_tables(const std::vector<std::unique_ptr<World>>& worlds, Image& im) {
+    const size_t nw = worlds.size();
+    const size_t nb = im.n_bodies;
+    im.excl.clear();
+    struct GJ {
+        Joint j;
+        uint32_t world, local, s1, s2, color;
+        bool st1, st2;
+    };
+    std::vector<GJ> gj;
+    for (size_t w = 0; w < nw; ++w) {
+        const World& W = *worlds[w];
+        const uint32_t base = im.world_base[w];
         for (const auto& pr : W.excluded) {
             const int s1 = W.find(pr.first), s2 = W.find(pr.second);
             if (s1 < 0 || s2 < 0 || s1 == s2) continue;
@@ -314,7 +312,8 @@ inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image&
             const int s1 = W.find(j.id1);
             const int s2 = joint_has_two_bodies(j) ? W.find(j.id2) : s1;
             if (s1 < 0 || s2 < 0) return R2D_ERR_INVALID_BODY_ID;
-            gj.push_back({j, (uint32_t)w, (uint32_t)k, im.dev_of_host[base + (uint32_t)s1], im.dev_of_host[base + (uint32_t)s2], 0u});
+            gj.push_back({j, (uint32_t)w, (uint32_t)k, im.dev_of_host[base + (uint32_t)s1], im.dev_of_host[base + (uint32_t)s2], 0u,
+                          W.bodies[s1].is_static, W.bodies[s2].is_static});
         }
     }
     std::sort(im.excl.begin(), im.excl.end());
@@ -367,7 +366,7 @@ inline int build_image(const std::vector<std::unique_ptr<World>>& worlds, Image&
             const bool two = joint_has_two_bodies(g.j);
             im.j_dep[k].x = im.body_nj[g.s1]++;
             if (two) {
-                if (g.s2 == g.s1 || (f2u(im.shape[g.s1].z) & FLAG_STATIC) || (f2u(im.shape[g.s2].z) & FLAG_STATIC)) im.joints_flow_ok = false;
+                if (g.s2 == g.s1 || g.st1 || g.st2) im.joints_flow_ok = false;
                 if (g.s2 != g.s1) im.j_dep[k].z = im.body_nj[g.s2]++;
             }
         }
@@ -472,6 +471,10 @@ struct BatchBase {
     // does the periodic spatial re-sort pay for this batch?  (not for batches of small worlds: their kernels keep a whole
     // world in shared memory, the order of its bodies in HBM is irrelevant, and the re-sort goes through the host)
     virtual bool backend_reorder_pays() const { return true; }
+    // re-sort on the device (keys, radix sort and permutation of the body arrays there; the host only rebuilds the tables
+    // that name device slots).  A backend without one answers REORDER_ON_HOST and reorder() goes through the host.
+    static constexpr int REORDER_ON_HOST = -1000;
+    virtual int backend_reorder() { return REORDER_ON_HOST; }
 
     float grid_cell() const { return mode != R2D_MODE_FAST ? 4.0f : cell_width; }      // lib.zig:254-255 (Q2)
     uint32_t grid_mult() const { return mode != R2D_MODE_FAST ? 2u : (table_mult ? table_mult : 1u); }
@@ -526,16 +529,24 @@ struct BatchBase {
     };
     const Readback* readback = nullptr;
     bool readback_done = false;
-    // process() calls between spatial re-sorts of the device order (0 = never).  The re-sort goes through the host (download,
-    // sort, upload: 5.6 ms for 100 k bodies = 14 steps), and a settled pile loses only ~3 % over 650 steps without one
-    // (profiles/reorder_cost.py), so it is rare by default; r2d_reorder() forces one.
+    // process() calls between spatial re-sorts of the device order (0 = never); r2d_reorder() forces one.  With the state
+    // resident on the device the re-sort happens there (backend_reorder: ~0.4 ms for 100 k bodies); a backend without that
+    // path, a stale device image, or a changed fine cell go through the host (download, sort, upload: 5.6 ms for 100 k).
     uint32_t reorder_interval = 1024;
     uint32_t steps_since_upload = 0;
-    int reorder() {  // re-derive the device order from the current positions (download, sort, upload)
+    int reorder_through_host() {
         const int st = ensure_host();
         if (st != R2D_OK) return st;
         dev_fresh = false;
         return R2D_OK;
+    }
+    int reorder() {  // re-derive the device order from the current positions
+        if (dev_fresh && image.fine_for_cell == grid_cell()) {
+            const int st = backend_reorder();
+            if (st == R2D_OK) steps_since_upload = 0;
+            if (st != REORDER_ON_HOST) return st;
+        }
+        return reorder_through_host();
     }
     bool poisoned = false;
     int process(float dt, uint32_t sub_steps, uint32_t iters, const Readback* rb = nullptr) {
@@ -545,7 +556,7 @@ struct BatchBase {
             if (sr != R2D_OK) return sr;
         }
         if (dev_fresh && image.fine_for_cell != grid_cell()) {  // the mode changed: the fine cell depends on the coarse one
-            const int sr = reorder();
+            const int sr = reorder_through_host();
             if (sr != R2D_OK) return sr;
         }
         if (!dev_fresh) steps_since_upload = 0;

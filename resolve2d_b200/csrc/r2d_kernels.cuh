@@ -1689,6 +1689,66 @@ __global__ void __launch_bounds__(TPB) k_import_forces(Dev d, const uint32_t* __
     }
 }
 
+// ---- spatial re-sort of the device slots, on the device (BatchBase::reorder; the host's build_image derives the same order) -------
+// k_resort_min: per world the minimum position over its bodies without a NaN coordinate (ordered-int atomicMin, one per warp
+// when the warp holds one world).  k_resort_keys: in HOST slot order (ties of the stable sort keep insertion order, as on the
+// host) key = world << 32 | resort_key.  A library radix sort (cub::DeviceRadixSort, r2d_runtime.cu) orders them.
+// k_resort_gather: device slot j takes the body whose host slot the sort put there; the inverse map is written on the way.
+__global__ void __launch_bounds__(TPB) k_resort_init(int2* wmin, uint32_t n_worlds) {
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_worlds; w += gridDim.x * blockDim.x)
+        wmin[w] = make_int2(RESORT_NO_MIN, RESORT_NO_MIN);
+}
+__global__ void __launch_bounds__(TPB) k_resort_min(Dev d, int2* wmin) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;   // (grid covers the bodies: whole warps reach the shuffles)
+    const bool in = i < d.n_bodies;
+    const float4 p = in ? d.pos[i] : make_float4(0, 0, 0, 0);
+    const uint32_t w = in ? body_flags(d, i) >> FLAG_WORLD_SHIFT : 0xFFFFFFFFu;
+    const bool ok = in && p.x == p.x && p.y == p.y;
+    int kx = ok ? resort_float_order(p.x) : RESORT_NO_MIN, ky = ok ? resort_float_order(p.y) : RESORT_NO_MIN;
+    const uint32_t w0 = __shfl_sync(0xffffffffu, w, 0);
+    if (__all_sync(0xffffffffu, !in || w == w0)) {
+        kx = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), kx, cg::less<int>());
+        ky = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), ky, cg::less<int>());
+        if ((threadIdx.x & 31u) == 0 && w0 != 0xFFFFFFFFu && kx != RESORT_NO_MIN) {
+            atomicMin(&wmin[w0].x, kx);
+            atomicMin(&wmin[w0].y, ky);
+        }
+    } else if (ok) {
+        atomicMin(&wmin[w].x, kx);
+        atomicMin(&wmin[w].y, ky);
+    }
+}
+__global__ void __launch_bounds__(TPB) k_resort_keys(Dev d, const uint32_t* __restrict__ dev_of_host, const int2* __restrict__ wmin,
+                                                     unsigned long long* keys, uint32_t* vals) {
+    for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < d.n_bodies; h += gridDim.x * blockDim.x) {
+        const uint32_t s = dev_of_host[h];
+        const float4 p = d.pos[s];
+        const uint32_t w = body_flags(d, s) >> FLAG_WORLD_SHIFT;
+        const int2 m = wmin[w];
+        const float mx = m.x == RESORT_NO_MIN ? 0.0f : resort_float_unorder(m.x), my = m.x == RESORT_NO_MIN ? 0.0f : resort_float_unorder(m.y);
+        keys[h] = ((unsigned long long)w << 32) | resort_key(p.x, p.y, mx, my);
+        vals[h] = h;
+    }
+}
+struct ResortArrays {
+    float4 *pos, *mom, *frc, *prop, *shape, *aabb;
+    uint32_t* sleep_cnt;
+};
+__global__ void __launch_bounds__(TPB) k_resort_gather(Dev d, const uint32_t* __restrict__ host_of_new, const uint32_t* __restrict__ old_dev_of_host,
+                                                       uint32_t* new_dev_of_host, ResortArrays o) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < d.n_bodies; j += gridDim.x * blockDim.x) {
+        const uint32_t h = host_of_new[j], s = old_dev_of_host[h];
+        o.pos[j] = d.pos[s];
+        o.mom[j] = d.mom[s];
+        o.frc[j] = d.frc[s];
+        o.prop[j] = d.prop[s];
+        o.shape[j] = d.shape[s];
+        o.aabb[j] = d.aabb[s];
+        o.sleep_cnt[j] = d.sleep_cnt[s];
+        new_dev_of_host[h] = j;
+    }
+}
+
 }  // namespace r2d
 
 #include "r2d_world.cuh"

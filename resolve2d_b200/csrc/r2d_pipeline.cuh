@@ -204,6 +204,36 @@ struct Dev {
 R2D_HD uint32_t body_flags(const Dev& d, uint32_t i) { return f2u(d.shape[i].z); }
 R2D_HD uint32_t body_id(const Dev& d, uint32_t i) { return f2u(d.shape[i].w); }
 
+// ---- spatial order of the device slots (host: build_image; device: k_resort_*) ---------------------------------------------
+// Sort key of a body inside its world: Morton code of the position on a 2 m lattice whose origin is the minimum over the
+// world's bodies (NaN coordinates sort first).  One definition, evaluated by the host at upload and by the device at a
+// re-sort, so that both derive the same order.
+R2D_HD uint32_t morton16(uint32_t x, uint32_t y) {
+    uint32_t v[2] = {x & 0xFFFFu, y & 0xFFFFu};
+    for (int k = 0; k < 2; ++k) {
+        v[k] = (v[k] | (v[k] << 8)) & 0x00FF00FFu;
+        v[k] = (v[k] | (v[k] << 4)) & 0x0F0F0F0Fu;
+        v[k] = (v[k] | (v[k] << 2)) & 0x33333333u;
+        v[k] = (v[k] | (v[k] << 1)) & 0x55555555u;
+    }
+    return v[0] | (v[1] << 1);
+}
+R2D_HD uint32_t resort_key(float pos_x, float pos_y, float min_x, float min_y) {
+    float fx = fmul(fsub(pos_x, min_x), 0.5f), fy = fmul(fsub(pos_y, min_y), 0.5f);
+    if (!(fx >= 0.0f)) fx = 0.0f;
+    if (!(fy >= 0.0f)) fy = 0.0f;
+    if (fx > 65535.0f) fx = 65535.0f;
+    if (fy > 65535.0f) fy = 65535.0f;
+    return morton16((uint32_t)fx, (uint32_t)fy);
+}
+// order-preserving map float -> int for the per-world minimum (atomicMin on ints); NaNs are never passed in
+R2D_HD int resort_float_order(float f) {
+    const int i = (int)f2u(f);
+    return i >= 0 ? i : (int)((uint32_t)i ^ 0x7FFFFFFFu);
+}
+R2D_HD float resort_float_unorder(int k) { return u2f((uint32_t)(k >= 0 ? k : (int)((uint32_t)k ^ 0x7FFFFFFFu))); }
+constexpr int RESORT_NO_MIN = 0x7FFFFFFF;   // (the image of a NaN pattern: never produced by a finite or infinite coordinate)
+
 // ---- atomics: real ones on the device, plain read-modify-write in the serial host emulator ---------------------------
 R2D_HD uint32_t atomic_add_u32(uint32_t* p, uint32_t v) {
 #if defined(__CUDA_ARCH__)

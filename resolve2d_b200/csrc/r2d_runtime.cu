@@ -8,6 +8,7 @@
 //   S x { k_integrate_forces ; I x { joint colours ; contact colours } ; k_integrate_positions }   (lib.zig:199-250)
 // There is no CPU fallback anywhere: a missing device is an error.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <cstdio>
 #include <cstdlib>
@@ -220,6 +221,8 @@ struct CudaBatch : BatchBase {
         if (env_is("R2D_WORLD_SOLVER", "0")) world_solver = false;           // batches through the single-world kernels
         if (env_is("R2D_FLOW_COLORING", "0")) flow_coloring = false;         // Jones-Plassmann rounds only
         if (env_is("R2D_TILE_SOLVER", "0")) tile_solver = false;             // k_solve_persistent instead of k_solve_tiles
+        if (env_is("R2D_DEVICE_RESORT", "0")) device_resort = false;         // the periodic re-sort through the host
+        if (env_is("R2D_RESORT_CHECK", "1")) resort_check = true;            // (tests) device order == build_image's order
         if (const char* e = getenv("R2D_TILE_MAX_TASKS")) tile_max_tasks = std::min<uint32_t>((uint32_t)atoi(e), TILE_MAX_TASKS);
         if (env_is("R2D_ZERO_COPY", "0")) zero_copy = false;                 // bulk reads through the staging buffer
         if (env_is("R2D_BROADPHASE", "buckets")) fine_grid = false;          // every body through the hashed 4 m buckets
@@ -309,19 +312,98 @@ struct CudaBatch : BatchBase {
         int st;
         if ((st = up(pos, image.pos)) || (st = up(mom, image.mom)) || (st = up(frc, image.frc)) || (st = up(prop, image.prop)) ||
             (st = up(shape, image.shape)) || (st = up(aabb, image.aabb)) || (st = up(world_base, image.world_base)) ||
-            (st = up(grav_off, image.grav_off)) || (st = up(grav, image.grav)) || (st = up(excl, image.excl)) ||
-            (st = up(j_hdr, image.j_hdr)) || (st = up(j_par, image.j_par)) || (st = up(j_vec, image.j_vec)) ||
-            (st = up(j_dep, image.j_dep)) || (st = up(body_nj, image.body_nj)) || (st = up(sleep_cnt, image.sleep)) ||
-            (st = up(joint_color_start, image.joint_color_start)) || (st = up(dev_of_host, image.dev_of_host)))
+            (st = up(grav_off, image.grav_off)) || (st = up(grav, image.grav)) || (st = up(sleep_cnt, image.sleep)) ||
+            (st = up(dev_of_host, image.dev_of_host)) || (st = upload_slot_tables()))
             return st;
         R2D_CUDA(cudaStreamSynchronize(stream));  // the image vectors are pageable and may change after we return
         magic_for_mult = 0;   // (the bucket count of a world depends on the mode's table multiplier: refreshed in process())
-        last_pairs = 0;
-        tile_declined = false;
-        world_broad_declined = false;
+        after_new_order();
         max_world_bodies = 0;
         for (size_t w = 0; w + 1 < image.world_base.size(); ++w)
             max_world_bodies = std::max(max_world_bodies, image.world_base[w + 1] - image.world_base[w]);
+        return R2D_OK;
+    }
+    // what names bodies by device slot besides the per-body arrays (host::build_slot_tables)
+    int upload_slot_tables() {
+        int st;
+        if ((st = up(excl, image.excl)) || (st = up(j_hdr, image.j_hdr)) || (st = up(j_par, image.j_par)) || (st = up(j_vec, image.j_vec)) ||
+            (st = up(j_dep, image.j_dep)) || (st = up(body_nj, image.body_nj)) || (st = up(joint_color_start, image.joint_color_start)))
+            return st;
+        return R2D_OK;
+    }
+    void after_new_order() {   // results of the last step that name device slots are void
+        last_pairs = 0;
+        tile_declined = false;
+        world_broad_declined = false;
+    }
+    // ---- re-sort on the device: keys, radix sort, permutation of the seven per-body arrays; 4 B per body come back ----
+    DBuf<unsigned long long> resort_keys[2];
+    DBuf<uint32_t> resort_vals[2], resort_doh, resort_sleep;
+    DBuf<int2> resort_min;
+    DBuf<float4> resort_f4[6];
+    DBuf<unsigned char> resort_tmp;
+    std::vector<uint32_t> resort_order;   // host slot at every new device slot
+    bool device_resort = true;            // R2D_DEVICE_RESORT=0: through the host
+    bool resort_check = false;            // R2D_RESORT_CHECK=1 (tests): the order must equal the one build_image derives
+    int backend_reorder() override {
+        const uint32_t nb = image.n_bodies, nw = (uint32_t)worlds.size();
+        if (!device_resort || nb == 0) return REORDER_ON_HOST;
+        R2D_CUDA(cudaSetDevice(device));
+        R2D_TRY(join_forces());   // (a pending force import scatters through the old dev_of_host)
+        for (int k = 0; k < 2; ++k) {
+            R2D_TRY(resort_keys[k].reserve(nb));
+            R2D_TRY(resort_vals[k].reserve(nb));
+        }
+        for (auto& b : resort_f4) R2D_TRY(b.reserve(nb));   // (swapped with the body arrays below: every buffer holds >= nb)
+        R2D_TRY(resort_sleep.reserve(nb));
+        R2D_TRY(resort_doh.reserve(nb));
+        R2D_TRY(resort_min.reserve(nw));
+        int world_bits = 0;
+        while (world_bits < 31 && (1u << world_bits) < nw) ++world_bits;
+        size_t tmp_bytes = 0;
+        R2D_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, resort_keys[0].p, resort_keys[1].p, resort_vals[0].p, resort_vals[1].p,
+                                                 (int)nb, 0, 32 + world_bits, stream));
+        R2D_TRY(resort_tmp.reserve(tmp_bytes + 256));
+        fill_dev();
+        k_resort_init<<<grid_for(nw), TPB, 0, stream>>>(resort_min.p, nw);
+        k_resort_min<<<(nb + TPB - 1) / TPB, TPB, 0, stream>>>(d, resort_min.p);
+        k_resort_keys<<<grid_for(nb), TPB, 0, stream>>>(d, dev_of_host.p, resort_min.p, resort_keys[0].p, resort_vals[0].p);
+        R2D_CUDA(cub::DeviceRadixSort::SortPairs(resort_tmp.p, tmp_bytes, resort_keys[0].p, resort_keys[1].p, resort_vals[0].p, resort_vals[1].p,
+                                                 (int)nb, 0, 32 + world_bits, stream));
+        const ResortArrays out = {resort_f4[0].p, resort_f4[1].p, resort_f4[2].p, resort_f4[3].p, resort_f4[4].p, resort_f4[5].p, resort_sleep.p};
+        k_resort_gather<<<grid_for(nb), TPB, 0, stream>>>(d, resort_vals[1].p, dev_of_host.p, resort_doh.p, out);
+        resort_order.resize(nb);
+        R2D_CUDA(cudaMemcpyAsync(resort_order.data(), resort_vals[1].p, (size_t)nb * 4, cudaMemcpyDeviceToHost, stream));
+        R2D_CUDA(cudaStreamSynchronize(stream));
+        R2D_CUDA(cudaGetLastError());
+        auto swap_buf = [](auto& a, auto& b) {
+            std::swap(a.p, b.p);
+            std::swap(a.cap, b.cap);
+        };
+        swap_buf(pos, resort_f4[0]); swap_buf(mom, resort_f4[1]); swap_buf(frc, resort_f4[2]); swap_buf(prop, resort_f4[3]);
+        swap_buf(shape, resort_f4[4]); swap_buf(aabb, resort_f4[5]); swap_buf(sleep_cnt, resort_sleep); swap_buf(dev_of_host, resort_doh);
+        // host side: the two maps, the shape image (ids and world indices by device slot), the slot tables
+        {
+            std::vector<float4> sh(nb);
+            for (uint32_t j = 0; j < nb; ++j) sh[j] = image.shape[image.dev_of_host[resort_order[j]]];
+            image.shape.swap(sh);
+            for (uint32_t j = 0; j < nb; ++j) {
+                image.host_of_dev[j] = resort_order[j];
+                image.dev_of_host[resort_order[j]] = j;
+            }
+        }
+        const int bt = host::build_slot_tables(worlds, image);
+        if (bt != R2D_OK) return bt;
+        R2D_TRY(upload_slot_tables());
+        R2D_CUDA(cudaStreamSynchronize(stream));
+        after_new_order();
+        if (resort_check) {   // the order build_image would derive from the same state
+            R2D_TRY(backend_download());
+            host::Image ref;
+            const int st = host::build_image(worlds, ref, grid_cell());
+            if (st != R2D_OK) return st;
+            if (ref.host_of_dev != image.host_of_dev) return R2D_ERR_BAD_STATE;
+        }
         return R2D_OK;
     }
     bool backend_reorder_pays() const override {

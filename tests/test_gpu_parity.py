@@ -450,6 +450,57 @@ def test_gpu_reorder_does_not_change_results():
     assert_manifolds_equal(a.read_manifolds(), b.read_manifolds(), "reorder")
 
 
+def test_gpu_device_resort_equals_host_resort(monkeypatch):
+    """The periodic re-sort runs on the device (keys, radix sort, permutation of the body arrays; the host only rebuilds
+    the exclusion list and the joints).  R2D_RESORT_CHECK=1 makes every device re-sort compare its order with the one
+    build_image derives from the same state (a difference fails the call), and the results must equal — bit for bit —
+    those of the host re-sort (R2D_DEVICE_RESORT=0) and of never re-sorting: joints, exclusions, sleeping counters and a
+    batch of several larger worlds ride along."""
+    def single(build, interval, sleeping=False):
+        s = Solver(2.0, 4)
+        if sleeping:
+            s.set_option(OPT_SLEEPING, 1)
+        cfg = build(s) or {"sub_steps": 4, "iters": 4}
+        s.set_reorder_interval(interval)
+        for _ in range(45):
+            s.process(scenes.DT, cfg["sub_steps"], cfg["iters"])
+        s.reorder()
+        s.process(scenes.DT, cfg["sub_steps"], cfg["iters"])
+        out = s.read_bodies(), s.read_pairs(), s.read_manifolds()
+        s.deinit()
+        return out
+
+    def batch(interval):
+        b = Batch(3, 2.0, 4)
+        for w in range(3):
+            scenes.build_mixed(b.world(w), 30 + 5 * w, 20, n_large=2, seed=100 + w)
+        b.set_reorder_interval(interval)
+        for _ in range(30):
+            b.process(scenes.DT, 4, 4)
+        out = b.read_bodies(), b.world(2).read_pairs(), b.world(2).read_manifolds()
+        b.destroy()
+        return out
+
+    cases = {
+        "pyramid": lambda iv: single(lambda s: scenes.build_pyramid(s, base=24, n_spinners=3), iv),
+        "car platformer": lambda iv: single(scenes.setup_0_1_car_platformer, iv),
+        "box1k sleeping": lambda iv: single(scenes.build_box1k, iv, sleeping=True),
+        "batch of 3 mixed worlds": batch,
+    }
+    for name, run in cases.items():
+        monkeypatch.setenv("R2D_RESORT_CHECK", "1")
+        monkeypatch.delenv("R2D_DEVICE_RESORT", raising=False)
+        dev = run(5)
+        never = run(0)
+        monkeypatch.delenv("R2D_RESORT_CHECK")
+        monkeypatch.setenv("R2D_DEVICE_RESORT", "0")
+        host = run(5)
+        for other, what in ((host, "host re-sort"), (never, "no re-sort")):
+            assert_bodies_equal(dev[0], other[0], f"{name}: device re-sort vs {what}")
+            assert np.array_equal(dev[1], other[1]), f"{name}: pairs, device re-sort vs {what}"
+            assert_manifolds_equal(dev[2], other[2], f"{name}: device re-sort vs {what}")
+
+
 def test_gpu_fast_mode_grid_parameters():
     """MODE_FAST honours cell_width / table_mult (the reference stores but ignores them, lib.zig:254-255); the oracle
     in the same mode must agree bit for bit, and the candidate set must equal the parity-mode one on this scene."""
