@@ -698,9 +698,10 @@ __global__ void __launch_bounds__(TPB, NARROW_CTAS) k_narrow(Dev d) {
 // sequential greedy colouring in descending priority, so it is a pure function of the contact graph and the body ids.
 constexpr int COLOR_REG_SLOTS = 2;  // pending manifolds a thread keeps in registers across the rounds
 constexpr uint32_t COLOR_COMPACT_ROUND = 3;   // from this round on the streamed manifolds are kept in compacted lists
-constexpr int FLOW_SLOTS = 8;       // manifolds per thread the dataflow colouring can hold (registers)
+constexpr int FLOW_SLOTS = 8;       // manifolds per thread the dataflow colouring can hold in registers
+constexpr int FLOW_BIG_SLOTS = 24;  // ... and in a compacted per-thread list in local memory (worlds of ~10^6 bodies)
 
-__global__ void __launch_bounds__(TPB, 4) k_color(Dev d) {
+__global__ void __launch_bounds__(TPB, 4) k_color(Dev d, uint32_t flow_reg_slots) {
     cg::grid_group grid = cg::this_grid();
     const bool dead = overflowed(d);
     const uint32_t n = dead ? 0u : live_pairs(d);
@@ -715,8 +716,67 @@ __global__ void __launch_bounds__(TPB, 4) k_color(Dev d) {
     // resident (cooperative launch) and every pending manifold keeps being probed, so the pending manifold with the
     // globally highest priority — which is always ready — always gets its turn: no deadlock.
     // (flow_abort is only written by the narrowphase, so the decision is the same for every thread of the grid)
-    const bool flow = d.flow != 0u && d.counters->flow_abort == 0u && n <= (uint32_t)FLOW_SLOTS * nth;
-    if (flow) {
+    const bool flow_any = d.flow != 0u && d.counters->flow_abort == 0u;
+    // (flow_reg_slots = FLOW_SLOTS; 0 sends every world through the list flavour: R2D_FLOW_LIST=1, tests)
+    const bool flow_big = flow_any && n > flow_reg_slots * nth && n <= (uint32_t)FLOW_BIG_SLOTS * nth;
+    const bool flow = flow_any && n <= (uint32_t)FLOW_BIG_SLOTS * nth;
+    if (flow_big) {
+        // The same probing with the thread's pending manifolds in a list (local memory) that shrinks as they are coloured:
+        // a pass of a thread gets shorter and shorter, so the few long chains (the contacts of a hub body colour one after
+        // the other) are probed at the rate of a short list, not of FLOW_BIG_SLOTS gathers.
+        uint32_t fa[FLOW_BIG_SLOTS], fb[FLOW_BIG_SLOTS], fm[FLOW_BIG_SLOTS], fp[FLOW_BIG_SLOTS];
+        uint32_t cnt = 0;
+        for (int k = 0; k < FLOW_BIG_SLOTS; ++k) {
+            const uint32_t p = tid + (uint32_t)k * nth;
+            if (p < n && d.m_color[p] == COLOR_PENDING) {
+                const uint4 h = d.m_hdr[p];
+                fa[cnt] = h.x;
+                fb[cnt] = h.y;
+                fm[cnt] = (h.w & 3u) | (flow_ranks(d, h, d.m_prio[p]) << 2);
+                fp[cnt] = p;
+                cnt += 1u;
+            }
+        }
+        uint32_t idle = 0;
+        for (;;) {
+            bool progress = false;
+            uint32_t min_lag = 0xFFFFFFFFu;
+            for (uint32_t k = 0; k < cnt;) {
+                uint32_t c = 0, lag = 0;
+                const int r = flow_try(d, fp[k], fa[k], fb[k], fm[k] & 3u, (fm[k] >> 2) & 0xFFFFu, &c, &lag);
+                if (r == 1) {
+                    atomicAdd(&s_hist[c], 1u);
+                    owner_bit_set(d, fa[k], fb[k], fm[k] & 3u, c);
+                    cnt -= 1u;
+                    fa[k] = fa[cnt];
+                    fb[k] = fb[cnt];
+                    fm[k] = fm[cnt];
+                    fp[k] = fp[cnt];
+                    progress = true;
+                } else if (r == 0) {
+                    min_lag = lag < min_lag ? lag : min_lag;
+                    ++k;
+                } else {
+                    cnt = 0u;  // colour overflow: flow_fail is set, everybody leaves
+                }
+            }
+            if (!__any_sync(0xffffffffu, cnt != 0u)) break;
+            if (__any_sync(0xffffffffu, progress)) {
+                idle = 0;
+                continue;
+            }
+            const uint32_t warp_lag = __reduce_min_sync(0xffffffffu, min_lag);
+            if (warp_lag > 1u) backoff_ns((warp_lag < 8u ? warp_lag - 1u : 7u) * FLOW_SLEEP_UNIT);
+            if ((++idle & 63u) == 0u) {
+                if (*((volatile uint32_t*)&d.counters->flow_fail)) break;
+                if (idle > (1u << 20)) {
+                    atomicOr(&d.counters->err, ERR_FLOW_STALL);
+                    atomicOr(&d.counters->flow_fail, 1u);
+                    break;
+                }
+            }
+        }
+    } else if (flow) {
         uint32_t fa[FLOW_SLOTS], fb[FLOW_SLOTS], fm[FLOW_SLOTS];  // ref slot, inc slot, dyn mask | ranks << 2 | pending << 31
         uint32_t n_pending = 0;
 #pragma unroll

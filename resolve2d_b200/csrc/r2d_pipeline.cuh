@@ -40,8 +40,9 @@ constexpr uint32_t S_EMPTY = 0x400u;              // s_hdr.z: padding slot (colo
 constexpr uint32_t S_WARM = 0x800u;               // s_hdr.z: the record carries warm-start terms (s_warm0 / s_warm1)
 constexpr uint32_t COLOR_ALIGN = 32;
 constexpr uint32_t COLOR_WORDS = MAX_COLORS / 64;
-constexpr uint32_t ADJ_CAP = 32;                   // manifolds a non-static body can list for the dataflow colouring
+constexpr uint32_t ADJ_CAP = 32;                   // manifolds a body lists in place for the dataflow colouring; further ones are chained
 constexpr uint32_t FLOW_COLORS = 96;               // colours the 16-byte colouring word of a body can hold
+constexpr uint32_t ADJ_MAX = FLOW_COLORS;          // a body with more manifolds needs more colours than that anyway: rounds
 constexpr uint32_t MAX_COLOR_ROUNDS = 4000;        // < 2^12 (round tag field of the priority word)
 constexpr uint32_t BIG_BODY_CELLS = 64;            // bodies covering more cells are walked by a whole CTA
 constexpr int64_t MAX_BODY_CELLS = 1 << 22;        // beyond this the pose is garbage (NaN/inf): R2D_ERR_GRID_RANGE
@@ -72,13 +73,13 @@ struct Counters {
     uint32_t n_mid;          // SMALL_BUCKET+1..HEAVY_BUCKET entries (a warp or a CTA each, see medium_by_cta)
     uint32_t n_heavy;        // buckets holding more (a CTA each)
     uint32_t n_dropped;      // manifolds left without a colour (COLOR_DROPPED)
-    uint32_t flow_abort;     // set by the narrowphase: a body has more than ADJ_CAP manifolds, colour by rounds
+    uint32_t flow_abort;     // set by the narrowphase: a body has more than ADJ_MAX manifolds (or the chain pool is full), colour by rounds
     uint32_t flow_fail;      // set inside the dataflow colouring: more than FLOW_COLORS colours needed (or a stall)
     uint32_t flow_used;      // the colours of this step come from the dataflow colouring (masks in cstate, not in used)
     uint32_t tile_fallback;  // k_solve_tiles declined (a tile has too many bodies / tasks): the host runs k_solve_persistent
     uint32_t max_world_m;    // k_world_solve: most slots (contact points) found in one world of the batch (the host sizes the
     uint32_t n_big;          // bodies covering more than BIG_BODY_CELLS cells, listed by the count kernel (big_bodies)
-    uint32_t pad2;
+    uint32_t n_adj_over;     // entries taken from adj_pool (manifolds beyond ADJ_CAP of a body)
     uint32_t broad_fallback; // shared-memory cache of the next call from it) | k_world_broad: a world's grid does not fit
 };
 
@@ -151,8 +152,11 @@ struct Dev {
     // dataflow colouring (single worlds): the manifolds of a body, and one 16-byte word per body that is both the wait
     // target and the data — {96-bit colour mask, manifolds coloured so far}
     uint32_t flow;                // 1: k_narrow lists every manifold on its non-static bodies (adj_*), k_color may use them
-    uint32_t* adj_cnt;            // NB: manifolds on the body (may exceed ADJ_CAP: then the colouring falls back to rounds)
+    uint32_t* adj_cnt;            // NB: manifolds on the body (more than ADJ_MAX: the colouring falls back to rounds)
     unsigned long long* adj_prio; // NB * ADJ_CAP: their priorities, in arrival order
+    uint32_t* adj_head;           // NB: 1 + index of the body's first chained entry in adj_pool (0 = none); zeroed per step
+    uint4* adj_pool;              // {priority lo, priority hi, 1 + next entry, -}: manifolds ADJ_CAP.. of a body (hub bodies)
+    uint32_t adj_pool_cap;
     uint4* cstate;                // NB
     uint32_t own_words;           // W = ceil(NB / 32)
     uint32_t* own_bits;           // MAX_COLORS x W: bit (c, b) set iff body b owns a manifold of colour c (at most one)
@@ -258,6 +262,15 @@ R2D_HD void atomic_max_u32(uint32_t* p, uint32_t v) {
     atomicMax(p, v);
 #else
     if (*p < v) *p = v;
+#endif
+}
+R2D_HD uint32_t atomic_exch_u32(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return atomicExch(p, v);
+#else
+    const uint32_t o = *p;
+    *p = v;
+    return o;
 #endif
 }
 R2D_HD void atomic_or_u32(uint32_t* p, uint32_t v) {
@@ -715,10 +728,20 @@ R2D_HD void sort_item_pairs(uint2* out, uint32_t n) {
 // the manifold lists of the dataflow colouring (arrival order is irrelevant: only "how many have a higher priority" is used)
 R2D_HD void adj_append(const Dev& d, uint32_t body, unsigned long long prio) {
     const uint32_t k = atomic_add_u32(&d.adj_cnt[body], 1u);
-    if (k < ADJ_CAP)
+    if (k < ADJ_CAP) {
         d.adj_prio[(size_t)body * ADJ_CAP + k] = prio;
-    else
-        atomic_or_u32(&d.counters->flow_abort, 1u);
+        return;
+    }
+    // a hub (a large body resting on many small ones): the rest of its list is a chain through a shared pool
+    if (k < ADJ_MAX) {
+        const uint32_t e = atomic_add_u32(&d.counters->n_adj_over, 1u);
+        if (e < d.adj_pool_cap) {
+            const uint32_t next = atomic_exch_u32(&d.adj_head[body], e + 1u);
+            d.adj_pool[e] = make_uint4((uint32_t)prio, (uint32_t)(prio >> 32), next, 0u);   // (read by the colouring kernel only)
+            return;
+        }
+    }
+    atomic_or_u32(&d.counters->flow_abort, 1u);
 }
 // K6: one candidate pair -> raw manifold slot.  Returns the number of contact points, or -1 if SAT finds a gap.
 R2D_HD int narrow_pair_thread(const Dev& d, uint32_t p) {
@@ -830,9 +853,16 @@ R2D_HD uint32_t flow_ranks(const Dev& d, const uint4& h, unsigned long long prio
     for (int q = 0; q < 2; ++q) {
         if (!(h.w & (1u << q))) continue;
         uint32_t n = d.adj_cnt[bs[q]];
-        if (n > ADJ_CAP) n = ADJ_CAP;  // overflow: the colouring is abandoned anyway
+        const bool chained = n > ADJ_CAP;
+        if (chained) n = ADJ_CAP;
         const unsigned long long* list = d.adj_prio + (size_t)bs[q] * ADJ_CAP;
         for (uint32_t k = 0; k < n; ++k) r[q] += list[k] > prio ? 1u : 0u;
+        if (chained)
+            for (uint32_t e = d.adj_head[bs[q]]; e != 0u && e <= d.adj_pool_cap;) {   // (at most ADJ_MAX - ADJ_CAP entries)
+                const uint4 x = d.adj_pool[e - 1u];
+                r[q] += (((unsigned long long)x.y << 32) | x.x) > prio ? 1u : 0u;
+                e = x.z;
+            }
     }
     return r[0] | (r[1] << 8);
 }

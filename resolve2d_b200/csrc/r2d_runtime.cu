@@ -145,11 +145,13 @@ struct CudaBatch : BatchBase {
     DBuf<unsigned char> zeroed;
     size_t zeroed_bytes = 0, scan_state_cap = 0;
     size_t off_counters = 0, off_color_misc = 0, off_scan = 0, off_maxprio0 = 0, off_maxprio1 = 0, off_used = 0, off_own_bits = 0;
-    size_t off_adj_cnt = 0, off_cstate = 0, off_body_shared = 0, off_pend_cnt = 0;
+    size_t off_adj_cnt = 0, off_adj_head = 0, off_cstate = 0, off_body_shared = 0, off_pend_cnt = 0;
     bool tile_solver = true;          // k_solve_tiles for single worlds without joints that fit (R2D_TILE_SOLVER=0: never)
     uint32_t tile_bodies_now = 0, tile_max_tasks = TILE_MAX_TASKS;
     bool tile_declined = false;
     DBuf<unsigned long long> adj_prio;
+    DBuf<uint4> adj_pool;   // chained entries of bodies with more than ADJ_CAP manifolds (dataflow colouring)
+    bool flow_list_only = false;      // R2D_FLOW_LIST=1 (tests): the list flavour of the dataflow colouring for every size
     bool flow_coloring = true, flow_now = false;   // dataflow colouring of single worlds (R2D_FLOW_COLORING=0: rounds only)
     unsigned long long* scan_state(int which) { return (unsigned long long*)(zeroed.p + off_scan) + (size_t)which * scan_state_cap; }
     DBuf<uint32_t> own_pos;
@@ -221,6 +223,7 @@ struct CudaBatch : BatchBase {
         if (env_is("R2D_WORLD_SOLVER", "0")) world_solver = false;           // batches through the single-world kernels
         if (env_is("R2D_FLOW_COLORING", "0")) flow_coloring = false;         // Jones-Plassmann rounds only
         if (env_is("R2D_TILE_SOLVER", "0")) tile_solver = false;             // k_solve_persistent instead of k_solve_tiles
+        if (env_is("R2D_FLOW_LIST", "1")) flow_list_only = true;
         if (env_is("R2D_DEVICE_RESORT", "0")) device_resort = false;         // the periodic re-sort through the host
         if (env_is("R2D_RESORT_CHECK", "1")) resort_check = true;            // (tests) device order == build_image's order
         if (const char* e = getenv("R2D_TILE_MAX_TASKS")) tile_max_tasks = std::min<uint32_t>((uint32_t)atoi(e), TILE_MAX_TASKS);
@@ -634,6 +637,9 @@ struct CudaBatch : BatchBase {
         d.counters = (Counters*)(zeroed.p + off_counters);
         d.flow = flow_now ? 1u : 0u;
         d.adj_cnt = (uint32_t*)(zeroed.p + off_adj_cnt);
+        d.adj_head = (uint32_t*)(zeroed.p + off_adj_head);
+        d.adj_pool = adj_pool.p;
+        d.adj_pool_cap = (uint32_t)std::min<size_t>(adj_pool.cap, 0x7FFFFFFFu);
         d.cstate = (uint4*)(zeroed.p + off_cstate);
         d.adj_prio = adj_prio.p;
         d.tile_bodies = tile_bodies_now;
@@ -755,6 +761,7 @@ struct CudaBatch : BatchBase {
             off_used = o; o = align(o + (size_t)nb * COLOR_WORDS * 8);
             off_own_bits = o; o = align(o + own_w * MAX_COLORS * 4);
             off_adj_cnt = o; o = align(o + (size_t)nb * 4);
+            off_adj_head = o; o = align(o + (size_t)nb * 4);
             off_cstate = o; o = align(o + (size_t)nb * 16);
             off_body_shared = o; o = align(o + (size_t)nb * 4);
             off_pend_cnt = o; o = align(o + (MAX_COLOR_ROUNDS + 2) * 4);
@@ -780,8 +787,8 @@ struct CudaBatch : BatchBase {
         const bool many_small_worlds = world_solver && worlds.size() >= (size_t)n_sms / 2;
         const bool color_per_world = many_small_worlds && max_world_bodies <= COLOR_WORLD_MAX_BODIES;
         const size_t pairs_guess = last_pairs ? (size_t)last_pairs : (size_t)nb * 3;
-        flow_now = flow_coloring && !color_per_world && pairs_guess <= (size_t)FLOW_SLOTS * color_blocks * TPB;
-        if (flow_now && (st = adj_prio.reserve((size_t)nb * ADJ_CAP))) return st;
+        flow_now = flow_coloring && !color_per_world && pairs_guess <= (size_t)FLOW_BIG_SLOTS * color_blocks * TPB;
+        if (flow_now && ((st = adj_prio.reserve((size_t)nb * ADJ_CAP)) || (st = adj_pool.reserve(cap_pairs / 2 + 1024)))) return st;
         // solver flavour: CTA-per-world for batches of small worlds; one spatial tile of bodies per SM for a single world
         // without joints that fits (k_solve_tiles may still decline on the device); else the persistent dataflow sweep
         if ((opt_warm_start || opt_sleeping) && (mode == R2D_MODE_REFERENCE_ORDER || !persistent_solver)) {
@@ -941,7 +948,8 @@ struct CudaBatch : BatchBase {
                 }
             } else {
                 prof_begin(R2D_KCLASS_COLORING);
-                void* args[] = {(void*)&d};
+                uint32_t reg_slots = flow_list_only ? 0u : (uint32_t)FLOW_SLOTS;
+                void* args[] = {(void*)&d, (void*)&reg_slots};
                 R2D_CUDA(cudaLaunchCooperativeKernel((void*)k_color, dim3(color_blocks), dim3(TPB), args, 0, stream));
                 prof_end();
                 launches += 1;

@@ -30,7 +30,8 @@ struct EmuBatch : BatchBase {
     std::vector<float2> s_acc0, s_acc1;
     std::vector<uint4> s_dep;
     std::vector<unsigned long long> maxprio0, maxprio1, used, m_prio, adj_prio;
-    std::vector<uint32_t> adj_cnt;
+    std::vector<uint32_t> adj_cnt, adj_head;
+    std::vector<uint4> adj_pool;
     std::vector<uint4> cstate;
     std::vector<uint32_t> color_count, color_start, color_cursor, round_left, own_bits, own_pos;
     std::vector<uint64_t> world_magic;
@@ -233,6 +234,8 @@ struct EmuBatch : BatchBase {
         d.flow = (getenv("R2D_EMU_FLOW") && atoi(getenv("R2D_EMU_FLOW")) == 0) ? 0u : 1u;
         adj_cnt.assign(nb, 0); adj_prio.assign((size_t)nb * ADJ_CAP, 0); cstate.assign(nb, make_uint4(0, 0, 0, 0));
         d.adj_cnt = adj_cnt.data(); d.adj_prio = adj_prio.data(); d.cstate = cstate.data();
+        adj_head.assign(nb, 0); adj_pool.assign((size_t)P / 2 + 1024, make_uint4(0, 0, 0, 0));
+        d.adj_head = adj_head.data(); d.adj_pool = adj_pool.data(); d.adj_pool_cap = (uint32_t)adj_pool.size();
         uint32_t M = 0, K = 0;
         for (uint32_t p = 0; p < P; ++p) {
             const int np = narrow_pair_thread(d, p);

@@ -33,10 +33,14 @@ def test_emu_colouring_by_rounds_only(monkeypatch):
 def test_emu_dataflow_colouring_is_used_and_falls_back_on_hubs():
     cand, _ = run_parity(lambda: EmuSolver(2.0, 4), scenes.build_box1k, 40, check_every=10, what="box1k flow")
     assert cand.stats().n_color_rounds == 0          # coloured without rounds
-    # a plank on 48 discs: more manifolds on one body than its list holds -> rounds, same colours as the oracle
+    # a plank on 48 discs: more manifolds on one body than its in-place list holds -> the rest is chained, still no rounds
     cand, _ = run_parity(lambda: EmuSolver(2.0, 4), scenes.build_hub, 60, check_every=10, what="hub")
     st = cand.stats()
-    assert st.n_colors >= 40 and st.n_color_rounds > 0
+    assert st.n_colors >= 40 and st.n_color_rounds == 0
+    # a plank on 120 discs needs more colours than a body's colouring word holds -> rounds, same colours as the oracle
+    cand, _ = run_parity(lambda: EmuSolver(2.0, 4), lambda s: scenes.build_hub(s, n_discs=120), 30, check_every=10, what="hub120")
+    st = cand.stats()
+    assert st.n_colors >= 100 and st.n_color_rounds > 0
 
 
 # ---- fine-grid broadphase (small bodies in a fine home-cell table, only large bodies in the hashed 4 m buckets) ----------

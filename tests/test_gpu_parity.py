@@ -115,13 +115,17 @@ def test_gpu_box1k():
 
 
 def test_gpu_dataflow_colouring_and_its_fallback():
-    """single worlds are coloured by the dataflow kernel phase (no rounds); a body with more manifolds than its list
-    holds (a plank on 48 discs) makes the same launch fall back to Jones-Plassmann rounds — same colours either way"""
+    """single worlds are coloured by the dataflow kernel phase (no rounds); a body with more manifolds than its in-place
+    list holds (a plank on 48 discs) chains the rest; one with more than a colouring word holds (120 discs) makes the
+    same launch fall back to Jones-Plassmann rounds — same colours either way"""
     cand, _ = run_parity(lambda: Solver(2.0, 4), scenes.build_box1k, 60, check_every=10, what="box1k flow")
     assert cand.stats().n_color_rounds == 0
     cand, _ = run_parity(lambda: Solver(2.0, 4), scenes.build_hub, 90, check_every=10, what="hub")
     st = cand.stats()
-    assert st.n_colors >= 40 and st.n_color_rounds > 0
+    assert st.n_colors >= 40 and st.n_color_rounds == 0
+    cand, _ = run_parity(lambda: Solver(2.0, 4), lambda s: scenes.build_hub(s, n_discs=120), 40, check_every=10, what="hub120")
+    st = cand.stats()
+    assert st.n_colors >= 100 and st.n_color_rounds > 0
 
 
 def test_gpu_hub_body_beyond_256_colours_keeps_stepping():
@@ -448,6 +452,17 @@ def test_gpu_reorder_does_not_change_results():
     assert_bodies_equal(a.read_bodies(), b.read_bodies(), "reorder")
     assert np.array_equal(a.read_pairs(), b.read_pairs())
     assert_manifolds_equal(a.read_manifolds(), b.read_manifolds(), "reorder")
+
+
+def test_gpu_dataflow_colouring_list_flavour(monkeypatch):
+    """Worlds with more candidate pairs than the register slots of the dataflow colouring hold (> 1.2 M) keep each
+    thread's pending manifolds in a compacted list; R2D_FLOW_LIST=1 sends small worlds through that flavour: same
+    colours, no rounds — hubs (chained lists) and mixed shapes included."""
+    monkeypatch.setenv("R2D_FLOW_LIST", "1")
+    for name, build, steps in (("hub", scenes.build_hub, 40), ("pile", lambda s: scenes.build_pile(s, 100, 40), 60),
+                               ("mixed", lambda s: scenes.build_mixed(s, 80, 40, n_large=4), 40)):
+        cand, _ = run_parity(lambda: Solver(2.0, 4), build, steps, check_every=10, what=f"{name}, list flavour")
+        assert cand.stats().n_color_rounds == 0, name
 
 
 def test_gpu_device_resort_equals_host_resort(monkeypatch):
