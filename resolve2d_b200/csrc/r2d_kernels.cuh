@@ -1265,14 +1265,31 @@ __global__ void __launch_bounds__(SOLVE_TPB) k_solve_joints(Dev d, uint32_t begi
 // SOLVE_SMEM_SLOTS of them are copied once into shared memory (record k of thread x at index k * PSOLVE_TPB + x of each array)
 // and every sweep reads its constants — and keeps its accumulated impulses — there; only the two body words of a
 // manifold go through L2.  Records beyond the cache (worlds with more than ~245k manifolds) stream from global memory.
-constexpr int PSOLVE_TPB = 256;      // threads per CTA of the persistent solver (one CTA per SM; 512 x 3 slots measured the same)
-constexpr int SOLVE_SMEM_SLOTS = 6;
+// threads per CTA of the persistent solver (one CTA per SM) x cached records per thread: 256 x 6 while most records fit the
+// cache (512 x 3 measured the same on pile100k); 512 x 3 for worlds whose records mostly stream from HBM — twice the
+// threads walk half as long a sequence of exposed record fetches each (mixed1M, 2.2 M manifolds)
+constexpr int PSOLVE_TPB = 256, PSOLVE_TPB_BIG = 512;
+constexpr int SOLVE_SMEM_SLOTS = 6, SOLVE_SMEM_SLOTS_BIG = 3;
 constexpr int SOLVE_SMEM_BYTES_PER_RECORD = 6 * 16 + 8 + 2 * 16 + 8;  // hdr nf inv dep r0 pm0 | acc0 | r1 pm1 | acc1 = 144
 constexpr size_t SOLVE_SMEM_BYTES = (size_t)SOLVE_SMEM_SLOTS * PSOLVE_TPB * SOLVE_SMEM_BYTES_PER_RECORD;
 
-__global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float sub_dt, uint32_t S, uint32_t I,
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_record_l2(const Dev& d, uint32_t m) {
+    prefetch_l2(&d.s_hdr[m]);
+    prefetch_l2(&d.s_nf[m]);
+    prefetch_l2(&d.s_inv[m]);
+    prefetch_l2(&d.s_dep[m]);
+    prefetch_l2(&d.s_r0[m]);
+    prefetch_l2(&d.s_pm0[m]);
+    prefetch_l2(&d.s_acc0[m]);
+    prefetch_l2(&d.s_r1[m]);     // (whether the record has a second point is in its header: not known yet)
+    prefetch_l2(&d.s_pm1[m]);
+    prefetch_l2(&d.s_acc1[m]);
+}
+template <int PT, int SLOTS>
+__global__ void __launch_bounds__(PT) k_solve_persistent(Dev d, float sub_dt, uint32_t S, uint32_t I,
                                                           const uint32_t* __restrict__ joint_color_start, uint32_t n_joint_colors,
-                                                          uint32_t smem_slots) {
+                                                          uint32_t smem_slots, uint32_t prefetch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::grid_group grid = cg::this_grid();
     if (overflowed(d) || d.counters->err != 0u) return;  // uniform across the grid
@@ -1282,7 +1299,7 @@ __global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float su
     // ---- stage my records ----
     Dev ds = d;  // same code path, record arrays redirected to shared memory
     {
-        const size_t n = (size_t)SOLVE_SMEM_SLOTS * PSOLVE_TPB;
+        const size_t n = (size_t)SLOTS * PT;
         unsigned char* q = smem_raw;
         ds.s_hdr = (uint4*)q;    q += n * 16;
         ds.s_nf = (float4*)q;    q += n * 16;
@@ -1297,7 +1314,7 @@ __global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float su
     }
     auto stage = [&]() {
         for (uint32_t k = 0; k < smem_slots; ++k) {
-            const uint32_t m = tid + k * nth, l = k * PSOLVE_TPB + threadIdx.x;
+            const uint32_t m = tid + k * nth, l = k * PT + threadIdx.x;
             if (m >= n_manifolds) break;
             const uint4 h = d.s_hdr[m];
             ds.s_hdr[l] = h;
@@ -1339,8 +1356,14 @@ __global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float su
             const bool first = warm && s == 0 && it == 0;
             uint32_t k = 0;
             for (uint32_t m = tid; m < n_manifolds; m += nth, ++k) {
+                // records beyond the cache stream from HBM: while this one waits for its bodies and runs, the lines of the
+                // thread's next `prefetch` records are already on their way into L2 (a thread walks a fixed sequence)
+                if (prefetch && k + prefetch >= smem_slots) {
+                    const size_t mp = (size_t)m + (size_t)prefetch * nth;
+                    if (mp < n_manifolds) prefetch_record_l2(d, (uint32_t)mp);
+                }
                 if (k < smem_slots && !first)
-                    solve_contact_thread<true>(ds, k * PSOLVE_TPB + threadIdx.x, sub_dt, it);  // cached record
+                    solve_contact_thread<true>(ds, k * PT + threadIdx.x, sub_dt, it);  // cached record
                 else
                     solve_contact_thread<true>(d, m, sub_dt, it, first);
             }
@@ -1353,7 +1376,7 @@ __global__ void __launch_bounds__(PSOLVE_TPB) k_solve_persistent(Dev d, float su
     }
     if (warm && S * I > 0u)   // k_warm_save reads what every contact accumulated: flush the cached ones
         for (uint32_t k = 0; k < smem_slots; ++k) {
-            const uint32_t m = tid + k * nth, l = k * PSOLVE_TPB + threadIdx.x;
+            const uint32_t m = tid + k * nth, l = k * PT + threadIdx.x;
             if (m >= n_manifolds) break;
             const uint4 h = ds.s_hdr[l];
             if (h.z & S_EMPTY) continue;

@@ -151,6 +151,8 @@ struct CudaBatch : BatchBase {
     bool tile_declined = false;
     DBuf<unsigned long long> adj_prio;
     DBuf<uint4> adj_pool;   // chained entries of bodies with more than ADJ_CAP manifolds (dataflow colouring)
+    int solve_wide = -1;              // k_solve_persistent with 512 threads per CTA: -1 by manifold count, 0 never, 1 always (R2D_SOLVE_WIDE)
+    uint32_t solve_prefetch = 2;      // k_solve_persistent: streamed records fetched into L2 this many records ahead (R2D_SOLVE_PREFETCH)
     bool flow_list_only = false;      // R2D_FLOW_LIST=1 (tests): the list flavour of the dataflow colouring for every size
     bool flow_coloring = true, flow_now = false;   // dataflow colouring of single worlds (R2D_FLOW_COLORING=0: rounds only)
     unsigned long long* scan_state(int which) { return (unsigned long long*)(zeroed.p + off_scan) + (size_t)which * scan_state_cap; }
@@ -206,7 +208,8 @@ struct CudaBatch : BatchBase {
         int per_sm = 0;
         R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_color, TPB, 0));
         color_blocks = std::max(1, std::min(per_sm, 4)) * n_sms;
-        R2D_CUDA(cudaFuncSetAttribute(k_solve_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_BYTES));
+        R2D_CUDA(cudaFuncSetAttribute(k_solve_persistent<PSOLVE_TPB, SOLVE_SMEM_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_BYTES));
+        R2D_CUDA(cudaFuncSetAttribute(k_solve_persistent<PSOLVE_TPB_BIG, SOLVE_SMEM_SLOTS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_BYTES));
         solve_blocks = n_sms;   // one CTA per SM (the record cache takes the whole shared memory)
         R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bucket_count, TPB, 0));
         pair_blocks = (per_sm < 1 ? 1 : per_sm) * n_sms;  // resident CTAs: a CTA per heavy bucket, a warp per light one, grid-stride
@@ -224,6 +227,8 @@ struct CudaBatch : BatchBase {
         if (env_is("R2D_FLOW_COLORING", "0")) flow_coloring = false;         // Jones-Plassmann rounds only
         if (env_is("R2D_TILE_SOLVER", "0")) tile_solver = false;             // k_solve_persistent instead of k_solve_tiles
         if (env_is("R2D_FLOW_LIST", "1")) flow_list_only = true;
+        if (const char* e = getenv("R2D_SOLVE_WIDE")) solve_wide = atoi(e);
+        if (const char* e = getenv("R2D_SOLVE_PREFETCH")) solve_prefetch = (uint32_t)atoi(e);
         if (env_is("R2D_DEVICE_RESORT", "0")) device_resort = false;         // the periodic re-sort through the host
         if (env_is("R2D_RESORT_CHECK", "1")) resort_check = true;            // (tests) device order == build_image's order
         if (const char* e = getenv("R2D_TILE_MAX_TASKS")) tile_max_tasks = std::min<uint32_t>((uint32_t)atoi(e), TILE_MAX_TASKS);
@@ -716,9 +721,16 @@ struct CudaBatch : BatchBase {
         const uint32_t* jcs_dev = joint_color_start.p;
         uint32_t n_jc = (uint32_t)image.joint_color_start.size() - 1, S_ = S, I_ = I;
         float sd = sub_dt;
-        uint32_t slots = solve_smem_slots;
-        void* args[] = {(void*)&d, (void*)&sd, (void*)&S_, (void*)&I_, (void*)&jcs_dev, (void*)&n_jc, (void*)&slots};
-        R2D_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(solve_blocks), dim3(PSOLVE_TPB), args, SOLVE_SMEM_BYTES, stream));
+        // most records beyond the cache (sized from the previous call's manifold count): the wide flavour
+        const bool wide = solve_wide == 1 || (solve_wide < 0 && (size_t)stats.n_manifolds > 4 * (size_t)SOLVE_SMEM_SLOTS * PSOLVE_TPB * solve_blocks);
+        uint32_t slots = wide ? std::min<uint32_t>(solve_smem_slots, SOLVE_SMEM_SLOTS_BIG) : solve_smem_slots, prefetch = solve_prefetch;
+        void* args[] = {(void*)&d, (void*)&sd, (void*)&S_, (void*)&I_, (void*)&jcs_dev, (void*)&n_jc, (void*)&slots, (void*)&prefetch};
+        if (wide)
+            R2D_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_persistent<PSOLVE_TPB_BIG, SOLVE_SMEM_SLOTS_BIG>, dim3(solve_blocks),
+                                                 dim3(PSOLVE_TPB_BIG), args, SOLVE_SMEM_BYTES, stream));
+        else
+            R2D_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_persistent<PSOLVE_TPB, SOLVE_SMEM_SLOTS>, dim3(solve_blocks), dim3(PSOLVE_TPB),
+                                                 args, SOLVE_SMEM_BYTES, stream));
         prof_end();
         launches += 1;
         return R2D_OK;
