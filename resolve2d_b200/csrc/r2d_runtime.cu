@@ -97,7 +97,7 @@ struct CudaBatch : BatchBase {
     uint32_t max_world_bodies = 0;   // false: one launch per colour (kept for A/B measurements)
     // bodies
     DBuf<float4> pos, mom, frc, prop, shape, aabb, pose, view;
-    DBuf<uint32_t> ncells, world_base, grav_off, joint_color_start, dev_of_host;
+    DBuf<uint32_t> ncells, world_base, grav_off, joint_color_start, dev_of_host, host_of_dev;
     DBuf<float> grav;
     DBuf<uint64_t> excl;
     DBuf<uint4> j_hdr, bkt, j_dep;
@@ -153,6 +153,8 @@ struct CudaBatch : BatchBase {
     DBuf<uint4> adj_pool;   // chained entries of bodies with more than ADJ_CAP manifolds (dataflow colouring)
     int solve_wide = -1;              // k_solve_persistent with 512 threads per CTA: -1 by manifold count, 0 never, 1 always (R2D_SOLVE_WIDE)
     uint32_t solve_prefetch = 2;      // k_solve_persistent: streamed records fetched into L2 this many records ahead (R2D_SOLVE_PREFETCH)
+    bool world_export = true;         // k_world_solve exports into page-locked read-back arrays itself (R2D_WORLD_EXPORT=0: separate kernel)
+    bool world_exported = false;
     bool flow_list_only = false;      // R2D_FLOW_LIST=1 (tests): the list flavour of the dataflow colouring for every size
     bool flow_coloring = true, flow_now = false;   // dataflow colouring of single worlds (R2D_FLOW_COLORING=0: rounds only)
     unsigned long long* scan_state(int which) { return (unsigned long long*)(zeroed.p + off_scan) + (size_t)which * scan_state_cap; }
@@ -227,6 +229,7 @@ struct CudaBatch : BatchBase {
         if (env_is("R2D_FLOW_COLORING", "0")) flow_coloring = false;         // Jones-Plassmann rounds only
         if (env_is("R2D_TILE_SOLVER", "0")) tile_solver = false;             // k_solve_persistent instead of k_solve_tiles
         if (env_is("R2D_FLOW_LIST", "1")) flow_list_only = true;
+        if (env_is("R2D_WORLD_EXPORT", "0")) world_export = false;
         if (const char* e = getenv("R2D_SOLVE_WIDE")) solve_wide = atoi(e);
         if (const char* e = getenv("R2D_SOLVE_PREFETCH")) solve_prefetch = (uint32_t)atoi(e);
         if (env_is("R2D_DEVICE_RESORT", "0")) device_resort = false;         // the periodic re-sort through the host
@@ -321,7 +324,7 @@ struct CudaBatch : BatchBase {
         if ((st = up(pos, image.pos)) || (st = up(mom, image.mom)) || (st = up(frc, image.frc)) || (st = up(prop, image.prop)) ||
             (st = up(shape, image.shape)) || (st = up(aabb, image.aabb)) || (st = up(world_base, image.world_base)) ||
             (st = up(grav_off, image.grav_off)) || (st = up(grav, image.grav)) || (st = up(sleep_cnt, image.sleep)) ||
-            (st = up(dev_of_host, image.dev_of_host)) || (st = upload_slot_tables()))
+            (st = up(dev_of_host, image.dev_of_host)) || (st = up(host_of_dev, image.host_of_dev)) || (st = upload_slot_tables()))
             return st;
         R2D_CUDA(cudaStreamSynchronize(stream));  // the image vectors are pageable and may change after we return
         magic_for_mult = 0;   // (the bucket count of a world depends on the mode's table multiplier: refreshed in process())
@@ -390,6 +393,8 @@ struct CudaBatch : BatchBase {
         };
         swap_buf(pos, resort_f4[0]); swap_buf(mom, resort_f4[1]); swap_buf(frc, resort_f4[2]); swap_buf(prop, resort_f4[3]);
         swap_buf(shape, resort_f4[4]); swap_buf(aabb, resort_f4[5]); swap_buf(sleep_cnt, resort_sleep); swap_buf(dev_of_host, resort_doh);
+        R2D_TRY(host_of_dev.reserve(nb));
+        R2D_CUDA(cudaMemcpyAsync(host_of_dev.p, resort_vals[1].p, (size_t)nb * 4, cudaMemcpyDeviceToDevice, stream));
         // host side: the two maps, the shape image (ids and world indices by device slot), the slot tables
         {
             std::vector<float4> sh(nb);
@@ -455,6 +460,16 @@ struct CudaBatch : BatchBase {
         R2D_CUDA(cudaStreamSynchronize(stream));  // `v` lives on the caller's stack
         return R2D_OK;
     }
+    // device address of a page-locked (UVA-mapped) host buffer, or null (pageable memory, R2D_ZERO_COPY=0)
+    void* mapped_host(void* host) const {
+        if (!host || !zero_copy) return nullptr;
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+    }
     // enqueues the export (kernel + copies) of bodies [first, first + n) on the main stream; the caller synchronises
     int enqueue_read_bodies(uint32_t first, uint32_t n, uint32_t* ids, float* pos_xy, float* angle, float* momentum_xy,
                             float* ang_momentum, float* aabb_xywh) {
@@ -478,15 +493,7 @@ struct CudaBatch : BatchBase {
         // Pinned (page-locked, UVA-mapped) destinations are written by the export kernel itself: the stores stream over
         // PCIe as the warps finish, instead of one kernel followed by up to six separate DMA copies.  R2D_ZERO_COPY=0 or
         // any pageable destination: repack into the staging buffer and copy.
-        auto mapped = [&](void* host) -> void* {
-            if (!host || !zero_copy) return nullptr;
-            cudaPointerAttributes a{};
-            if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
-                cudaGetLastError();
-                return nullptr;
-            }
-            return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
-        };
+        auto mapped = [&](void* host) -> void* { return mapped_host(host); };
         void* m_ids = mapped(ids); void* m_pos = mapped(pos_xy); void* m_ang = mapped(angle); void* m_mom = mapped(momentum_xy);
         void* m_l = mapped(ang_momentum); void* m_aabb = mapped(aabb_xywh);
         const bool direct = (!ids || m_ids) && (!pos_xy || m_pos) && (!angle || m_ang) && (!momentum_xy || m_mom) &&
@@ -847,6 +854,7 @@ struct CudaBatch : BatchBase {
         }
         for (int attempt = 0;; ++attempt) {
             fill_dev();
+            world_exported = false;
             R2D_CUDA(cudaMemsetAsync(zeroed.p, 0, zeroed_bytes, stream));  // counters, colour tables, scan states, masks
             // ---- broadphase ----
             if (use_world_broad) {   // one CTA per world, the world's grid in shared memory (r2d_world.cuh)
@@ -982,13 +990,27 @@ struct CudaBatch : BatchBase {
                 uint32_t nb_cap = 0, R = 0;
                 const size_t smem = world_cache(nb_cap, R);
                 const uint32_t blocks = (uint32_t)std::min<size_t>(worlds.size(), (size_t)n_sms * 16);
+                // r2d_process_read into page-locked arrays: every CTA exports its world as soon as it is done (WorldExport)
+                WorldExport ex = {nullptr, nullptr, nullptr, nullptr, host_of_dev.p};
+                if (readback && world_export && S > 0 && !readback->ids && !readback->aabb_xywh && readback->pos_xy && readback->angle &&
+                    readback->momentum_xy && readback->ang_momentum) {
+                    void* m[4] = {mapped_host(readback->pos_xy), mapped_host(readback->angle), mapped_host(readback->momentum_xy),
+                                  mapped_host(readback->ang_momentum)};
+                    if (m[0] && m[1] && m[2] && m[3]) {
+                        ex.pos = (float2*)m[0];
+                        ex.angle = (float*)m[1];
+                        ex.mom = (float2*)m[2];
+                        ex.ang_mom = (float*)m[3];
+                    }
+                }
                 prof_begin(R2D_KCLASS_SOLVE_CONTACTS);
                 if (max_world_bodies <= 2u * WORLD_SOLVE_TPB)
-                    k_world_solve<2><<<blocks, WORLD_SOLVE_TPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R);
+                    k_world_solve<2><<<blocks, WORLD_SOLVE_TPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, ex);
                 else
-                    k_world_solve<4><<<blocks, WORLD_SOLVE_TPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R);
+                    k_world_solve<4><<<blocks, WORLD_SOLVE_TPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, ex);
                 prof_end();
                 launches += 1;
+                world_exported = ex.pos != nullptr;
             } else if (use_tile_solver) {
                 prof_begin(R2D_KCLASS_SOLVE_CONTACTS);
                 uint32_t S_ = S, I_ = I, cache = TILE_CACHE_TASKS, max_tasks = tile_max_tasks;
@@ -1009,7 +1031,9 @@ struct CudaBatch : BatchBase {
                 fill_dev();
             }
             // r2d_process_read: the export of the new state rides behind the solver, inside the same synchronisation
-            if (readback && persistent_solver) {
+            if (readback && world_exported) {
+                readback_done = true;   // (k_world_solve wrote the caller's arrays; the synchronisation below completes them)
+            } else if (readback && persistent_solver) {
                 const uint32_t keep = launches;
                 if ((st = enqueue_read_bodies(0, nb, readback->ids, readback->pos_xy, readback->angle, readback->momentum_xy,
                                               readback->ang_momentum, readback->aabb_xywh)))

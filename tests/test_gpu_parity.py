@@ -742,6 +742,18 @@ def test_gpu_process_read_equals_process_then_read():
     ref = batch2.read_bodies()
     assert np.array_equal(out["pos"].view(np.uint32), ref["pos"].view(np.uint32))
     assert np.array_equal(out["angle"].view(np.uint32), ref["angle"].view(np.uint32))
+    # pos / angle / momentum / ang_momentum all page-locked: k_world_solve exports every world itself, in the caller's order
+    # (the device order is re-sorted on the way: the export goes through host_of_dev)
+    pin = lambda *shape: torch.empty(shape, dtype=torch.float32).pin_memory().numpy()
+    out = {"id": None, "pos": pin(n, 2), "angle": pin(n), "momentum": pin(n, 2), "ang_momentum": pin(n), "aabb": None}
+    for step in range(30):
+        if step % 7 == 3:
+            batch.reorder()
+        batch.process_read(scenes.DT, 4, 4, out)
+        batch2.process(scenes.DT, 4, 4)
+    ref = batch2.read_bodies()
+    for k in ("pos", "angle", "momentum", "ang_momentum"):
+        assert np.array_equal(out[k].view(np.uint32), ref[k].view(np.uint32)), f"in-kernel export: {k}"
 
 
 def _pile_metrics(s):
