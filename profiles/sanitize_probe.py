@@ -42,4 +42,20 @@ sb = ShardedBatch(90, [0, 0])                                   # two shards on 
 for w in range(90): scenes.build_batch_world(sb.world(w), w, nx=8, ny=4)
 for _ in range(30): sb.process(scenes.DT, 4, 4)
 sb.read_bodies()
+# device-side re-sort (k_resort_*, cub radix sort) with joints / exclusions / a batch; in-kernel read-back of k_world_solve
+s.reorder(); s.process(scenes.DT, 4, 4); j.reorder(); j.process(scenes.DT, 4, 10); b.reorder()
+nb_ = b.num_bodies()
+pin = lambda *shape: torch.empty(shape, dtype=torch.float32).pin_memory().numpy()
+outb = {"id": None, "pos": pin(nb_, 2), "angle": pin(nb_), "momentum": pin(nb_, 2), "ang_momentum": pin(nb_), "aabb": None}
+for _ in range(3): b.process_read(scenes.DT, 4, 4, outb)
+# list flavour of the dataflow colouring with chained hub lists (normally worlds of ~10^6 bodies)
+import os
+os.environ["R2D_FLOW_LIST"] = "1"
+hl = Solver(2.0, 4); scenes.build_hub(hl)
+for _ in range(10): hl.process(scenes.DT, 4, 4)
+ml = Solver(2.0, 4); scenes.build_mixed(ml, 40, 20, n_large=3)
+for _ in range(40): ml.process(scenes.DT, 4, 4)
+os.environ["R2D_SOLVE_WIDE"] = "1"                              # 512-thread persistent sweep + record prefetch
+pw = Solver(2.0, 4); scenes.build_pyramid(pw, base=12, n_spinners=1)
+for _ in range(10): pw.process(scenes.DT, 4, 10)
 print("sanitize probe done", s.stats().n_manifolds, m.stats().n_manifolds, b.stats().n_manifolds)

@@ -153,6 +153,7 @@ struct CudaBatch : BatchBase {
     DBuf<uint4> adj_pool;   // chained entries of bodies with more than ADJ_CAP manifolds (dataflow colouring)
     int solve_wide = -1;              // k_solve_persistent with 512 threads per CTA: -1 by manifold count, 0 never, 1 always (R2D_SOLVE_WIDE)
     uint32_t solve_prefetch = 2;      // k_solve_persistent: streamed records fetched into L2 this many records ahead (R2D_SOLVE_PREFETCH)
+    bool world_single = true;         // one world of <= 1,024 bodies without joints: k_world_solve with one CTA of 512 threads (R2D_WORLD_SINGLE=0: tiles)
     bool world_export = true;         // k_world_solve exports into page-locked read-back arrays itself (R2D_WORLD_EXPORT=0: separate kernel)
     bool world_exported = false;
     bool flow_list_only = false;      // R2D_FLOW_LIST=1 (tests): the list flavour of the dataflow colouring for every size
@@ -218,6 +219,7 @@ struct CudaBatch : BatchBase {
         R2D_CUDA(cudaFuncSetAttribute(k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES));
         R2D_CUDA(cudaFuncSetAttribute(k_world_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
         R2D_CUDA(cudaFuncSetAttribute(k_world_solve<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
+        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<2, WORLD_SINGLE_TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
         // Flavour switches for A/B measurements and tests.  Every one of them selects between paths that produce
         // bit-identical results; they are read here once, never inside process().
         auto env_is = [](const char* name, const char* value) {
@@ -230,6 +232,7 @@ struct CudaBatch : BatchBase {
         if (env_is("R2D_TILE_SOLVER", "0")) tile_solver = false;             // k_solve_persistent instead of k_solve_tiles
         if (env_is("R2D_FLOW_LIST", "1")) flow_list_only = true;
         if (env_is("R2D_WORLD_EXPORT", "0")) world_export = false;
+        if (env_is("R2D_WORLD_SINGLE", "0")) world_single = false;
         if (const char* e = getenv("R2D_SOLVE_WIDE")) solve_wide = atoi(e);
         if (const char* e = getenv("R2D_SOLVE_PREFETCH")) solve_prefetch = (uint32_t)atoi(e);
         if (env_is("R2D_DEVICE_RESORT", "0")) device_resort = false;         // the periodic re-sort through the host
@@ -830,9 +833,10 @@ struct CudaBatch : BatchBase {
             if (s_warm0.cap < s_hdr.cap && ((st = s_warm0.reserve(s_hdr.cap)) || (st = s_warm1.reserve(s_hdr.cap)))) return st;
         }
         if (opt_sleeping && (st = sleep_state.reserve(nb))) return st;
+        // one CTA per world: batches with enough worlds to fill the GPU, or ONE world small enough for one CTA of 512 threads
+        const bool single_small = world_single && worlds.size() == 1 && nb <= WORLD_SINGLE_MAX_BODIES;
         const bool use_world_solver = persistent_solver && world_solver && image.j_hdr.empty() && !opt_warm_start &&
-                                      max_world_bodies <= WORLD_MAX_BODIES &&
-                                      worlds.size() >= (size_t)n_sms / 2;  // enough worlds to fill the GPU with one CTA each
+                                      ((max_world_bodies <= WORLD_MAX_BODIES && worlds.size() >= (size_t)n_sms / 2) || single_small);
         world_fused_now = use_world_solver;
         const uint32_t tile_b = (nb + (uint32_t)n_sms - 1) / (uint32_t)n_sms;
         const bool use_tile_solver = persistent_solver && tile_solver && !tile_declined && !use_world_solver && image.j_hdr.empty() &&
@@ -1004,7 +1008,9 @@ struct CudaBatch : BatchBase {
                     }
                 }
                 prof_begin(R2D_KCLASS_SOLVE_CONTACTS);
-                if (max_world_bodies <= 2u * WORLD_SOLVE_TPB)
+                if (single_small)
+                    k_world_solve<2, WORLD_SINGLE_TPB><<<1, WORLD_SINGLE_TPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, ex);
+                else if (max_world_bodies <= 2u * WORLD_SOLVE_TPB)
                     k_world_solve<2><<<blocks, WORLD_SOLVE_TPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, ex);
                 else
                     k_world_solve<4><<<blocks, WORLD_SOLVE_TPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, ex);

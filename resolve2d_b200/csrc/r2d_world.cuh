@@ -31,6 +31,10 @@ namespace r2d {
 
 constexpr uint32_t WORLD_MAX_BODIES = 512;
 constexpr int WORLD_SOLVE_TPB = 128;
+// ONE small world without joints (a scene of game size) runs on the same kernel with one CTA of 512 threads: a colour phase
+// is then one pass of the CTA over shared memory instead of a round of L2 hand-offs between 148 tiles of a few bodies each
+constexpr int WORLD_SINGLE_TPB = 512;
+constexpr uint32_t WORLD_SINGLE_MAX_BODIES = 1024;   // (the slot header holds 10-bit body indices)
 // slot header: ref | inc << 10 (world-local body slots) | flags << 20
 constexpr uint32_t WS_ST1 = 1u << 20, WS_ST2 = 1u << 21;
 constexpr uint32_t WS_SKIP = 1u << 22;    // depth >= 0: the point is skipped and its accumulated impulses are zeroed (:154-158)
@@ -78,7 +82,7 @@ struct WorldExport {
 };
 
 // Everything after the colour counts are known, for one world.  BPT = bodies a thread integrates (registers).
-template <bool SMEM, int BPT>
+template <bool SMEM, int BPT, int WTPB>
 __device__ __forceinline__ void world_run(const Dev& d, const WorldSlots<SMEM>& rc, uint32_t w, uint32_t b0, uint32_t nb,
                                           uint32_t p0, uint32_t p1, uint32_t nc, float sub_dt, uint32_t S, uint32_t I,
                                           float4* s_mom, float* s_ii, const unsigned char* s_st, const uint32_t* s_cnt,
@@ -140,7 +144,7 @@ __device__ __forceinline__ void world_run(const Dev& d, const WorldSlots<SMEM>& 
     for (uint32_t s = 0; s < S; ++s) {
 #pragma unroll
         for (int k = 0; k < BPT; ++k) {
-            const uint32_t i = tid + (uint32_t)k * WORLD_SOLVE_TPB;
+            const uint32_t i = tid + (uint32_t)k * WTPB;
             if (i >= nb) continue;
             const bool st = s_st[i] != 0;
             float4 m = s_mom[i];
@@ -254,7 +258,7 @@ __device__ __forceinline__ void world_run(const Dev& d, const WorldSlots<SMEM>& 
         uint32_t xj[BPT];
 #pragma unroll
         for (int k = 0; k < BPT; ++k) {
-            const uint32_t i = tid + (uint32_t)k * WORLD_SOLVE_TPB;
+            const uint32_t i = tid + (uint32_t)k * WTPB;
             xj[k] = 0xFFFFFFFFu;
             if (i >= nb) continue;
             const float4 m = s_mom[i];
@@ -293,8 +297,8 @@ __device__ __forceinline__ void world_run(const Dev& d, const WorldSlots<SMEM>& 
     }
 }
 
-template <int BPT>
-__global__ void __launch_bounds__(WORLD_SOLVE_TPB, BPT == 2 ? 6 : 4) k_world_solve(Dev d, float sub_dt, uint32_t S, uint32_t I,
+template <int BPT, int WTPB = WORLD_SOLVE_TPB>
+__global__ void __launch_bounds__(WTPB, WTPB > 128 ? 1 : (BPT == 2 ? 6 : 4)) k_world_solve(Dev d, float sub_dt, uint32_t S, uint32_t I,
                                                                                   uint32_t nb_cap, uint32_t R, WorldExport ex) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_cnt[MAX_COLORS];      // per colour: one-point manifolds | two-point manifolds << 16
@@ -316,14 +320,15 @@ __global__ void __launch_bounds__(WORLD_SOLVE_TPB, BPT == 2 ? 6 : 4) k_world_sol
     for (uint32_t w = blockIdx.x; w < d.n_worlds; w += gridDim.x) {
         const uint32_t b0 = d.world_base[w], b1 = d.world_base[w + 1], nb = b1 - b0;
         // the world's candidate pairs: body-major list with the fine grid, bucket-major without
-        const uint32_t p0 = d.fine_on ? d.pair_cnt[b0 + 1] : d.ent_off[d.table_mult * b0];
-        const uint32_t p1 = d.fine_on ? d.pair_cnt[b1 + 1] : d.ent_off[d.table_mult * b1];
+        // (a single world owns the whole list, whatever kernels wrote it)
+        const uint32_t p0 = d.n_worlds == 1u ? 0u : (d.fine_on ? d.pair_cnt[b0 + 1] : d.ent_off[d.table_mult * b0]);
+        const uint32_t p1 = d.n_worlds == 1u ? live_pairs(d) : (d.fine_on ? d.pair_cnt[b1 + 1] : d.ent_off[d.table_mult * b1]);
         for (uint32_t c = tid; c < MAX_COLORS; c += nth) s_cnt[c] = s_cur[c] = 0u;
         // ---- stage the bodies ----
         float4 rp[BPT], rf[BPT];   // pose + mass, force + inertia of the bodies this thread integrates
 #pragma unroll
         for (int k = 0; k < BPT; ++k) {
-            const uint32_t i = tid + (uint32_t)k * WORLD_SOLVE_TPB;
+            const uint32_t i = tid + (uint32_t)k * WTPB;
             rp[k] = rf[k] = make_float4(0, 0, 0, 0);
             if (i >= nb) continue;
             const float4 p = d.pos[b0 + i], m = d.mom[b0 + i], f = d.frc[b0 + i], pr = d.prop[b0 + i];
@@ -375,14 +380,14 @@ __global__ void __launch_bounds__(WORLD_SOLVE_TPB, BPT == 2 ? 6 : 4) k_world_sol
         __syncthreads();
         const uint32_t nc = s_nc;
         if (s_fits) {
-            world_run<true, BPT>(d, sm, w, b0, nb, p0, p1, nc, sub_dt, S, I, s_mom, s_ii, s_st, s_cnt, s_cur, s_beg, rp, rf, ex);
+            world_run<true, BPT, WTPB>(d, sm, w, b0, nb, p0, p1, nc, sub_dt, S, I, s_mom, s_ii, s_st, s_cnt, s_cur, s_beg, rp, rf, ex);
         } else {   // the world's own slice of the global record arrays (see the header comment)
             WorldSlots<false> rg;
             rg.hdr_[0] = (uint32_t*)d.s_acc0 + p0;  rg.hdr_[1] = (uint32_t*)d.s_acc1 + p0;
             rg.nfb_[0] = d.s_nf + p0;               rg.nfb_[1] = d.s_inv + p0;
             rg.r_[0] = d.s_r0 + p0;                 rg.r_[1] = d.s_r1 + p0;
             rg.ma_[0] = d.s_pm0 + p0;               rg.ma_[1] = d.s_pm1 + p0;
-            world_run<false, BPT>(d, rg, w, b0, nb, p0, p1, nc, sub_dt, S, I, s_mom, s_ii, s_st, s_cnt, s_cur, s_beg, rp, rf, ex);
+            world_run<false, BPT, WTPB>(d, rg, w, b0, nb, p0, p1, nc, sub_dt, S, I, s_mom, s_ii, s_st, s_cnt, s_cur, s_beg, rp, rf, ex);
         }
         __syncthreads();   // the next world of this CTA reuses the shared arrays
     }
