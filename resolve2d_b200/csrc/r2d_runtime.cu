@@ -848,9 +848,9 @@ struct CudaBatch : BatchBase {
         const uint32_t wb_nb_cap = (max_world_bodies + 3u) & ~3u, wb_tw_cap = grid_mult() * max_world_bodies;
         const uint32_t wb_ent_cap = wb_nb_cap + 256u;   // one entry per small body + the cells of the large ones
         const size_t wb_smem = world_broad_smem_bytes(wb_nb_cap, wb_tw_cap, wb_ent_cap);
-        bool use_world_broad = world_broad && !world_broad_declined && many_small_worlds && fine_now && !ll_now &&
-                               max_world_bodies <= WORLD_MAX_BODIES && wb_smem <= 100 * 1024 &&
-                               worlds.size() + 2 <= scan_state_cap;
+        bool use_world_broad = world_broad && !world_broad_declined && fine_now && !ll_now && worlds.size() + 2 <= scan_state_cap &&
+                               ((many_small_worlds && max_world_bodies <= WORLD_MAX_BODIES && wb_smem <= 100 * 1024) ||
+                                (single_small && use_world_solver && wb_smem <= WORLD_SMEM_MAX));   // (one world: one CTA of 1,024 threads)
         if (opt_sleeping) {   // once per call, not per attempt: it edits the static flags
             fill_dev();
             if ((st = join_forces())) return st;   // user forces wake
@@ -864,7 +864,7 @@ struct CudaBatch : BatchBase {
             if (use_world_broad) {   // one CTA per world, the world's grid in shared memory (r2d_world.cuh)
                 const uint32_t blocks = (uint32_t)std::min<size_t>(worlds.size(), (size_t)n_sms * 16);
                 prof_begin(R2D_KCLASS_BROADPHASE);
-                k_world_broad<<<blocks, WORLD_BROAD_TPB, wb_smem, stream>>>(d, wb_nb_cap, wb_tw_cap, wb_ent_cap, scan_state(0),
+                k_world_broad<<<blocks, single_small ? 1024 : WORLD_BROAD_TPB, wb_smem, stream>>>(d, wb_nb_cap, wb_tw_cap, wb_ent_cap, scan_state(0),
                                                                              (uint32_t*)(scan_state(0) + scan_state_cap - 1));
                 prof_end();
                 launches += 1;

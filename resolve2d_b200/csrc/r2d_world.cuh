@@ -435,7 +435,7 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* s_w
     return base + inc - v;
 }
 
-__global__ void __launch_bounds__(WORLD_BROAD_TPB) k_world_broad(Dev d, uint32_t nb_cap, uint32_t tw_cap, uint32_t ent_cap,
+__global__ void __launch_bounds__(1024) k_world_broad(Dev d, uint32_t nb_cap, uint32_t tw_cap, uint32_t ent_cap,
                                                                  unsigned long long* state, uint32_t* ticket) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_warp[32], s_big[WORLD_BROAD_BIG];
