@@ -217,9 +217,12 @@ struct CudaBatch : BatchBase {
         R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bucket_count, TPB, 0));
         pair_blocks = (per_sm < 1 ? 1 : per_sm) * n_sms;  // resident CTAs: a CTA per heavy bucket, a warp per light one, grid-stride
         R2D_CUDA(cudaFuncSetAttribute(k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES));
-        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
-        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
-        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<2, WORLD_SINGLE_TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
+        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<2, WORLD_SOLVE_TPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
+        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<2, WORLD_SOLVE_TPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
+        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<4, WORLD_SOLVE_TPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
+        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<4, WORLD_SOLVE_TPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
+        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<2, WORLD_SINGLE_TPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
+        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<2, WORLD_SINGLE_TPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
         // Flavour switches for A/B measurements and tests.  Every one of them selects between paths that produce
         // bit-identical results; they are read here once, never inside process().
         auto env_is = [](const char* name, const char* value) {
@@ -1008,12 +1011,21 @@ struct CudaBatch : BatchBase {
                     }
                 }
                 prof_begin(R2D_KCLASS_SOLVE_CONTACTS);
+                const bool exporting = ex.pos != nullptr;
+#define R2D_WORLD_SOLVE(BPT, WTPB, GRID)                                                                              \
+    do {                                                                                                              \
+        if (exporting)                                                                                                \
+            k_world_solve<BPT, WTPB, true><<<GRID, WTPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, ex);             \
+        else                                                                                                          \
+            k_world_solve<BPT, WTPB, false><<<GRID, WTPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, ex);            \
+    } while (0)
                 if (single_small)
-                    k_world_solve<2, WORLD_SINGLE_TPB><<<1, WORLD_SINGLE_TPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, ex);
+                    R2D_WORLD_SOLVE(2, WORLD_SINGLE_TPB, 1);
                 else if (max_world_bodies <= 2u * WORLD_SOLVE_TPB)
-                    k_world_solve<2><<<blocks, WORLD_SOLVE_TPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, ex);
+                    R2D_WORLD_SOLVE(2, WORLD_SOLVE_TPB, blocks);
                 else
-                    k_world_solve<4><<<blocks, WORLD_SOLVE_TPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, ex);
+                    R2D_WORLD_SOLVE(4, WORLD_SOLVE_TPB, blocks);
+#undef R2D_WORLD_SOLVE
                 prof_end();
                 launches += 1;
                 world_exported = ex.pos != nullptr;

@@ -82,7 +82,7 @@ struct WorldExport {
 };
 
 // Everything after the colour counts are known, for one world.  BPT = bodies a thread integrates (registers).
-template <bool SMEM, int BPT, int WTPB>
+template <bool SMEM, int BPT, int WTPB, bool EXPORT>
 __device__ __forceinline__ void world_run(const Dev& d, const WorldSlots<SMEM>& rc, uint32_t w, uint32_t b0, uint32_t nb,
                                           uint32_t p0, uint32_t p1, uint32_t nc, float sub_dt, uint32_t S, uint32_t I,
                                           float4* s_mom, float* s_ii, const unsigned char* s_st, const uint32_t* s_cnt,
@@ -268,13 +268,13 @@ __device__ __forceinline__ void world_run(const Dev& d, const WorldSlots<SMEM>& 
                 d.frc[b0 + i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 d.mom[b0 + i] = make_float4(m.x, m.y, m.z, 0.0f);
             }
-            if (ex.pos) {
+            if (EXPORT) {
                 xa[k] = make_float4(rp[k].x, rp[k].y, m.x, m.y);
                 xb[k] = make_float2(rp[k].z, m.z);
                 xj[k] = ex.host_of_dev[b0 + i] - b0;
             }
         }
-        if (ex.pos) {   // (uniform) through shared memory into the caller's order, then whole lines to the host
+        if (EXPORT) {   // through shared memory into the caller's order, then whole lines to the host
             float4* s_xa = s_mom;                                   // 16 B per body
             float2* s_xb = reinterpret_cast<float2*>(s_ii);         // 1 / inertia and the static flags: 8 B per body, contiguous
             __syncthreads();
@@ -297,7 +297,7 @@ __device__ __forceinline__ void world_run(const Dev& d, const WorldSlots<SMEM>& 
     }
 }
 
-template <int BPT, int WTPB = WORLD_SOLVE_TPB>
+template <int BPT, int WTPB = WORLD_SOLVE_TPB, bool EXPORT = false>
 __global__ void __launch_bounds__(WTPB, WTPB > 128 ? 1 : (BPT == 2 ? 6 : 4)) k_world_solve(Dev d, float sub_dt, uint32_t S, uint32_t I,
                                                                                   uint32_t nb_cap, uint32_t R, WorldExport ex) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -380,14 +380,14 @@ __global__ void __launch_bounds__(WTPB, WTPB > 128 ? 1 : (BPT == 2 ? 6 : 4)) k_w
         __syncthreads();
         const uint32_t nc = s_nc;
         if (s_fits) {
-            world_run<true, BPT, WTPB>(d, sm, w, b0, nb, p0, p1, nc, sub_dt, S, I, s_mom, s_ii, s_st, s_cnt, s_cur, s_beg, rp, rf, ex);
+            world_run<true, BPT, WTPB, EXPORT>(d, sm, w, b0, nb, p0, p1, nc, sub_dt, S, I, s_mom, s_ii, s_st, s_cnt, s_cur, s_beg, rp, rf, ex);
         } else {   // the world's own slice of the global record arrays (see the header comment)
             WorldSlots<false> rg;
             rg.hdr_[0] = (uint32_t*)d.s_acc0 + p0;  rg.hdr_[1] = (uint32_t*)d.s_acc1 + p0;
             rg.nfb_[0] = d.s_nf + p0;               rg.nfb_[1] = d.s_inv + p0;
             rg.r_[0] = d.s_r0 + p0;                 rg.r_[1] = d.s_r1 + p0;
             rg.ma_[0] = d.s_pm0 + p0;               rg.ma_[1] = d.s_pm1 + p0;
-            world_run<false, BPT, WTPB>(d, rg, w, b0, nb, p0, p1, nc, sub_dt, S, I, s_mom, s_ii, s_st, s_cnt, s_cur, s_beg, rp, rf, ex);
+            world_run<false, BPT, WTPB, EXPORT>(d, rg, w, b0, nb, p0, p1, nc, sub_dt, S, I, s_mom, s_ii, s_st, s_cnt, s_cur, s_beg, rp, rf, ex);
         }
         __syncthreads();   // the next world of this CTA reuses the shared arrays
     }
