@@ -534,6 +534,21 @@ struct BatchBase {
     // path, a stale device image, or a changed fine cell go through the host (download, sort, upload: 5.6 ms for 100 k).
     uint32_t reorder_interval = 1024;
     uint32_t steps_since_upload = 0;
+    // A backend re-sorted its body arrays itself: `host_of_new[j]` = host slot of the body now at device slot j.  Updates
+    // the two maps, the shape image (ids and world indices by device slot) and everything that names bodies by device slot;
+    // the backend then uploads the slot tables (exclusions, joints).
+    int adopt_device_order(const std::vector<uint32_t>& host_of_new) {
+        const size_t nb = image.n_bodies;
+        if (host_of_new.size() != nb) return R2D_ERR_BAD_STATE;
+        std::vector<float4> sh(nb);
+        for (size_t j = 0; j < nb; ++j) sh[j] = image.shape[image.dev_of_host[host_of_new[j]]];
+        image.shape.swap(sh);
+        for (size_t j = 0; j < nb; ++j) {
+            image.host_of_dev[j] = host_of_new[j];
+            image.dev_of_host[host_of_new[j]] = (uint32_t)j;
+        }
+        return build_slot_tables(worlds, image);
+    }
     int reorder_through_host() {
         const int st = ensure_host();
         if (st != R2D_OK) return st;

@@ -401,17 +401,7 @@ struct CudaBatch : BatchBase {
         swap_buf(shape, resort_f4[4]); swap_buf(aabb, resort_f4[5]); swap_buf(sleep_cnt, resort_sleep); swap_buf(dev_of_host, resort_doh);
         R2D_TRY(host_of_dev.reserve(nb));
         R2D_CUDA(cudaMemcpyAsync(host_of_dev.p, resort_vals[1].p, (size_t)nb * 4, cudaMemcpyDeviceToDevice, stream));
-        // host side: the two maps, the shape image (ids and world indices by device slot), the slot tables
-        {
-            std::vector<float4> sh(nb);
-            for (uint32_t j = 0; j < nb; ++j) sh[j] = image.shape[image.dev_of_host[resort_order[j]]];
-            image.shape.swap(sh);
-            for (uint32_t j = 0; j < nb; ++j) {
-                image.host_of_dev[j] = resort_order[j];
-                image.dev_of_host[resort_order[j]] = j;
-            }
-        }
-        const int bt = host::build_slot_tables(worlds, image);
+        const int bt = adopt_device_order(resort_order);   // host side: maps, shape image, exclusions and joints by device slot
         if (bt != R2D_OK) return bt;
         R2D_TRY(upload_slot_tables());
         R2D_CUDA(cudaStreamSynchronize(stream));

@@ -48,6 +48,14 @@ class EmuBatch:
         if st != 0:
             raise _abi.R2DError(st, "emu_batch_process")
 
+    def reorder(self):
+        st = self._lib.emu_batch_reorder(self._h)
+        if st != 0:
+            raise _abi.R2DError(st, "emu_batch_reorder")
+
+    def set_reorder_interval(self, steps):
+        assert self._lib.emu_batch_set_reorder_interval(self._h, C.c_uint32(steps)) == 0
+
     def __del__(self):
         try:
             self._lib.emu_batch_destroy(self._h)

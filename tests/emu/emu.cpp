@@ -48,6 +48,49 @@ struct EmuBatch : BatchBase {
         n_pairs_last = 0;
         return R2D_OK;
     }
+    // the device-side re-sort (k_resort_min / k_resort_keys / radix sort / k_resort_gather of r2d_kernels.cuh), serially:
+    // same key function, same stable order, then the host bookkeeping shared with the CUDA backend (adopt_device_order)
+    int backend_reorder() override {
+        if (getenv("R2D_EMU_RESORT") && atoi(getenv("R2D_EMU_RESORT")) == 0) return REORDER_ON_HOST;
+        if (getenv("R2D_EMU_RESORT") && atoi(getenv("R2D_EMU_RESORT")) == 2) return R2D_ERR_BAD_STATE;   // (test: is this path taken?)
+        const uint32_t nb = image.n_bodies, nw = (uint32_t)worlds.size();
+        if (nb == 0) return REORDER_ON_HOST;
+        std::vector<int> wmx(nw, RESORT_NO_MIN), wmy(nw, RESORT_NO_MIN);
+        for (uint32_t i = 0; i < nb; ++i) {
+            const float4 p = pos[i];
+            if (!(p.x == p.x) || !(p.y == p.y)) continue;
+            const uint32_t w = f2u(shape[i].z) >> FLAG_WORLD_SHIFT;
+            wmx[w] = std::min(wmx[w], resort_float_order(p.x));
+            wmy[w] = std::min(wmy[w], resort_float_order(p.y));
+        }
+        std::vector<std::pair<unsigned long long, uint32_t>> keyed(nb);
+        for (uint32_t h = 0; h < nb; ++h) {
+            const uint32_t s = image.dev_of_host[h];
+            const uint32_t w = f2u(shape[s].z) >> FLAG_WORLD_SHIFT;
+            const float mx = wmx[w] == RESORT_NO_MIN ? 0.0f : resort_float_unorder(wmx[w]);
+            const float my = wmx[w] == RESORT_NO_MIN ? 0.0f : resort_float_unorder(wmy[w]);
+            keyed[h] = {((unsigned long long)w << 32) | resort_key(pos[s].x, pos[s].y, mx, my), h};
+        }
+        std::stable_sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+        std::vector<uint32_t> order(nb);
+        std::vector<float4> p2(nb), m2(nb), f2(nb), pr2(nb), s2(nb), a2(nb);
+        for (uint32_t j = 0; j < nb; ++j) {
+            order[j] = keyed[j].second;
+            const uint32_t o = image.dev_of_host[order[j]];
+            p2[j] = pos[o]; m2[j] = mom[o]; f2[j] = frc[o]; pr2[j] = prop[o]; s2[j] = shape[o]; a2[j] = aabb[o];
+        }
+        pos.swap(p2); mom.swap(m2); frc.swap(f2); prop.swap(pr2); shape.swap(s2); aabb.swap(a2);
+        const int st = adopt_device_order(order);
+        if (st != R2D_OK) return st;
+        n_pairs_last = 0;
+        // (always checked here: the order must be the one build_image derives from the same state)
+        const int sd = backend_download();
+        if (sd != R2D_OK) return sd;
+        host::Image ref;
+        const int sb = host::build_image(worlds, ref, grid_cell());
+        if (sb != R2D_OK) return sb;
+        return ref.host_of_dev == image.host_of_dev ? R2D_OK : R2D_ERR_BAD_STATE;
+    }
     int backend_download() override {
         for (auto& w : worlds) {
             const uint32_t base = image.world_base[w->index];

@@ -6,7 +6,7 @@ import pytest
 
 from emu import EmuBatch, EmuSolver
 from oracle import ORDER_COLORED, OracleSolver
-from parity import assert_bodies_equal, run_parity
+from parity import assert_bodies_equal, assert_manifolds_equal, run_parity
 from resolve2d_b200 import R2DError, scenes
 
 
@@ -230,3 +230,47 @@ def test_emu_hub_body_beyond_256_colours_keeps_stepping():
     assert st.n_colors == 256 and st.n_dropped >= 40 and st.n_dropped == orc.stats().n_dropped
     man = cand.read_manifolds()
     assert np.count_nonzero(man["color"] == 0xFFFFFFFD) == st.n_dropped
+
+
+def test_emu_backend_resort_keeps_results_and_derives_the_host_order(monkeypatch):
+    """BatchBase::reorder with a backend that re-sorts its own arrays (the CUDA backend does it on the device; the emulator
+    restates it serially and always compares the order with build_image's): re-sorting every few steps must not change a
+    bit — joints, exclusion pairs, a batch of several worlds — against the host path and against never re-sorting."""
+    def single(build, interval):
+        s = EmuSolver(2.0, 4)
+        build(s)
+        s.set_reorder_interval(interval)
+        for k in range(40):
+            if interval and k % 9 == 4:
+                s.reorder()
+            s.process(scenes.DT, 4, 4)
+        return s.read_bodies(), s.read_pairs(), s.read_manifolds()
+
+    def batch(interval):
+        b = EmuBatch(3, 2.0, 4)
+        for w in range(3):
+            scenes.build_mixed(b.world(w), 12 + 2 * w, 8, n_large=1, seed=50 + w)
+        b.set_reorder_interval(interval)
+        for k in range(25):
+            if interval and k % 9 == 4:
+                b.reorder()
+            b.process(scenes.DT, 4, 4)
+        bodies = [b.world(w).read_bodies() for w in range(3)]
+        merged = {k: np.concatenate([x[k] for x in bodies]) for k in bodies[0]}
+        return merged, b.world(1).read_pairs(), b.world(1).read_manifolds()
+
+    monkeypatch.setenv("R2D_EMU_RESORT", "2")      # the backend path is the one reorder() takes
+    with pytest.raises(R2DError):
+        single(scenes.setup_0_3_many_boxes, 3)
+    for name, run in (("0_1", lambda iv: single(scenes.setup_0_1_car_platformer, iv)),
+                      ("pyramid", lambda iv: single(lambda s: scenes.build_pyramid(s, base=10, n_spinners=2), iv)),
+                      ("batch", batch)):
+        monkeypatch.delenv("R2D_EMU_RESORT", raising=False)
+        own = run(3)
+        never = run(0)
+        monkeypatch.setenv("R2D_EMU_RESORT", "0")
+        host = run(3)
+        for other, what in ((host, "host re-sort"), (never, "no re-sort")):
+            assert_bodies_equal(own[0], other[0], f"{name}: backend re-sort vs {what}")
+            assert np.array_equal(own[1], other[1]), f"{name}: pairs vs {what}"
+            assert_manifolds_equal(own[2], other[2], f"{name}: manifolds vs {what}")
