@@ -141,6 +141,7 @@ __device__ __forceinline__ void world_run(const Dev& d, const WorldSlots<SMEM>& 
     }
     // ---- substeps ----
     const uint32_t g_lo = d.grav_off[w], g_hi = d.grav_off[w + 1];
+    __syncthreads();   // the pre-step above reads 1 / mass out of the momentum words the body phase below rewrites (same bits, but a race)
     for (uint32_t s = 0; s < S; ++s) {
 #pragma unroll
         for (int k = 0; k < BPT; ++k) {
@@ -219,6 +220,7 @@ __device__ __forceinline__ void world_run(const Dev& d, const WorldSlots<SMEM>& 
                     const float bx = __shfl_down_sync(0xffffffffu, dp.x, 1), by = __shfl_down_sync(0xffffffffu, dp.y, 1);
                     const float bc1 = __shfl_down_sync(0xffffffffu, c1, 1), bc2 = __shfl_down_sync(0xffffffffu, c2, 1);
                     const bool b_applied = __shfl_down_sync(0xffffffffu, applied ? 1 : 0, 1) != 0 && (h & WS_A) != 0;
+                    __syncwarp();   // the lane of a second point has read the two body words its neighbour is about to write
                     if (live && !(h & WS_B)) {
                         v2 lin1 = mk2(0.0f, 0.0f), lin2 = mk2(0.0f, 0.0f);
                         float rot1 = 0.0f, rot2 = 0.0f;
