@@ -826,8 +826,9 @@ struct CudaBatch : BatchBase {
             if (s_warm0.cap < s_hdr.cap && ((st = s_warm0.reserve(s_hdr.cap)) || (st = s_warm1.reserve(s_hdr.cap)))) return st;
         }
         if (opt_sleeping && (st = sleep_state.reserve(nb))) return st;
-        // one CTA per world: batches with enough worlds to fill the GPU, or ONE world small enough for one CTA of 512 threads
-        const bool single_small = world_single && worlds.size() == 1 && nb <= WORLD_SINGLE_MAX_BODIES;
+        // one CTA per world: batches with enough worlds to fill the GPU with 128-thread CTAs, or a FEW worlds (one world, a handful
+        // of worlds per GPU of a sharded batch) each small enough for one CTA of 512 threads
+        const bool single_small = world_single && worlds.size() < (size_t)n_sms / 2 && max_world_bodies <= WORLD_SINGLE_MAX_BODIES;
         const bool use_world_solver = persistent_solver && world_solver && image.j_hdr.empty() && !opt_warm_start &&
                                       ((max_world_bodies <= WORLD_MAX_BODIES && worlds.size() >= (size_t)n_sms / 2) || single_small);
         world_fused_now = use_world_solver;
@@ -1010,7 +1011,7 @@ struct CudaBatch : BatchBase {
             k_world_solve<BPT, WTPB, false><<<GRID, WTPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, ex);            \
     } while (0)
                 if (single_small)
-                    R2D_WORLD_SOLVE(2, WORLD_SINGLE_TPB, 1);
+                    R2D_WORLD_SOLVE(2, WORLD_SINGLE_TPB, blocks);
                 else if (max_world_bodies <= 2u * WORLD_SOLVE_TPB)
                     R2D_WORLD_SOLVE(2, WORLD_SOLVE_TPB, blocks);
                 else
