@@ -394,6 +394,19 @@ def test_gpu_sharded_batch_equals_one_batch():
             assert_bodies_equal(o, outs[0], f"sharded variant {k} step {step}")
     assert variants[0].stats().n_manifolds == one.stats().n_manifolds > 5000
     assert np.array_equal(variants[1].world(150).read_pairs(), one.world(150).read_pairs())
+    # page-locked destinations: every shard's k_world_solve writes its slice of the caller's arrays itself (from its own device)
+    import torch
+    pin = lambda *shape: torch.empty(shape, dtype=torch.float32).pin_memory().numpy()
+    for step in range(6):
+        outs = []
+        for x in [one] + variants:
+            out = {"id": None, "pos": pin(n, 2), "angle": pin(n), "momentum": pin(n, 2), "ang_momentum": pin(n), "aabb": None}
+            outs.append(x.process_read(scenes.DT, 4, 4, out))
+        for k, o in enumerate(outs[1:]):
+            for key in ("pos", "angle", "momentum", "ang_momentum"):
+                assert np.array_equal(o[key].view(np.uint32), outs[0][key].view(np.uint32)), f"sharded variant {k}, pinned {key}, step {step}"
+        ref = one.read_bodies()
+        assert np.array_equal(outs[0]["pos"].view(np.uint32), ref["pos"].view(np.uint32))
 
 
 def test_gpu_large_batch_with_joints_uses_per_world_colouring_and_dataflow_sweep():
