@@ -165,6 +165,7 @@ struct CudaBatch : BatchBase {
     PinnedStep* pinned = nullptr;
     size_t cap_entries = 0, cap_pairs = 0;
     uint32_t last_pairs = 0;
+    uint32_t last_manifolds = 0;   // M of the previous call (picks the wide persistent sweep; `stats` is reset at the start of a call)
     Dev d{};
     // profiling
     bool profiling = false;
@@ -725,7 +726,7 @@ struct CudaBatch : BatchBase {
         uint32_t n_jc = (uint32_t)image.joint_color_start.size() - 1, S_ = S, I_ = I;
         float sd = sub_dt;
         // most records beyond the cache (sized from the previous call's manifold count): the wide flavour
-        const bool wide = solve_wide == 1 || (solve_wide < 0 && (size_t)stats.n_manifolds > 4 * (size_t)SOLVE_SMEM_SLOTS * PSOLVE_TPB * solve_blocks);
+        const bool wide = solve_wide == 1 || (solve_wide < 0 && (size_t)last_manifolds > 4 * (size_t)SOLVE_SMEM_SLOTS * PSOLVE_TPB * solve_blocks);
         uint32_t slots = wide ? std::min<uint32_t>(solve_smem_slots, SOLVE_SMEM_SLOTS_BIG) : solve_smem_slots, prefetch = solve_prefetch;
         void* args[] = {(void*)&d, (void*)&sd, (void*)&S_, (void*)&I_, (void*)&jcs_dev, (void*)&n_jc, (void*)&slots, (void*)&prefetch};
         if (wide)
@@ -1104,6 +1105,7 @@ struct CudaBatch : BatchBase {
         stats.n_entries = c.n_entries;
         stats.n_pairs = c.n_pairs;
         stats.n_manifolds = c.n_manifolds;
+        last_manifolds = c.n_manifolds;
         stats.n_points = c.n_points;
         stats.n_colors = c.n_colors;
         stats.n_color_rounds = c.n_rounds;
