@@ -137,6 +137,7 @@ struct Image {
     std::vector<float4> j_par, j_vec;
     std::vector<uint32_t> joint_color_start;   // n_joint_colors + 1
     std::vector<uint32_t> joint_world, joint_local_index, joint_color;  // per sorted joint
+    std::vector<uint32_t> world_joint_start, world_joint;              // the sorted joints of every world (indices), sweep order kept
     // joints inside the dataflow sweep (r2d_pipeline.cuh solve_joint_flow): per sorted joint {rank among the joints of its
     // first body, that body's joint count, same for the second body}; per device slot the number of joints naming the body.
     // `joints_flow_ok`: no two-body joint names a static body or the same body twice (those write a static body's momentum,
@@ -349,7 +350,7 @@ inline int build_slot_tables(const std::vector<std::unique_ptr<World>>& worlds, 
         im.joint_color_start.assign(n_colors + 1, 0);
         for (size_t k = 0; k < nj; ++k) {
             const GJ& g = gj[k];
-            im.j_hdr[k] = make_uint4((uint32_t)g.j.type, g.s1, g.s2, 0u);
+            im.j_hdr[k] = make_uint4((uint32_t)g.j.type, g.s1, g.s2, g.color);
             im.j_par[k] = mkf4(g.j.power_max, g.j.power_min, g.j.beta, g.j.target);
             im.j_vec[k] = mkf4(g.j.r1x, g.j.r1y, g.j.r2x, g.j.r2y);
             im.joint_world[k] = g.world;
@@ -358,6 +359,15 @@ inline int build_slot_tables(const std::vector<std::unique_ptr<World>>& worlds, 
             im.joint_color_start[g.color + 1] += 1;
         }
         for (size_t c = 0; c < n_colors; ++c) im.joint_color_start[c + 1] += im.joint_color_start[c];
+        // per world, in sweep order (the sorted order is (colour, list index): a stable counting sort by world keeps it)
+        im.world_joint_start.assign(nw + 1, 0u);
+        for (size_t k = 0; k < nj; ++k) im.world_joint_start[gj[k].world + 1] += 1;
+        for (size_t w = 0; w < nw; ++w) im.world_joint_start[w + 1] += im.world_joint_start[w];
+        im.world_joint.resize(nj);
+        {
+            std::vector<uint32_t> cur(im.world_joint_start.begin(), im.world_joint_start.end() - 1);
+            for (size_t k = 0; k < nj; ++k) im.world_joint[cur[gj[k].world]++] = (uint32_t)k;
+        }
         im.body_nj.assign(nb, 0u);
         im.j_dep.assign(nj, make_uint4(0u, 0u, 0u, 0u));
         im.joints_flow_ok = nj > 0;

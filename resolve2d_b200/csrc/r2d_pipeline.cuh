@@ -193,7 +193,10 @@ struct Dev {
     uint32_t* sleep_state;         // NB: bit 0 asleep in this call, bit 1 moved fast in this call
     // ---- joints, grouped by colour -----------------------------------------------------------------------------------
     uint32_t n_joints;
-    const uint4* j_hdr;           // type, slot1, slot2, -
+    const uint4* j_hdr;           // type, slot1, slot2, joint colour
+    uint32_t n_joint_colors;
+    const uint32_t* world_joint_start;  // NW + 1: the joints of world w are world_joint[start[w] .. start[w + 1]), in sweep order
+    const uint32_t* world_joint;        // indices into j_hdr / j_par / j_vec (k_world_solve: joints of a world solved by its CTA)
     const float4* j_par;          // power_max, power_min, beta, target (distance | omega)
     const float4* j_vec;          // r1.x, r1.y, r2.x, r2.y  |  target.x, target.y, -, -
     // joints inside the dataflow sweep: the update sequence of a body in one iteration is [its joints in sweep order

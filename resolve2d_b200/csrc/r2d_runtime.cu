@@ -97,7 +97,7 @@ struct CudaBatch : BatchBase {
     uint32_t max_world_bodies = 0;   // false: one launch per colour (kept for A/B measurements)
     // bodies
     DBuf<float4> pos, mom, frc, prop, shape, aabb, pose, view;
-    DBuf<uint32_t> ncells, world_base, grav_off, joint_color_start, dev_of_host, host_of_dev;
+    DBuf<uint32_t> ncells, world_base, grav_off, joint_color_start, dev_of_host, host_of_dev, world_joint_start, world_joint;
     DBuf<float> grav;
     DBuf<uint64_t> excl;
     DBuf<uint4> j_hdr, bkt, j_dep;
@@ -153,6 +153,7 @@ struct CudaBatch : BatchBase {
     DBuf<uint4> adj_pool;   // chained entries of bodies with more than ADJ_CAP manifolds (dataflow colouring)
     int solve_wide = -1;              // k_solve_persistent with 512 threads per CTA: -1 by manifold count, 0 never, 1 always (R2D_SOLVE_WIDE)
     uint32_t solve_prefetch = 2;      // k_solve_persistent: streamed records fetched into L2 this many records ahead (R2D_SOLVE_PREFETCH)
+    bool world_joints = true;         // worlds with joints through k_world_solve too (R2D_WORLD_JOINTS=0: the device-wide persistent sweep)
     bool world_single = true;         // one world of <= 1,024 bodies without joints: k_world_solve with one CTA of 512 threads (R2D_WORLD_SINGLE=0: tiles)
     bool world_export = true;         // k_world_solve exports into page-locked read-back arrays itself (R2D_WORLD_EXPORT=0: separate kernel)
     bool world_exported = false;
@@ -218,12 +219,15 @@ struct CudaBatch : BatchBase {
         R2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bucket_count, TPB, 0));
         pair_blocks = (per_sm < 1 ? 1 : per_sm) * n_sms;  // resident CTAs: a CTA per heavy bucket, a warp per light one, grid-stride
         R2D_CUDA(cudaFuncSetAttribute(k_solve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES));
-        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<2, WORLD_SOLVE_TPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
-        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<2, WORLD_SOLVE_TPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
-        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<4, WORLD_SOLVE_TPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
-        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<4, WORLD_SOLVE_TPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
-        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<2, WORLD_SINGLE_TPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
-        R2D_CUDA(cudaFuncSetAttribute(k_world_solve<2, WORLD_SINGLE_TPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));
+#define R2D_WS_ATTR(BPT, WTPB)                                                                                                             \
+    R2D_CUDA(cudaFuncSetAttribute(k_world_solve<BPT, WTPB, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX)); \
+    R2D_CUDA(cudaFuncSetAttribute(k_world_solve<BPT, WTPB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));  \
+    R2D_CUDA(cudaFuncSetAttribute(k_world_solve<BPT, WTPB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX));  \
+    R2D_CUDA(cudaFuncSetAttribute(k_world_solve<BPT, WTPB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WORLD_SMEM_MAX))
+        R2D_WS_ATTR(2, WORLD_SOLVE_TPB);
+        R2D_WS_ATTR(4, WORLD_SOLVE_TPB);
+        R2D_WS_ATTR(2, WORLD_SINGLE_TPB);
+#undef R2D_WS_ATTR
         // Flavour switches for A/B measurements and tests.  Every one of them selects between paths that produce
         // bit-identical results; they are read here once, never inside process().
         auto env_is = [](const char* name, const char* value) {
@@ -237,6 +241,7 @@ struct CudaBatch : BatchBase {
         if (env_is("R2D_FLOW_LIST", "1")) flow_list_only = true;
         if (env_is("R2D_WORLD_EXPORT", "0")) world_export = false;
         if (env_is("R2D_WORLD_SINGLE", "0")) world_single = false;
+        if (env_is("R2D_WORLD_JOINTS", "0")) world_joints = false;
         if (const char* e = getenv("R2D_SOLVE_WIDE")) solve_wide = atoi(e);
         if (const char* e = getenv("R2D_SOLVE_PREFETCH")) solve_prefetch = (uint32_t)atoi(e);
         if (env_is("R2D_DEVICE_RESORT", "0")) device_resort = false;         // the periodic re-sort through the host
@@ -345,7 +350,8 @@ struct CudaBatch : BatchBase {
     int upload_slot_tables() {
         int st;
         if ((st = up(excl, image.excl)) || (st = up(j_hdr, image.j_hdr)) || (st = up(j_par, image.j_par)) || (st = up(j_vec, image.j_vec)) ||
-            (st = up(j_dep, image.j_dep)) || (st = up(body_nj, image.body_nj)) || (st = up(joint_color_start, image.joint_color_start)))
+            (st = up(j_dep, image.j_dep)) || (st = up(body_nj, image.body_nj)) || (st = up(joint_color_start, image.joint_color_start)) ||
+            (st = up(world_joint_start, image.world_joint_start)) || (st = up(world_joint, image.world_joint)))
             return st;
         return R2D_OK;
     }
@@ -672,6 +678,8 @@ struct CudaBatch : BatchBase {
         d.s_dep = s_dep.p;
         d.n_joints = (uint32_t)image.j_hdr.size();
         d.j_hdr = j_hdr.p; d.j_par = j_par.p; d.j_vec = j_vec.p;
+        d.n_joint_colors = (uint32_t)image.joint_color_start.size() - 1;
+        d.world_joint_start = world_joint_start.p; d.world_joint = world_joint.p;
         d.j_dep = j_dep.p; d.body_nj = body_nj.p;
         // (a sleeper is a static body for the call, and two-body joints write a static body's momentum, Q10: barrier sweep)
         d.joints_flow = (joints_flow && image.joints_flow_ok && mode != R2D_MODE_REFERENCE_ORDER && !opt_sleeping) ? 1u : 0u;
@@ -716,8 +724,9 @@ struct CudaBatch : BatchBase {
         else
             R = seen_world_m + seen_world_m / 32 + 4;
         R = (R + 3u) & ~3u;
-        while (world_smem_bytes(nb_cap, R) > WORLD_SMEM_MAX && R > 0) R = R / 2 & ~3u;
-        return world_smem_bytes(nb_cap, R);
+        const bool joints = !image.j_hdr.empty();
+        while (world_smem_bytes(nb_cap, R, joints) > WORLD_SMEM_MAX && R > 0) R = R / 2 & ~3u;
+        return world_smem_bytes(nb_cap, R, joints);
     }
 
     int launch_persistent(float sub_dt, uint32_t S, uint32_t I) {
@@ -830,7 +839,9 @@ struct CudaBatch : BatchBase {
         // one CTA per world: batches with enough worlds to fill the GPU with 128-thread CTAs, or a FEW worlds (one world, a handful
         // of worlds per GPU of a sharded batch) each small enough for one CTA of 512 threads
         const bool single_small = world_single && worlds.size() < (size_t)n_sms / 2 && max_world_bodies <= WORLD_SINGLE_MAX_BODIES;
-        const bool use_world_solver = persistent_solver && world_solver && image.j_hdr.empty() && !opt_warm_start &&
+        // (worlds with joints: their CTA solves them between the contact colours, R2D_WORLD_JOINTS=0: the device-wide sweep)
+        const bool world_has_joints = !image.j_hdr.empty();
+        const bool use_world_solver = persistent_solver && world_solver && (!world_has_joints || world_joints) && !opt_warm_start &&
                                       ((max_world_bodies <= WORLD_MAX_BODIES && worlds.size() >= (size_t)n_sms / 2) || single_small);
         world_fused_now = use_world_solver;
         const uint32_t tile_b = (nb + (uint32_t)n_sms - 1) / (uint32_t)n_sms;
@@ -1004,12 +1015,19 @@ struct CudaBatch : BatchBase {
                 }
                 prof_begin(R2D_KCLASS_SOLVE_CONTACTS);
                 const bool exporting = ex.pos != nullptr;
-#define R2D_WORLD_SOLVE(BPT, WTPB, GRID)                                                                              \
+#define R2D_WORLD_SOLVE_J(BPT, WTPB, GRID, JOINTS)                                                                      \
     do {                                                                                                              \
         if (exporting)                                                                                                \
-            k_world_solve<BPT, WTPB, true><<<GRID, WTPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, ex);             \
+            k_world_solve<BPT, WTPB, true, JOINTS><<<GRID, WTPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, ex);     \
         else                                                                                                          \
-            k_world_solve<BPT, WTPB, false><<<GRID, WTPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, ex);            \
+            k_world_solve<BPT, WTPB, false, JOINTS><<<GRID, WTPB, smem, stream>>>(d, sub_dt, S, I, nb_cap, R, ex);    \
+    } while (0)
+#define R2D_WORLD_SOLVE(BPT, WTPB, GRID)                                                                              \
+    do {                                                                                                              \
+        if (world_has_joints)                                                                                         \
+            R2D_WORLD_SOLVE_J(BPT, WTPB, GRID, true);                                                                 \
+        else                                                                                                          \
+            R2D_WORLD_SOLVE_J(BPT, WTPB, GRID, false);                                                                \
     } while (0)
                 if (single_small)
                     R2D_WORLD_SOLVE(2, WORLD_SINGLE_TPB, blocks);
@@ -1017,6 +1035,7 @@ struct CudaBatch : BatchBase {
                     R2D_WORLD_SOLVE(2, WORLD_SOLVE_TPB, blocks);
                 else
                     R2D_WORLD_SOLVE(4, WORLD_SOLVE_TPB, blocks);
+#undef R2D_WORLD_SOLVE_J
 #undef R2D_WORLD_SOLVE
                 prof_end();
                 launches += 1;

@@ -44,8 +44,9 @@ constexpr uint32_t WS_A = 1u << 25;       // first point of a two-point manifold
 constexpr uint32_t WORLD_SLOT_BYTES = 4 + 3 * 16;    // hdr, nfb, r, ma
 constexpr uint32_t WORLD_BODY_BYTES = 16 + 4 + 1;    // momentum word, 1 / inertia, static flag
 
-__host__ __device__ inline size_t world_smem_bytes(uint32_t nb_cap, uint32_t R) {
-    return (size_t)nb_cap * 24 + (size_t)R * WORLD_SLOT_BYTES + 16;   // (nb_cap is a multiple of 4: the byte flags round up to 4 per body)
+__host__ __device__ inline size_t world_smem_bytes(uint32_t nb_cap, uint32_t R, bool joints = false) {
+    // (nb_cap is a multiple of 4: the byte flags round up to 4 per body; worlds with joints also keep pose + torque per body)
+    return (size_t)nb_cap * (joints ? 40 : 24) + (size_t)R * WORLD_SLOT_BYTES + 16;
 }
 
 // where the slots of a world live
@@ -81,13 +82,64 @@ struct WorldExport {
     const uint32_t* host_of_dev;   // device slot -> host slot (the caller's order; a permutation inside every world)
 };
 
+// One joint of a world inside k_world_solve (Constraints/*.zig through the same solve_* functions as solve_joint_thread): the
+// bodies' momentum words are the shared ones, pose and torque the copies the body phase of this substep published.
+__device__ __noinline__ void world_solve_joint(const Dev& d, uint32_t j, uint32_t b0, float sub_dt, float4* s_mom, const float4* s_pose,
+                                               const unsigned char* s_st) {
+    const uint4 h = d.j_hdr[j];
+    const float4 par = d.j_par[j], vec = d.j_vec[j];
+    const float power_max = par.x, power_min = par.y, beta = par.z, target = par.w;
+    auto load = [&](uint32_t slot) {
+        const uint32_t i = slot - b0;
+        const float4 p = s_pose[i], m = s_mom[i], pr = d.prop[slot];
+        JointBody b;
+        b.pos = mk2(p.x, p.y);
+        b.angle = p.z;
+        b.mom = mk2(m.x, m.y);
+        b.ang = m.z;
+        b.mass = pr.x;
+        b.inertia = pr.y;
+        b.torque = p.w;
+        b.is_static = s_st[i] != 0;
+        return b;
+    };
+    auto store = [&](uint32_t slot, const JointBody& b) {
+        const uint32_t i = slot - b0;
+        s_mom[i] = make_float4(b.mom.x, b.mom.y, b.ang, s_mom[i].w);
+    };
+    switch (h.x) {
+        case 0: {  // distance
+            JointBody b1 = load(h.y), b2 = load(h.z);
+            solve_distance(b1, b2, target, beta, power_min, power_max);
+            store(h.y, b1);
+            store(h.z, b2);
+        } break;
+        case 1: {  // offset distance
+            JointBody b1 = load(h.y), b2 = load(h.z);
+            solve_offset_distance(b1, b2, mk2(vec.x, vec.y), mk2(vec.z, vec.w), target, beta, power_min, power_max);
+            store(h.y, b1);
+            store(h.z, b2);
+        } break;
+        case 2: {  // fixed position
+            JointBody b = load(h.y);
+            solve_fixed_position(b, mk2(vec.x, vec.y), beta, power_min, power_max);
+            store(h.y, b);
+        } break;
+        default: {  // motor
+            JointBody b = load(h.y);
+            solve_motor(b, target, beta, power_min, power_max, sub_dt);
+            store(h.y, b);
+        } break;
+    }
+}
+
 // Everything after the colour counts are known, for one world.  BPT = bodies a thread integrates (registers).
-template <bool SMEM, int BPT, int WTPB, bool EXPORT>
+template <bool SMEM, int BPT, int WTPB, bool EXPORT, bool JOINTS>
 __device__ __forceinline__ void world_run(const Dev& d, const WorldSlots<SMEM>& rc, uint32_t w, uint32_t b0, uint32_t nb,
                                           uint32_t p0, uint32_t p1, uint32_t nc, float sub_dt, uint32_t S, uint32_t I,
                                           float4* s_mom, float* s_ii, const unsigned char* s_st, const uint32_t* s_cnt,
                                           uint32_t* s_cur, const uint32_t* s_beg, float4 (&rp)[BPT], float4 (&rf)[BPT],
-                                          const WorldExport& ex) {
+                                          const WorldExport& ex, float4* s_pose) {
     const uint32_t tid = threadIdx.x, nth = blockDim.x, lane = tid & 31u;
     // ---- place + preStep (collision.zig:102-133; once per call, Q5) ----
     for (uint32_t p = p0 + tid; p < p1; p += nth) {
@@ -158,6 +210,7 @@ __device__ __forceinline__ void world_run(const Dev& d, const WorldSlots<SMEM>& 
                 const float4 sh = d.shape[b0 + i];
                 d.aabb[b0 + i] = refreshed_aabb(rp[k], f2u(sh.z), sh.x, sh.y);
             }
+            if (JOINTS) s_pose[i] = make_float4(rp[k].x, rp[k].y, rp[k].z, rf[k].z);   // what the joints of this substep read (torque: MotorJoint)
             if (st) continue;
             float4 f = rf[k];
             const float mass = rp[k].w;
@@ -172,7 +225,17 @@ __device__ __forceinline__ void world_run(const Dev& d, const WorldSlots<SMEM>& 
             s_mom[i] = m;
         }
         __syncthreads();
-        for (uint32_t it = 0; it < I; ++it)
+        for (uint32_t it = 0; it < I; ++it) {
+            if (JOINTS) {   // lib.zig:226-231: the joints of the world in sweep order = (colour, list index), a barrier per colour
+                const uint32_t j0 = d.world_joint_start[w], j1 = d.world_joint_start[w + 1];
+                for (uint32_t jc = 0; jc < d.n_joint_colors; ++jc) {
+                    for (uint32_t e = j0 + tid; e < j1; e += nth) {
+                        const uint32_t j = d.world_joint[e];
+                        if (d.j_hdr[j].w == jc) world_solve_joint(d, j, b0, sub_dt, s_mom, s_pose, s_st);
+                    }
+                    __syncthreads();
+                }
+            }
             for (uint32_t c = 0; c < nc; ++c) {
                 const uint32_t cnt = s_cnt[c];
                 if (cnt == 0u) continue;   // uniform
@@ -252,6 +315,7 @@ __device__ __forceinline__ void world_run(const Dev& d, const WorldSlots<SMEM>& 
                 }
                 __syncthreads();
             }
+        }
     }
     // ---- export ----
     if (S > 0) {
@@ -269,6 +333,8 @@ __device__ __forceinline__ void world_run(const Dev& d, const WorldSlots<SMEM>& 
                 d.pos[b0 + i] = make_float4(rp[k].x, rp[k].y, rp[k].z, 0.0f);
                 d.frc[b0 + i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 d.mom[b0 + i] = make_float4(m.x, m.y, m.z, 0.0f);
+            } else if (JOINTS) {
+                d.mom[b0 + i] = make_float4(m.x, m.y, m.z, 0.0f);   // distance joints write momentum into static bodies too (Q10)
             }
             if (EXPORT) {
                 xa[k] = make_float4(rp[k].x, rp[k].y, m.x, m.y);
@@ -299,7 +365,7 @@ __device__ __forceinline__ void world_run(const Dev& d, const WorldSlots<SMEM>& 
     }
 }
 
-template <int BPT, int WTPB = WORLD_SOLVE_TPB, bool EXPORT = false>
+template <int BPT, int WTPB = WORLD_SOLVE_TPB, bool EXPORT = false, bool JOINTS = false>
 __global__ void __launch_bounds__(WTPB, WTPB > 128 ? 1 : (BPT == 2 ? 6 : 4)) k_world_solve(Dev d, float sub_dt, uint32_t S, uint32_t I,
                                                                                   uint32_t nb_cap, uint32_t R, WorldExport ex) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -317,7 +383,8 @@ __global__ void __launch_bounds__(WTPB, WTPB > 128 ? 1 : (BPT == 2 ? 6 : 4)) k_w
     sm.ma_ = (float4*)q;          q += (size_t)R * 16;
     sm.hdr_ = (uint32_t*)q;       q += (size_t)R * 4;
     float* s_ii = (float*)q;      q += (size_t)nb_cap * 4;    // 1 / inertia (0: static)
-    unsigned char* s_st = q;                                  // 1: static
+    unsigned char* s_st = q;      q += (size_t)nb_cap * 4;    // 1: static
+    float4* s_pose = (float4*)q;                              // JOINTS: x, y, angle, torque as of the start of the substep
     const uint32_t tid = threadIdx.x, nth = blockDim.x;
     for (uint32_t w = blockIdx.x; w < d.n_worlds; w += gridDim.x) {
         const uint32_t b0 = d.world_base[w], b1 = d.world_base[w + 1], nb = b1 - b0;
@@ -382,14 +449,14 @@ __global__ void __launch_bounds__(WTPB, WTPB > 128 ? 1 : (BPT == 2 ? 6 : 4)) k_w
         __syncthreads();
         const uint32_t nc = s_nc;
         if (s_fits) {
-            world_run<true, BPT, WTPB, EXPORT>(d, sm, w, b0, nb, p0, p1, nc, sub_dt, S, I, s_mom, s_ii, s_st, s_cnt, s_cur, s_beg, rp, rf, ex);
+            world_run<true, BPT, WTPB, EXPORT, JOINTS>(d, sm, w, b0, nb, p0, p1, nc, sub_dt, S, I, s_mom, s_ii, s_st, s_cnt, s_cur, s_beg, rp, rf, ex, s_pose);
         } else {   // the world's own slice of the global record arrays (see the header comment)
             WorldSlots<false> rg;
             rg.hdr_[0] = (uint32_t*)d.s_acc0 + p0;  rg.hdr_[1] = (uint32_t*)d.s_acc1 + p0;
             rg.nfb_[0] = d.s_nf + p0;               rg.nfb_[1] = d.s_inv + p0;
             rg.r_[0] = d.s_r0 + p0;                 rg.r_[1] = d.s_r1 + p0;
             rg.ma_[0] = d.s_pm0 + p0;               rg.ma_[1] = d.s_pm1 + p0;
-            world_run<false, BPT, WTPB, EXPORT>(d, rg, w, b0, nb, p0, p1, nc, sub_dt, S, I, s_mom, s_ii, s_st, s_cnt, s_cur, s_beg, rp, rf, ex);
+            world_run<false, BPT, WTPB, EXPORT, JOINTS>(d, rg, w, b0, nb, p0, p1, nc, sub_dt, S, I, s_mom, s_ii, s_st, s_cnt, s_cur, s_beg, rp, rf, ex, s_pose);
         }
         __syncthreads();   // the next world of this CTA reuses the shared arrays
     }
